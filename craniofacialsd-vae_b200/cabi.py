@@ -1,0 +1,311 @@
+"""ctypes binding of the C ABI in ``include/sdvae_b200.h``.
+
+This is the only place that touches ``libsdvae_b200.so``.  Every wrapper takes
+torch CUDA tensors, checks dtype / contiguity / device, and passes raw device
+pointers plus the current CUDA stream.  A non-zero return code becomes a
+``RuntimeError`` carrying ``sdvae_last_error()``.  There is no CPU fallback: a
+missing library or a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsdvae_b200.so")
+
+ACT_NONE, ACT_ELU = 0, 1
+
+_lib = None
+
+_c_fp = C.c_void_p
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "sdvae_abi_version": (C.c_int, []),
+    "sdvae_last_error": (C.c_char_p, []),
+    "sdvae_spiralconv_fwd": (C.c_int, [_c_fp] * 5 + [C.c_int] * 7 + [_c_fp]),
+    "sdvae_weight_transpose": (C.c_int, [_c_fp, _c_fp, C.c_int, C.c_int, C.c_int, _c_fp]),
+    "sdvae_spiralconv_bwd_x": (C.c_int, [_c_fp] * 6 + [C.c_int] * 6 + [_c_fp]),
+    "sdvae_spiralconv_bwd_w_workspace": (C.c_size_t, [C.c_longlong, C.c_int, C.c_int, C.c_int]),
+    "sdvae_spiralconv_bwd_w": (C.c_int, [_c_fp] * 6 + [C.c_int] * 6 + [_c_fp]),
+    "sdvae_dense_fwd": (C.c_int, [_c_fp] * 4 + [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, _c_fp]),
+    "sdvae_transpose2d": (C.c_int, [_c_fp, _c_fp, C.c_int, C.c_int, _c_fp]),
+    "sdvae_pool_ell_fwd": (C.c_int, [_c_fp] * 4 + [C.c_int] * 5 + [_c_fp]),
+    "sdvae_csr_rowsum": (C.c_int, [_c_fp] * 6 + [C.c_int] * 4 + [_c_fp]),
+    "sdvae_elu_fwd": (C.c_int, [_c_fp, _c_fp, C.c_longlong, _c_fp]),
+    "sdvae_elu_bwd": (C.c_int, [_c_fp, _c_fp, _c_fp, C.c_longlong, _c_fp]),
+    "sdvae_reparam_fwd": (C.c_int, [_c_fp] * 4 + [C.c_longlong, _c_fp]),
+    "sdvae_reparam_bwd": (C.c_int, [_c_fp] * 5 + [C.c_longlong, C.c_int, _c_fp]),
+    "sdvae_axpy3": (C.c_int, [_c_fp, _c_fp, C.c_float, _c_fp, C.c_float, _c_fp, C.c_longlong, _c_fp]),
+    "sdvae_swap": (C.c_int, [_c_fp] * 3 + [C.c_int] * 5 + [_c_fp]),
+    "sdvae_mse_lap_partial_floats": (C.c_size_t, [C.c_int, C.c_int]),
+    "sdvae_mse_lap_fwd": (C.c_int, [_c_fp] * 4 + [C.c_int] + [_c_fp] * 3 + [C.c_int, C.c_int, C.c_float, _c_fp]),
+    "sdvae_mse_lap_bwd": (C.c_int, [_c_fp] * 7 + [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, _c_fp, _c_fp]),
+    "sdvae_kl_fwd_bwd": (C.c_int, [_c_fp] * 6 + [C.c_int, C.c_int, C.c_float, _c_fp]),
+    "sdvae_lc_fwd_bwd": (C.c_int, [_c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float] + [_c_fp] * 4 + [_c_fp]),
+    "sdvae_total_loss": (C.c_int, [_c_fp, C.c_float, C.c_float, C.c_float, C.c_float, _c_fp]),
+    "sdvae_adam_tick": (C.c_int, [_c_fp, _c_fp]),
+    "sdvae_adam_step": (C.c_int, [_c_fp] * 4 + [C.c_longlong, _c_fp, C.c_int] + [C.c_float] * 6 + [_c_fp]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def load(build_if_missing: bool = False):
+    """Load the shared library (once).  Raises if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if build_if_missing:
+            from . import build as _build
+            _build.build_library()
+        else:
+            raise RuntimeError(
+                "sdvae_b200: %s is missing -- run `python __graft_entry__.py build` "
+                "(nvcc, sm_100a).  There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+# kernels launched per ABI call (for bench.py's `gpu_launches`)
+_KERNELS_PER_CALL = {
+    "spiralconv_fwd": 1, "weight_transpose": 1, "spiralconv_bwd_x": 1, "spiralconv_bwd_w": 3,
+    "dense_fwd": 1, "transpose2d": 1, "pool_ell_fwd": 1, "csr_rowsum": 1, "elu_fwd": 1,
+    "elu_bwd": 1, "reparam_fwd": 1, "reparam_bwd": 1, "axpy3": 1, "swap": 1, "mse_lap_fwd": 3,
+    "mse_lap_bwd": 1, "kl_fwd_bwd": 2, "lc_fwd_bwd": 3, "total_loss": 1, "adam_tick": 1,
+    "adam_step": 1,
+}
+_launches = 0
+
+
+def launch_count() -> int:
+    """Number of sdvae_b200 kernels launched (or replayed from a graph) by this process."""
+    return _launches
+
+
+def add_launches(n: int):
+    global _launches
+    _launches += int(n)
+
+
+def _err(code: int, what: str):
+    msg = load().sdvae_last_error().decode("utf-8", "replace")
+    raise RuntimeError("sdvae_b200 %s failed (code %d): %s" % (what, code, msg))
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: torch.Tensor, dtype, name: str) -> int:
+    if not t.is_cuda:
+        raise RuntimeError("sdvae_b200: %s must be a CUDA tensor (no CPU fallback)" % name)
+    if t.dtype != dtype:
+        raise TypeError("sdvae_b200: %s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("sdvae_b200: %s must be contiguous" % name)
+    return t.data_ptr()
+
+
+def _f(t, name):
+    return _chk(t, torch.float32, name)
+
+
+def _i(t, name):
+    return _chk(t, torch.int32, name)
+
+
+def _fo(t: Optional[torch.Tensor], name):
+    return None if t is None else _f(t, name)
+
+
+# ---------------------------------------------------------------------------------
+def spiralconv_fwd(x, idx32, weight, bias, y, B, Vin, Vout, S, Cin, Cout, act):
+    rc = load().sdvae_spiralconv_fwd(_f(x, "x"), _i(idx32, "idx"), _f(weight, "weight"),
+                                     _fo(bias, "bias"), _f(y, "y"), B, Vin, Vout, S, Cin, Cout,
+                                     act, _stream())
+    if rc:
+        _err(rc, "spiralconv_fwd")
+    add_launches(_KERNELS_PER_CALL["spiralconv_fwd"])
+
+
+def weight_transpose(weight, wt, Cout, Cin, S):
+    rc = load().sdvae_weight_transpose(_f(weight, "weight"), _f(wt, "wt"), Cout, Cin, S, _stream())
+    if rc:
+        _err(rc, "weight_transpose")
+    add_launches(_KERNELS_PER_CALL["weight_transpose"])
+
+
+def spiralconv_bwd_x(dpre, cell_ptr, cell_src, wt, gate, dx, B, Vrows, Vdst, S, Cout, Cin):
+    rc = load().sdvae_spiralconv_bwd_x(_f(dpre, "dpre"), _i(cell_ptr, "cell_ptr"),
+                                       _i(cell_src, "cell_src"), _f(wt, "wt"), _fo(gate, "gate"),
+                                       _f(dx, "dx"), B, Vrows, Vdst, S, Cout, Cin, _stream())
+    if rc:
+        _err(rc, "spiralconv_bwd_x")
+    add_launches(_KERNELS_PER_CALL["spiralconv_bwd_x"])
+
+
+def spiralconv_bwd_w_workspace(M, S, Cin, Cout) -> int:
+    return int(load().sdvae_spiralconv_bwd_w_workspace(M, S, Cin, Cout))
+
+
+def spiralconv_bwd_w(x, idx32, dpre, dW, db, workspace, B, Vin, Vout, S, Cin, Cout):
+    rc = load().sdvae_spiralconv_bwd_w(_f(x, "x"), _i(idx32, "idx"), _f(dpre, "dpre"),
+                                       _f(dW, "dW"), _fo(db, "db"), _f(workspace, "workspace"),
+                                       B, Vin, Vout, S, Cin, Cout, _stream())
+    if rc:
+        _err(rc, "spiralconv_bwd_w")
+    add_launches(_KERNELS_PER_CALL["spiralconv_bwd_w"])
+
+
+def dense_fwd(inp, weight, bias, out, M, K, N, ldw, act):
+    rc = load().sdvae_dense_fwd(_f(inp, "in"), _f(weight, "weight"), _fo(bias, "bias"),
+                                _f(out, "out"), M, K, N, ldw, act, _stream())
+    if rc:
+        _err(rc, "dense_fwd")
+    add_launches(_KERNELS_PER_CALL["dense_fwd"])
+
+
+def transpose2d(inp, out, R, Ccols):
+    rc = load().sdvae_transpose2d(_f(inp, "in"), _f(out, "out"), R, Ccols, _stream())
+    if rc:
+        _err(rc, "transpose2d")
+    add_launches(_KERNELS_PER_CALL["transpose2d"])
+
+
+def pool_ell_fwd(x, col, val, out, B, Vin, Vout, Wd, Cc):
+    rc = load().sdvae_pool_ell_fwd(_f(x, "x"), _i(col, "col"), _f(val, "val"), _f(out, "out"),
+                                   B, Vin, Vout, Wd, Cc, _stream())
+    if rc:
+        _err(rc, "pool_ell_fwd")
+    add_launches(_KERNELS_PER_CALL["pool_ell_fwd"])
+
+
+def csr_rowsum(dy, ptr, src, val, gate, dx, B, Vsrc, Vdst, Cc):
+    rc = load().sdvae_csr_rowsum(_f(dy, "dy"), _i(ptr, "ptr"), _i(src, "src"), _fo(val, "val"),
+                                 _fo(gate, "gate"), _f(dx, "dx"), B, Vsrc, Vdst, Cc, _stream())
+    if rc:
+        _err(rc, "csr_rowsum")
+    add_launches(_KERNELS_PER_CALL["csr_rowsum"])
+
+
+def elu_fwd(x, y):
+    rc = load().sdvae_elu_fwd(_f(x, "x"), _f(y, "y"), x.numel(), _stream())
+    if rc:
+        _err(rc, "elu_fwd")
+    add_launches(_KERNELS_PER_CALL["elu_fwd"])
+
+
+def elu_bwd(dy, y, dx):
+    rc = load().sdvae_elu_bwd(_f(dy, "dy"), _f(y, "y"), _f(dx, "dx"), dy.numel(), _stream())
+    if rc:
+        _err(rc, "elu_bwd")
+    add_launches(_KERNELS_PER_CALL["elu_bwd"])
+
+
+def reparam_fwd(mu, logvar, eps, z):
+    rc = load().sdvae_reparam_fwd(_f(mu, "mu"), _f(logvar, "logvar"), _f(eps, "eps"), _f(z, "z"),
+                                  mu.numel(), _stream())
+    if rc:
+        _err(rc, "reparam_fwd")
+    add_launches(_KERNELS_PER_CALL["reparam_fwd"])
+
+
+def reparam_bwd(dz, logvar, eps, dmu, dlogvar, accumulate=False):
+    rc = load().sdvae_reparam_bwd(_f(dz, "dz"), _f(logvar, "logvar"), _f(eps, "eps"),
+                                  _f(dmu, "dmu"), _f(dlogvar, "dlogvar"), dz.numel(),
+                                  1 if accumulate else 0, _stream())
+    if rc:
+        _err(rc, "reparam_bwd")
+    add_launches(_KERNELS_PER_CALL["reparam_bwd"])
+
+
+def axpy3(a, b, sb, c, sc, out):
+    rc = load().sdvae_axpy3(_fo(a, "a"), _fo(b, "b"), sb, _fo(c, "c"), sc, _f(out, "out"),
+                            out.numel(), _stream())
+    if rc:
+        _err(rc, "axpy3")
+    add_launches(_KERNELS_PER_CALL["axpy3"])
+
+
+def swap(x, mask_u8, out, bs, i0, i1, V, Cc):
+    rc = load().sdvae_swap(_f(x, "x"), _chk(mask_u8, torch.uint8, "mask"), _f(out, "out"),
+                           bs, i0, i1, V, Cc, _stream())
+    if rc:
+        _err(rc, "swap")
+    add_launches(_KERNELS_PER_CALL["swap"])
+
+
+def mse_lap_partial_floats(B, V) -> int:
+    return int(load().sdvae_mse_lap_partial_floats(B, V))
+
+
+def mse_lap_fwd(recon, x, lcol, lval, lw, qn, partial, losses, B, V, scale=1.0):
+    rc = load().sdvae_mse_lap_fwd(_f(recon, "recon"), _f(x, "x"),
+                                  None if lcol is None else _i(lcol, "lcol"), _fo(lval, "lval"), lw,
+                                  _fo(qn, "qn"), _f(partial, "partial"), _f(losses, "losses"),
+                                  B, V, scale, _stream())
+    if rc:
+        _err(rc, "mse_lap_fwd")
+    add_launches(_KERNELS_PER_CALL["mse_lap_fwd"])
+
+
+def mse_lap_bwd(recon, x, qn, tptr, trow, tval, drecon, B, V, g_mse, g_lap, scale=1.0, dscale=None):
+    rc = load().sdvae_mse_lap_bwd(_f(recon, "recon"), _f(x, "x"), _fo(qn, "qn"),
+                                  None if tptr is None else _i(tptr, "tptr"),
+                                  None if trow is None else _i(trow, "trow"), _fo(tval, "tval"),
+                                  _f(drecon, "drecon"), B, V, g_mse, g_lap, scale,
+                                  _fo(dscale, "dscale"), _stream())
+    if rc:
+        _err(rc, "mse_lap_bwd")
+    add_launches(_KERNELS_PER_CALL["mse_lap_bwd"])
+
+
+def kl_fwd_bwd(mu, logvar, dmu, dlogvar, partial, losses, B, D, scale=1.0):
+    rc = load().sdvae_kl_fwd_bwd(_f(mu, "mu"), _f(logvar, "logvar"), _f(dmu, "dmu"),
+                                 _f(dlogvar, "dlogvar"), _f(partial, "partial"),
+                                 _f(losses, "losses"), B, D, scale, _stream())
+    if rc:
+        _err(rc, "kl_fwd_bwd")
+    add_launches(_KERNELS_PER_CALL["kl_fwd_bwd"])
+
+
+def lc_fwd_bwd(z, bs, D, r0, r1, eta1, eta2, act_ws, partial, dz, losses):
+    rc = load().sdvae_lc_fwd_bwd(_f(z, "z"), bs, D, r0, r1, eta1, eta2,
+                                 _chk(act_ws, torch.uint8, "act_ws"), _f(partial, "partial"),
+                                 _f(dz, "dz"), _f(losses, "losses"), _stream())
+    if rc:
+        _err(rc, "lc_fwd_bwd")
+    add_launches(_KERNELS_PER_CALL["lc_fwd_bwd"])
+
+
+def total_loss(losses, w_kl, w_lc, w_lap, w_cls=0.0):
+    rc = load().sdvae_total_loss(_f(losses, "losses"), w_kl, w_lc, w_lap, w_cls, _stream())
+    if rc:
+        _err(rc, "total_loss")
+    add_launches(_KERNELS_PER_CALL["total_loss"])
+
+
+def adam_tick(step_dev):
+    rc = load().sdvae_adam_tick(_i(step_dev, "step"), _stream())
+    if rc:
+        _err(rc, "adam_tick")
+    add_launches(_KERNELS_PER_CALL["adam_tick"])
+
+
+def adam_step(p, grad, m, v, step_dev, step_host, lr, b1, b2, eps, wd, gscale=1.0):
+    rc = load().sdvae_adam_step(_f(p, "p"), _f(grad, "grad"), _f(m, "m"), _f(v, "v"), p.numel(),
+                                None if step_dev is None else _i(step_dev, "step"), step_host,
+                                lr, b1, b2, eps, wd, gscale, _stream())
+    if rc:
+        _err(rc, "adam_step")
+    add_launches(_KERNELS_PER_CALL["adam_step"])

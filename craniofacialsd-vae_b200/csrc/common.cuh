@@ -1,0 +1,83 @@
+// Shared helpers for the sdvae_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace sdvae {
+
+// ---- error plumbing: C ABI returns int codes + a per-process message -------
+enum : int { SDVAE_OK = 0, SDVAE_ERR_ARG = 1, SDVAE_ERR_CUDA = 2, SDVAE_ERR_UNSUPPORTED = 3 };
+
+extern char g_last_error[512];
+
+inline int set_error(int code, const char* msg) {
+    strncpy(g_last_error, msg, sizeof(g_last_error) - 1);
+    g_last_error[sizeof(g_last_error) - 1] = 0;
+    return code;
+}
+
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        char buf[512];
+        snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+        return set_error(SDVAE_ERR_CUDA, buf);
+    }
+    return SDVAE_OK;
+}
+
+#define SDVAE_REQUIRE(cond, msg) \
+    do { if (!(cond)) return ::sdvae::set_error(::sdvae::SDVAE_ERR_ARG, msg); } while (0)
+
+constexpr int kNumSMs = 148;   // B200
+
+// ---- device helpers --------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N)); }
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// F.elu with alpha = 1 (reference model.py:68,84): x > 0 ? x : expm1(x)
+__device__ __forceinline__ float elu_f(float v) { return v > 0.f ? v : expm1f(v); }
+// d elu / d pre expressed through the OUTPUT y = elu(pre): 1 if y > 0 else y + 1 (= exp(pre))
+__device__ __forceinline__ float elu_grad_from_out(float y) { return y > 0.f ? 1.f : y + 1.f; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block reduction (fixed tree); result valid in thread 0.
+template <int THREADS>
+__device__ __forceinline__ float block_sum(float v, float* scratch /* >= THREADS/32 floats */) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    float r = 0.f;
+    if (w == 0) {
+        r = lane < THREADS / 32 ? scratch[lane] : 0.f;
+        r = warp_sum(r);
+    }
+    __syncthreads();
+    return r;
+}
+
+}  // namespace sdvae

@@ -1,0 +1,367 @@
+// C ABI of sdvae_b200 (see include/sdvae_b200.h).  Host-side dispatch only: argument
+// checks, template selection, launches.  Build:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+#include "../../include/sdvae_b200.h"
+#include "common.cuh"
+#include "spiral_conv.cuh"
+#include "pool_misc.cuh"
+#include "loss.cuh"
+
+namespace sdvae {
+char g_last_error[512] = "";
+
+static inline unsigned blocks_for(long long n, int threads) {
+    return (unsigned)((n + threads - 1) / threads);
+}
+
+// ---- tiled gather-contraction dispatch ----------------------------------------
+template <int KS, int NT, int TM, int TN, int NWARPS, bool RAGGED>
+static int launch_gc(const GcArgs& a, int epi, cudaStream_t st) {
+    using Cfg = GcCfg<KS, NT, TM, TN, NWARPS>;
+    const size_t smem = Cfg::smem_bytes(a.S, RAGGED);
+    const dim3 grid((unsigned)((a.M + Cfg::BM - 1) / Cfg::BM), (unsigned)((a.n_real + NT - 1) / NT));
+    auto kern = gc_tile_kernel<KS, NT, TM, TN, NWARPS, RAGGED>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_done = true;
+    }
+    GcArgs b = a;
+    b.epi = epi;
+    kern<<<grid, Cfg::THREADS, smem, st>>>(b);
+    return check_launch("gc_tile_kernel");
+}
+
+template <bool RAGGED>
+static int dispatch_gc(const GcArgs& a, int KS, int epi, cudaStream_t st) {
+    if (a.M <= 0) return SDVAE_OK;
+    const int N = a.n_real;
+    const bool w_ok = (a.ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.W) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(a.in) & 15) == 0);
+    if (w_ok && a.S <= 64) {
+        if (KS == 32 && N % 32 == 0 && N % 64 != 0) return launch_gc<32, 32, 4, 8, 8, RAGGED>(a, epi, st);
+        if (KS == 32 && N % 64 == 0) return launch_gc<32, 64, 4, 8, 8, RAGGED>(a, epi, st);
+        if (KS == 64 && N % 32 == 0 && N % 64 != 0) return launch_gc<64, 32, 4, 8, 8, RAGGED>(a, epi, st);
+        if (KS == 64 && N % 64 == 0) return launch_gc<64, 64, 4, 8, 8, RAGGED>(a, epi, st);
+        if (KS == 32 && N <= 4) return launch_gc<32, 4, 2, 4, 4, RAGGED>(a, epi, st);
+        if (KS == 64 && N <= 4) return launch_gc<64, 4, 2, 4, 4, RAGGED>(a, epi, st);
+    }
+    if (KS == 3 && a.S * 3 <= 32 && N % 32 == 0) return launch_gc<3, 32, 4, 8, 8, RAGGED>(a, epi, st);
+    // shape-agnostic fallback
+    const long long total = a.M * a.n_real;
+    gc_generic_kernel<RAGGED><<<blocks_for(total, 256), 256, 0, st>>>(a, KS, epi);
+    return check_launch("gc_generic_kernel");
+}
+
+// ---- weight gradient dispatch ---------------------------------------------------
+constexpr int kBwBMW = 16;
+constexpr int kBwMaxSplit = 592;     // 4 CTAs per SM
+constexpr int kBwMinRows = 256;
+
+static inline void bw_split(long long M, long long* rows_per_cta, int* nsplit) {
+    long long rows = (M + kBwMaxSplit - 1) / kBwMaxSplit;
+    if (rows < kBwMinRows) rows = kBwMinRows;
+    rows = (rows + kBwBMW - 1) / kBwBMW * kBwBMW;
+    *rows_per_cta = rows;
+    *nsplit = (int)((M + rows - 1) / rows);
+    if (*nsplit < 1) *nsplit = 1;
+}
+
+template <int KS, int S_, int NT, int TK, int TN>
+static int launch_bw(const BwArgs& a, int nsplit, cudaStream_t st) {
+    using Cfg = BwCfg<KS, S_, NT, TK, TN, kBwBMW>;
+    auto kern = bw_outer_kernel<KS, S_, NT, TK, TN, kBwBMW>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_done = true;
+    }
+    kern<<<nsplit, Cfg::THREADS, Cfg::SMEM, st>>>(a);
+    return check_launch("bw_outer_kernel");
+}
+
+}  // namespace sdvae
+
+using namespace sdvae;
+
+extern "C" {
+
+int sdvae_abi_version(void) { return 1; }
+const char* sdvae_last_error(void) { return g_last_error; }
+
+int sdvae_spiralconv_fwd(const float* x, const int32_t* idx, const float* W, const float* bias,
+                         float* y, int B, int Vin, int Vout, int S, int Cin, int Cout, int act,
+                         sdvae_stream_t stream) {
+    SDVAE_REQUIRE(x && idx && W && y, "spiralconv_fwd: null pointer");
+    SDVAE_REQUIRE(B >= 0 && Vin > 0 && Vout > 0 && S > 0 && Cin > 0 && Cout > 0, "spiralconv_fwd: bad shape");
+    SDVAE_REQUIRE((long long)B * Vin < 2147483647LL, "spiralconv_fwd: B*Vin exceeds int32 rows");
+    GcArgs a{};
+    a.in = x; a.idx = idx; a.W = W; a.bias = bias; a.out = y;
+    a.M = (long long)B * Vout; a.in_rows = Vin; a.Vout = Vout; a.S = S;
+    a.ldw = S * Cin; a.ldo = Cout; a.n_real = Cout;
+    const int epi = act == SDVAE_ACT_ELU ? EPI_BIAS_ELU : EPI_BIAS;
+    return dispatch_gc<false>(a, Cin, epi, (cudaStream_t)stream);
+}
+
+int sdvae_weight_transpose(const float* W, float* Wt, int Cout, int Cin, int S, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(W && Wt && Cout > 0 && Cin > 0 && S > 0, "weight_transpose: bad argument");
+    const int total = Cout * Cin * S;
+    weight_transpose_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(W, Wt, Cout, Cin, S);
+    return check_launch("weight_transpose_kernel");
+}
+
+int sdvae_spiralconv_bwd_x(const float* dpre, const int32_t* cell_ptr, const int32_t* cell_src,
+                           const float* Wt, const float* gate, float* dx, int B, int Vrows,
+                           int Vdst, int S, int Cout, int Cin, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(dpre && cell_ptr && cell_src && Wt && dx, "spiralconv_bwd_x: null pointer");
+    SDVAE_REQUIRE(B >= 0 && Vrows > 0 && Vdst > 0 && S > 0 && Cin > 0 && Cout > 0, "spiralconv_bwd_x: bad shape");
+    SDVAE_REQUIRE((long long)B * Vrows < 2147483647LL, "spiralconv_bwd_x: B*Vrows exceeds int32 rows");
+    GcArgs a{};
+    a.in = dpre; a.cell_ptr = cell_ptr; a.cell_src = cell_src; a.W = Wt; a.gate = gate; a.out = dx;
+    a.M = (long long)B * Vdst; a.in_rows = Vrows; a.Vout = Vdst; a.S = S;
+    a.ldw = S * Cout; a.ldo = Cin; a.n_real = Cin;
+    return dispatch_gc<true>(a, Cout, gate ? EPI_GATE : EPI_NONE, (cudaStream_t)stream);
+}
+
+size_t sdvae_spiralconv_bwd_w_workspace(long long M, int S, int Cin, int Cout) {
+    long long rows; int nsplit;
+    bw_split(M, &rows, &nsplit);
+    return (size_t)nsplit * (size_t)Cout * ((size_t)S * Cin + 1) * sizeof(float);
+}
+
+int sdvae_spiralconv_bwd_w(const float* x, const int32_t* idx, const float* dpre, float* dW,
+                           float* db, void* workspace, int B, int Vin, int Vout, int S, int Cin,
+                           int Cout, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(x && idx && dpre && dW && workspace, "spiralconv_bwd_w: null pointer");
+    SDVAE_REQUIRE(B >= 0 && Vin > 0 && Vout > 0 && S > 0 && Cin > 0 && Cout > 0, "spiralconv_bwd_w: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int K = S * Cin;
+    BwArgs a{};
+    a.in = x; a.idx = idx; a.g = dpre;
+    a.M = (long long)B * Vout; a.in_rows = Vin; a.Vout = Vout; a.n_real = Cout;
+    int nsplit;
+    bw_split(a.M, &a.rows_per_cta, &nsplit);
+    a.part = static_cast<float*>(workspace);
+    a.part_b = a.part + (size_t)nsplit * Cout * K;
+    int rc = SDVAE_OK;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dpre) & 15) == 0);
+    if (a.M == 0) {
+        cudaMemsetAsync(dW, 0, sizeof(float) * Cout * K, st);
+        if (db) cudaMemsetAsync(db, 0, sizeof(float) * Cout, st);
+        return check_launch("bwd_w memset");
+    }
+    if (aligned && S == 9 && Cin == 32 && Cout == 32) rc = launch_bw<32, 9, 32, 8, 8>(a, nsplit, st);
+    else if (aligned && S == 9 && Cin == 32 && Cout == 64) rc = launch_bw<32, 9, 64, 8, 8>(a, nsplit, st);
+    else if (aligned && S == 9 && Cin == 64 && Cout == 64) rc = launch_bw<64, 9, 64, 8, 8>(a, nsplit, st);
+    else if (aligned && S == 9 && Cin == 64 && Cout == 32) rc = launch_bw<64, 9, 32, 8, 8>(a, nsplit, st);
+    else if (aligned && S == 9 && Cin == 32 && Cout == 3) rc = launch_bw<32, 9, 4, 2, 4>(a, nsplit, st);
+    else if (S == 9 && Cin == 3 && Cout == 32 && aligned) rc = launch_bw<3, 9, 32, 2, 4>(a, nsplit, st);
+    else {
+        const dim3 grid((unsigned)nsplit, blocks_for((long long)Cout * (K + 1), 128));
+        bw_generic_kernel<<<grid, 128, 0, st>>>(a, Cin, S);
+        rc = check_launch("bw_generic_kernel");
+    }
+    if (rc) return rc;
+    const long long len = (long long)Cout * K;
+    split_reduce_kernel<<<blocks_for(len, 256), 256, 0, st>>>(a.part, dW, nsplit, len);
+    if (db) split_reduce_kernel<<<blocks_for(Cout, 256), 256, 0, st>>>(a.part_b, db, nsplit, Cout);
+    return check_launch("split_reduce_kernel");
+}
+
+int sdvae_dense_fwd(const float* in, const float* W, const float* bias, float* out, long long M,
+                    int K, int N, int ldw, int act, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(in && W && out && M >= 0 && K > 0 && N > 0 && ldw >= K, "dense_fwd: bad argument");
+    SDVAE_REQUIRE(M < 2147483647LL, "dense_fwd: M exceeds int32 rows");
+    GcArgs a{};
+    a.in = in; a.idx = nullptr; a.W = W; a.bias = bias; a.out = out;
+    a.M = M; a.in_rows = (int)(M > 0 ? M : 1); a.Vout = (int)(M > 0 ? M : 1); a.S = 1;
+    a.ldw = ldw; a.ldo = N; a.n_real = N;
+    const int epi = act == SDVAE_ACT_ELU ? EPI_BIAS_ELU : (bias ? EPI_BIAS : EPI_NONE);
+    return dispatch_gc<false>(a, K, epi, (cudaStream_t)stream);
+}
+
+__global__ void transpose2d_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        if (r < R && c < C) tile[i][threadIdx.x] = in[(size_t)r * C + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < R && c < C) out[(size_t)c * R + r] = tile[threadIdx.x][i];
+    }
+}
+
+int sdvae_transpose2d(const float* in, float* out, int R, int C, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(in && out && R > 0 && C > 0, "transpose2d: bad argument");
+    const dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
+    transpose2d_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, out, R, C);
+    return check_launch("transpose2d_kernel");
+}
+
+int sdvae_pool_ell_fwd(const float* x, const int32_t* col, const float* val, float* out, int B,
+                       int Vin, int Vout, int Wd, int C, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(x && col && val && out, "pool_ell_fwd: null pointer");
+    SDVAE_REQUIRE(B >= 0 && Vin > 0 && Vout > 0 && Wd > 0 && C > 0, "pool_ell_fwd: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    const long long total = (long long)B * Vout * (vec ? C / 4 : C);
+    if (total == 0) return SDVAE_OK;
+    if (vec) pool_ell_fwd_kernel<true><<<blocks_for(total, 256), 256, 0, st>>>(x, col, val, out, total, Vin, Vout, Wd, C);
+    else pool_ell_fwd_kernel<false><<<blocks_for(total, 256), 256, 0, st>>>(x, col, val, out, total, Vin, Vout, Wd, C);
+    return check_launch("pool_ell_fwd_kernel");
+}
+
+int sdvae_csr_rowsum(const float* dy, const int32_t* ptr, const int32_t* src, const float* val,
+                     const float* gate, float* dx, int B, int Vsrc, int Vdst, int C,
+                     sdvae_stream_t stream) {
+    SDVAE_REQUIRE(dy && ptr && src && dx, "csr_rowsum: null pointer");
+    SDVAE_REQUIRE(B >= 0 && Vsrc > 0 && Vdst > 0 && C > 0, "csr_rowsum: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(dx) & 15) == 0) &&
+                     (!gate || (reinterpret_cast<uintptr_t>(gate) & 15) == 0);
+    const long long total = (long long)B * Vdst * (vec ? C / 4 : C);
+    if (total == 0) return SDVAE_OK;
+    if (vec) csr_rowsum_kernel<true><<<blocks_for(total, 256), 256, 0, st>>>(dy, ptr, src, val, gate, dx, total, Vsrc, Vdst, C);
+    else csr_rowsum_kernel<false><<<blocks_for(total, 256), 256, 0, st>>>(dy, ptr, src, val, gate, dx, total, Vsrc, Vdst, C);
+    return check_launch("csr_rowsum_kernel");
+}
+
+int sdvae_elu_fwd(const float* x, float* y, long long n, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(x && y && n >= 0, "elu_fwd: bad argument");
+    if (n == 0) return SDVAE_OK;
+    elu_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n);
+    return check_launch("elu_kernel");
+}
+
+int sdvae_elu_bwd(const float* dy, const float* y, float* dx, long long n, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(dy && y && dx && n >= 0, "elu_bwd: bad argument");
+    if (n == 0) return SDVAE_OK;
+    elu_gate_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, y, dx, n);
+    return check_launch("elu_gate_kernel");
+}
+
+int sdvae_reparam_fwd(const float* mu, const float* logvar, const float* eps, float* z,
+                      long long n, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(mu && logvar && eps && z && n >= 0, "reparam_fwd: bad argument");
+    if (n == 0) return SDVAE_OK;
+    reparam_fwd_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(mu, logvar, eps, z, n);
+    return check_launch("reparam_fwd_kernel");
+}
+
+int sdvae_reparam_bwd(const float* dz, const float* logvar, const float* eps, float* dmu,
+                      float* dlogvar, long long n, int accumulate, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(dz && logvar && eps && dmu && dlogvar && n >= 0, "reparam_bwd: bad argument");
+    if (n == 0) return SDVAE_OK;
+    reparam_bwd_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(dz, logvar, eps, dmu, dlogvar, n, accumulate);
+    return check_launch("reparam_bwd_kernel");
+}
+
+int sdvae_axpy3(const float* a, const float* b, float sb, const float* c, float sc, float* out,
+                long long n, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(out && n >= 0, "axpy3: bad argument");
+    if (n == 0) return SDVAE_OK;
+    axpy3_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, sb, c, sc, out, n);
+    return check_launch("axpy3_kernel");
+}
+
+int sdvae_swap(const float* x, const uint8_t* mask, float* out, int bs, int i0, int i1, int V,
+               int C, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(x && mask && out, "swap: null pointer");
+    SDVAE_REQUIRE(bs > 0 && i0 >= 0 && i1 >= i0 && i1 <= bs && V > 0 && C > 0, "swap: bad shape");
+    const long long total = (long long)(i1 - i0) * bs * V * C;
+    if (total == 0) return SDVAE_OK;
+    swap_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, mask, out, bs, i0, i1, V, C);
+    return check_launch("swap_kernel");
+}
+
+size_t sdvae_mse_lap_partial_floats(int B, int V) {
+    return 2 * (size_t)blocks_for((long long)B * V, kLossThreads);
+}
+
+int sdvae_mse_lap_fwd(const float* recon, const float* x, const int32_t* lcol, const float* lval,
+                      int lw, float* qn, float* partial, float* losses, int B, int V,
+                      float inv_count_scale, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(recon && x && partial && losses && B > 0 && V > 0, "mse_lap_fwd: bad argument");
+    SDVAE_REQUIRE(!lcol || (lval && qn && lw > 0), "mse_lap_fwd: Laplacian tables incomplete");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long BV = (long long)B * V;
+    const unsigned grid = blocks_for(BV, kLossThreads);
+    mse_lap_fwd_kernel<<<grid, kLossThreads, 0, st>>>(recon, x, lcol, lval, lw, qn, partial, BV, V);
+    finish_sum_kernel<<<1, kLossThreads, 0, st>>>(partial, grid, 2, 0, inv_count_scale / (float)((double)BV * 3.0), losses, 0);
+    if (lcol) finish_sum_kernel<<<1, kLossThreads, 0, st>>>(partial, grid, 2, 1, inv_count_scale / (float)BV, losses, 3);
+    return check_launch("mse_lap_fwd");
+}
+
+int sdvae_mse_lap_bwd(const float* recon, const float* x, const float* qn, const int32_t* tptr,
+                      const int32_t* trow, const float* tval, float* drecon, int B, int V,
+                      float g_mse, float g_lap, float inv_count_scale, const float* dscale,
+                      sdvae_stream_t stream) {
+    SDVAE_REQUIRE(recon && x && drecon && B > 0 && V > 0, "mse_lap_bwd: bad argument");
+    SDVAE_REQUIRE(!tptr || (trow && tval && qn), "mse_lap_bwd: Laplacian tables incomplete");
+    const long long BV = (long long)B * V;
+    const float c_mse = g_mse * inv_count_scale / (float)((double)BV * 3.0);
+    const float c_lap = g_lap * inv_count_scale / (float)BV;
+    mse_lap_bwd_kernel<<<blocks_for(BV, 256), 256, 0, (cudaStream_t)stream>>>(
+        recon, x, qn, tptr, trow, tval, drecon, BV, V, c_mse, c_lap, dscale);
+    return check_launch("mse_lap_bwd_kernel");
+}
+
+int sdvae_kl_fwd_bwd(const float* mu, const float* logvar, float* dmu, float* dlogvar,
+                     float* partial, float* losses, int B, int D, float inv_count_scale,
+                     sdvae_stream_t stream) {
+    SDVAE_REQUIRE(mu && logvar && dmu && dlogvar && partial && losses && B > 0 && D > 0, "kl: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = (long long)B * D;
+    const unsigned grid = blocks_for(n, kLossThreads);
+    const float inv_b = inv_count_scale / (float)B;
+    kl_fwd_bwd_kernel<<<grid, kLossThreads, 0, st>>>(mu, logvar, dmu, dlogvar, partial, n, inv_b);
+    finish_sum_kernel<<<1, kLossThreads, 0, st>>>(partial, grid, 1, 0, inv_b, losses, 1);
+    return check_launch("kl_fwd_bwd");
+}
+
+int sdvae_lc_fwd_bwd(const float* z, int bs, int D, int r0, int r1, float eta1, float eta2,
+                     uint8_t* act_ws, float* partial, float* dz, float* losses,
+                     sdvae_stream_t stream) {
+    SDVAE_REQUIRE(z && act_ws && partial && dz && losses, "lc: null pointer");
+    SDVAE_REQUIRE(bs >= 2 && D > 0 && r0 >= 0 && r1 > r0 && r1 <= D, "lc: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long nh = (long long)bs * (bs - 1) / 2 * bs;
+    const unsigned grid = blocks_for(nh, kLossThreads);
+    const double norm = (double)bs * bs * bs - (double)bs * bs;
+    lc_hinge_kernel<<<grid, kLossThreads, 0, st>>>(z, bs, D, r0, r1, eta1, eta2, act_ws, partial);
+    finish_sum_kernel<<<1, kLossThreads, 0, st>>>(partial, grid, 1, 0, (float)(1.0 / norm), losses, 2);
+    const long long ng = (long long)bs * bs * D;
+    lc_grad_kernel<<<blocks_for(ng, 256), 256, 0, st>>>(z, act_ws, bs, D, r0, r1, (float)(2.0 / norm), dz);
+    return check_launch("lc_fwd_bwd");
+}
+
+int sdvae_total_loss(float* losses, float w_kl, float w_lc, float w_lap, float w_cls,
+                     sdvae_stream_t stream) {
+    SDVAE_REQUIRE(losses, "total_loss: null pointer");
+    total_loss_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(losses, w_kl, w_lc, w_lap, w_cls);
+    return check_launch("total_loss_kernel");
+}
+
+int sdvae_adam_tick(int32_t* step_dev, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(step_dev, "adam_tick: null pointer");
+    adam_tick_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step_dev);
+    return check_launch("adam_tick_kernel");
+}
+
+int sdvae_adam_step(float* p, const float* grad, float* m, float* v, long long n,
+                    const int32_t* step_dev, int step_host, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, float gscale, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(p && grad && m && v && n >= 0, "adam_step: bad argument");
+    SDVAE_REQUIRE(step_dev || step_host >= 1, "adam_step: step must be >= 1");
+    if (n == 0) return SDVAE_OK;
+    adam_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        p, grad, m, v, n, step_dev, step_host, lr, beta1, beta2, eps, weight_decay, gscale);
+    return check_launch("adam_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,464 @@
+"""Fused training step for the SD-VAE hot path (one process per GPU).
+
+``TrainEngine.step`` is the B200 form of ``ModelManager._do_iteration`` (reference
+model_manager.py:274-326): feature swap, forward, the four loss terms, backward,
+Adam -- as an explicit sequence of kernel launches through the C ABI on
+preallocated buffers, without autograd:
+
+* the feature swap (swap_batch_transform.py:13-52) runs on the device, so only
+  the ``bs`` un-swapped meshes cross PCIe, not the ``bs^2`` swapped ones;
+* encoder blocks convolve only the vertices their selection down-transform keeps;
+* the ELU derivative is applied in the epilogue of the kernel that *produces* a
+  gradient (backward-to-input conv or pool-transpose), so every gradient tensor is
+  written once, already w.r.t. the pre-activation;
+* all parameters / gradients / Adam moments live in flat arenas ordered in
+  backward-ready order, so the data-parallel all-reduce is four contiguous buckets
+  launched on a side stream as soon as their layers are done (NCCL over NVLink),
+  overlapping the rest of backward; Adam is one launch over the arena;
+* the seven loss scalars come back in ONE 28-byte D2H copy (the reference issues
+  seven ``.item()`` syncs, model_manager.py:320-326);
+* on a single GPU the whole step is replayed from a CUDA graph (one per swapped
+  region, since the region's latent slice is a kernel argument).
+
+Data parallelism: rank r owns rows ``[r*bs/N, (r+1)*bs/N)`` of the
+``bs x bs`` swap grid.  Mean losses are normalised by the GLOBAL counts, the
+latent-consistency loss is evaluated on the all-gathered ``z`` on every rank and
+only the local slice of its gradient is back-propagated, so a SUM all-reduce of the
+gradient arenas reproduces the single-GPU gradient.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import cabi
+from .losses import LaplacianTable
+from .tables import PoolTable, SpiralTable, pool_table, restricted_spiral_table, spiral_table
+
+LOSS_KEYS = ['reconstruction', 'kl', 'latent_consistency', 'laplacian',
+             'classification', 'classification_acc', 'tot']      # model_manager.py:150-154
+
+
+@dataclass
+class StepConfig:
+    """The ``optimization`` section of the reference YAML (craniofacial.yaml:16-27)."""
+    batch_size: int = 4                  # bs; the step processes bs*bs swapped meshes
+    lr: float = 1e-4
+    weight_decay: float = 0.0
+    laplacian_weight: float = 0.1
+    kl_weight: float = 1e-4
+    latent_consistency_weight: float = 0.5
+    latent_consistency_eta1: float = 0.5
+    latent_consistency_eta2: float = 0.5
+    betas: tuple = (0.9, 0.999)
+    eps: float = 1e-8
+
+
+class TrainEngine:
+    def __init__(self, model, laplacian: Optional[LaplacianTable], region_features: Sequence[np.ndarray],
+                 latent_regions: Sequence[Sequence[int]], cfg: StepConfig, process_group=None,
+                 use_graph: bool = True):
+        """``model``: a ``sdvae_b200.model.Model`` on the CUDA device.
+        ``region_features[k]``: vertex ids swapped for region k; ``latent_regions[k]`` = [r0, r1]."""
+        self.model = model
+        self.cfg = cfg
+        self.dev = next(model.parameters()).device
+        if self.dev.type != 'cuda':
+            raise RuntimeError('TrainEngine needs the model on a CUDA device (no CPU fallback)')
+        self.pg = process_group
+        if process_group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(process_group)
+            self.rank = dist.get_rank(process_group)
+        else:
+            self.world, self.rank = 1, 0
+        bs = cfg.batch_size
+        if bs % self.world:
+            raise ValueError('grid rows (batch_size=%d) must divide over %d ranks' % (bs, self.world))
+        self.bs = bs
+        self.rows = bs // self.world
+        self.i0 = self.rank * self.rows
+        self.B = self.rows * bs                          # local meshes per step
+        self.is_vae = bool(model.is_vae)
+        self.L = len(model.out_channels)
+        self.lap = laplacian if cfg.laplacian_weight > 0 else None
+        self.latent_regions = [tuple(int(t) for t in r) for r in latent_regions]
+        self.use_lc = cfg.latent_consistency_weight > 0
+        self.use_graph = use_graph and self.world == 1
+        self._graphs: Dict[int, torch.cuda.CUDAGraph] = {}
+        self.fixed_eps: Optional[torch.Tensor] = None
+        self.launches_per_step = 0
+
+        self._build_tables()
+        V0 = self.V[0]
+        masks = np.zeros((len(region_features), V0), np.uint8)
+        for k, idx in enumerate(region_features):
+            masks[k, np.asarray(idx, np.int64)] = 1
+        self.masks = torch.from_numpy(masks).to(self.dev)
+        self._build_arenas()
+        self._alloc_buffers()
+        self.side = torch.cuda.Stream(device=self.dev) if self.world > 1 else None
+
+    # ------------------------------------------------------------------ tables
+    def _build_tables(self):
+        m = self.model
+        self.V = [int(s.shape[0]) for s in m.spiral_indices] + [int(m.num_vert)]
+        self.C = [int(m.in_channels)] + [int(c) for c in m.out_channels]
+        self.S = [int(s.shape[1]) for s in m.spiral_indices]
+        self.full: List[SpiralTable] = [spiral_table(s) for s in m.spiral_indices]
+        self.sub: List[SpiralTable] = []
+        self.up: List[PoolTable] = [pool_table(u) for u in m.up_transform]
+        for lvl in range(self.L):
+            sub = restricted_spiral_table(m.spiral_indices[lvl], pool_table(m.down_transform[lvl]))
+            if sub is None:
+                raise RuntimeError(
+                    'TrainEngine: down_transform[%d] is not a pure vertex selection; use the '
+                    'autograd path (sdvae_b200.model.Model + losses) for general matrices' % lvl)
+            self.sub.append(sub)
+
+    # ------------------------------------------------------------------ arenas
+    def _build_arenas(self):
+        m, L = self.model, self.L
+        de_convs = [m.de_layers[L + 1].layer] + [m.de_layers[i].conv.layer for i in range(L, 0, -1)]
+        lin = [m.de_layers[0]] + [m.en_layers[i] for i in range(len(m.en_layers) - 1, L - 1, -1)]
+        en_convs = [m.en_layers[i].conv.layer for i in range(L - 1, -1, -1)]
+        groups = [de_convs, lin[:1], lin[1:], en_convs]       # backward-ready order
+        prms = []
+        self.buckets = []
+        off = 0
+        for g in groups:
+            start = off
+            for mod in g:
+                for p in (mod.weight, mod.bias):
+                    prms.append(p)
+                    off += (p.numel() + 3) // 4 * 4            # keep every tensor 16-byte aligned
+            self.buckets.append((start, off))
+        n = off
+        self.n_params = sum(p.numel() for p in prms)
+        self.flat_p = torch.zeros(n, device=self.dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(n, device=self.dev, dtype=torch.float32)
+        self.flat_m = torch.zeros(n, device=self.dev, dtype=torch.float32)
+        self.flat_v = torch.zeros(n, device=self.dev, dtype=torch.float32)
+        self.step_dev = torch.zeros(1, device=self.dev, dtype=torch.int32)
+        self.grad: Dict[int, torch.Tensor] = {}
+        off = 0
+        for p in prms:
+            k = p.numel()
+            view = self.flat_p[off:off + k].view(p.shape)
+            view.copy_(p.data)
+            p.data = view                                       # the module now lives in the arena
+            self.grad[id(p)] = self.flat_g[off:off + k].view(p.shape)
+            off += (k + 3) // 4 * 4
+
+    def g(self, p):
+        return self.grad[id(p)]
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc_buffers(self):
+        B, V, C, L, dev = self.B, self.V, self.C, self.L, self.dev
+        f = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
+        D = int(self.model.latent_size)
+        self.D = D
+        self.x_in = f(self.bs, V[0], C[0])                      # un-swapped batch (all ranks hold all bs)
+        self.x0 = f(B, V[0], C[0])
+        self.a = [f(B, V[l + 1], C[l + 1]) for l in range(L)]   # encoder block outputs
+        self.mu, self.logvar = f(B, D), f(B, D)
+        self.eps, self.z = f(B, D), f(B, D)
+        self.h = f(B, V[L], C[L])
+        # decoder level l (L-1 .. 0): u[l] = Pool(up[l]) output, d[l] = elu(conv) output
+        self.cin_de = [C[min(l + 2, L)] for l in range(L)]      # channels entering deblock at level l
+        self.u = [f(B, V[l], self.cin_de[l]) for l in range(L)]
+        self.d = [f(B, V[l], C[l + 1]) for l in range(L)]
+        self.recon = f(B, V[0], C[0])
+        # gradients
+        self.drecon = f(B, V[0], C[0])
+        self.qn = f(B, V[0], C[0]) if self.lap is not None else None
+        self.dd = [f(B, V[l], C[l + 1]) for l in range(L)]      # d loss / d pre-activation of deblock l
+        self.du = [f(B, V[l], self.cin_de[l]) for l in range(L)]
+        self.dh = f(B, V[L], C[L])
+        self.dz, self.dmu, self.dlv = f(B, D), f(B, D), f(B, D)
+        self.dmu_kl, self.dlv_kl = f(B, D), f(B, D)
+        self.da = [f(B, V[l + 1], C[l + 1]) for l in range(L)]  # d loss / d pre-activation of enblock l
+        self.da_raw = f(B, V[L], C[L])
+        gmax = max(V[l + 1] * self.S[l] * C[l] for l in range(1, L)) if L > 1 else 4
+        self.G = f(B * gmax)
+        self.wt = [f(self.cin_de[l], self.S[l] * C[l + 1]) for l in range(L)]       # decoder bwd_x weights
+        self.wt_out = f(C[1], self.S[0] * C[0])
+        self.wT = [f(self.S[l] * C[l], C[l + 1]) for l in range(L)]                 # encoder dense weights
+        ws = 16
+        for l in range(L):
+            ws = max(ws, cabi.spiralconv_bwd_w_workspace(B * V[l + 1], self.S[l], C[l], C[l + 1]))
+            ws = max(ws, cabi.spiralconv_bwd_w_workspace(B * V[l], self.S[l], self.cin_de[l], C[l + 1]))
+        ws = max(ws, cabi.spiralconv_bwd_w_workspace(B * V[0], self.S[0], C[1], C[0]))
+        self.ws = f(ws // 4 + 4)
+        self.losses = torch.zeros(8, device=dev, dtype=torch.float32)
+        self.losses_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self.part_mse = f(cabi.mse_lap_partial_floats(B, V[0]))
+        self.part_kl = f((B * D + 255) // 256)
+        nh = self.bs * (self.bs - 1) // 2 * self.bs
+        self.part_lc = f(max(1, (nh + 255) // 256))
+        self.act_lc = torch.empty(max(2, 2 * nh), device=dev, dtype=torch.uint8)
+        self.z_all = f(self.bs * self.bs, D) if self.world > 1 else None
+        self.dz_lc = f(self.bs * self.bs, D)
+
+    # ------------------------------------------------------------------ pieces
+    def _conv(self, x, table, layer, out, act, B, Vin, Cin, Cout):
+        cabi.spiralconv_fwd(x, table.idx, layer.weight.data, layer.bias.data, out, B, Vin,
+                            table.n_rows, table.seq, Cin, Cout, act)
+
+    def forward(self, B=None):
+        """x0 -> recon, z, mu, logvar (training mode)."""
+        m, L, V, C = self.model, self.L, self.V, self.C
+        B = self.B if B is None else B
+        x = self.x0
+        for l in range(L):
+            self._conv(x, self.sub[l], m.en_layers[l].conv.layer, self.a[l], cabi.ACT_ELU,
+                       B, V[l], C[l], C[l + 1])
+            x = self.a[l]
+        flat = x.view(B, V[L] * C[L])
+        lin_mu = m.en_layers[-1]
+        torch.addmm(lin_mu.bias.data, flat, lin_mu.weight.data.t(), out=self.mu)
+        if self.is_vae:
+            lin_lv = m.en_layers[-2]
+            torch.addmm(lin_lv.bias.data, flat, lin_lv.weight.data.t(), out=self.logvar)
+            if self.fixed_eps is None:
+                self.eps.normal_()
+            # else: tests injected the oracle's noise into self.eps via set_fixed_eps()
+            cabi.reparam_fwd(self.mu, self.logvar, self.eps, self.z)
+            z = self.z
+        else:
+            if m.pre_z_sigmoid:
+                torch.sigmoid(self.mu, out=self.mu)
+            z = self.mu
+        lin0 = m.de_layers[0]
+        torch.addmm(lin0.bias.data, z, lin0.weight.data.t(), out=self.h.view(B, V[L] * C[L]))
+        x = self.h
+        for l in range(L - 1, -1, -1):
+            up = self.up[l]
+            cabi.pool_ell_fwd(x, up.ell_col, up.ell_val, self.u[l], B, V[l + 1], V[l], up.width,
+                              self.cin_de[l])
+            self._conv(self.u[l], self.full[l], m.de_layers[L - l].conv.layer, self.d[l],
+                       cabi.ACT_ELU, B, V[l], self.cin_de[l], C[l + 1])
+            x = self.d[l]
+        self._conv(x, self.full[0], m.de_layers[L + 1].layer, self.recon, cabi.ACT_NONE,
+                   B, V[0], C[1], C[0])
+        return z
+
+    def _bwd_w(self, x, table, dpre, layer, B, Vin, Cin, Cout):
+        cabi.spiralconv_bwd_w(x, table.idx, dpre, self.g(layer.weight), self.g(layer.bias), self.ws,
+                              B, Vin, table.n_rows, table.seq, Cin, Cout)
+
+    def _allreduce_bucket(self, k):
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+        s, e = self.buckets[k]
+        self.side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side):
+            dist.all_reduce(self.flat_g[s:e], op=dist.ReduceOp.SUM, group=self.pg)
+
+    def losses_and_backward(self, z, region: Optional[int]):
+        m, L, V, C, S, cfg = self.model, self.L, self.V, self.C, self.S, self.cfg
+        B = self.B
+        scale = 1.0 / self.world                       # local means -> global means
+        lap = self.lap
+        if lap is not None:
+            cabi.mse_lap_fwd(self.recon, self.x0, lap.ell_col, lap.ell_val, lap.width, self.qn,
+                             self.part_mse, self.losses, B, V[0], scale)
+        else:
+            cabi.mse_lap_fwd(self.recon, self.x0, None, None, 0, None, self.part_mse, self.losses,
+                             B, V[0], scale)
+        if self.is_vae and cfg.kl_weight > 0:
+            cabi.kl_fwd_bwd(self.mu, self.logvar, self.dmu_kl, self.dlv_kl, self.part_kl,
+                            self.losses, B, self.D, scale)
+        use_lc = self.use_lc and region is not None
+        if use_lc:
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_gather_into_tensor(self.z_all, z.contiguous(), group=self.pg)
+                z_all = self.z_all
+            else:
+                z_all = z
+            r0, r1 = self.latent_regions[region]
+            cabi.lc_fwd_bwd(z_all, self.bs, self.D, r0, r1, cfg.latent_consistency_eta1,
+                            cfg.latent_consistency_eta2, self.act_lc, self.part_lc, self.dz_lc,
+                            self.losses)
+        # ---- backward: decoder ------------------------------------------------------
+        if lap is not None:
+            cabi.mse_lap_bwd(self.recon, self.x0, self.qn, lap.t_ptr, lap.t_row, lap.t_val,
+                             self.drecon, B, V[0], 1.0, cfg.laplacian_weight, scale, None)
+        else:
+            cabi.mse_lap_bwd(self.recon, self.x0, None, None, None, None, self.drecon, B, V[0],
+                             1.0, 0.0, scale, None)
+        out_layer = m.de_layers[L + 1].layer
+        self._bwd_w(self.d[0], self.full[0], self.drecon, out_layer, B, V[0], C[1], C[0])
+        cabi.weight_transpose(out_layer.weight.data, self.wt_out, C[0], C[1], S[0])
+        cp, cs = self.full[0].inverse()
+        cabi.spiralconv_bwd_x(self.drecon, cp, cs, self.wt_out, self.d[0], self.dd[0], B, V[0], V[0],
+                              S[0], C[0], C[1])
+        for l in range(L):                               # deblock at level l, fine -> coarse
+            layer = m.de_layers[L - l].conv.layer
+            cin, cout = self.cin_de[l], C[l + 1]
+            self._bwd_w(self.u[l], self.full[l], self.dd[l], layer, B, V[l], cin, cout)
+            cabi.weight_transpose(layer.weight.data, self.wt[l], cout, cin, S[l])
+            cp, cs = self.full[l].inverse()
+            cabi.spiralconv_bwd_x(self.dd[l], cp, cs, self.wt[l], None, self.du[l], B, V[l], V[l],
+                                  S[l], cout, cin)
+            up = self.up[l]
+            if l + 1 < L:    # gradient w.r.t. the coarser deblock's pre-activation (ELU' fused)
+                cabi.csr_rowsum(self.du[l], up.t_ptr, up.t_row, up.t_val, self.d[l + 1],
+                                self.dd[l + 1], B, V[l], V[l + 1], cin)
+            else:
+                cabi.csr_rowsum(self.du[l], up.t_ptr, up.t_row, up.t_val, None, self.dh, B, V[l],
+                                V[l + 1], cin)
+        self._allreduce_bucket(0)
+        # ---- latent block -------------------------------------------------------------
+        lin0 = m.de_layers[0]
+        dh2 = self.dh.view(B, V[L] * C[L])
+        zin = z
+        torch.mm(dh2.t(), zin, out=self.g(lin0.weight))
+        torch.sum(dh2, dim=0, out=self.g(lin0.bias))
+        torch.mm(dh2, lin0.weight.data, out=self.dz)
+        self._allreduce_bucket(1)
+        if use_lc:
+            lo = self.i0 * self.bs
+            cabi.axpy3(self.dz, self.dz_lc[lo:lo + B], cfg.latent_consistency_weight, None, 0.0,
+                       self.dz)
+        flat = self.a[L - 1].view(B, V[L] * C[L])
+        lin_mu = m.en_layers[-1]
+        if self.is_vae:
+            lin_lv = m.en_layers[-2]
+            cabi.reparam_bwd(self.dz, self.logvar, self.eps, self.dmu, self.dlv, False)
+            if cfg.kl_weight > 0:
+                cabi.axpy3(self.dmu, self.dmu_kl, cfg.kl_weight, None, 0.0, self.dmu)
+                cabi.axpy3(self.dlv, self.dlv_kl, cfg.kl_weight, None, 0.0, self.dlv)
+            torch.mm(self.dmu.t(), flat, out=self.g(lin_mu.weight))
+            torch.sum(self.dmu, dim=0, out=self.g(lin_mu.bias))
+            torch.mm(self.dlv.t(), flat, out=self.g(lin_lv.weight))
+            torch.sum(self.dlv, dim=0, out=self.g(lin_lv.bias))
+            raw = self.da_raw.view(B, V[L] * C[L])
+            torch.mm(self.dmu, lin_mu.weight.data, out=raw)
+            raw.addmm_(self.dlv, lin_lv.weight.data)
+        else:
+            dmu = self.dz
+            if m.pre_z_sigmoid:
+                dmu = self.dz * self.mu * (1.0 - self.mu)
+            torch.mm(dmu.t(), flat, out=self.g(lin_mu.weight))
+            torch.sum(dmu, dim=0, out=self.g(lin_mu.bias))
+            torch.mm(dmu, lin_mu.weight.data, out=self.da_raw.view(B, V[L] * C[L]))
+        self._allreduce_bucket(2)
+        cabi.elu_bwd(self.da_raw, self.a[L - 1], self.da[L - 1])
+        # ---- backward: encoder ----------------------------------------------------------
+        for l in range(L - 1, -1, -1):
+            layer = m.en_layers[l].conv.layer
+            x_in = self.a[l - 1] if l > 0 else self.x0
+            self._bwd_w(x_in, self.sub[l], self.da[l], layer, B, V[l], C[l], C[l + 1])
+            if l > 0:
+                K = S[l] * C[l]
+                cabi.transpose2d(layer.weight.data, self.wT[l], C[l + 1], K)
+                R = self.sub[l].n_rows
+                G = self.G[:B * R * K].view(B, R * S[l], C[l])
+                cabi.dense_fwd(self.da[l], self.wT[l], None, G, B * R, C[l + 1], K, C[l + 1],
+                               cabi.ACT_NONE)
+                ptr, src = self.sub[l].inverse_flat()
+                cabi.csr_rowsum(G, ptr, src, None, self.a[l - 1], self.da[l - 1], B, R * S[l], V[l],
+                                C[l])
+        self._allreduce_bucket(3)
+        if self.world > 1:
+            # slots 0/1/3 hold this rank's share of the global means; slot 2 is the full
+            # latent-consistency loss, identical on every rank
+            import torch.distributed as dist
+            self.losses[2:3].mul_(1.0 / self.world)
+            dist.all_reduce(self.losses, op=dist.ReduceOp.SUM, group=self.pg)
+        cabi.total_loss(self.losses, cfg.kl_weight if self.is_vae else 0.0,
+                        cfg.latent_consistency_weight if use_lc else 0.0,
+                        cfg.laplacian_weight if lap is not None else 0.0, 0.0)
+
+    def optimizer_step(self):
+        cfg = self.cfg
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
+        cabi.adam_tick(self.step_dev)
+        cabi.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.step_dev, 0, cfg.lr,
+                       cfg.betas[0], cfg.betas[1], cfg.eps, cfg.weight_decay, 1.0)
+
+    # ------------------------------------------------------------------ public step
+    def _body(self, region: Optional[int]):
+        if region is not None:
+            cabi.swap(self.x_in, self.masks[region], self.x0, self.bs, self.i0, self.i0 + self.rows,
+                      self.V[0], self.C[0])
+        z = self.forward()
+        self.losses.zero_()
+        self.losses_and_backward(z, region)
+        self.optimizer_step()
+
+    def load_batch(self, x_host_or_dev: torch.Tensor):
+        """Copy the un-swapped batch ``[bs, V, 3]`` (pinned host or device) into the
+        engine's input buffer, asynchronously on the current stream."""
+        self.x_in.copy_(x_host_or_dev, non_blocking=True)
+
+    def set_fixed_eps(self, eps: Optional[torch.Tensor]):
+        """Parity tests: use this re-parameterisation noise instead of drawing it."""
+        self.fixed_eps = eps
+        if eps is not None:
+            self.eps.copy_(eps)
+
+    def prepare(self, regions):
+        """Capture the step graphs for these regions up front (keeps capture out of timed loops)."""
+        if not self.use_graph:
+            return
+        keep = [t.clone() for t in (self.flat_p, self.flat_m, self.flat_v, self.step_dev)]
+        for r in regions:
+            self.step(r)
+        torch.cuda.synchronize(self.dev)
+        for dst, src in zip((self.flat_p, self.flat_m, self.flat_v, self.step_dev), keep):
+            dst.copy_(src)
+
+    def load_local(self, x_local: torch.Tensor):
+        """Copy this rank's ``B`` already-assembled meshes straight into the network input
+        (use with ``step(region=None)``: no device-side swap, no latent-consistency term
+        unless ``lc_region`` is given)."""
+        self.x0.copy_(x_local, non_blocking=True)
+
+    def step(self, region: Optional[int], sync_losses: bool = False):
+        """One training iteration on the batch previously given to ``load_batch``.
+        ``region`` = index of the swapped region (None: ``x_in`` already holds the local
+        ``B`` meshes un-swapped in ``x0``... i.e. no swap and no latent-consistency term)."""
+        if self.use_graph:
+            key = -1 if region is None else int(region)
+            gph = self._graphs.get(key)
+            if gph is None:
+                n0 = cabi.launch_count()
+                # warm-up outside capture (lazy allocations, cuBLAS handles) on a scratch copy
+                # of the optimiser state, so that the warm-up is not a training step
+                keep = [t.clone() for t in (self.flat_p, self.flat_m, self.flat_v, self.step_dev)]
+                self._body(region)
+                for dst, src in zip((self.flat_p, self.flat_m, self.flat_v, self.step_dev), keep):
+                    dst.copy_(src)
+                torch.cuda.synchronize(self.dev)
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph):
+                    self._body(region)
+                self._graphs[key] = gph
+                self.launches_per_step = (cabi.launch_count() - n0) // 2   # warm-up + capture
+            gph.replay()
+            cabi.add_launches(self.launches_per_step)
+        else:
+            self._body(region)
+        self.losses_host.copy_(self.losses, non_blocking=True)
+        if sync_losses:
+            torch.cuda.current_stream().synchronize()
+            return self.loss_dict()
+        return None
+
+    def loss_dict(self) -> Dict[str, float]:
+        v = self.losses_host.tolist()
+        return {k: v[i] for i, k in enumerate(LOSS_KEYS)}
+
+    def zero_state(self):
+        self.flat_m.zero_()
+        self.flat_v.zero_()
+        self.step_dev.zero_()

@@ -1,0 +1,257 @@
+"""Derived index tables for the kernels (host side, NumPy, bit-exact integer work).
+
+The reference hands the network two kinds of static tables:
+``indices`` -- ``LongTensor[V, S]`` spiral neighbour lists -- and ``trans`` --
+uncoalesced fp32 ``torch.sparse_coo`` matrices.  The kernels want
+
+* int32 copies (values are range-checked here, once, never at kernel time),
+* for the backward-to-input pass the *inverse* spiral table in "cell" form:
+  for every input vertex ``u`` and slot ``s`` the ascending list of output rows
+  ``r`` with ``idx[r, s] == u`` (CSR over the ``V*S`` cells),
+* ELL rows for ``Pool`` that keep each row's entries in **storage order** (the
+  reference adds them in that order, model.py:53-54), plus the transposed matrix
+  in CSR for the backward pass, again in storage order,
+* detection of pure selection matrices (one entry of value 1.0 per row, the
+  shape every quadric-collapse down-transform has, mesh_simplification.py:174-188),
+  which lets an encoder block convolve only the vertices it keeps.
+
+Derived tables are cached per source tensor (keyed on ``data_ptr``; the source
+tensor is kept alive by the cache entry so the pointer cannot be recycled).
+Caller tensors are never modified.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+INT32_MAX = 2 ** 31 - 1
+
+
+# ---------------------------------------------------------------------------
+# pure NumPy builders
+# ---------------------------------------------------------------------------
+def check_indices(idx: np.ndarray, n_src: Optional[int] = None) -> np.ndarray:
+    """int64 ``[V,S]`` -> int32 with range checks (0 <= idx < n_src <= 2^31-1)."""
+    idx = np.asarray(idx)
+    if idx.ndim != 2:
+        raise ValueError('spiral indices must be 2-D [V, S], got shape %s' % (idx.shape,))
+    if idx.size:
+        lo, hi = int(idx.min()), int(idx.max())
+        if lo < 0:
+            raise IndexError('negative spiral index %d' % lo)
+        if n_src is not None and hi >= n_src:
+            raise IndexError('spiral index %d out of range for %d vertices' % (hi, n_src))
+        if hi > INT32_MAX:
+            raise IndexError('spiral index %d does not fit int32' % hi)
+    return np.ascontiguousarray(idx.astype(np.int32))
+
+
+def inverse_cells(idx: np.ndarray, n_src: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Inverse of a spiral table in cell-CSR form.
+
+    ``idx`` is ``[R, S]`` (row r gathers ``idx[r, s]`` at slot s).  Returns
+    ``cell_ptr [n_src*S + 1]`` and ``cell_src [R*S]`` such that the rows ``r`` with
+    ``idx[r, s] == u`` are ``cell_src[cell_ptr[u*S+s] : cell_ptr[u*S+s+1]]``, ascending."""
+    idx = np.asarray(idx, np.int64)
+    R, S = idx.shape
+    cell = (idx * S + np.arange(S, dtype=np.int64)[None, :]).ravel()
+    rows = np.repeat(np.arange(R, dtype=np.int64), S)
+    order = np.lexsort((rows, cell))                      # by cell, then by row
+    counts = np.bincount(cell, minlength=n_src * S)
+    ptr = np.zeros(n_src * S + 1, np.int64)
+    np.cumsum(counts, out=ptr[1:])
+    if ptr[-1] > INT32_MAX:
+        raise IndexError('inverse spiral table does not fit int32')
+    return ptr.astype(np.int32), rows[order].astype(np.int32)
+
+
+def inverse_rows_flat(idx: np.ndarray, n_src: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Inverse table as a CSR over input vertices whose entries are flat
+    ``r*S + s`` positions (ascending): ``dx[u] = sum_e G[flat_e]`` scatters the
+    per-slot input gradients ``G [R*S, Cin]`` of a fused encoder block."""
+    idx = np.asarray(idx, np.int64)
+    R, S = idx.shape
+    flat = np.arange(R * S, dtype=np.int64)
+    tgt = idx.ravel()
+    order = np.lexsort((flat, tgt))
+    counts = np.bincount(tgt, minlength=n_src)
+    ptr = np.zeros(n_src + 1, np.int64)
+    np.cumsum(counts, out=ptr[1:])
+    return ptr.astype(np.int32), flat[order].astype(np.int32)
+
+
+def ell_from_coo(row: np.ndarray, col: np.ndarray, val: np.ndarray, n_rows: int, n_cols: int):
+    """COO in storage order -> (ell_col [n_rows, W] int32 with -1 padding,
+    ell_val [n_rows, W] fp32); a row's entries stay in storage order."""
+    row = np.asarray(row, np.int64)
+    col = np.asarray(col, np.int64)
+    val = np.asarray(val, np.float32)
+    if row.size and (row.min() < 0 or row.max() >= n_rows or col.min() < 0 or col.max() >= n_cols):
+        raise IndexError('sparse matrix index out of range')
+    counts = np.bincount(row, minlength=n_rows)
+    width = int(counts.max()) if row.size else 1
+    width = max(width, 1)
+    order = np.argsort(row, kind='stable')                # keeps storage order inside a row
+    start = np.zeros(n_rows + 1, np.int64)
+    np.cumsum(counts, out=start[1:])
+    pos = np.arange(row.size, dtype=np.int64) - start[row[order]]
+    ell_col = np.full((n_rows, width), -1, np.int32)
+    ell_val = np.zeros((n_rows, width), np.float32)
+    ell_col[row[order], pos] = col[order].astype(np.int32)
+    ell_val[row[order], pos] = val[order]
+    return ell_col, ell_val
+
+
+def transposed_csr(row: np.ndarray, col: np.ndarray, val: np.ndarray, n_cols: int):
+    """CSR of the transposed matrix: for column k the (row, val) entries in storage order."""
+    row = np.asarray(row, np.int64)
+    col = np.asarray(col, np.int64)
+    order = np.argsort(col, kind='stable')
+    counts = np.bincount(col, minlength=n_cols)
+    ptr = np.zeros(n_cols + 1, np.int64)
+    np.cumsum(counts, out=ptr[1:])
+    return (ptr.astype(np.int32), row[order].astype(np.int32),
+            np.asarray(val, np.float32)[order].copy())
+
+
+def selection_columns(row, col, val, n_rows) -> Optional[np.ndarray]:
+    """If the matrix is a pure row selection (exactly one entry per row, value 1.0)
+    return ``kept[r] = col of row r``; otherwise ``None``."""
+    row = np.asarray(row, np.int64)
+    val = np.asarray(val, np.float32)
+    if row.size != n_rows or not np.all(val == np.float32(1.0)):
+        return None
+    if not np.array_equal(np.sort(row), np.arange(n_rows)):
+        return None
+    kept = np.empty(n_rows, np.int64)
+    kept[row] = np.asarray(col, np.int64)
+    return kept
+
+
+# ---------------------------------------------------------------------------
+# device-side bundles
+# ---------------------------------------------------------------------------
+def _dev(a: np.ndarray, device) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device)
+
+
+@dataclass
+class SpiralTable:
+    """Device copies of one (possibly row-restricted) spiral table."""
+    idx: torch.Tensor            # int32 [R, S]
+    n_rows: int
+    n_src: int
+    seq: int
+    _np_idx: np.ndarray
+    _inv: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+    _inv_flat: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+
+    @staticmethod
+    def build(idx_np: np.ndarray, n_src: int, device) -> "SpiralTable":
+        i32 = check_indices(idx_np, n_src)
+        return SpiralTable(_dev(i32, device), int(i32.shape[0]), int(n_src), int(i32.shape[1]), i32)
+
+    def inverse(self):
+        """(cell_ptr, cell_src) on the device, built on first use."""
+        if self._inv is None:
+            ptr, src = inverse_cells(self._np_idx, self.n_src)
+            self._inv = (_dev(ptr, self.idx.device), _dev(src, self.idx.device))
+        return self._inv
+
+    def inverse_flat(self):
+        if self._inv_flat is None:
+            ptr, src = inverse_rows_flat(self._np_idx, self.n_src)
+            self._inv_flat = (_dev(ptr, self.idx.device), _dev(src, self.idx.device))
+        return self._inv_flat
+
+    def restrict(self, kept: np.ndarray) -> "SpiralTable":
+        """Table of the rows in ``kept`` only (fused conv + selection pooling)."""
+        return SpiralTable.build(self._np_idx[np.asarray(kept, np.int64)], self.n_src,
+                                 self.idx.device)
+
+
+@dataclass
+class PoolTable:
+    """Device copies of one sparse transform: ELL forward rows, transposed CSR."""
+    n_rows: int
+    n_cols: int
+    width: int
+    ell_col: torch.Tensor        # int32 [n_rows, W]
+    ell_val: torch.Tensor        # fp32  [n_rows, W]
+    t_ptr: torch.Tensor          # int32 [n_cols + 1]
+    t_row: torch.Tensor          # int32 [nnz]
+    t_val: torch.Tensor          # fp32  [nnz]
+    kept: Optional[np.ndarray]   # selection columns or None
+
+    @staticmethod
+    def build(row, col, val, shape, device) -> "PoolTable":
+        n_rows, n_cols = int(shape[0]), int(shape[1])
+        ec, ev = ell_from_coo(row, col, val, n_rows, n_cols)
+        tp, tr, tv = transposed_csr(row, col, val, n_cols)
+        return PoolTable(n_rows, n_cols, int(ec.shape[1]), _dev(ec, device), _dev(ev, device),
+                         _dev(tp, device), _dev(tr, device), _dev(tv, device),
+                         selection_columns(row, col, val, n_rows))
+
+
+# ---------------------------------------------------------------------------
+# caches keyed on the caller's tensors
+# ---------------------------------------------------------------------------
+_spiral_cache: Dict[tuple, tuple] = {}
+_pool_cache: Dict[tuple, tuple] = {}
+_restricted_cache: Dict[tuple, SpiralTable] = {}
+
+
+def _key(t: torch.Tensor):
+    return (t.data_ptr(), tuple(t.shape), str(t.device), t.dtype)
+
+
+def spiral_table(indices: torch.Tensor, n_src: Optional[int] = None) -> SpiralTable:
+    """``SpiralTable`` for a caller-owned ``LongTensor[V,S]`` (model.py:12-17).
+    ``n_src`` defaults to V (every use in the reference's Model has V_out == V_in)."""
+    k = _key(indices) + (n_src,)
+    hit = _spiral_cache.get(k)
+    if hit is not None:
+        return hit[1]
+    if indices.dim() != 2:
+        raise ValueError('indices must be [V, S]')
+    n_src_eff = int(indices.shape[0]) if n_src is None else int(n_src)
+    tab = SpiralTable.build(indices.detach().cpu().numpy(), n_src_eff, indices.device)
+    _spiral_cache[k] = (indices, tab)
+    return tab
+
+
+def pool_table(trans: torch.Tensor) -> PoolTable:
+    """``PoolTable`` for a caller-owned sparse COO matrix (model.py:50-52); only
+    ``_indices()``, ``_values()`` and the shape are read, as in the reference."""
+    ind, val = trans._indices(), trans._values()
+    k = (ind.data_ptr(), val.data_ptr(), tuple(trans.shape), str(ind.device))
+    hit = _pool_cache.get(k)
+    if hit is not None:
+        return hit[1]
+    ind_np = ind.detach().cpu().numpy()
+    tab = PoolTable.build(ind_np[0], ind_np[1], val.detach().cpu().numpy().astype(np.float32),
+                          (trans.size(0), trans.size(1)), ind.device)
+    _pool_cache[k] = ((ind, val), tab)
+    return tab
+
+
+def restricted_spiral_table(indices: torch.Tensor, pool: PoolTable) -> Optional[SpiralTable]:
+    """Spiral table restricted to the rows a selection down-transform keeps, or None
+    if ``pool`` is not a pure selection."""
+    if pool.kept is None or int(indices.shape[0]) != pool.n_cols:
+        return None
+    k = _key(indices) + (id(pool),)
+    hit = _restricted_cache.get(k)
+    if hit is None:
+        hit = spiral_table(indices).restrict(pool.kept)
+        _restricted_cache[k] = hit
+    return hit
+
+
+def clear_caches():
+    _spiral_cache.clear()
+    _pool_cache.clear()
+    _restricted_cache.clear()

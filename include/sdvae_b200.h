@@ -1,0 +1,163 @@
+/* sdvae_b200 -- C ABI of the B200-native SD-VAE mesh encoder/decoder hot path.
+ *
+ * Drop-in boundary for the reference's `model.py` operators (SpiralConv, Pool) and the
+ * loss / optimiser arithmetic of `model_manager.py::_do_iteration`.  The reference is pure
+ * PyTorch, so "what its FFI would bind" is one entry point per ATen op group it calls on the
+ * path; each declaration cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (fp32 / int32 / uint8); tensors are dense row-major
+ *   - the caller allocates every output and workspace; nothing is allocated or cached inside
+ *   - no thread-local or global state except the last-error string; safe to call from the
+ *     autograd engine thread; the CUDA device must be current, `stream` is a cudaStream_t
+ *   - return 0 on success, non-zero on error (1 bad argument, 2 CUDA error, 3 unsupported);
+ *     sdvae_last_error() then describes it.  There is no CPU fallback.
+ *   - index tables are int32 (the reference stores int64 with values < 2^31; range-checked on
+ *     the host when the tables are derived, never at kernel time)
+ */
+#ifndef SDVAE_B200_H
+#define SDVAE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* sdvae_stream_t;   /* cudaStream_t */
+
+#define SDVAE_ACT_NONE 0
+#define SDVAE_ACT_ELU  1
+
+int         sdvae_abi_version(void);
+const char* sdvae_last_error(void);
+
+/* ---- SpiralConv ------------------------------------------------------------------------- */
+
+/* y[b,v,o] = act(bias[o] + sum_{s,c} W[o, s*Cin+c] * x[b, idx[v,s], c])
+ * x [B,Vin,Cin], idx [Vout,S] (values in [0,Vin)), W [Cout, S*Cin] (nn.Linear layout),
+ * bias [Cout] or NULL, y [B,Vout,Cout].  Vout may be a SUBSET of the vertices (rows of the
+ * spiral table restricted to the vertices a selection down-transform keeps), which fuses
+ * `Pool(elu(conv(x)), down)`.
+ * Replaces: model.py:27-41 (index_select + nn.Linear) and F.elu at model.py:68,84. */
+int sdvae_spiralconv_fwd(const float* x, const int32_t* idx, const float* W, const float* bias,
+                         float* y, int B, int Vin, int Vout, int S, int Cin, int Cout, int act,
+                         sdvae_stream_t stream);
+
+/* Wt[c, s*Cout+o] = W[o, s*Cin+c]: weight of the transposed convolution used by bwd_x. */
+int sdvae_weight_transpose(const float* W, float* Wt, int Cout, int Cin, int S,
+                           sdvae_stream_t stream);
+
+/* dx[b,u,c] = gate * sum_{s} sum_{r in cell(u,s)} sum_o dpre[b,r,o] * W[o, s*Cin+c]
+ * dpre [B,Vrows,Cout] (gradient w.r.t. the pre-activation), cell_ptr [Vdst*S+1] / cell_src:
+ * for input vertex u and slot s the ascending list of output rows r with idx[r,s]==u,
+ * Wt from sdvae_weight_transpose, gate [B,Vdst,Cin] or NULL (if given, dx *= elu'(gate), i.e.
+ * the ELU derivative of the layer that produced x, evaluated from its output), dx [B,Vdst,Cin].
+ * Deterministic: fixed summation order, no atomics.
+ * Replaces: autograd of model.py:34 (index_select backward = index_add_ with atomics) and of
+ * model.py:40 (grad_input GEMM). */
+int sdvae_spiralconv_bwd_x(const float* dpre, const int32_t* cell_ptr, const int32_t* cell_src,
+                           const float* Wt, const float* gate, float* dx, int B, int Vrows,
+                           int Vdst, int S, int Cout, int Cin, sdvae_stream_t stream);
+
+/* dW[o, s*Cin+c] = sum_{b,v} dpre[b,v,o] * x[b, idx[v,s], c];  db[o] = sum_{b,v} dpre[b,v,o]
+ * workspace: sdvae_spiralconv_bwd_w_workspace(...) bytes.  Split-M partial sums are added in a
+ * fixed order.  db may be NULL.
+ * Replaces: autograd of model.py:40 (grad_weight / grad_bias GEMMs over the materialised gather). */
+size_t sdvae_spiralconv_bwd_w_workspace(long long M, int S, int Cin, int Cout);
+int sdvae_spiralconv_bwd_w(const float* x, const int32_t* idx, const float* dpre, float* dW,
+                           float* db, void* workspace, int B, int Vin, int Vout, int S, int Cin,
+                           int Cout, sdvae_stream_t stream);
+
+/* out[m, n] = act(bias[n] + sum_k in[m,k] * W[n*ldw + k]),  dense [M,K] x [K,N] on the same
+ * tiled kernel (identity gather).  Used for the per-slot input gradients of the fused encoder
+ * blocks.  K must be 32 or 64 for the tiled path (anything else takes the generic kernel). */
+int sdvae_dense_fwd(const float* in, const float* W, const float* bias, float* out, long long M,
+                    int K, int N, int ldw, int act, sdvae_stream_t stream);
+
+/* out[c, r] = in[r, c] */
+int sdvae_transpose2d(const float* in, float* out, int R, int C, sdvae_stream_t stream);
+
+/* ---- Pool --------------------------------------------------------------------------------- */
+
+/* out[b,r,:] = sum_{j<Wd, col[r,j]>=0} val[r,j] * x[b, col[r,j], :]   (entries in storage order,
+ * product rounded before each add).  x [B,Vin,C], col/val [Vout,Wd] (ELL, -1 padding).
+ * Replaces: model.py:50-55 (index_select * value -> torch_scatter.scatter_add). */
+int sdvae_pool_ell_fwd(const float* x, const int32_t* col, const float* val, float* out, int B,
+                       int Vin, int Vout, int Wd, int C, sdvae_stream_t stream);
+
+/* dx[b,k,:] = gate * sum_{e in [ptr[k],ptr[k+1])} val[e] * dy[b, src[e], :]
+ * CSR of the TRANSPOSED matrix, entries in storage order; val NULL = all ones; gate NULL = none.
+ * Replaces: autograd of model.py:53-54 (scatter_add / index_select backward, atomics). */
+int sdvae_csr_rowsum(const float* dy, const int32_t* ptr, const int32_t* src, const float* val,
+                     const float* gate, float* dx, int B, int Vsrc, int Vdst, int C,
+                     sdvae_stream_t stream);
+
+/* ---- elementwise ---------------------------------------------------------------------------- */
+int sdvae_elu_fwd(const float* x, float* y, long long n, sdvae_stream_t stream);          /* model.py:68,84 */
+int sdvae_elu_bwd(const float* dy, const float* y, float* dx, long long n, sdvae_stream_t stream);
+/* z = mu + eps * exp(logvar/2)                                           model.py:184-188 */
+int sdvae_reparam_fwd(const float* mu, const float* logvar, const float* eps, float* z,
+                      long long n, sdvae_stream_t stream);
+int sdvae_reparam_bwd(const float* dz, const float* logvar, const float* eps, float* dmu,
+                      float* dlogvar, long long n, int accumulate, sdvae_stream_t stream);
+/* out = a + sb*b + sc*c (any of a, b, c may be NULL) */
+int sdvae_axpy3(const float* a, const float* b, float sb, const float* c, float sc, float* out,
+                long long n, sdvae_stream_t stream);
+
+/* ---- feature swap ---------------------------------------------------------------------------- */
+/* out[(i-i0)*bs + j, v, :] = mask[v] ? x[j,v,:] : x[i,v,:]  for i in [i0,i1)
+ * Replaces: swap_batch_transform.py:13-52 (CPU double loop in the DataLoader collate). */
+int sdvae_swap(const float* x, const uint8_t* mask, float* out, int bs, int i0, int i1, int V,
+               int C, sdvae_stream_t stream);
+
+/* ---- losses (slots follow ModelManager.loss_keys, model_manager.py:150-154:
+ *      0 reconstruction, 1 kl, 2 latent_consistency, 3 laplacian, 4 classification,
+ *      5 classification_acc, 6 tot) ------------------------------------------------------------ */
+
+/* losses[0] = mean((recon-x)^2)          model_manager.py:332-334
+ * losses[3] = sum_b sum_v |(L recon_b)_v| / V / B   (if lcol != NULL)   model_manager.py:343-349
+ * lcol/lval [V,lw] ELL of the random-walk Laplacian; qn [B,V,3] receives q/|q| for the backward;
+ * partial: sdvae_mse_lap_partial_floats(B,V) floats. */
+size_t sdvae_mse_lap_partial_floats(int B, int V);
+int sdvae_mse_lap_fwd(const float* recon, const float* x, const int32_t* lcol, const float* lval,
+                      int lw, float* qn, float* partial, float* losses, int B, int V,
+                      float inv_count_scale, sdvae_stream_t stream);
+/* drecon = g_mse * d mse/d recon + g_lap * d lap/d recon; tptr/trow/tval = CSR of L^T;
+ * dscale (device, 2 floats, may be NULL) multiplies g_mse, g_lap. */
+int sdvae_mse_lap_bwd(const float* recon, const float* x, const float* qn, const int32_t* tptr,
+                      const int32_t* trow, const float* tval, float* drecon, int B, int V,
+                      float g_mse, float g_lap, float inv_count_scale, const float* dscale,
+                      sdvae_stream_t stream);
+
+/* losses[1] = mean_b(-1/2 sum_d(1 + lv - mu^2 - exp(lv))); dmu, dlv = its gradients.
+ * model_manager.py:351-354.  partial: ceil(B*D/256) floats. */
+int sdvae_kl_fwd_bwd(const float* mu, const float* logvar, float* dmu, float* dlogvar,
+                     float* partial, float* losses, int B, int D, float inv_count_scale,
+                     sdvae_stream_t stream);
+
+/* losses[2] = latent-consistency loss of z [bs*bs, D] on the swap grid, region columns [r0,r1);
+ * dz = its gradient.  act_ws: bs*bs*(bs-1) bytes; partial: ceil(bs*bs*(bs-1)/2/256) floats.
+ * model_manager.py:360-393. */
+int sdvae_lc_fwd_bwd(const float* z, int bs, int D, int r0, int r1, float eta1, float eta2,
+                     uint8_t* act_ws, float* partial, float* dz, float* losses,
+                     sdvae_stream_t stream);
+
+/* losses[6] = losses[0] + w_kl*losses[1] + w_lc*losses[2] + w_lap*losses[3] + w_cls*losses[4]
+ * model_manager.py:308-312 */
+int sdvae_total_loss(float* losses, float w_kl, float w_lc, float w_lap, float w_cls,
+                     sdvae_stream_t stream);
+
+/* ---- optimiser --------------------------------------------------------------------------------- */
+/* torch.optim.Adam step (model_manager.py:69-72, 316) over a flat parameter arena.
+ * step_dev: device int holding t (>=1), or NULL to use step_host.  gscale multiplies the gradient
+ * (1/world_size after a SUM all-reduce). */
+int sdvae_adam_tick(int32_t* step_dev, sdvae_stream_t stream);
+int sdvae_adam_step(float* p, const float* grad, float* m, float* v, long long n,
+                    const int32_t* step_dev, int step_host, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, float gscale, sdvae_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDVAE_B200_H */

@@ -290,4 +290,4 @@ class Trainer:
         if train:
             tot.backward()
             self.opt.step()
-        return {k: float(v) for k, v in terms.items()}
+        return {k: float(v.detach()) for k, v in terms.items()}

@@ -1,0 +1,171 @@
+"""End-to-end parity of the drop-in Model / losses / TrainEngine with the oracle and
+with vectors produced by the reference's own code (GPU box only)."""
+import numpy as np
+import pytest
+import torch
+
+from _util import TOL, build_pair, nerr, rand
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+W = dict(kl=1e-4, lc=0.5, lap=0.1, eta1=0.5, eta2=0.5)      # craniofacial.yaml:22-27
+
+
+def samp(t, stride=97):
+    return t.detach().reshape(-1)[::stride].cpu()
+
+
+@pytest.fixture(scope='module')
+def case_a(golden, cranio):
+    from oracle import sdvae_oracle as orc
+    net, params, model = build_pair(cranio, 3, [32, 32, 32, 64], 75, False, True, 1234, DEV)
+    x2 = torch.from_numpy(golden['A_x_unswapped'])
+    key = str(golden['A_swapped_key'])
+    feat = torch.from_numpy(dict(cranio.regions)[key])
+    xa = orc.swap_features(x2, feat)
+    return net, params, model, x2, xa, key
+
+
+def test_eval_forward_vs_reference_golden(golden, case_a):
+    _, _, model, _, xa, _ = case_a
+    model.eval()
+    with torch.no_grad():
+        rec, z, mu, lv = model(xa.to(DEV))
+    assert nerr(rec[0], golden['A_eval_recon0']) < TOL
+    assert nerr(samp(rec), golden['A_eval_recon_sample']) < TOL
+    assert nerr(mu, golden['A_eval_mu']) < TOL and nerr(lv, golden['A_eval_logvar']) < TOL
+    assert torch.equal(z, mu)
+    enc = model.encode(xa.to(DEV))[0]
+    assert torch.equal(enc, mu)
+    dec = model.decode(mu)
+    assert torch.equal(dec, rec)
+
+
+def test_train_step_autograd_vs_reference_golden(golden, case_a, cranio, monkeypatch):
+    """The reference's _do_iteration composition (model_manager.py:281-315) on the drop-in
+    modules: losses and all 24 gradients against the reference's own numbers."""
+    from sdvae_b200 import losses
+    _, _, model, _, xa, key = case_a
+    model.train()
+    model.zero_grad()
+    eps = torch.from_numpy(golden['A_eps']).to(DEV)
+    monkeypatch.setattr(torch, 'randn_like', lambda t: eps)
+    x = xa.to(DEV)
+    rec, z, mu, lv = model(x)
+    assert nerr(z, golden['A_train_z']) < TOL
+    lt = losses.LaplacianTable.from_sparse(cranio.laplacian_tensor(DEV))
+    region = cranio.latent_regions(75)[key]
+    l_rec = losses.mse_loss(rec, x)
+    l_lap = losses.laplacian_regularizer(rec, lt)
+    l_kl = losses.kl_divergence(mu, lv)
+    l_lc = losses.latent_consistency(z, 2, region, W['eta1'], W['eta2'])
+    tot = l_rec + W['kl'] * l_kl + W['lc'] * l_lc + W['lap'] * l_lap
+    tot.backward()
+    ref = golden['A_losses']
+    for got, want in zip((l_rec, l_kl, l_lc, l_lap, tot), ref):
+        assert float(got) == pytest.approx(float(want), rel=2e-5)
+    for k, p in model.named_parameters():
+        g = p.grad
+        if 'A_grad/' + k in golden:
+            assert nerr(g, golden['A_grad/' + k]) < 5 * TOL, k
+        else:
+            assert nerr(samp(g), golden['A_grad_sample/' + k]) < 5 * TOL, k
+
+
+def test_small_ae_model_vs_reference_golden(golden):
+    """Odd channel counts / S=7 / plain AE with sigmoid: the generic kernels and the unfused
+    enblock path."""
+    from sdvae_b200 import fixtures as fx, losses
+    stab = fx.synthetic_tables(203, 2, seq_length=7, n_regions=3, seed=5)
+    _, _, model = build_pair(stab, 3, [8, 16], 6, True, False, 99, DEV, bias_scale=0.1)
+    model.train()
+    x = torch.from_numpy(golden['B_x']).to(DEV)
+    rec, z, mu, lv = model(x)
+    assert lv is None and nerr(rec, golden['B_recon']) < TOL and nerr(z, golden['B_z']) < TOL
+    key = str(golden['B_region_key'])
+    lt = losses.LaplacianTable.build(*stab.lap, 203, DEV)
+    mse, lap = losses.mse_and_laplacian(rec, x, lt)
+    lc = losses.latent_consistency(z, 3, stab.latent_regions(6)[key], 0.3, 0.7)
+    ref = golden['B_losses']
+    assert float(mse) == pytest.approx(float(ref[0]), rel=2e-5)
+    assert float(lc) == pytest.approx(float(ref[1]), rel=2e-5)
+    assert float(lap) == pytest.approx(float(ref[2]), rel=2e-5)
+    (mse + lc + lap).backward()
+    for k, p in model.named_parameters():
+        assert nerr(p.grad, golden['B_grad/' + k]) < 5 * TOL, k
+
+
+def _engine(model, tabs, bs, use_graph, **kw):
+    from sdvae_b200 import losses
+    from sdvae_b200.engine import StepConfig, TrainEngine
+    cfg = StepConfig(batch_size=bs, **kw)
+    lt = losses.LaplacianTable.build(*tabs.lap, tabs.num_vertices[0], DEV)
+    lat = tabs.latent_regions(model.latent_size)
+    return TrainEngine(model, lt, [r[1] for r in tabs.regions], [lat[k] for k in tabs.region_keys()],
+                       cfg, use_graph=use_graph)
+
+
+@pytest.mark.parametrize('use_graph', [False, True])
+def test_engine_steps_vs_oracle_trainer(golden, cranio, use_graph):
+    """Three fused training steps (swap on device, fwd, 4 losses, bwd, Adam) against the
+    oracle's _do_iteration with torch.optim.Adam."""
+    from oracle import sdvae_oracle as orc
+    net, params, model = build_pair(cranio, 3, [32, 32, 32, 64], 75, False, True, 77, DEV)
+    eng = _engine(model, cranio, 2, use_graph, lr=1e-3)
+    lap = tuple(torch.from_numpy(a) for a in cranio.lap)
+    trainer = orc.Trainer(net, params, lap, W, lr=1e-3)
+    x2 = torch.from_numpy(golden['A_x_unswapped'])
+    keys = cranio.region_keys()
+    for it, ridx in enumerate((3, 10, 3)):
+        eps = rand((4, 75), 100 + it)
+        feat = torch.from_numpy(cranio.regions[ridx][1])
+        xa = orc.swap_features(x2 * (1.0 + 0.1 * it), feat)
+        want = trainer.step(xa, 2, cranio.latent_regions(75)[keys[ridx]], eps=eps)
+        eng.set_fixed_eps(eps.to(DEV))
+        eng.load_batch((x2 * (1.0 + 0.1 * it)).to(DEV))
+        got = eng.step(ridx, sync_losses=True)
+        for k in ('reconstruction', 'kl', 'latent_consistency', 'laplacian', 'tot'):
+            assert got[k] == pytest.approx(want[k], rel=5e-5), (it, k)
+    sd = model.state_dict()
+    for k, v in trainer.params.items():
+        # after 3 Adam steps of size 1e-3 the parameters moved by ~3e-3; compare the UPDATE
+        delta_ref = v.detach() - params[k]
+        delta = sd[k].cpu() - params[k]
+        assert nerr(delta, delta_ref) < 2e-3, k
+        assert nerr(sd[k], v) < 1e-5, k
+
+
+def test_engine_body_config_no_vae(cranio):
+    """body.yaml-like model section (plain AE, 3 levels, latent 33) on synthetic tables."""
+    from oracle import sdvae_oracle as orc
+    from sdvae_b200 import fixtures as fx
+    stab = fx.synthetic_tables(689, 3, seq_length=9, n_regions=11, seed=2, name='body-small')
+    net, params, model = build_pair(stab, 3, [32, 32, 64], 33, False, False, 5, DEV)
+    w = dict(kl=0.0, lc=1.0, lap=1.0, eta1=0.5, eta2=0.5)
+    eng = _engine(model, stab, 3, False, lr=1e-3, kl_weight=0.0, latent_consistency_weight=1.0,
+                  laplacian_weight=1.0)
+    lap = tuple(torch.from_numpy(a) for a in stab.lap)
+    trainer = orc.Trainer(net, params, lap, w, lr=1e-3)
+    x = rand((3, 689, 3), 6)
+    feat = torch.from_numpy(stab.regions[4][1])
+    want = trainer.step(orc.swap_features(x, feat), 3, stab.latent_regions(33)[stab.region_keys()[4]])
+    eng.load_batch(x.to(DEV))
+    got = eng.step(4, sync_losses=True)
+    for k in ('reconstruction', 'latent_consistency', 'laplacian', 'tot'):
+        assert got[k] == pytest.approx(want[k], rel=5e-5), k
+    assert got['kl'] == 0.0
+    sd = model.state_dict()
+    for k, v in trainer.params.items():
+        assert nerr(sd[k], v) < 1e-5, k
+
+
+def test_checkpoint_roundtrip_keys(cranio, tmp_path):
+    """save_weights/resume format (model_manager.py:682-706): {'model': state_dict} with
+    the reference's keys, strict load."""
+    _, params, model = build_pair(cranio, 3, [32, 32, 32, 64], 75, False, True, 3, DEV)
+    path = tmp_path / 'model_00000001.pt'
+    torch.save({'model': model.state_dict()}, path)
+    _, _, other = build_pair(cranio, 3, [32, 32, 32, 64], 75, False, True, 4, DEV)
+    other.load_state_dict(torch.load(path)['model'], strict=True)
+    for k, v in other.state_dict().items():
+        assert torch.equal(v.cpu(), params[k])

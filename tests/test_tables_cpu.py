@@ -1,0 +1,122 @@
+"""Host-side table derivation (bit-exact integer work) and package plumbing -- no GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from sdvae_b200 import cabi, fixtures as fx, tables as tb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_inverse_cells_roundtrip(cranio):
+    for lvl, idx in enumerate(cranio.spirals):
+        V, S = idx.shape
+        ptr, src = tb.inverse_cells(idx, V)
+        assert ptr[0] == 0 and ptr[-1] == V * S and np.all(np.diff(ptr) >= 0)
+        cell = np.repeat(np.arange(V * S), np.diff(ptr))
+        u, s = cell // S, cell % S
+        assert np.array_equal(idx[src, s], u)                 # every entry points back
+        # ascending rows inside each cell
+        same = cell[1:] == cell[:-1]
+        assert np.all(src[1:][same] > src[:-1][same])
+        # slot 0 is the vertex itself: exactly one entry, itself
+        assert np.array_equal(np.diff(ptr)[::S], np.ones(V, np.int32))
+
+
+def test_inverse_flat_matches_cells(cranio):
+    idx = cranio.spirals[1]
+    V, S = idx.shape
+    ptr, flat = tb.inverse_rows_flat(idx, V)
+    assert ptr[-1] == V * S
+    tgt = np.repeat(np.arange(V), np.diff(ptr))
+    assert np.array_equal(idx.ravel()[flat], tgt)
+
+
+def test_restricted_table_is_row_subset(cranio):
+    dn = cranio.down[0]
+    kept = tb.selection_columns(dn[0], dn[1], dn[2], dn[3][0])
+    assert kept is not None and np.array_equal(kept, dn[1])
+    assert np.all(np.diff(kept) > 0)
+    up = cranio.up[0]
+    assert tb.selection_columns(up[0], up[1], up[2], up[3][0]) is None
+
+
+def test_ell_keeps_storage_order(cranio):
+    row, col, val, shape = cranio.up[0]
+    ec, ev = tb.ell_from_coo(row, col, val, *shape)
+    assert ec.shape == (shape[0], 3) and np.all(ec >= 0)
+    # rebuild the COO row by row and compare with a stable sort of the original
+    order = np.argsort(row, kind='stable')
+    assert np.array_equal(ec.ravel(), col[order].astype(np.int32))
+    assert np.array_equal(ev.ravel(), val[order])
+    tp, tr, tv = tb.transposed_csr(row, col, val, shape[1])
+    deg = np.diff(tp)
+    assert deg.min() >= 1 and deg.max() == 96 and tp[-1] == row.size
+    # storage is column-major, so the transposed CSR is the storage order itself
+    assert np.array_equal(tr, row.astype(np.int32)) and np.array_equal(tv, val)
+
+
+def test_ell_ragged_padding():
+    row = np.array([2, 0, 2, 2]); col = np.array([1, 3, 0, 2]); val = np.array([1., 2., 3., 4.], np.float32)
+    ec, ev = tb.ell_from_coo(row, col, val, 3, 4)
+    assert ec.tolist() == [[3, -1, -1], [-1, -1, -1], [1, 0, 2]]
+    assert ev[2].tolist() == [1., 3., 4.]
+
+
+def test_index_range_checks():
+    with pytest.raises(IndexError):
+        tb.check_indices(np.array([[0, 5]]), n_src=5)
+    with pytest.raises(IndexError):
+        tb.check_indices(np.array([[-1, 0]]), n_src=5)
+    with pytest.raises(ValueError):
+        tb.check_indices(np.arange(4))
+
+
+def test_laplacian_rows_sum_to_zero(cranio):
+    row, col, val = cranio.lap
+    V = cranio.num_vertices[0]
+    assert row.size == 118595
+    sums = np.bincount(row, weights=val.astype(np.float64), minlength=V)
+    assert np.abs(sums).max() < 1e-6
+
+
+def test_cabi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, 'include', 'sdvae_b200.h')).read()
+    declared = set(re.findall(r'\b(sdvae_[a-z0-9_]+)\s*\(', hdr))
+    assert declared == set(cabi.EXPORTED_SYMBOLS)
+    lib = ctypes.CDLL(cabi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert cabi.load().sdvae_abi_version() == 1
+
+
+def test_model_state_dict_keys_match_reference_layout(cranio):
+    from oracle import sdvae_oracle as orc
+    from sdvae_b200.model import Model, MLPClassifier
+    sp, dn, up = cranio.spiral_tensors(), cranio.down_tensors(), cranio.up_tensors()
+    m = Model(3, [32, 32, 32, 64], 75, sp, dn, up, False, True)
+    shapes = orc.Net(3, [32, 32, 32, 64], 75, sp, dn, up, False, True).param_shapes()
+    sd = m.state_dict()
+    assert list(sd) == list(shapes)
+    assert all(tuple(sd[k].shape) == shapes[k] for k in shapes)
+    assert sum(v.numel() for v in sd.values()) == 1081881
+    assert all(float(v.abs().max()) == 0.0 for k, v in sd.items() if k.endswith('bias'))
+    assert repr(m.en_layers[0].conv) == 'SpiralConv(3, 32, seq_length=9)'
+    clf = MLPClassifier(75, [16, 8], 5)
+    out, lab = clf(torch.randn(4, 75))
+    assert out.shape == (4, 5) and lab.shape == (4,) and float(out.min()) >= 0.0
+
+
+def test_cpu_tensors_are_rejected(cranio):
+    from sdvae_b200.model import SpiralConv, Pool
+    conv = SpiralConv(3, 8, cranio.spiral_tensors()[3])
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        conv(torch.randn(2, 267, 3))
+    with pytest.raises(RuntimeError, match='expected to be 2 or 3'):
+        conv(torch.randn(1, 2, 267, 3))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        Pool(torch.randn(2, 67, 4), cranio.up_tensors()[3])
