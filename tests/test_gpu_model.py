@@ -105,10 +105,20 @@ def _engine(model, tabs, bs, use_graph, **kw):
                        cfg, use_graph=use_graph)
 
 
+def _check_grads(eng, model, trainer, tol):
+    """Engine gradient arena vs the oracle's autograd gradients (taken BEFORE any Adam noise:
+    Adam turns rounding-level gradients into +-lr updates, so parameters after a step are not a
+    meaningful parity target; gradients and losses are)."""
+    named = dict(model.named_parameters())
+    for k, v in trainer.params.items():
+        assert nerr(eng.g(named[k]), v.grad) < tol, k
+
+
 @pytest.mark.parametrize('use_graph', [False, True])
 def test_engine_steps_vs_oracle_trainer(golden, cranio, use_graph):
-    """Three fused training steps (swap on device, fwd, 4 losses, bwd, Adam) against the
-    oracle's _do_iteration with torch.optim.Adam."""
+    """Fused training steps (swap on device, fwd, 4 losses, bwd, Adam) against the oracle's
+    _do_iteration with torch.optim.Adam: all 24 gradients on the first step, the five loss
+    values on three consecutive steps (i.e. through two Adam updates)."""
     from oracle import sdvae_oracle as orc
     net, params, model = build_pair(cranio, 3, [32, 32, 32, 64], 75, False, True, 77, DEV)
     eng = _engine(model, cranio, 2, use_graph, lr=1e-3)
@@ -126,13 +136,12 @@ def test_engine_steps_vs_oracle_trainer(golden, cranio, use_graph):
         got = eng.step(ridx, sync_losses=True)
         for k in ('reconstruction', 'kl', 'latent_consistency', 'laplacian', 'tot'):
             assert got[k] == pytest.approx(want[k], rel=5e-5), (it, k)
+        if it == 0:
+            _check_grads(eng, model, trainer, 5 * TOL)
     sd = model.state_dict()
-    for k, v in trainer.params.items():
-        # after 3 Adam steps of size 1e-3 the parameters moved by ~3e-3; compare the UPDATE
-        delta_ref = v.detach() - params[k]
-        delta = sd[k].cpu() - params[k]
-        assert nerr(delta, delta_ref) < 2e-3, k
-        assert nerr(sd[k], v) < 1e-5, k
+    for k, v in trainer.params.items():          # every element moved by at most ~lr per step
+        assert float((sd[k].cpu() - v.detach()).abs().max()) < 3 * 2.1e-3, k
+        assert float((sd[k].cpu() - params[k]).abs().max()) > 0.0, k
 
 
 def test_engine_body_config_no_vae(cranio):
@@ -154,9 +163,7 @@ def test_engine_body_config_no_vae(cranio):
     for k in ('reconstruction', 'latent_consistency', 'laplacian', 'tot'):
         assert got[k] == pytest.approx(want[k], rel=5e-5), k
     assert got['kl'] == 0.0
-    sd = model.state_dict()
-    for k, v in trainer.params.items():
-        assert nerr(sd[k], v) < 1e-5, k
+    _check_grads(eng, model, trainer, 5 * TOL)
 
 
 def test_checkpoint_roundtrip_keys(cranio, tmp_path):
