@@ -36,6 +36,7 @@ import torch
 
 from . import cabi
 from .losses import LaplacianTable
+from .parallel import grid_rows, mean_loss_scale
 from .tables import PoolTable, SpiralTable, pool_table, restricted_spiral_table, spiral_table
 
 LOSS_KEYS = ['reconstruction', 'kl', 'latent_consistency', 'laplacian',
@@ -76,11 +77,9 @@ class TrainEngine:
         else:
             self.world, self.rank = 1, 0
         bs = cfg.batch_size
-        if bs % self.world:
-            raise ValueError('grid rows (batch_size=%d) must divide over %d ranks' % (bs, self.world))
         self.bs = bs
-        self.rows = bs // self.world
-        self.i0 = self.rank * self.rows
+        self.i0, i1 = grid_rows(bs, self.world, self.rank)
+        self.rows = i1 - self.i0
         self.B = self.rows * bs                          # local meshes per step
         self.is_vae = bool(model.is_vae)
         self.L = len(model.out_channels)
@@ -263,7 +262,7 @@ class TrainEngine:
     def losses_and_backward(self, z, region: Optional[int]):
         m, L, V, C, S, cfg = self.model, self.L, self.V, self.C, self.S, self.cfg
         B = self.B
-        scale = 1.0 / self.world                       # local means -> global means
+        scale = mean_loss_scale(self.world)            # local means -> global means
         lap = self.lap
         if lap is not None:
             cabi.mse_lap_fwd(self.recon, self.x0, lap.ell_col, lap.ell_val, lap.width, self.qn,

@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""Data-parallel parity check (run under torchrun with N >= 2 GPUs):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tools/dp_check.py
+
+Every rank runs one DP training step of the craniofacial model on its rows of the bs x bs swap
+grid; rank 0 additionally runs the same step on ONE GPU with the whole grid and compares the
+all-reduced gradient arena, the seven losses and the updated parameters."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from oracle import sdvae_oracle as orc
+    from sdvae_b200 import fixtures as fx, losses
+    from sdvae_b200.engine import StepConfig, TrainEngine
+    from sdvae_b200.model import Model
+
+    tabs = fx.craniofacial_tables()
+    sp, dn, up = tabs.spiral_tensors(), tabs.down_tensors(), tabs.up_tensors()
+    shapes = orc.Net(3, [32, 32, 32, 64], 75, sp, dn, up, False, True).param_shapes()
+    params = orc.xavier_params(shapes, seed=5, bias_scale=0.05)
+    bs = 2 * world
+    cfg = StepConfig(batch_size=bs, lr=1e-3)
+    lat = tabs.latent_regions(75)
+
+    def make(pg):
+        model = Model(3, [32, 32, 32, 64], 75, [s.to(dev) for s in sp], [d.to(dev) for d in dn],
+                      [u.to(dev) for u in up], False, True).to(dev)
+        model.load_state_dict({k: v.to(dev) for k, v in params.items()})
+        lt = losses.LaplacianTable.build(*tabs.lap, tabs.num_vertices[0], dev)
+        return TrainEngine(model, lt, [r[1] for r in tabs.regions],
+                           [lat[k] for k in tabs.region_keys()], cfg, process_group=pg, use_graph=False)
+
+    rng = np.random.RandomState(1)
+    x = torch.from_numpy(rng.randn(bs, tabs.num_vertices[0], 3).astype(np.float32)).to(dev)
+    eps = torch.from_numpy(rng.randn(bs * bs, 75).astype(np.float32)).to(dev)
+    region = 6
+
+    eng = make(dist.group.WORLD)
+    lo = eng.i0 * bs
+    eng.set_fixed_eps(eps[lo:lo + eng.B])
+    eng.load_batch(x)
+    got = eng.step(region, sync_losses=True)
+    torch.cuda.synchronize()
+    ok = True
+    if rank == 0:
+        ref = make(None)
+        ref.set_fixed_eps(eps)
+        ref.load_batch(x)
+        want = ref.step(region, sync_losses=True)
+        torch.cuda.synchronize()
+        gerr = float((eng.flat_g - ref.flat_g).abs().max() / ref.flat_g.abs().max())
+        perr = float((eng.flat_p - ref.flat_p).abs().max())
+        lerr = max(abs(got[k] - want[k]) / max(abs(want[k]), 1e-12) for k in want if want[k] != 0)
+        print("dp_check world=%d: grad normwise err %.2e, max |param diff| %.2e, loss rel err %.2e"
+              % (world, gerr, perr, lerr))
+        print("losses dp  ", got)
+        print("losses 1gpu", want)
+        ok = gerr < 5e-5 and lerr < 5e-5
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    dist.barrier()
+    dist.destroy_process_group()
+    if int(flag.item()) != 1:
+        raise SystemExit("dp_check FAILED")
+    if rank == 0:
+        print("dp_check OK")
+
+
+if __name__ == "__main__":
+    main()
