@@ -4,6 +4,7 @@
 #include "../../include/sdvae_b200.h"
 #include "common.cuh"
 #include "spiral_conv.cuh"
+#include "spiral_conv_umma.cuh"
 #include "pool_misc.cuh"
 #include "loss.cuh"
 
@@ -80,6 +81,51 @@ static int launch_bw(const BwArgs& a, int nsplit, cudaStream_t st) {
     return check_launch("bw_outer_kernel");
 }
 
+// ---- tcgen05 (tensor-core) gather-contraction dispatch ------------------------------------
+static inline int tc_tile_n(int N) { return N <= 16 ? 16 : (N <= 32 ? 32 : (N <= 64 ? 64 : 0)); }
+
+static bool tc_shape_ok(int S, int KS, int N) {
+    if (KS != 32 && KS != 64) return false;
+    const int NT = tc_tile_n(N);
+    if (NT == 0 || N < 1) return false;
+    const int nch = S * (KS / 32);
+    if (nch % 3 != 0 || S < 1 || S > 11) return false;
+    const int b_bytes = nch * 2 * NT * 128;
+    const int budget = 225 * 1024 - 2048 - b_bytes - 2 * umma::kBM * (S + 2) * 4;
+    return budget >= 2 * (2 * umma::kBM * 128);          // at least two A stages next to the resident weights
+}
+
+template <int KS, int NT, bool RAGGED>
+static int launch_umma(const GcArgs& g, const float* wimg, cudaStream_t st) {
+    using Cfg = umma::UmmaCfg<KS, NT>;
+    auto kern = umma::gc_umma_kernel<KS, NT, RAGGED>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_done = true;
+    }
+    umma::UmmaArgs ua;
+    ua.g = g;
+    ua.wimg = wimg;
+    ua.nstages = Cfg::stages(g.S);
+    ua.ntiles = (int)((g.M + umma::kBM - 1) / umma::kBM);
+    const int grid = ua.ntiles < kNumSMs ? ua.ntiles : kNumSMs;
+    kern<<<grid, umma::kThreads, Cfg::smem_bytes(g.S, ua.nstages), st>>>(ua);
+    return check_launch("gc_umma_kernel");
+}
+
+template <bool RAGGED>
+static int dispatch_umma(const GcArgs& g, int KS, const float* wimg, cudaStream_t st) {
+    if (g.M <= 0) return SDVAE_OK;
+    const int NT = tc_tile_n(g.n_real);
+    if (KS == 32 && NT == 16) return launch_umma<32, 16, RAGGED>(g, wimg, st);
+    if (KS == 32 && NT == 32) return launch_umma<32, 32, RAGGED>(g, wimg, st);
+    if (KS == 32 && NT == 64) return launch_umma<32, 64, RAGGED>(g, wimg, st);
+    if (KS == 64 && NT == 16) return launch_umma<64, 16, RAGGED>(g, wimg, st);
+    if (KS == 64 && NT == 32) return launch_umma<64, 32, RAGGED>(g, wimg, st);
+    return set_error(SDVAE_ERR_UNSUPPORTED, "tcgen05 path: unsupported layer shape");
+}
+
 }  // namespace sdvae
 
 using namespace sdvae;
@@ -121,6 +167,61 @@ int sdvae_spiralconv_bwd_x(const float* dpre, const int32_t* cell_ptr, const int
     a.M = (long long)B * Vdst; a.in_rows = Vrows; a.Vout = Vdst; a.S = S;
     a.ldw = S * Cout; a.ldo = Cin; a.n_real = Cin;
     return dispatch_gc<true>(a, Cout, gate ? EPI_GATE : EPI_NONE, (cudaStream_t)stream);
+}
+
+int sdvae_tc_supported(int S, int KS, int N) { return tc_shape_ok(S, KS, N) ? 1 : 0; }
+
+size_t sdvae_tc_wimg_floats(int S, int KS, int N) {
+    const int NT = tc_tile_n(N);
+    return (size_t)S * (KS / 32) * 2 * NT * 32;
+}
+
+int sdvae_tc_pack_weights(const float* W, float* wimg, int S, int Cin, int Cout, int transposed,
+                          sdvae_stream_t stream) {
+    SDVAE_REQUIRE(W && wimg && S > 0 && Cin > 0 && Cout > 0, "tc_pack_weights: bad argument");
+    const int KS = transposed ? Cout : Cin, N = transposed ? Cin : Cout;
+    if (!tc_shape_ok(S, KS, N)) return set_error(SDVAE_ERR_UNSUPPORTED, "tc_pack_weights: unsupported layer shape");
+    SDVAE_REQUIRE((reinterpret_cast<uintptr_t>(wimg) & 15) == 0, "tc_pack_weights: wimg must be 16-byte aligned");
+    umma::PackArgs a;
+    a.W = W; a.img = wimg; a.NT = tc_tile_n(N); a.KS = KS; a.S = S; a.n_real = N; a.ldw = S * Cin;
+    a.transposed = transposed ? 1 : 0; a.cin = Cin;
+    const long long total = (long long)S * (KS / 32) * 2 * a.NT * 32;
+    umma::umma_pack_weights_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a);
+    return check_launch("umma_pack_weights_kernel");
+}
+
+int sdvae_spiralconv_fwd_tc(const float* x, const int32_t* idx, const float* wimg, const float* bias,
+                            float* y, int B, int Vin, int Vout, int S, int Cin, int Cout, int act,
+                            sdvae_stream_t stream) {
+    SDVAE_REQUIRE(x && idx && wimg && y, "spiralconv_fwd_tc: null pointer");
+    SDVAE_REQUIRE(B >= 0 && Vin > 0 && Vout > 0 && S > 0 && Cin > 0 && Cout > 0, "spiralconv_fwd_tc: bad shape");
+    SDVAE_REQUIRE((long long)B * Vin < 2147483647LL, "spiralconv_fwd_tc: B*Vin exceeds int32 rows");
+    SDVAE_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wimg)) & 15) == 0,
+                  "spiralconv_fwd_tc: x and wimg must be 16-byte aligned");
+    if (!tc_shape_ok(S, Cin, Cout)) return set_error(SDVAE_ERR_UNSUPPORTED, "spiralconv_fwd_tc: unsupported layer shape");
+    GcArgs a{};
+    a.in = x; a.idx = idx; a.bias = bias; a.out = y;
+    a.M = (long long)B * Vout; a.in_rows = Vin; a.Vout = Vout; a.S = S;
+    a.ldw = S * Cin; a.ldo = Cout; a.n_real = Cout;
+    a.epi = act == SDVAE_ACT_ELU ? EPI_BIAS_ELU : EPI_BIAS;
+    return dispatch_umma<false>(a, Cin, wimg, (cudaStream_t)stream);
+}
+
+int sdvae_spiralconv_bwd_x_tc(const float* dpre, const int32_t* cell_ptr, const int32_t* cell_src,
+                              const float* wimg_t, const float* gate, float* dx, int B, int Vrows,
+                              int Vdst, int S, int Cout, int Cin, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(dpre && cell_ptr && cell_src && wimg_t && dx, "spiralconv_bwd_x_tc: null pointer");
+    SDVAE_REQUIRE(B >= 0 && Vrows > 0 && Vdst > 0 && S > 0 && Cin > 0 && Cout > 0, "spiralconv_bwd_x_tc: bad shape");
+    SDVAE_REQUIRE((long long)B * Vrows < 2147483647LL, "spiralconv_bwd_x_tc: B*Vrows exceeds int32 rows");
+    SDVAE_REQUIRE(((reinterpret_cast<uintptr_t>(dpre) | reinterpret_cast<uintptr_t>(wimg_t)) & 15) == 0,
+                  "spiralconv_bwd_x_tc: dpre and wimg must be 16-byte aligned");
+    if (!tc_shape_ok(S, Cout, Cin)) return set_error(SDVAE_ERR_UNSUPPORTED, "spiralconv_bwd_x_tc: unsupported layer shape");
+    GcArgs a{};
+    a.in = dpre; a.cell_ptr = cell_ptr; a.cell_src = cell_src; a.gate = gate; a.out = dx;
+    a.M = (long long)B * Vdst; a.in_rows = Vrows; a.Vout = Vdst; a.S = S;
+    a.ldw = S * Cout; a.ldo = Cin; a.n_real = Cin;
+    a.epi = gate ? EPI_GATE : EPI_NONE;
+    return dispatch_umma<true>(a, Cout, wimg_t, (cudaStream_t)stream);
 }
 
 size_t sdvae_spiralconv_bwd_w_workspace(long long M, int S, int Cin, int Cout) {

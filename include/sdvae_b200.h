@@ -60,6 +60,28 @@ int sdvae_spiralconv_bwd_x(const float* dpre, const int32_t* cell_ptr, const int
                            const float* Wt, const float* gate, float* dx, int B, int Vrows,
                            int Vdst, int S, int Cout, int Cin, sdvae_stream_t stream);
 
+/* ---- SpiralConv on the 5th-gen tensor cores (tcgen05.mma + TMEM accumulators) ----------------
+ * Same contractions as sdvae_spiralconv_fwd / sdvae_spiralconv_bwd_x, for the wide layers
+ * (channels per slot KS in {32, 64}; outputs N <= 64; the S*KS/32 chunks must be a multiple of 3).
+ * Arithmetic: error-compensated 3xTF32 (hi/lo operand split, fp32 accumulation in TMEM) -- the
+ * parity bar of this path is stated separately in tests/ (normwise vs the fp64 oracle).
+ * The weight operand is a packed image (already split and laid out as the 128B-swizzled UMMA
+ * tiles) produced by sdvae_tc_pack_weights from the nn.Linear weight W [Cout, S*Cin]
+ * (model.py:16-21); `transposed` != 0 packs the backward-to-input operand
+ * Wt[c, s*Cout+o] = W[o, s*Cin+c] instead.  Re-pack whenever W changes. */
+int    sdvae_tc_supported(int S, int KS, int N);
+size_t sdvae_tc_wimg_floats(int S, int KS, int N);
+int sdvae_tc_pack_weights(const float* W, float* wimg, int S, int Cin, int Cout, int transposed,
+                          sdvae_stream_t stream);
+/* Replaces: model.py:27-41 + F.elu (model.py:68,84), as sdvae_spiralconv_fwd. */
+int sdvae_spiralconv_fwd_tc(const float* x, const int32_t* idx, const float* wimg, const float* bias,
+                            float* y, int B, int Vin, int Vout, int S, int Cin, int Cout, int act,
+                            sdvae_stream_t stream);
+/* Replaces: autograd of model.py:34,40 w.r.t. the input, as sdvae_spiralconv_bwd_x. */
+int sdvae_spiralconv_bwd_x_tc(const float* dpre, const int32_t* cell_ptr, const int32_t* cell_src,
+                              const float* wimg_t, const float* gate, float* dx, int B, int Vrows,
+                              int Vdst, int S, int Cout, int Cin, sdvae_stream_t stream);
+
 /* dW[o, s*Cin+c] = sum_{b,v} dpre[b,v,o] * x[b, idx[v,s], c];  db[o] = sum_{b,v} dpre[b,v,o]
  * workspace: sdvae_spiralconv_bwd_w_workspace(...) bytes.  Split-M partial sums are added in a
  * fixed order.  db may be NULL.
