@@ -84,45 +84,49 @@ static int launch_bw(const BwArgs& a, int nsplit, cudaStream_t st) {
 // ---- tcgen05 (tensor-core) gather-contraction dispatch ------------------------------------
 static inline int tc_tile_n(int N) { return N <= 16 ? 16 : (N <= 32 ? 32 : (N <= 64 ? 64 : 0)); }
 
-static bool tc_shape_ok(int S, int KS, int N) {
-    if (KS != 32 && KS != 64) return false;
+// raw ring depth for a layer shape (0 = the resident weight image leaves no room)
+static int tc_raw_stages(int S, int KS, int N, int rcap) {
     const int NT = tc_tile_n(N);
-    if (NT == 0 || N < 1) return false;
-    const int nch = S * (KS / 32);
-    if (nch % 3 != 0 || S < 1 || S > 11) return false;
-    const int b_bytes = nch * 2 * NT * 128;
-    const int budget = 225 * 1024 - 2048 - b_bytes - 2 * umma::kBM * (S + 2) * 4;
-    return budget >= 2 * (2 * umma::kBM * 128);          // at least two A stages next to the resident weights
+    if (NT == 0) return 0;
+    const long long b_bytes = (long long)S * (KS / 32) * 2 * NT * 128;
+    const long long budget = 226LL * 1024 - 2048 - b_bytes;
+    long long st = budget / ((long long)rcap * 128);
+    if (st > umma::kMaxRaw) st = umma::kMaxRaw;
+    return st < 0 ? 0 : (int)st;
 }
 
-template <int KS, int NT, bool RAGGED>
-static int launch_umma(const GcArgs& g, const float* wimg, cudaStream_t st) {
+static bool tc_shape_ok(int S, int KS, int N, int rcap) {
+    if (KS != 32 && KS != 64) return false;
+    if (N < 1 || tc_tile_n(N) == 0 || S < 1) return false;
+    if (rcap < 16 || rcap > umma::kMaxRcap || rcap % 16 != 0) return false;
+    return tc_raw_stages(S, KS, N, rcap) >= 3;
+}
+
+template <int KS, int NT>
+static int launch_umma(umma::UmmaArgs& ua, cudaStream_t st) {
     using Cfg = umma::UmmaCfg<KS, NT>;
-    auto kern = umma::gc_umma_kernel<KS, NT, RAGGED>;
+    auto kern = umma::gc_umma_kernel<KS, NT>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_done = true;
     }
-    umma::UmmaArgs ua;
-    ua.g = g;
-    ua.wimg = wimg;
-    ua.nstages = Cfg::stages(g.S);
-    ua.ntiles = (int)((g.M + umma::kBM - 1) / umma::kBM);
-    const int grid = ua.ntiles < kNumSMs ? ua.ntiles : kNumSMs;
-    kern<<<grid, umma::kThreads, Cfg::smem_bytes(g.S, ua.nstages), st>>>(ua);
+    ua.nraw = Cfg::raw_stages(ua.S, ua.rcap);
+    const long long ntiles = (long long)ua.B * ua.L;
+    const int grid = ntiles < kNumSMs ? (int)ntiles : kNumSMs;
+    kern<<<grid, umma::kThreads, Cfg::smem_bytes(ua.S, ua.rcap, ua.nraw), st>>>(ua);
     return check_launch("gc_umma_kernel");
 }
 
-template <bool RAGGED>
-static int dispatch_umma(const GcArgs& g, int KS, const float* wimg, cudaStream_t st) {
-    if (g.M <= 0) return SDVAE_OK;
-    const int NT = tc_tile_n(g.n_real);
-    if (KS == 32 && NT == 16) return launch_umma<32, 16, RAGGED>(g, wimg, st);
-    if (KS == 32 && NT == 32) return launch_umma<32, 32, RAGGED>(g, wimg, st);
-    if (KS == 32 && NT == 64) return launch_umma<32, 64, RAGGED>(g, wimg, st);
-    if (KS == 64 && NT == 16) return launch_umma<64, 16, RAGGED>(g, wimg, st);
-    if (KS == 64 && NT == 32) return launch_umma<64, 32, RAGGED>(g, wimg, st);
+static int dispatch_umma(umma::UmmaArgs& ua, int KS, cudaStream_t st) {
+    if (ua.B <= 0) return SDVAE_OK;
+    const int NT = tc_tile_n(ua.n_real);
+    if (KS == 32 && NT == 16) return launch_umma<32, 16>(ua, st);
+    if (KS == 32 && NT == 32) return launch_umma<32, 32>(ua, st);
+    if (KS == 32 && NT == 64) return launch_umma<32, 64>(ua, st);
+    if (KS == 64 && NT == 16) return launch_umma<64, 16>(ua, st);
+    if (KS == 64 && NT == 32) return launch_umma<64, 32>(ua, st);
+    if (KS == 64 && NT == 64) return launch_umma<64, 64>(ua, st);
     return set_error(SDVAE_ERR_UNSUPPORTED, "tcgen05 path: unsupported layer shape");
 }
 
@@ -169,7 +173,7 @@ int sdvae_spiralconv_bwd_x(const float* dpre, const int32_t* cell_ptr, const int
     return dispatch_gc<true>(a, Cout, gate ? EPI_GATE : EPI_NONE, (cudaStream_t)stream);
 }
 
-int sdvae_tc_supported(int S, int KS, int N) { return tc_shape_ok(S, KS, N) ? 1 : 0; }
+int sdvae_tc_supported(int S, int KS, int N, int rcap) { return tc_shape_ok(S, KS, N, rcap) ? 1 : 0; }
 
 size_t sdvae_tc_wimg_floats(int S, int KS, int N) {
     const int NT = tc_tile_n(N);
@@ -180,7 +184,7 @@ int sdvae_tc_pack_weights(const float* W, float* wimg, int S, int Cin, int Cout,
                           sdvae_stream_t stream) {
     SDVAE_REQUIRE(W && wimg && S > 0 && Cin > 0 && Cout > 0, "tc_pack_weights: bad argument");
     const int KS = transposed ? Cout : Cin, N = transposed ? Cin : Cout;
-    if (!tc_shape_ok(S, KS, N)) return set_error(SDVAE_ERR_UNSUPPORTED, "tc_pack_weights: unsupported layer shape");
+    if (!tc_shape_ok(S, KS, N, 128)) return set_error(SDVAE_ERR_UNSUPPORTED, "tc_pack_weights: unsupported layer shape");
     SDVAE_REQUIRE((reinterpret_cast<uintptr_t>(wimg) & 15) == 0, "tc_pack_weights: wimg must be 16-byte aligned");
     umma::PackArgs a;
     a.W = W; a.img = wimg; a.NT = tc_tile_n(N); a.KS = KS; a.S = S; a.n_real = N; a.ldw = S * Cin;
@@ -190,38 +194,84 @@ int sdvae_tc_pack_weights(const float* W, float* wimg, int S, int Cin, int Cout,
     return check_launch("umma_pack_weights_kernel");
 }
 
-int sdvae_spiralconv_fwd_tc(const float* x, const int32_t* idx, const float* wimg, const float* bias,
-                            float* y, int B, int Vin, int Vout, int S, int Cin, int Cout, int act,
-                            sdvae_stream_t stream) {
-    SDVAE_REQUIRE(x && idx && wimg && y, "spiralconv_fwd_tc: null pointer");
-    SDVAE_REQUIRE(B >= 0 && Vin > 0 && Vout > 0 && S > 0 && Cin > 0 && Cout > 0, "spiralconv_fwd_tc: bad shape");
-    SDVAE_REQUIRE((long long)B * Vin < 2147483647LL, "spiralconv_fwd_tc: B*Vin exceeds int32 rows");
-    SDVAE_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wimg)) & 15) == 0,
-                  "spiralconv_fwd_tc: x and wimg must be 16-byte aligned");
-    if (!tc_shape_ok(S, Cin, Cout)) return set_error(SDVAE_ERR_UNSUPPORTED, "spiralconv_fwd_tc: unsupported layer shape");
-    GcArgs a{};
-    a.in = x; a.idx = idx; a.bias = bias; a.out = y;
-    a.M = (long long)B * Vout; a.in_rows = Vin; a.Vout = Vout; a.S = S;
-    a.ldw = S * Cin; a.ldo = Cout; a.n_real = Cout;
-    a.epi = act == SDVAE_ACT_ELU ? EPI_BIAS_ELU : EPI_BIAS;
-    return dispatch_umma<false>(a, Cin, wimg, (cudaStream_t)stream);
+int sdvae_tc_plan_tiles(int out_rows) { return (out_rows + umma::kBM - 1) / umma::kBM; }
+
+int sdvae_tc_plan_max_rows(const int32_t* cell_ptr, int out_rows, int S) {
+    if (!cell_ptr || out_rows <= 0 || S <= 0) return -1;
+    const int L = sdvae_tc_plan_tiles(out_rows);
+    int mx = 0;
+    for (int jt = 0; jt < L; ++jt)
+        for (int s = 0; s < S; ++s) {
+            int n = 0;
+            const int r1 = (jt + 1) * umma::kBM < out_rows ? (jt + 1) * umma::kBM : out_rows;
+            for (int r = jt * umma::kBM; r < r1; ++r) n += cell_ptr[(size_t)r * S + s + 1] - cell_ptr[(size_t)r * S + s];
+            if (n > mx) mx = n;
+        }
+    return mx;
 }
 
-int sdvae_spiralconv_bwd_x_tc(const float* dpre, const int32_t* cell_ptr, const int32_t* cell_src,
-                              const float* wimg_t, const float* gate, float* dx, int B, int Vrows,
-                              int Vdst, int S, int Cout, int Cin, sdvae_stream_t stream) {
-    SDVAE_REQUIRE(dpre && cell_ptr && cell_src && wimg_t && dx, "spiralconv_bwd_x_tc: null pointer");
-    SDVAE_REQUIRE(B >= 0 && Vrows > 0 && Vdst > 0 && S > 0 && Cin > 0 && Cout > 0, "spiralconv_bwd_x_tc: bad shape");
-    SDVAE_REQUIRE((long long)B * Vrows < 2147483647LL, "spiralconv_bwd_x_tc: B*Vrows exceeds int32 rows");
-    SDVAE_REQUIRE(((reinterpret_cast<uintptr_t>(dpre) | reinterpret_cast<uintptr_t>(wimg_t)) & 15) == 0,
-                  "spiralconv_bwd_x_tc: dpre and wimg must be 16-byte aligned");
-    if (!tc_shape_ok(S, Cout, Cin)) return set_error(SDVAE_ERR_UNSUPPORTED, "spiralconv_bwd_x_tc: unsupported layer shape");
-    GcArgs a{};
-    a.in = dpre; a.cell_ptr = cell_ptr; a.cell_src = cell_src; a.gate = gate; a.out = dx;
-    a.M = (long long)B * Vdst; a.in_rows = Vrows; a.Vout = Vdst; a.S = S;
-    a.ldw = S * Cout; a.ldo = Cin; a.n_real = Cin;
-    a.epi = gate ? EPI_GATE : EPI_NONE;
-    return dispatch_umma<true>(a, Cout, wimg_t, (cudaStream_t)stream);
+int sdvae_tc_plan_build(const int32_t* cell_ptr, const int32_t* cell_src, int out_rows, int S,
+                        int rcap, int32_t* cnt, int32_t* src, int32_t* cell) {
+    SDVAE_REQUIRE(cell_ptr && cell_src && cnt && src && cell, "tc_plan_build: null pointer");
+    SDVAE_REQUIRE(out_rows > 0 && S > 0 && rcap >= 16 && rcap % 16 == 0 && rcap <= umma::kMaxRcap, "tc_plan_build: bad shape");
+    const int L = sdvae_tc_plan_tiles(out_rows);
+    for (int jt = 0; jt < L; ++jt)
+        for (int s = 0; s < S; ++s) {
+            int n = 0;
+            int32_t* srow = src + ((size_t)jt * S + s) * rcap;
+            int32_t* crow = cell + ((size_t)jt * S + s) * umma::kBM;
+            for (int lr = 0; lr < umma::kBM; ++lr) {
+                const int r = jt * umma::kBM + lr;
+                int c = 0;
+                if (r < out_rows) {
+                    const int e0 = cell_ptr[(size_t)r * S + s], e1 = cell_ptr[(size_t)r * S + s + 1];
+                    c = e1 - e0;
+                    SDVAE_REQUIRE(c >= 0 && n + c <= rcap, "tc_plan_build: a (tile, slot) stages more rows than rcap");
+                    for (int e = e0; e < e1; ++e) srow[n + (e - e0)] = cell_src[e];
+                }
+                crow[lr] = (int32_t)((uint32_t)n | ((uint32_t)c << 16));
+                n += c;
+            }
+            for (int e = n; e < rcap; ++e) srow[e] = 0;
+            cnt[(size_t)jt * S + s] = n;
+        }
+    return SDVAE_OK;
+}
+
+static int tc_conv(const float* in, const int32_t* plan_cnt, const int32_t* plan_src,
+                   const int32_t* plan_cell, int rcap, const float* wimg, const float* bias,
+                   const float* gate, float* out, int B, int in_rows, int out_rows, int S, int KS,
+                   int N, int epi, cudaStream_t st, const char* who) {
+    SDVAE_REQUIRE(in && plan_cnt && plan_src && plan_cell && wimg && out, "spiralconv tc: null pointer");
+    SDVAE_REQUIRE(B >= 0 && in_rows > 0 && out_rows > 0 && S > 0 && KS > 0 && N > 0, "spiralconv tc: bad shape");
+    SDVAE_REQUIRE((long long)B * in_rows < 2147483647LL, "spiralconv tc: B*rows exceeds int32");
+    SDVAE_REQUIRE(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(wimg)) & 15) == 0,
+                  "spiralconv tc: input and wimg must be 16-byte aligned");
+    if (!tc_shape_ok(S, KS, N, rcap)) return set_error(SDVAE_ERR_UNSUPPORTED, who);
+    umma::UmmaArgs ua{};
+    ua.in = in; ua.plan_cnt = plan_cnt; ua.plan_src = plan_src; ua.plan_cell = plan_cell;
+    ua.wimg = wimg; ua.bias = bias; ua.gate = gate; ua.out = out;
+    ua.B = B; ua.in_rows = in_rows; ua.out_rows = out_rows; ua.L = sdvae_tc_plan_tiles(out_rows);
+    ua.S = S; ua.rcap = rcap; ua.n_real = N; ua.ldo = N; ua.epi = epi;
+    return dispatch_umma(ua, KS, st);
+}
+
+int sdvae_spiralconv_fwd_tc(const float* x, const int32_t* plan_cnt, const int32_t* plan_src,
+                            const int32_t* plan_cell, int rcap, const float* wimg, const float* bias,
+                            float* y, int B, int Vin, int Vout, int S, int Cin, int Cout, int act,
+                            sdvae_stream_t stream) {
+    const int epi = act == SDVAE_ACT_ELU ? EPI_BIAS_ELU : EPI_BIAS;
+    return tc_conv(x, plan_cnt, plan_src, plan_cell, rcap, wimg, bias, nullptr, y, B, Vin, Vout, S, Cin,
+                   Cout, epi, (cudaStream_t)stream, "spiralconv_fwd_tc: unsupported layer shape");
+}
+
+int sdvae_spiralconv_bwd_x_tc(const float* dpre, const int32_t* plan_cnt, const int32_t* plan_src,
+                              const int32_t* plan_cell, int rcap, const float* wimg_t, const float* gate,
+                              float* dx, int B, int Vrows, int Vdst, int S, int Cout, int Cin,
+                              sdvae_stream_t stream) {
+    return tc_conv(dpre, plan_cnt, plan_src, plan_cell, rcap, wimg_t, nullptr, gate, dx, B, Vrows, Vdst, S,
+                   Cout, Cin, gate ? EPI_GATE : EPI_NONE, (cudaStream_t)stream,
+                   "spiralconv_bwd_x_tc: unsupported layer shape");
 }
 
 size_t sdvae_spiralconv_bwd_w_workspace(long long M, int S, int Cin, int Cout) {

@@ -273,7 +273,7 @@ gc_tile_kernel(const GcArgs a) {
 #pragma unroll
             for (int j = 0; j < TN; ++j) {
                 float v = acc[i][j] + bj[j];
-                if (EPI == EPI_BIAS_ELU) v = elu_f(v);
+                if (EPI == EPI_BIAS_ELU) v = elu_fast(v);
                 C_s[(warp * WM + rl + RL * i) * CP + cl + CL * j] = v;
             }
     }

@@ -1,30 +1,37 @@
 // Spiral convolution on the 5th-generation tensor cores (tcgen05 + TMEM), for the wide
-// layers (C_in in {32, 64}: K = S*C_in = 288 / 576).  Reference op: model.py:27-41 + F.elu
-// (model.py:68,84); its backward-to-input is the same contraction over the inverse table.
+// layers (channels per slot KS in {32, 64}: K = S*KS = 288 / 576).  Reference op:
+// model.py:27-41 + F.elu (model.py:68,84); its backward-to-input (autograd of model.py:34,40)
+// is the same contraction over the inverse table.
 //
-//   y[m, n] = epi( sum_{s,c} A[m, s*KS + c] * W[n, s*KS + c] ),   A[m, s*KS+c] = x[src(m,s), c]
+//   y[m, n] = epi( sum_{s,c} A[m, s*KS + c] * W[n, s*KS + c] ),
+//   A[m, s*KS + c] = sum_{r in cell(m, s)} x[r, c]        (one source row per cell in the forward pass)
 //
 // Precision: error-compensated 3xTF32.  Every fp32 operand v is split into
 //   hi = v with the low 13 mantissa bits cleared (exact in TF32),  lo = v - hi (exact in fp32)
 // and the product is accumulated in fp32 (TMEM) as  A_hi*W_hi + A_hi*W_lo + A_lo*W_hi.
-// The first two terms are ONE tcgen05.mma with N = 2*NT (the weight image stacks the W_hi
-// rows over the W_lo rows; the two halves land in adjacent TMEM column ranges and are added
-// in the epilogue), the third is a second MMA with N = NT onto the first half.
+// The first two terms are ONE tcgen05.mma with N = 2*NT (the weight image stacks the W_hi rows
+// over the W_lo rows; the halves land in adjacent TMEM column ranges and are added in the
+// epilogue), the third is a second MMA with N = NT onto the first half.
 //
-// Persistent, warp-specialised CTA (one per SM, 416 threads):
-//   warp 0      : TMEM allocation, MMA issue (one elected lane), tcgen05.commit -> mbarriers
-//   warps 1..4  : epilogue: tcgen05.ld accumulator -> registers -> bias/ELU/ELU'-gate -> global
-//   warps 5..12 : producers: gather rows of x (LDG.128, 8 lanes per 128-byte row), split hi/lo in
-//                 registers, store both into the 128B-swizzled K-major UMMA tile in shared memory
-// Pipelines: A-tile ring (full/empty mbarriers), double-buffered TMEM accumulator
-// (tmem_full/tmem_empty), static round-robin tile schedule.  The weight image (already split,
-// permuted into the swizzled layout by umma_pack_weights_kernel) stays resident in shared
-// memory for the whole kernel.
+// The gather is driven by a host-built TILE PLAN (tc_plan.h): for every tile of 128 output
+// rows of a mesh and every spiral slot, the list of source rows to stage and, per output row,
+// the [start, count) range of staged rows whose sum is that row's A-operand cell.
 //
-// Shared-memory operand layout (both A and B): K-major, SWIZZLE_128B.  One 32-float K chunk
-// of a row is 128 bytes = one swizzle row; 8 rows form a 1024-byte atom (SBO = 1024); the
-// 16-byte column j of row r sits at  r*128 + ((j ^ (r & 7)) * 16).  One tcgen05.mma consumes
-// K = 8 tf32 (32 bytes): the descriptor start address advances by 32 bytes per k-step.
+// Persistent, warp-specialised CTA (one per SM, 20 warps):
+//   warp 19      : TMEM allocation, MMA issue (one elected lane), tcgen05.commit -> mbarriers
+//   warps 0..3   : epilogue: tcgen05.ld accumulator -> bias/ELU/ELU'-gate -> global
+//   warps 4..11  : splitters: staged rows (LDS.128, conflict-free through the 128B swizzle) -> in-order
+//                  sum -> hi/lo split in registers -> tcgen05.st into the TMEM A-operand ring
+//   warps 12..18 : loaders: cp.async 16 B (8 lanes per 128-byte row piece) into the raw shared-memory ring,
+//                  several chunks in flight (cp.async groups), no register staging
+// A never passes through shared memory on its way into the MMA (TS form: A from TMEM, B from
+// shared memory), so no generic->async proxy fence sits on the gather path.  The weight image
+// (split and laid out by umma_pack_weights_kernel) stays resident in shared memory.
+//
+// B operand layout: K-major, SWIZZLE_128B: one 32-float K chunk of a row is 128 bytes = one
+// swizzle row; 8 rows form a 1024-byte atom (SBO = 1024); the 16-byte column j of row r sits at
+// r*128 + ((j ^ (r & 7)) * 16).  One tcgen05.mma consumes K = 8 tf32: the descriptor start
+// address advances by 32 bytes, the TMEM A address by 8 columns, per k-step.
 #pragma once
 #include "common.cuh"
 #include "spiral_conv.cuh"
@@ -32,15 +39,24 @@
 namespace sdvae {
 namespace umma {
 
-constexpr int kProducerWarps = 8;
-constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kEpilogueWarps = 4;
-constexpr int kFirstEpilogueWarp = 1;
-constexpr int kFirstProducerWarp = kFirstEpilogueWarp + kEpilogueWarps;     // 5
-constexpr int kThreads = (kFirstProducerWarp + kProducerWarps) * 32;        // 416
-constexpr int kBM = 128;                                                    // rows per tile (UMMA M)
-constexpr int kPrefetch = 2;                                                // producer register prefetch distance (chunks)
-constexpr long long kSpinLimit = 4000000000LL;                              // cycles before a stuck wait traps
+constexpr int kSplitWarps = 8;
+constexpr int kLoadWarps = 7;
+constexpr int kFirstEpilogueWarp = 0;
+constexpr int kFirstSplitWarp = kFirstEpilogueWarp + kEpilogueWarps;      // 4
+constexpr int kFirstLoadWarp = kFirstSplitWarp + kSplitWarps;             // 12
+constexpr int kMmaWarp = kFirstLoadWarp + kLoadWarps;                     // 19: the issuer gets the highest warp id (scheduler priority)
+constexpr int kThreads = (kMmaWarp + 1) * 32;                             // 640
+constexpr int kLoadThreads = kLoadWarps * 32;                             // 224
+constexpr int kLoadRows = kLoadThreads / 8;                               // staged rows covered per pass (8 lanes per row)
+constexpr int kBM = 128;                  // rows per tile (UMMA M)
+constexpr int kAStages = 4;               // TMEM A-operand ring (64 columns each: 32 hi + 32 lo)
+constexpr int kAColBase = 256;            // TMEM columns [0,256): accumulators, [256,512): A ring
+constexpr int kTmemCols = 512;
+constexpr int kMaxRcap = 192;             // staged rows per (tile, slot) the kernel supports
+constexpr int kMaxRaw = kLoadWarps;       // raw ring depth limit: loader warp w owns raw stage w
+constexpr uint32_t kSuspendHintNs = 100000;          // mbarrier.try_wait suspend-time hint
+constexpr int kSpinLimit = 1 << 22;                 // failed try_waits before a stuck wait traps
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -51,29 +67,49 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: a waiting warp sleeps in hardware until the phase completes (or
+// the hint expires) instead of re-polling -- with 21 warps per CTA a polling loop would take issue
+// slots from the warps that have work.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n.reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(kSuspendHintNs) : "memory");
     return ok != 0;
 }
 // Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    int spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > kSpinLimit) __trap();
+        if (++spins > kSpinLimit) __trap();
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {
+    switch (n) {
+        case 0: cp_async_wait<0>(); break;
+        case 1: cp_async_wait<1>(); break;
+        case 2: cp_async_wait<2>(); break;
+        case 3: cp_async_wait<3>(); break;
+        case 4: cp_async_wait<4>(); break;
+        case 5: cp_async_wait<5>(); break;
+        default: cp_async_wait<6>(); break;
+    }
+}
+
+// One lane of a converged warp (elect.sync): ptxas then emits the tcgen05 issue sequence as straight
+// uniform-datapath code; guarding it with `lane == 0` instead wraps every UTCHMMA in an ELECT retry loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n.reg .b32 rx;\n.reg .pred px;\nelect.sync rx|px, 0xffffffff;\n@px mov.s32 %0, 1;\n}\n" : "+r"(pred));
+    return pred != 0;
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -85,12 +121,12 @@ __device__ __forceinline__ void tmem_relinquish() {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by one thread for the CTA.
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem desc], kind::tf32, issued by one thread for the CTA.
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // Arrive on an mbarrier once every previously issued MMA of this thread has completed
 // (implies tcgen05.fence::before_thread_sync).
@@ -110,6 +146,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// thread t of the warp -> lane (base_lane + t), 32 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr),
+          "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]),
+          "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]),
+          "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]),
+          "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors -----------------------------------------------------------------------------
 // Shared-memory matrix descriptor, K-major, SWIZZLE_128B, 8-row atoms 1024 B apart.
@@ -133,8 +183,8 @@ __host__ __device__ __forceinline__ int sw128_off(int r, int q) { return r * 128
 // img[chunk][j][32]:  j < NT -> hi part of W row j,  j >= NT -> lo part of row j-NT; rows >= n_real
 // are zero.  `transposed` selects the backward-to-input weight  Wt[c, s*Cout + o] = W[o, s*Cin + c]
 // read straight from the forward weight (so no separate transpose pass is needed):
-//   forward   : n = output channel, k = s*KS + c      -> W[n*ldw + k]                 (KS = Cin)
-//   transposed: n = input channel c, k = s*KS + o     -> W[o*ldw + s*n_real_src + n]  (KS = Cout)
+//   forward   : n = output channel, k = s*KS + c      -> W[n*ldw + k]            (KS = Cin)
+//   transposed: n = input channel c, k = s*KS + o     -> W[o*ldw + s*cin + n]    (KS = Cout)
 struct PackArgs {
     const float* W;
     float* img;
@@ -167,73 +217,101 @@ __global__ void umma_pack_weights_kernel(const PackArgs a) {
 }
 
 // ---- main kernel -----------------------------------------------------------------------------
+struct UmmaArgs {
+    const float* in;          // [B, in_rows, KS]
+    const int* plan_cnt;      // [L, S]            staged rows of (tile, slot)
+    const int* plan_src;      // [L, S, rcap]      source row (within the mesh) of each staged row
+    const int* plan_cell;     // [L, S, 128]       start | count << 16 : staged rows summed into tile row lr
+    const float* wimg;        // packed weight image
+    const float* bias;        // [n_real] or nullptr
+    const float* gate;        // EPI_GATE: out *= elu'(gate), aligned with out
+    float* out;               // [B, out_rows, ldo]
+    int B, in_rows, out_rows, L, S, rcap;
+    int n_real, ldo, epi;
+    int nraw;                 // raw ring depth (= active loader warps)
+};
+
+
+// Position of a CTA in its static schedule: chunk g = (tile iteration it, chunk ch of the tile),
+// kept incrementally so that the per-chunk role loops contain no integer division.
+struct ChunkCursor {
+    int g, ch, b, jt, rs;
+    uint32_t rph;
+    int nch, nraw, L, db, djt;
+    __device__ __forceinline__ ChunkCursor(const UmmaArgs& a, int nch_, int nraw_)
+        : g(0), ch(0), rs(0), rph(0), nch(nch_), nraw(nraw_), L(a.L) {
+        b = (int)blockIdx.x / L; jt = (int)blockIdx.x - b * L;
+        db = (int)gridDim.x / L; djt = (int)gridDim.x - db * L;       // tile stride, split into (mesh, tile-in-mesh)
+    }
+    __device__ __forceinline__ void advance() {
+        ++g;
+        if (++rs == nraw) { rs = 0; rph ^= 1; }
+        if (++ch == nch) {
+            ch = 0; b += db; jt += djt;
+            if (jt >= L) { jt -= L; ++b; }
+        }
+    }
+};
+
 template <int KS, int NT>
 struct UmmaCfg {
     static constexpr int CPS = KS / 32;                  // 32-wide chunks per spiral slot
-    static constexpr int A_STAGE = 2 * kBM * 128;        // hi tile + lo tile
     static constexpr int B_CHUNK = 2 * NT * 128;
-    static constexpr int TMEM_COLS = 4 * NT < 32 ? 32 : 4 * NT;   // two accumulators of 2*NT columns
-    static int stages(int S) {
-        const int budget = 225 * 1024 - 2048 - S * CPS * B_CHUNK - 2 * kBM * (S + 2) * 4;
-        int st = budget / A_STAGE;
-        return st > 6 ? 6 : st;
+    static size_t b_bytes(int S) { return (size_t)S * CPS * B_CHUNK; }
+    static int raw_stages(int S, int rcap) {
+        const long long budget = 226LL * 1024 - 1024 /*align*/ - 1024 /*barriers*/ - (long long)b_bytes(S);
+        long long st = budget / ((long long)rcap * 128);
+        return (int)(st > kMaxRaw ? kMaxRaw : st);
     }
-    static size_t smem_bytes(int S, int nst) {
-        return 1024 /*align slack*/ + (size_t)S * CPS * B_CHUNK + (size_t)nst * A_STAGE +
-               (size_t)2 * kBM * (S + 2) * 4 + 1024 /*barriers*/;
+    static size_t smem_bytes(int S, int rcap, int nraw) {
+        return 1024 + b_bytes(S) + (size_t)nraw * rcap * 128 + 1024;
     }
 };
 
-struct UmmaArgs {
-    GcArgs g;            // in / idx / cell_ptr / cell_src / bias / gate / out / M / in_rows / Vout / S / ldo / n_real / epi
-    const float* wimg;   // packed weight image (umma_pack_weights_kernel)
-    int nstages;
-    int ntiles;
-};
-
-template <int KS, int NT, bool RAGGED>
+template <int KS, int NT>
 __global__ void __launch_bounds__(kThreads, 1)
-gc_umma_kernel(const UmmaArgs ua) {
+gc_umma_kernel(const UmmaArgs a) {
     using Cfg = UmmaCfg<KS, NT>;
-    constexpr int CPS = Cfg::CPS, A_STAGE = Cfg::A_STAGE, B_CHUNK = Cfg::B_CHUNK;
-    const GcArgs& a = ua.g;
+    constexpr int CPS = Cfg::CPS, B_CHUNK = Cfg::B_CHUNK;
+    static_assert(4 * NT <= kAColBase, "accumulators overlap the A ring");
     const int S = a.S;
     const int NCH = S * CPS;
-    const int NST = ua.nstages;
-    const int TS = S + 1;                                  // table row stride (ragged keeps S+1 cell bounds)
+    const int NRAW = a.nraw;
+    const int RAW_STAGE = a.rcap * 128;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-    uint8_t* B_s = smem;                                   // [NCH][2NT][128 B]
-    uint8_t* A_s = B_s + (size_t)NCH * B_CHUNK;            // [NST][hi 16 KB | lo 16 KB]
-    int* T_s = reinterpret_cast<int*>(A_s + (size_t)NST * A_STAGE);      // [2][kBM][TS] source-row tables
-    int* R_s = T_s + 2 * kBM * TS;                         // [2][kBM] ragged: first row of the mesh in `in`
-    uint64_t* bars = reinterpret_cast<uint64_t*>(R_s + 2 * kBM);
-    bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bars) + 15) & ~(uintptr_t)15);
-    uint64_t* full_bar = bars;                             // [NST]  producers -> MMA
-    uint64_t* empty_bar = bars + 8;                        // [NST]  MMA (commit) -> producers
-    uint64_t* tfull_bar = bars + 16;                       // [2]    MMA (commit) -> epilogue
-    uint64_t* tempty_bar = bars + 18;                      // [2]    epilogue -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    uint8_t* B_s = smem;                                   // [NCH][2NT][128 B]   resident weight image
+    uint8_t* R_s = B_s + (size_t)NCH * B_CHUNK;            // [NRAW][rcap][128 B] staged source rows (swizzled)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(R_s + (size_t)NRAW * RAW_STAGE);
+    uint64_t* raw_full = bars;                             // [NRAW]     loaders  -> splitters
+    uint64_t* raw_empty = bars + kMaxRaw;                  // [NRAW]     splitters -> loaders
+    uint64_t* a_full = bars + 2 * kMaxRaw;                 // [kAStages] splitters -> MMA
+    uint64_t* a_empty = a_full + kAStages;                 // [kAStages] MMA (commit) -> splitters
+    uint64_t* t_full = a_empty + kAStages;                 // [2]        MMA (commit) -> epilogue
+    uint64_t* t_empty = t_full + 2;                        // [2]        epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // ---- one-time setup ---------------------------------------------------------------------
     if (tid == 0) {
-        for (int i = 0; i < NST; ++i) { mbar_init(full_bar + i, kProducerThreads); mbar_init(empty_bar + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, kEpilogueWarps * 32); }
+        for (int i = 0; i < NRAW; ++i) { mbar_init(raw_full + i, 32); mbar_init(raw_empty + i, 128); }
+        for (int i = 0; i < kAStages; ++i) { mbar_init(a_full + i, 128); mbar_init(a_empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, kEpilogueWarps * 32); }
         fence_barrier_init();
     }
-    if (warp == 0) {
+    if (warp == kMmaWarp) {
         __syncwarp();
-        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_alloc(tmem_slot, kTmemCols);
         tmem_relinquish();
     }
-    {   // resident weight image
+    {   // resident weight image (generic-proxy writes, read by the MMA through the async proxy)
         const int n16 = NCH * B_CHUNK / 16;
-        const float4* src = reinterpret_cast<const float4*>(ua.wimg);
+        const float4* src = reinterpret_cast<const float4*>(a.wimg);
         float4* dst = reinterpret_cast<float4*>(B_s);
+#pragma unroll 1
         for (int i = tid; i < n16; i += kThreads) dst[i] = __ldg(src + i);
         fence_async_smem();
     }
@@ -242,242 +320,221 @@ gc_umma_kernel(const UmmaArgs ua) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int ntiles = ua.ntiles;
+    const int ntiles = a.B * a.L;
     const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int G = my_tiles * NCH;                           // chunks this CTA processes
 
-    if (warp == 0) {
+    if (warp == kMmaWarp) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            constexpr uint32_t IDESC1 = idesc_tf32(kBM, 2 * NT);
-            constexpr uint32_t IDESC2 = idesc_tf32(kBM, NT);
-            const uint32_t a_base = smem_u32(A_s), b_base = smem_u32(B_s);
-            int stage = 0; uint32_t phase = 0;
-            for (int it = 0; it < my_tiles; ++it) {
-                const int acc = it & 1;
-                mbar_wait(tempty_bar + acc, ((it >> 1) & 1) ^ 1);
+        // the whole warp walks the schedule and waits on the barriers; one elected lane issues
+        constexpr uint32_t IDESC1 = idesc_tf32(kBM, 2 * NT);
+        constexpr uint32_t IDESC2 = idesc_tf32(kBM, NT);
+        const bool leader = elect_one();
+        const uint32_t b_base = smem_u32(B_s);
+        int as = 0; uint32_t aph = 0;
+#pragma unroll 1
+        for (int it = 0; it < my_tiles; ++it) {
+            const int acc = it & 1;
+            mbar_wait(t_empty + acc, ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * NT);
+#pragma unroll 1
+            for (int ch = 0; ch < NCH; ++ch) {
+                mbar_wait(a_full + as, aph);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * NT);
-                for (int ch = 0; ch < NCH; ++ch) {
-                    mbar_wait(full_bar + stage, phase);
-                    tc_fence_after();
-                    const uint32_t a_hi = a_base + stage * A_STAGE, a_lo = a_hi + kBM * 128;
+                if (leader) {
+                    const uint32_t a_hi = tmem_base + (uint32_t)(kAColBase + as * 64), a_lo = a_hi + 32;
                     const uint32_t b_ch = b_base + ch * B_CHUNK;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t bd = smem_desc_sw128(b_ch + k * 32);
-                        umma_tf32(d_tmem, smem_desc_sw128(a_hi + k * 32), bd, IDESC1, (ch | k) != 0);
-                        umma_tf32(d_tmem, smem_desc_sw128(a_lo + k * 32), bd, IDESC2, 1u);
+                        umma_tf32_ts(d_tmem, a_hi + k * 8, bd, IDESC1, (ch | k) != 0);
+                        umma_tf32_ts(d_tmem, a_lo + k * 8, bd, IDESC2, 1u);
                     }
-                    umma_commit(empty_bar + stage);
-                    if (++stage == NST) { stage = 0; phase ^= 1; }
+                    umma_commit(a_empty + as);
+                    if (ch == NCH - 1) umma_commit(t_full + acc);
                 }
-                umma_commit(tfull_bar + acc);
+                __syncwarp();
+                if (++as == kAStages) { as = 0; aph ^= 1; }
             }
         }
-        __syncwarp();
-    } else if (warp < kFirstProducerWarp) {
+    } else if (warp < kFirstSplitWarp) {
         // ================= epilogue =================
-        const int q4 = warp & 3;                                  // TMEM lane quarter this warp may read
+        const int q4 = warp & 3;                                  // TMEM lane quarter this warp may access
         const int EPI = a.epi;
         const int n_real = a.n_real, ldo = a.ldo;
+        const bool has_bias = (EPI == EPI_BIAS || EPI == EPI_BIAS_ELU) && a.bias != nullptr;
         const bool vec_ok = (n_real == NT) && ((ldo & 3) == 0) &&
                             ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0) &&
-                            (EPI != EPI_GATE || (reinterpret_cast<uintptr_t>(a.gate) & 15) == 0);
+                            (EPI != EPI_GATE || (reinterpret_cast<uintptr_t>(a.gate) & 15) == 0) &&
+                            (!has_bias || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0);
+#pragma unroll 1
         for (int it = 0; it < my_tiles; ++it) {
             const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            const int b = tile / a.L, jt = tile - b * a.L;
             const int acc = it & 1;
-            mbar_wait(tfull_bar + acc, (it >> 1) & 1);
+            mbar_wait(t_full + acc, (it >> 1) & 1);
             tc_fence_after();
-            const long long m = (long long)tile * kBM + q4 * 32 + lane;
+            const int r = jt * kBM + q4 * 32 + lane;              // row inside the mesh
+            const bool row_ok = r < a.out_rows;
+            const size_t m = (size_t)b * a.out_rows + r;
             const uint32_t t_row = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * 2 * NT);
-#pragma unroll
+#pragma unroll 1
             for (int c0 = 0; c0 < NT; c0 += 16) {
-                float d1[16], d2[16];
-                tmem_ld16(t_row + c0, d1);
+                float v[16], d2[16];
+                tmem_ld16(t_row + c0, v);
                 tmem_ld16(t_row + NT + c0, d2);
                 tmem_ld_wait();
                 if (c0 + 16 >= NT) {            // last read of this accumulator: hand it back to the MMA warp
                     tc_fence_before();
-                    mbar_arrive(tempty_bar + acc);
+                    mbar_arrive(t_empty + acc);
                 }
-                if (m < a.M) {
-                    float v[16];
+                if (!row_ok) continue;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        v[j] = d1[j] + d2[j];
-                        const int col = c0 + j;
-                        if ((EPI == EPI_BIAS || EPI == EPI_BIAS_ELU) && a.bias && col < n_real) v[j] += __ldg(a.bias + col);
-                        if (EPI == EPI_BIAS_ELU) v[j] = elu_f(v[j]);
-                    }
-                    const size_t off = (size_t)m * ldo + c0;
+                for (int j = 0; j < 16; ++j) v[j] += d2[j];
+                float* orow = a.out + m * ldo + c0;
+                const float* grow = a.gate + m * ldo + c0;
+                if (has_bias) {
                     if (vec_ok) {
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
-                            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                            if (EPI == EPI_GATE) {
-                                const float4 gt = ldg4(a.gate + off + j);
-                                o.x *= elu_grad_from_out(gt.x); o.y *= elu_grad_from_out(gt.y);
-                                o.z *= elu_grad_from_out(gt.z); o.w *= elu_grad_from_out(gt.w);
-                            }
-                            *reinterpret_cast<float4*>(a.out + off + j) = o;
+                            const float4 bv = ldg4(a.bias + c0 + j);
+                            v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
                         }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            if (c0 + j < n_real) {
-                                float o = v[j];
-                                if (EPI == EPI_GATE) o *= elu_grad_from_out(__ldg(a.gate + off + j));
-                                a.out[off + j] = o;
-                            }
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < n_real) v[j] += __ldg(a.bias + c0 + j);
+                    }
+                }
+                if (EPI == EPI_BIAS_ELU) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = elu_fast(v[j]);
+                }
+                if (vec_ok) {
+                    if (EPI == EPI_GATE) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 gt = ldg4(grow + j);
+                            v[j] *= elu_grad_from_out(gt.x); v[j + 1] *= elu_grad_from_out(gt.y);
+                            v[j + 2] *= elu_grad_from_out(gt.z); v[j + 3] *= elu_grad_from_out(gt.w);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(orow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+                    // narrow / unaligned outputs (e.g. the 3-channel output layer): scalar tail
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (c0 + j < n_real) {
+                            float o = v[j];
+                            if (EPI == EPI_GATE) o *= elu_grad_from_out(__ldg(grow + j));
+                            orow[j] = o;
                         }
                     }
                 }
             }
+        }
+    } else if (warp < kFirstLoadWarp) {
+        // ================= splitters =================
+        // warps 4..7 take the even chunks, warps 8..11 the odd ones; warp % 4 = TMEM lane quarter
+        const int set = (warp - kFirstSplitWarp) >> 2;
+        const int q4 = warp & 3;
+        const int lr = q4 * 32 + lane;                            // tile row owned by this thread
+        ChunkCursor cur(a, NCH, NRAW);                            // chunk being processed
+        ChunkCursor pre(a, NCH, NRAW);                            // chunk whose plan entry is prefetched
+        if (set) { cur.advance(); pre.advance(); }
+        auto cell_of = [&](const ChunkCursor& c) -> uint32_t {
+            return (uint32_t)__ldg(a.plan_cell + ((size_t)c.jt * S + c.ch / CPS) * kBM + lr);
+        };
+        uint32_t cell = cur.g < G ? cell_of(pre) : 0u;
+#pragma unroll 1
+        for (; cur.g < G; cur.advance(), cur.advance()) {
+            pre.advance(); pre.advance();
+            const uint32_t cell_next = pre.g < G ? cell_of(pre) : 0u;         // one own-chunk ahead
+            const int e0 = (int)(cell & 0xffffu), cnt = (int)(cell >> 16);
+            const int rs = cur.rs;
+            const int as = cur.g & (kAStages - 1);
+            const uint32_t aph = (uint32_t)((cur.g / kAStages) & 1);
+
+            mbar_wait(raw_full + rs, cur.rph);
+            const uint8_t* stage = R_s + (size_t)rs * RAW_STAGE;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+#pragma unroll 1
+            for (int e = e0; e < e0 + cnt; ++e) {                 // in-order sum: deterministic scatter-add
+                const uint8_t* row = stage + e * 128;
+                const int x7 = e & 7;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 t = *reinterpret_cast<const float4*>(row + ((j ^ x7) << 4));
+                    v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+                }
+            }
+            float lo[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { float h; split_tf32f(v[j], h, lo[j]); v[j] = h; }
+            mbar_wait(a_empty + as, aph ^ 1);
+            tc_fence_after();
+            const uint32_t t_a = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(kAColBase + as * 64);
+            tmem_st32(t_a, v);
+            tmem_st32(t_a + 32, lo);
+            mbar_arrive(raw_empty + rs);          // the staged rows are in registers (consumed by the stores above)
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(a_full + as);
+            cell = cell_next;
         }
     } else {
-        // ================= producers =================
-        const int p = tid - kFirstProducerWarp * 32;              // 0..255
-        const int q = p & 7, r0 = p >> 3;                         // 16-byte column, first row (rows r0 + 32*i)
-
-        // source-row table of one tile:  uniform: T[lr][s] = absolute row of x (or -1)
-        //                                ragged : T[lr][s] = first entry of cell (r,s), T[lr][S] = end; R[lr] = mesh base row
-        auto table_load = [&](int tile, int (&reg)[6]) {
+        // ================= loaders =================
+        // loader warp w (< NRAW) owns raw stage w and takes the chunks g = w (mod NRAW) whole: 4 staged rows
+        // per cp.async instruction (8 lanes x 16 B per row piece), the per-chunk bookkeeping is paid by one
+        // warp, and the warps together keep NRAW chunks in flight.  (One stage per warp also keeps every
+        // waiter within one phase of its mbarrier, which the parity wait requires.)
+        const int lw = warp - kFirstLoadWarp;
+        const int q = lane & 7, rsub = lane >> 3;
+        const uint32_t sw0 = (uint32_t)((q ^ rsub) << 4), sw1 = (uint32_t)((q ^ (rsub + 4)) << 4);
+        const uint32_t raw_base = smem_u32(R_s) + (uint32_t)rsub * 128u;
+        ChunkCursor cur(a, NCH, NRAW);
+        for (int i = 0; i < lw; ++i) cur.advance();
+        if (lw >= NRAW) cur.g = G;                                // more loader warps than stages: idle
+#pragma unroll 1
+        while (cur.g < G) {
+            const int s = cur.ch / CPS, h = cur.ch % CPS;
+            const int n = __ldg(a.plan_cnt + cur.jt * S + s);
+            const int* src = a.plan_src + ((size_t)cur.jt * S + s) * a.rcap + lane;   // entry 32*j + lane
+            int pv = __ldg(src);
+            mbar_wait(raw_empty + cur.rs, cur.rph ^ 1);
+            const uint32_t dst = raw_base + (uint32_t)cur.rs * (uint32_t)RAW_STAGE;
+            const float* base = a.in + (size_t)cur.b * a.in_rows * KS + h * 32 + 4 * q;
+#pragma unroll 1
+            for (int j = 0; 32 * j < n; ++j) {
+                const int pn = 32 * (j + 1) < n ? __ldg(src + 32 * (j + 1)) : 0;     // next 32 plan entries
 #pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                const int e = p + i * kProducerThreads;
-                int val = -1;
-                if (e < kBM * TS) {
-                    const int lr = e / TS, s = e - lr * TS;
-                    const long long m = (long long)tile * kBM + lr;
-                    if (m < a.M) {
-                        const int b = (int)(m / a.Vout);
-                        const int r = (int)(m - (long long)b * a.Vout);
-                        if (!RAGGED) {
-                            if (s < S) val = b * a.in_rows + __ldg(a.idx + r * S + s);
-                        } else {
-                            val = __ldg(a.cell_ptr + r * S + s);
-                        }
-                    } else if (RAGGED) {
-                        val = 0;
-                    }
+                for (int t = 0; t < 8; ++t) {
+                    const int sr = __shfl_sync(0xffffffffu, pv, 4 * t + rsub);
+                    if (32 * j + 4 * t + rsub < n)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n"
+                                     ::"r"(dst + (uint32_t)(32 * j + 4 * t) * 128u + ((t & 1) ? sw1 : sw0)),
+                                       "l"(base + (size_t)sr * KS));
                 }
-                reg[i] = val;
+                pv = pn;
             }
-        };
-        auto table_store = [&](int buf, int tile, const int (&reg)[6]) {
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                const int e = p + i * kProducerThreads;
-                if (e < kBM * TS) T_s[buf * kBM * TS + e] = reg[i];
-            }
-            if (RAGGED && p < kBM) {
-                const long long m = (long long)tile * kBM + p;
-                R_s[buf * kBM + p] = (m < a.M) ? (int)(m / a.Vout) * a.in_rows : 0;
-            }
-        };
-        auto gather = [&](int tb, int ch, float4 (&v)[4]) {
-            const int s = ch / CPS, h = ch - s * CPS;
-            const int* T = T_s + tb * kBM * TS;
-            if (!RAGGED) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int src = T[(r0 + 32 * i) * TS + s];
-                    v[i] = src >= 0 ? ldg4(a.in + (size_t)src * KS + h * 32 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            } else {
-                int e0[4], e1[4], s0[4];
-                const float* rb[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int lr = r0 + 32 * i;
-                    e0[i] = T[lr * TS + s];
-                    e1[i] = T[lr * TS + s + 1];
-                    rb[i] = a.in + (size_t)R_s[tb * kBM + lr] * KS + h * 32 + 4 * q;
-                    s0[i] = e1[i] > e0[i] ? __ldg(a.cell_src + e0[i]) : -1;
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    v[i] = s0[i] >= 0 ? ldg4(rb[i] + (size_t)s0[i] * KS) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)          // cells fed by several output rows: in-order sum (deterministic)
-                    for (int e = e0[i] + 1; e < e1[i]; ++e) {
-                        const float4 t = ldg4(rb[i] + (size_t)__ldg(a.cell_src + e) * KS);
-                        v[i].x += t.x; v[i].y += t.y; v[i].z += t.z; v[i].w += t.w;
-                    }
-            }
-        };
-
-        // table of the first tile
-        {
-            int reg[6];
-            table_load((int)blockIdx.x, reg);
-            table_store(0, (int)blockIdx.x, reg);
-            named_bar_sync(1, kProducerThreads);
-        }
-
-        // register ring of kPrefetch + 1 = 3 chunks; NCH % 3 == 0 (checked by the host) keeps the
-        // slot of chunk ch equal to ch % 3 in every tile, so all indices are compile-time
-        static_assert(kPrefetch == 2, "producer ring is written for a prefetch distance of 2");
-        float4 pre[3][4];
-        gather(0, 0, pre[0]);
-        gather(0, 1, pre[1]);
-
-        int stage = 0; uint32_t phase = 0;
-        int tb = 0;                              // table buffer of the tile whose chunks are being stored
-        int nreg[6];
-        for (int it = 0; it < my_tiles; ++it) {
-            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-            const bool has_next = it + 1 < my_tiles;
-            for (int ch0 = 0; ch0 < NCH; ch0 += 3) {
-#pragma unroll
-                for (int u = 0; u < 3; ++u) {
-                    const int ch = ch0 + u;
-                    // table of the next tile: loads at chunk 0, stores at chunk 1 between two producer
-                    // barriers (the first: nobody still reads the buffer being overwritten; the second: published)
-                    if (ch == 0 && has_next) table_load(tile + (int)gridDim.x, nreg);
-                    if (ch == 1) {
-                        named_bar_sync(1, kProducerThreads);
-                        if (has_next) table_store(tb ^ 1, tile + (int)gridDim.x, nreg);
-                        named_bar_sync(1, kProducerThreads);
-                    }
-                    // prefetch chunk ch + 2 (possibly of the next tile) into the free register slot
-                    {
-                        int pch = ch + 2, ptb = tb;
-                        bool ok = true;
-                        if (pch >= NCH) { pch -= NCH; ptb ^= 1; ok = has_next; }
-                        if (ok) gather(ptb, pch, pre[(u + 2) % 3]);
-                    }
-                    // split + store chunk ch
-                    mbar_wait(empty_bar + stage, phase ^ 1);
-                    {
-                        uint8_t* hi_t = A_s + (size_t)stage * A_STAGE;
-                        uint8_t* lo_t = hi_t + kBM * 128;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float4 x4 = pre[u][i];
-                            float4 hi, lo;
-                            split_tf32f(x4.x, hi.x, lo.x); split_tf32f(x4.y, hi.y, lo.y);
-                            split_tf32f(x4.z, hi.z, lo.z); split_tf32f(x4.w, hi.w, lo.w);
-                            const int off = sw128_off(r0 + 32 * i, q);
-                            *reinterpret_cast<float4*>(hi_t + off) = hi;
-                            *reinterpret_cast<float4*>(lo_t + off) = lo;
-                        }
-                    }
-                    fence_async_smem();
-                    mbar_arrive(full_bar + stage);
-                    if (++stage == NST) { stage = 0; phase ^= 1; }
-                }
-            }
-            tb ^= 1;
+            cp_async_commit();
+            cp_async_wait<0>();
+            mbar_arrive(raw_full + cur.rs);
+            for (int i = 0; i < NRAW; ++i) cur.advance();
         }
     }
 
     // ---- teardown ----------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
+    if (warp == kMmaWarp) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 

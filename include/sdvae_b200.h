@@ -60,27 +60,44 @@ int sdvae_spiralconv_bwd_x(const float* dpre, const int32_t* cell_ptr, const int
                            const float* Wt, const float* gate, float* dx, int B, int Vrows,
                            int Vdst, int S, int Cout, int Cin, sdvae_stream_t stream);
 
-/* ---- SpiralConv on the 5th-gen tensor cores (tcgen05.mma + TMEM accumulators) ----------------
+/* ---- SpiralConv on the 5th-gen tensor cores (tcgen05.mma + TMEM) ------------------------------
  * Same contractions as sdvae_spiralconv_fwd / sdvae_spiralconv_bwd_x, for the wide layers
- * (channels per slot KS in {32, 64}; outputs N <= 64; the S*KS/32 chunks must be a multiple of 3).
+ * (channels per slot KS in {32, 64}; outputs N <= 64).
  * Arithmetic: error-compensated 3xTF32 (hi/lo operand split, fp32 accumulation in TMEM) -- the
  * parity bar of this path is stated separately in tests/ (normwise vs the fp64 oracle).
- * The weight operand is a packed image (already split and laid out as the 128B-swizzled UMMA
- * tiles) produced by sdvae_tc_pack_weights from the nn.Linear weight W [Cout, S*Cin]
- * (model.py:16-21); `transposed` != 0 packs the backward-to-input operand
- * Wt[c, s*Cout+o] = W[o, s*Cin+c] instead.  Re-pack whenever W changes. */
-int    sdvae_tc_supported(int S, int KS, int N);
+ *
+ * Weight operand: a packed image (already split and laid out as the 128B-swizzled UMMA tiles)
+ * produced by sdvae_tc_pack_weights from the nn.Linear weight W [Cout, S*Cin] (model.py:16-21);
+ * `transposed` != 0 packs the backward-to-input operand Wt[c, s*Cout+o] = W[o, s*Cin+c].
+ * Re-pack whenever W changes.
+ *
+ * Gather operand: a TILE PLAN built once per index table on the HOST (sdvae_tc_plan_* take host
+ * pointers) and then copied to the device.  The table is given in cell form: for output row r and
+ * slot s the source rows cell_src[cell_ptr[r*S+s] .. cell_ptr[r*S+s+1]) whose SUM feeds the
+ * contraction.  The forward table idx [out_rows, S] (model.py:18, spirals.pkl) is the cell form
+ * with cell_ptr[i] = i, cell_src = idx; the backward table is the inverse (cell_ptr, cell_src)
+ * of sdvae_spiralconv_bwd_x.  Plan arrays, L = sdvae_tc_plan_tiles(out_rows) tiles of 128 rows:
+ *   cnt  [L, S]        rows staged for (tile, slot)
+ *   src  [L, S, rcap]  their source rows, rcap >= sdvae_tc_plan_max_rows(...) rounded up to 16
+ *   cell [L, S, 128]   start | count << 16 : staged rows summed (in order) into each tile row */
+int    sdvae_tc_supported(int S, int KS, int N, int rcap);
 size_t sdvae_tc_wimg_floats(int S, int KS, int N);
 int sdvae_tc_pack_weights(const float* W, float* wimg, int S, int Cin, int Cout, int transposed,
                           sdvae_stream_t stream);
+int sdvae_tc_plan_tiles(int out_rows);
+int sdvae_tc_plan_max_rows(const int32_t* cell_ptr, int out_rows, int S);
+int sdvae_tc_plan_build(const int32_t* cell_ptr, const int32_t* cell_src, int out_rows, int S,
+                        int rcap, int32_t* cnt, int32_t* src, int32_t* cell);
 /* Replaces: model.py:27-41 + F.elu (model.py:68,84), as sdvae_spiralconv_fwd. */
-int sdvae_spiralconv_fwd_tc(const float* x, const int32_t* idx, const float* wimg, const float* bias,
+int sdvae_spiralconv_fwd_tc(const float* x, const int32_t* plan_cnt, const int32_t* plan_src,
+                            const int32_t* plan_cell, int rcap, const float* wimg, const float* bias,
                             float* y, int B, int Vin, int Vout, int S, int Cin, int Cout, int act,
                             sdvae_stream_t stream);
 /* Replaces: autograd of model.py:34,40 w.r.t. the input, as sdvae_spiralconv_bwd_x. */
-int sdvae_spiralconv_bwd_x_tc(const float* dpre, const int32_t* cell_ptr, const int32_t* cell_src,
-                              const float* wimg_t, const float* gate, float* dx, int B, int Vrows,
-                              int Vdst, int S, int Cout, int Cin, sdvae_stream_t stream);
+int sdvae_spiralconv_bwd_x_tc(const float* dpre, const int32_t* plan_cnt, const int32_t* plan_src,
+                              const int32_t* plan_cell, int rcap, const float* wimg_t, const float* gate,
+                              float* dx, int B, int Vrows, int Vdst, int S, int Cout, int Cin,
+                              sdvae_stream_t stream);
 
 /* dW[o, s*Cin+c] = sum_{b,v} dpre[b,v,o] * x[b, idx[v,s], c];  db[o] = sum_{b,v} dpre[b,v,o]
  * workspace: sdvae_spiralconv_bwd_w_workspace(...) bytes.  Split-M partial sums are added in a

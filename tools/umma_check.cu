@@ -50,6 +50,19 @@ static T* dev_copy(const std::vector<T>& h) {
     return d;
 }
 
+
+struct DevPlan { int* cnt; int* src; int* cell; int rcap; };
+static DevPlan make_plan(const std::vector<int>& cell_ptr, const std::vector<int>& cell_src, int out_rows, int S) {
+    const int L = sdvae_tc_plan_tiles(out_rows);
+    const int mx = sdvae_tc_plan_max_rows(cell_ptr.data(), out_rows, S);
+    const int rcap = std::max(16, (mx + 15) / 16 * 16);
+    std::vector<int> cnt((size_t)L * S), src((size_t)L * S * rcap), cell((size_t)L * S * 128);
+    ABI(sdvae_tc_plan_build(cell_ptr.data(), cell_src.data(), out_rows, S, rcap, cnt.data(), src.data(), cell.data()));
+    printf("plan: %d tiles/mesh, max staged rows %d (rcap %d)\n", L, mx, rcap);
+    DevPlan d{dev_copy(cnt), dev_copy(src), dev_copy(cell), rcap};
+    return d;
+}
+
 static double elu_d(double v) { return v > 0 ? v : expm1(v); }
 
 int main(int argc, char** argv) {
@@ -84,7 +97,10 @@ int main(int argc, char** argv) {
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
 
     if (!bwdx) {
-        if (!sdvae_tc_supported(S, Cin, Cout)) { printf("shape not supported by the tcgen05 path\n"); return 4; }
+        std::vector<int> uptr((size_t)V * S + 1);
+        for (size_t i = 0; i <= (size_t)V * S; ++i) uptr[i] = (int)i;
+        DevPlan pl = make_plan(uptr, idx, V, S);
+        if (!sdvae_tc_supported(S, Cin, Cout, pl.rcap)) { printf("shape not supported by the tcgen05 path\n"); return 4; }
         std::vector<float> x((size_t)B * V * Cin);
         for (auto& t : x) t = 1.5f * frand();
         float* d_x = dev_copy(x);
@@ -95,7 +111,7 @@ int main(int argc, char** argv) {
         CK(cudaMalloc(&d_img, sdvae_tc_wimg_floats(S, Cin, Cout) * 4));
         ABI(sdvae_spiralconv_fwd(d_x, d_idx, d_W, d_bias, d_y0, B, V, V, S, Cin, Cout, flag, st));
         ABI(sdvae_tc_pack_weights(d_W, d_img, S, Cin, Cout, 0, st));
-        ABI(sdvae_spiralconv_fwd_tc(d_x, d_idx, d_img, d_bias, d_y1, B, V, V, S, Cin, Cout, flag, st));
+        ABI(sdvae_spiralconv_fwd_tc(d_x, pl.cnt, pl.src, pl.cell, pl.rcap, d_img, d_bias, d_y1, B, V, V, S, Cin, Cout, flag, st));
         CK(cudaDeviceSynchronize());
         std::vector<float> y0(ny), y1(ny);
         CK(cudaMemcpy(y0.data(), d_y0, ny * 4, cudaMemcpyDeviceToHost));
@@ -132,7 +148,7 @@ int main(int argc, char** argv) {
         for (int i = 0; i < iters; ++i) ABI(sdvae_spiralconv_fwd(d_x, d_idx, d_W, d_bias, d_y0, B, V, V, S, Cin, Cout, flag, st));
         CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms0, e0, e1));
         CK(cudaEventRecord(e0));
-        for (int i = 0; i < iters; ++i) ABI(sdvae_spiralconv_fwd_tc(d_x, d_idx, d_img, d_bias, d_y1, B, V, V, S, Cin, Cout, flag, st));
+        for (int i = 0; i < iters; ++i) ABI(sdvae_spiralconv_fwd_tc(d_x, pl.cnt, pl.src, pl.cell, pl.rcap, d_img, d_bias, d_y1, B, V, V, S, Cin, Cout, flag, st));
         CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms1, e0, e1));
         const double flops = 2.0 * B * V * (double)S * Cin * Cout, bytes = 4.0 * B * V * (double)(Cin + Cout);
         printf("time/launch: fma %.3f ms (%.1f TFLOP/s, %.0f GB/s alg)   tc %.3f ms (%.1f TFLOP/s, %.0f GB/s alg)   speedup %.2fx\n",
@@ -144,7 +160,6 @@ int main(int argc, char** argv) {
     }
 
     // ---- backward to the input ----------------------------------------------------------------
-    if (!sdvae_tc_supported(S, Cout, Cin)) { printf("shape not supported by the tcgen05 path\n"); return 4; }
     std::vector<int> cell_ptr((size_t)V * S + 1, 0), cell_src((size_t)V * S);
     for (int r = 0; r < V; ++r)
         for (int s = 0; s < S; ++s) cell_ptr[(size_t)idx[(size_t)r * S + s] * S + s + 1]++;
@@ -154,6 +169,8 @@ int main(int argc, char** argv) {
         for (int r = 0; r < V; ++r)
             for (int s = 0; s < S; ++s) cell_src[fill[(size_t)idx[(size_t)r * S + s] * S + s]++] = r;
     }
+    DevPlan pl = make_plan(cell_ptr, cell_src, V, S);
+    if (!sdvae_tc_supported(S, Cout, Cin, pl.rcap)) { printf("shape not supported by the tcgen05 path\n"); return 4; }
     std::vector<float> dpre((size_t)B * V * Cout), gate((size_t)B * V * Cin);
     for (auto& t : dpre) t = frand();
     for (auto& t : gate) t = frand();            // plays the layer output y: y>0 -> 1, else y+1
@@ -171,7 +188,7 @@ int main(int argc, char** argv) {
     ABI(sdvae_weight_transpose(d_W, d_wt, Cout, Cin, S, st));
     ABI(sdvae_spiralconv_bwd_x(d_dpre, d_cp, d_cs, d_wt, g, d_dx0, B, V, V, S, Cout, Cin, st));
     ABI(sdvae_tc_pack_weights(d_W, d_img, S, Cin, Cout, 1, st));
-    ABI(sdvae_spiralconv_bwd_x_tc(d_dpre, d_cp, d_cs, d_img, g, d_dx1, B, V, V, S, Cout, Cin, st));
+    ABI(sdvae_spiralconv_bwd_x_tc(d_dpre, pl.cnt, pl.src, pl.cell, pl.rcap, d_img, g, d_dx1, B, V, V, S, Cout, Cin, st));
     CK(cudaDeviceSynchronize());
     std::vector<float> x0(nx), x1(nx);
     CK(cudaMemcpy(x0.data(), d_dx0, nx * 4, cudaMemcpyDeviceToHost));
@@ -208,7 +225,7 @@ int main(int argc, char** argv) {
     for (int i = 0; i < iters; ++i) ABI(sdvae_spiralconv_bwd_x(d_dpre, d_cp, d_cs, d_wt, g, d_dx0, B, V, V, S, Cout, Cin, st));
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms0, e0, e1));
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < iters; ++i) ABI(sdvae_spiralconv_bwd_x_tc(d_dpre, d_cp, d_cs, d_img, g, d_dx1, B, V, V, S, Cout, Cin, st));
+    for (int i = 0; i < iters; ++i) ABI(sdvae_spiralconv_bwd_x_tc(d_dpre, pl.cnt, pl.src, pl.cell, pl.rcap, d_img, g, d_dx1, B, V, V, S, Cout, Cin, st));
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms1, e0, e1));
     const double flops = 2.0 * B * V * (double)S * Cin * Cout;
     printf("time/launch: fma %.3f ms (%.1f TFLOP/s)   tc %.3f ms (%.1f TFLOP/s)   speedup %.2fx\n",
