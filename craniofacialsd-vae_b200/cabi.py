@@ -29,6 +29,14 @@ _SIGNATURES = {
     "sdvae_spiralconv_fwd": (C.c_int, [_c_fp] * 5 + [C.c_int] * 7 + [_c_fp]),
     "sdvae_weight_transpose": (C.c_int, [_c_fp, _c_fp, C.c_int, C.c_int, C.c_int, _c_fp]),
     "sdvae_spiralconv_bwd_x": (C.c_int, [_c_fp] * 6 + [C.c_int] * 6 + [_c_fp]),
+    "sdvae_tc_supported": (C.c_int, [C.c_int] * 4),
+    "sdvae_tc_wimg_floats": (C.c_size_t, [C.c_int] * 3),
+    "sdvae_tc_pack_weights": (C.c_int, [_c_fp, _c_fp, C.c_int, C.c_int, C.c_int, C.c_int, _c_fp]),
+    "sdvae_tc_plan_tiles": (C.c_int, [C.c_int]),
+    "sdvae_tc_plan_max_rows": (C.c_int, [_c_fp, C.c_int, C.c_int]),
+    "sdvae_tc_plan_build": (C.c_int, [_c_fp, _c_fp, C.c_int, C.c_int, C.c_int, _c_fp, _c_fp, _c_fp]),
+    "sdvae_spiralconv_fwd_tc": (C.c_int, [_c_fp] * 4 + [C.c_int] + [_c_fp] * 3 + [C.c_int] * 7 + [_c_fp]),
+    "sdvae_spiralconv_bwd_x_tc": (C.c_int, [_c_fp] * 4 + [C.c_int] + [_c_fp] * 3 + [C.c_int] * 6 + [_c_fp]),
     "sdvae_spiralconv_bwd_w_workspace": (C.c_size_t, [C.c_longlong, C.c_int, C.c_int, C.c_int]),
     "sdvae_spiralconv_bwd_w": (C.c_int, [_c_fp] * 6 + [C.c_int] * 6 + [_c_fp]),
     "sdvae_dense_fwd": (C.c_int, [_c_fp] * 4 + [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, _c_fp]),
@@ -79,6 +87,7 @@ def load(build_if_missing: bool = False):
 # kernels launched per ABI call (for bench.py's `gpu_launches`)
 _KERNELS_PER_CALL = {
     "spiralconv_fwd": 1, "weight_transpose": 1, "spiralconv_bwd_x": 1, "spiralconv_bwd_w": 3,
+    "tc_pack_weights": 1, "spiralconv_fwd_tc": 1, "spiralconv_bwd_x_tc": 1,
     "dense_fwd": 1, "transpose2d": 1, "pool_ell_fwd": 1, "csr_rowsum": 1, "elu_fwd": 1,
     "elu_bwd": 1, "reparam_fwd": 1, "reparam_bwd": 1, "axpy3": 1, "swap": 1, "mse_lap_fwd": 3,
     "mse_lap_bwd": 1, "kl_fwd_bwd": 2, "lc_fwd_bwd": 3, "total_loss": 1, "adam_tick": 1,
@@ -152,6 +161,67 @@ def spiralconv_bwd_x(dpre, cell_ptr, cell_src, wt, gate, dx, B, Vrows, Vdst, S, 
     if rc:
         _err(rc, "spiralconv_bwd_x")
     add_launches(_KERNELS_PER_CALL["spiralconv_bwd_x"])
+
+
+# ---- tensor-core (tcgen05) SpiralConv ---------------------------------------------
+def tc_supported(S, KS, N, rcap=128) -> bool:
+    return bool(load().sdvae_tc_supported(S, KS, N, rcap))
+
+
+def tc_wimg_floats(S, KS, N) -> int:
+    return int(load().sdvae_tc_wimg_floats(S, KS, N))
+
+
+def tc_pack_weights(weight, wimg, S, Cin, Cout, transposed):
+    rc = load().sdvae_tc_pack_weights(_f(weight, "weight"), _f(wimg, "wimg"), S, Cin, Cout,
+                                      1 if transposed else 0, _stream())
+    if rc:
+        _err(rc, "tc_pack_weights")
+    add_launches(_KERNELS_PER_CALL["tc_pack_weights"])
+
+
+def tc_plan_build(cell_ptr, cell_src, out_rows, S):
+    """Host-side tile plan of a cell-form table (NumPy int32 arrays).  Returns
+    ``(cnt [L,S], src [L,S,rcap], cell [L,S,128], rcap)`` as NumPy arrays."""
+    import numpy as np
+    lib = load()
+    cell_ptr = np.ascontiguousarray(cell_ptr, np.int32)
+    cell_src = np.ascontiguousarray(cell_src, np.int32)
+    if cell_ptr.shape[0] != out_rows * S + 1:
+        raise ValueError("tc_plan_build: cell_ptr must have out_rows*S + 1 entries")
+    L = int(lib.sdvae_tc_plan_tiles(out_rows))
+    mx = int(lib.sdvae_tc_plan_max_rows(cell_ptr.ctypes.data, out_rows, S))
+    if mx < 0:
+        raise RuntimeError("tc_plan_build: bad table")
+    rcap = max(16, (mx + 15) // 16 * 16)
+    cnt = np.zeros((L, S), np.int32)
+    src = np.zeros((L, S, rcap), np.int32)
+    cell = np.zeros((L, S, 128), np.int32)
+    rc = lib.sdvae_tc_plan_build(cell_ptr.ctypes.data, cell_src.ctypes.data, out_rows, S, rcap,
+                                 cnt.ctypes.data, src.ctypes.data, cell.ctypes.data)
+    if rc:
+        _err(rc, "tc_plan_build")
+    return cnt, src, cell, rcap
+
+
+def spiralconv_fwd_tc(x, plan, wimg, bias, y, B, Vin, Vout, S, Cin, Cout, act):
+    rc = load().sdvae_spiralconv_fwd_tc(_f(x, "x"), _i(plan.cnt, "plan.cnt"), _i(plan.src, "plan.src"),
+                                        _i(plan.cell, "plan.cell"), plan.rcap, _f(wimg, "wimg"),
+                                        _fo(bias, "bias"), _f(y, "y"), B, Vin, Vout, S, Cin, Cout,
+                                        act, _stream())
+    if rc:
+        _err(rc, "spiralconv_fwd_tc")
+    add_launches(_KERNELS_PER_CALL["spiralconv_fwd_tc"])
+
+
+def spiralconv_bwd_x_tc(dpre, plan, wimg_t, gate, dx, B, Vrows, Vdst, S, Cout, Cin):
+    rc = load().sdvae_spiralconv_bwd_x_tc(_f(dpre, "dpre"), _i(plan.cnt, "plan.cnt"),
+                                          _i(plan.src, "plan.src"), _i(plan.cell, "plan.cell"),
+                                          plan.rcap, _f(wimg_t, "wimg_t"), _fo(gate, "gate"),
+                                          _f(dx, "dx"), B, Vrows, Vdst, S, Cout, Cin, _stream())
+    if rc:
+        _err(rc, "spiralconv_bwd_x_tc")
+    add_launches(_KERNELS_PER_CALL["spiralconv_bwd_x_tc"])
 
 
 def spiralconv_bwd_w_workspace(M, S, Cin, Cout) -> int:

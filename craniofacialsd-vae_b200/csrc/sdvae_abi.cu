@@ -248,6 +248,11 @@ static int tc_conv(const float* in, const int32_t* plan_cnt, const int32_t* plan
     SDVAE_REQUIRE(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(wimg)) & 15) == 0,
                   "spiralconv tc: input and wimg must be 16-byte aligned");
     if (!tc_shape_ok(S, KS, N, rcap)) return set_error(SDVAE_ERR_UNSUPPORTED, who);
+    if (tc_tile_n(N) >= 32) {       // full-width tiles use 16-byte epilogue accesses
+        const uintptr_t al = reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias) |
+                             reinterpret_cast<uintptr_t>(gate);
+        if (N != tc_tile_n(N) || (al & 15) != 0) return set_error(SDVAE_ERR_UNSUPPORTED, who);
+    }
     umma::UmmaArgs ua{};
     ua.in = in; ua.plan_cnt = plan_cnt; ua.plan_src = plan_src; ua.plan_cell = plan_cell;
     ua.wimg = wimg; ua.bias = bias; ua.gate = gate; ua.out = out;

@@ -235,17 +235,18 @@ struct UmmaArgs {
 // Position of a CTA in its static schedule: chunk g = (tile iteration it, chunk ch of the tile),
 // kept incrementally so that the per-chunk role loops contain no integer division.
 struct ChunkCursor {
-    int g, ch, b, jt, rs;
-    uint32_t rph;
-    int nch, nraw, L, db, djt;
-    __device__ __forceinline__ ChunkCursor(const UmmaArgs& a, int nch_, int nraw_)
-        : g(0), ch(0), rs(0), rph(0), nch(nch_), nraw(nraw_), L(a.L) {
+    int g, ch, b, jt, rs, as;
+    uint32_t rph, aph;
+    int nch, nraw, nast, L, db, djt;
+    __device__ __forceinline__ ChunkCursor(const UmmaArgs& a, int nch_, int nraw_, int nast_)
+        : g(0), ch(0), rs(0), as(0), rph(0), aph(0), nch(nch_), nraw(nraw_), nast(nast_), L(a.L) {
         b = (int)blockIdx.x / L; jt = (int)blockIdx.x - b * L;
         db = (int)gridDim.x / L; djt = (int)gridDim.x - db * L;       // tile stride, split into (mesh, tile-in-mesh)
     }
     __device__ __forceinline__ void advance() {
         ++g;
         if (++rs == nraw) { rs = 0; rph ^= 1; }
+        if (++as == nast) { as = 0; aph ^= 1; }
         if (++ch == nch) {
             ch = 0; b += db; jt += djt;
             if (jt >= L) { jt -= L; ++b; }
@@ -277,6 +278,10 @@ gc_umma_kernel(const UmmaArgs a) {
     const int S = a.S;
     const int NCH = S * CPS;
     const int NRAW = a.nraw;
+    // TMEM A-ring depth.  The parity waits need every waiter within one phase of its barrier: a splitter
+    // runs at most NAST chunks ahead of the (in-order) MMA, so NAST <= NRAW keeps chunk g - NRAW loaded
+    // before anyone waits for chunk g on the same raw stage.
+    const int NAST = NRAW < kAStages ? NRAW : kAStages;
     const int RAW_STAGE = a.rcap * 128;
 
     extern __shared__ uint8_t smem_raw[];
@@ -355,7 +360,7 @@ gc_umma_kernel(const UmmaArgs a) {
                     if (ch == NCH - 1) umma_commit(t_full + acc);
                 }
                 __syncwarp();
-                if (++as == kAStages) { as = 0; aph ^= 1; }
+                if (++as == NAST) { as = 0; aph ^= 1; }
             }
         }
     } else if (warp < kFirstSplitWarp) {
@@ -364,10 +369,9 @@ gc_umma_kernel(const UmmaArgs a) {
         const int EPI = a.epi;
         const int n_real = a.n_real, ldo = a.ldo;
         const bool has_bias = (EPI == EPI_BIAS || EPI == EPI_BIAS_ELU) && a.bias != nullptr;
-        const bool vec_ok = (n_real == NT) && ((ldo & 3) == 0) &&
-                            ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0) &&
-                            (EPI != EPI_GATE || (reinterpret_cast<uintptr_t>(a.gate) & 15) == 0) &&
-                            (!has_bias || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0);
+        // NT >= 32: full-width rows, 16-byte accesses (the host checks n_real == NT and the alignments);
+        // NT == 16: narrow outputs (e.g. the 3-channel output layer), scalar tail
+        constexpr bool vec_ok = NT >= 32;
 #pragma unroll 1
         for (int it = 0; it < my_tiles; ++it) {
             const int tile = (int)blockIdx.x + it * (int)gridDim.x;
@@ -442,8 +446,8 @@ gc_umma_kernel(const UmmaArgs a) {
         const int set = (warp - kFirstSplitWarp) >> 2;
         const int q4 = warp & 3;
         const int lr = q4 * 32 + lane;                            // tile row owned by this thread
-        ChunkCursor cur(a, NCH, NRAW);                            // chunk being processed
-        ChunkCursor pre(a, NCH, NRAW);                            // chunk whose plan entry is prefetched
+        ChunkCursor cur(a, NCH, NRAW, NAST);                      // chunk being processed
+        ChunkCursor pre(a, NCH, NRAW, NAST);                      // chunk whose plan entry is prefetched
         if (set) { cur.advance(); pre.advance(); }
         auto cell_of = [&](const ChunkCursor& c) -> uint32_t {
             return (uint32_t)__ldg(a.plan_cell + ((size_t)c.jt * S + c.ch / CPS) * kBM + lr);
@@ -455,9 +459,12 @@ gc_umma_kernel(const UmmaArgs a) {
             const uint32_t cell_next = pre.g < G ? cell_of(pre) : 0u;         // one own-chunk ahead
             const int e0 = (int)(cell & 0xffffu), cnt = (int)(cell >> 16);
             const int rs = cur.rs;
-            const int as = cur.g & (kAStages - 1);
-            const uint32_t aph = (uint32_t)((cur.g / kAStages) & 1);
+            const int as = cur.as;
+            const uint32_t aph = cur.aph;
 
+            // Order matters: once the MMAs of chunk g - NAST are done (a_empty), every chunk up to g - NAST
+            // has been loaded, so the raw barrier of this stage is at most one phase behind this waiter.
+            mbar_wait(a_empty + as, aph ^ 1);
             mbar_wait(raw_full + rs, cur.rph);
             const uint8_t* stage = R_s + (size_t)rs * RAW_STAGE;
             float v[32];
@@ -476,7 +483,6 @@ gc_umma_kernel(const UmmaArgs a) {
             float lo[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) { float h; split_tf32f(v[j], h, lo[j]); v[j] = h; }
-            mbar_wait(a_empty + as, aph ^ 1);
             tc_fence_after();
             const uint32_t t_a = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(kAColBase + as * 64);
             tmem_st32(t_a, v);
@@ -497,7 +503,7 @@ gc_umma_kernel(const UmmaArgs a) {
         const int q = lane & 7, rsub = lane >> 3;
         const uint32_t sw0 = (uint32_t)((q ^ rsub) << 4), sw1 = (uint32_t)((q ^ (rsub + 4)) << 4);
         const uint32_t raw_base = smem_u32(R_s) + (uint32_t)rsub * 128u;
-        ChunkCursor cur(a, NCH, NRAW);
+        ChunkCursor cur(a, NCH, NRAW, NAST);
         for (int i = 0; i < lw; ++i) cur.advance();
         if (lw >= NRAW) cur.g = G;                                // more loader warps than stages: idle
 #pragma unroll 1

@@ -61,9 +61,11 @@ class StepConfig:
 class TrainEngine:
     def __init__(self, model, laplacian: Optional[LaplacianTable], region_features: Sequence[np.ndarray],
                  latent_regions: Sequence[Sequence[int]], cfg: StepConfig, process_group=None,
-                 use_graph: bool = True):
+                 use_graph: bool = True, use_tc: bool = True):
         """``model``: a ``sdvae_b200.model.Model`` on the CUDA device.
-        ``region_features[k]``: vertex ids swapped for region k; ``latent_regions[k]`` = [r0, r1]."""
+        ``region_features[k]``: vertex ids swapped for region k; ``latent_regions[k]`` = [r0, r1].
+        ``use_tc``: run the wide SpiralConv contractions (C_in in {32, 64}) on the tcgen05 tensor-core
+        kernels (error-compensated 3xTF32); False keeps every contraction on the fp32-FMA kernels."""
         self.model = model
         self.cfg = cfg
         self.dev = next(model.parameters()).device
@@ -87,6 +89,7 @@ class TrainEngine:
         self.latent_regions = [tuple(int(t) for t in r) for r in latent_regions]
         self.use_lc = cfg.latent_consistency_weight > 0
         self.use_graph = use_graph and self.world == 1
+        self.use_tc = bool(use_tc)
         self._graphs: Dict[int, torch.cuda.CUDAGraph] = {}
         self.fixed_eps: Optional[torch.Tensor] = None
         self.launches_per_step = 0
@@ -193,6 +196,7 @@ class TrainEngine:
             ws = max(ws, cabi.spiralconv_bwd_w_workspace(B * V[l], self.S[l], self.cin_de[l], C[l + 1]))
         ws = max(ws, cabi.spiralconv_bwd_w_workspace(B * V[0], self.S[0], C[1], C[0]))
         self.ws = f(ws // 4 + 4)
+        self._alloc_tc()
         self.losses = torch.zeros(8, device=dev, dtype=torch.float32)
         self.losses_host = torch.zeros(8, dtype=torch.float32).pin_memory()
         self.part_mse = f(cabi.mse_lap_partial_floats(B, V[0]))
@@ -203,8 +207,50 @@ class TrainEngine:
         self.z_all = f(self.bs * self.bs, D) if self.world > 1 else None
         self.dz_lc = f(self.bs * self.bs, D)
 
+    # ------------------------------------------------------------------ tensor-core path
+    def _alloc_tc(self):
+        """Per conv layer: tile plans + packed-weight buffers for the tcgen05 kernels, where
+        the layer shape is supported.  Keys: ('f', name) forward, ('b', name) backward-to-input."""
+        self.tc = {}
+        if not self.use_tc:
+            return
+        m, L, C, S = self.model, self.L, self.C, self.S
+        f = lambda n: torch.empty(n, device=self.dev, dtype=torch.float32)
+
+        def add(kind, name, layer, table, cin, cout):
+            if kind == 'f':
+                plan, ks, n = table.plan_fwd(), cin, cout
+            else:
+                plan, ks, n = table.plan_bwd(), cout, cin
+            if ks not in (32, 64) or not cabi.tc_supported(table.seq, ks, n, plan.rcap):
+                return
+            self.tc[(kind, name)] = dict(layer=layer, plan=plan, cin=cin, cout=cout, seq=table.seq,
+                                         wimg=f(cabi.tc_wimg_floats(table.seq, ks, n)))
+
+        for l in range(L):
+            enc = m.en_layers[l].conv.layer
+            add('f', 'en%d' % l, enc, self.sub[l], C[l], C[l + 1])
+            if l > 0:
+                add('b', 'en%d' % l, enc, self.sub[l], C[l], C[l + 1])
+            dec = m.de_layers[L - l].conv.layer
+            add('f', 'de%d' % l, dec, self.full[l], self.cin_de[l], C[l + 1])
+            add('b', 'de%d' % l, dec, self.full[l], self.cin_de[l], C[l + 1])
+        out_layer = m.de_layers[L + 1].layer
+        add('f', 'out', out_layer, self.full[0], C[1], C[0])
+
+    def _pack_tc(self):
+        """Re-pack every tensor-core weight image from the current weights (they change each step)."""
+        for (kind, _), e in self.tc.items():
+            cabi.tc_pack_weights(e['layer'].weight.data, e['wimg'], e['seq'], e['cin'], e['cout'],
+                                 kind == 'b')
+
     # ------------------------------------------------------------------ pieces
-    def _conv(self, x, table, layer, out, act, B, Vin, Cin, Cout):
+    def _conv(self, x, table, layer, out, act, B, Vin, Cin, Cout, name=None):
+        e = self.tc.get(('f', name))
+        if e is not None:
+            cabi.spiralconv_fwd_tc(x, e['plan'], e['wimg'], layer.bias.data, out, B, Vin,
+                                   table.n_rows, table.seq, Cin, Cout, act)
+            return
         cabi.spiralconv_fwd(x, table.idx, layer.weight.data, layer.bias.data, out, B, Vin,
                             table.n_rows, table.seq, Cin, Cout, act)
 
@@ -212,10 +258,11 @@ class TrainEngine:
         """x0 -> recon, z, mu, logvar (training mode)."""
         m, L, V, C = self.model, self.L, self.V, self.C
         B = self.B if B is None else B
+        self._pack_tc()
         x = self.x0
         for l in range(L):
             self._conv(x, self.sub[l], m.en_layers[l].conv.layer, self.a[l], cabi.ACT_ELU,
-                       B, V[l], C[l], C[l + 1])
+                       B, V[l], C[l], C[l + 1], name='en%d' % l)
             x = self.a[l]
         flat = x.view(B, V[L] * C[L])
         lin_mu = m.en_layers[-1]
@@ -240,10 +287,10 @@ class TrainEngine:
             cabi.pool_ell_fwd(x, up.ell_col, up.ell_val, self.u[l], B, V[l + 1], V[l], up.width,
                               self.cin_de[l])
             self._conv(self.u[l], self.full[l], m.de_layers[L - l].conv.layer, self.d[l],
-                       cabi.ACT_ELU, B, V[l], self.cin_de[l], C[l + 1])
+                       cabi.ACT_ELU, B, V[l], self.cin_de[l], C[l + 1], name='de%d' % l)
             x = self.d[l]
         self._conv(x, self.full[0], m.de_layers[L + 1].layer, self.recon, cabi.ACT_NONE,
-                   B, V[0], C[1], C[0])
+                   B, V[0], C[1], C[0], name='out')
         return z
 
     def _bwd_w(self, x, table, dpre, layer, B, Vin, Cin, Cout):
@@ -302,10 +349,15 @@ class TrainEngine:
             layer = m.de_layers[L - l].conv.layer
             cin, cout = self.cin_de[l], C[l + 1]
             self._bwd_w(self.u[l], self.full[l], self.dd[l], layer, B, V[l], cin, cout)
-            cabi.weight_transpose(layer.weight.data, self.wt[l], cout, cin, S[l])
-            cp, cs = self.full[l].inverse()
-            cabi.spiralconv_bwd_x(self.dd[l], cp, cs, self.wt[l], None, self.du[l], B, V[l], V[l],
-                                  S[l], cout, cin)
+            e = self.tc.get(('b', 'de%d' % l))
+            if e is not None:
+                cabi.spiralconv_bwd_x_tc(self.dd[l], e['plan'], e['wimg'], None, self.du[l], B, V[l],
+                                         V[l], S[l], cout, cin)
+            else:
+                cabi.weight_transpose(layer.weight.data, self.wt[l], cout, cin, S[l])
+                cp, cs = self.full[l].inverse()
+                cabi.spiralconv_bwd_x(self.dd[l], cp, cs, self.wt[l], None, self.du[l], B, V[l], V[l],
+                                      S[l], cout, cin)
             up = self.up[l]
             if l + 1 < L:    # gradient w.r.t. the coarser deblock's pre-activation (ELU' fused)
                 cabi.csr_rowsum(self.du[l], up.t_ptr, up.t_row, up.t_val, self.d[l + 1],
@@ -355,7 +407,13 @@ class TrainEngine:
             layer = m.en_layers[l].conv.layer
             x_in = self.a[l - 1] if l > 0 else self.x0
             self._bwd_w(x_in, self.sub[l], self.da[l], layer, B, V[l], C[l], C[l + 1])
-            if l > 0:
+            e = self.tc.get(('b', 'en%d' % l)) if l > 0 else None
+            if e is not None:
+                # input gradient of the fused block straight from the kept rows (inverse table of the
+                # restricted spiral table), ELU' of the previous block fused in the epilogue
+                cabi.spiralconv_bwd_x_tc(self.da[l], e['plan'], e['wimg'], self.a[l - 1], self.da[l - 1],
+                                         B, self.sub[l].n_rows, V[l], S[l], C[l + 1], C[l])
+            elif l > 0:
                 K = S[l] * C[l]
                 cabi.transpose2d(layer.weight.data, self.wT[l], C[l + 1], K)
                 R = self.sub[l].n_rows

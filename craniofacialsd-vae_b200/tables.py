@@ -139,6 +139,26 @@ def _dev(a: np.ndarray, device) -> torch.Tensor:
 
 
 @dataclass
+class TilePlan:
+    """Tile plan of a cell-form table for the tcgen05 kernels (include/sdvae_b200.h,
+    ``sdvae_tc_plan_build``): per tile of 128 output rows and spiral slot, the source rows
+    to stage and, per output row, the range of staged rows summed into its cell."""
+    cnt: torch.Tensor            # int32 [L, S]
+    src: torch.Tensor            # int32 [L, S, rcap]
+    cell: torch.Tensor           # int32 [L, S, 128]   start | count << 16
+    rcap: int
+    out_rows: int
+    seq: int
+
+    @staticmethod
+    def build(cell_ptr: np.ndarray, cell_src: np.ndarray, out_rows: int, seq: int, device) -> "TilePlan":
+        from . import cabi
+        cnt, src, cell, rcap = cabi.tc_plan_build(cell_ptr, cell_src, out_rows, seq)
+        return TilePlan(_dev(cnt, device), _dev(src, device), _dev(cell, device), int(rcap),
+                        int(out_rows), int(seq))
+
+
+@dataclass
 class SpiralTable:
     """Device copies of one (possibly row-restricted) spiral table."""
     idx: torch.Tensor            # int32 [R, S]
@@ -148,6 +168,8 @@ class SpiralTable:
     _np_idx: np.ndarray
     _inv: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
     _inv_flat: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+    _plan_fwd: Optional["TilePlan"] = None
+    _plan_bwd: Optional["TilePlan"] = None
 
     @staticmethod
     def build(idx_np: np.ndarray, n_src: int, device) -> "SpiralTable":
@@ -166,6 +188,21 @@ class SpiralTable:
             ptr, src = inverse_rows_flat(self._np_idx, self.n_src)
             self._inv_flat = (_dev(ptr, self.idx.device), _dev(src, self.idx.device))
         return self._inv_flat
+
+    def plan_fwd(self) -> "TilePlan":
+        """Tile plan of the forward gather (one source row per cell: cell_ptr[i] = i)."""
+        if self._plan_fwd is None:
+            n = self.n_rows * self.seq
+            self._plan_fwd = TilePlan.build(np.arange(n + 1, dtype=np.int32), self._np_idx.ravel(),
+                                            self.n_rows, self.seq, self.idx.device)
+        return self._plan_fwd
+
+    def plan_bwd(self) -> "TilePlan":
+        """Tile plan of the backward-to-input gather (inverse table, rows = source vertices)."""
+        if self._plan_bwd is None:
+            ptr, src = inverse_cells(self._np_idx, self.n_src)
+            self._plan_bwd = TilePlan.build(ptr, src, self.n_src, self.seq, self.idx.device)
+        return self._plan_bwd
 
     def restrict(self, kept: np.ndarray) -> "SpiralTable":
         """Table of the rows in ``kept`` only (fused conv + selection pooling)."""

@@ -1,0 +1,62 @@
+"""Host-side tile plans of the tcgen05 path (sdvae_tc_plan_build): bit-exact index work, no GPU."""
+import numpy as np
+
+from sdvae_b200 import cabi
+from sdvae_b200.tables import inverse_cells
+
+
+def _check_plan(cell_ptr, cell_src, out_rows, S):
+    cnt, src, cell, rcap = cabi.tc_plan_build(cell_ptr, cell_src, out_rows, S)
+    L = (out_rows + 127) // 128
+    assert cnt.shape == (L, S) and src.shape == (L, S, rcap) and cell.shape == (L, S, 128)
+    assert rcap % 16 == 0 and cnt.max() <= rcap
+    start = cell.astype(np.uint32) & 0xffff
+    count = cell.astype(np.uint32) >> 16
+    for jt in range(L):
+        for s in range(S):
+            n = 0
+            for lr in range(128):
+                r = jt * 128 + lr
+                if r >= out_rows:
+                    assert count[jt, s, lr] == 0
+                    continue
+                e0, e1 = cell_ptr[r * S + s], cell_ptr[r * S + s + 1]
+                assert start[jt, s, lr] == n and count[jt, s, lr] == e1 - e0
+                assert np.array_equal(src[jt, s, n:n + e1 - e0], cell_src[e0:e1])   # storage order kept
+                n += e1 - e0
+            assert cnt[jt, s] == n
+            assert not src[jt, s, n:].any()
+    return rcap
+
+
+def test_forward_plan_is_the_table_itself(cranio):
+    idx = cranio.spiral_tensors()[2].numpy().astype(np.int32)
+    V, S = idx.shape
+    rcap = _check_plan(np.arange(V * S + 1, dtype=np.int32), idx.ravel(), V, S)
+    assert rcap == 128
+
+
+def test_backward_plan_of_inverse_table(cranio):
+    for lvl in (2, 3):
+        idx = cranio.spiral_tensors()[lvl].numpy().astype(np.int32)
+        V, S = idx.shape
+        ptr, src = inverse_cells(idx, V)
+        _check_plan(ptr, src, V, S)
+
+
+def test_ragged_tail_and_empty_cells():
+    rng = np.random.RandomState(0)
+    out_rows, S = 131, 3                               # second tile holds 3 rows
+    counts = rng.randint(0, 3, size=out_rows * S)
+    ptr = np.zeros(out_rows * S + 1, np.int32)
+    ptr[1:] = np.cumsum(counts)
+    src = rng.randint(0, 500, size=int(ptr[-1])).astype(np.int32)
+    _check_plan(ptr, src, out_rows, S)
+
+
+def test_shape_support_matrix():
+    assert cabi.tc_supported(9, 32, 32, 128) and cabi.tc_supported(9, 32, 32, 192)
+    assert not cabi.tc_supported(9, 64, 64, 128)       # 288 KB weight image does not fit next to the rings
+    assert cabi.tc_supported(9, 32, 3, 128) and cabi.tc_supported(9, 64, 32, 160)
+    assert not cabi.tc_supported(9, 3, 32, 128) and not cabi.tc_supported(9, 32, 128, 128)
+    assert cabi.tc_wimg_floats(9, 32, 32) == 9 * 2 * 32 * 32
