@@ -37,6 +37,8 @@ _SIGNATURES = {
     "sdvae_tc_plan_build": (C.c_int, [_c_fp, _c_fp, C.c_int, C.c_int, C.c_int, _c_fp, _c_fp, _c_fp]),
     "sdvae_spiralconv_fwd_tc": (C.c_int, [_c_fp] * 4 + [C.c_int] + [_c_fp] * 3 + [C.c_int] * 7 + [_c_fp]),
     "sdvae_spiralconv_bwd_x_tc": (C.c_int, [_c_fp] * 4 + [C.c_int] + [_c_fp] * 3 + [C.c_int] * 6 + [_c_fp]),
+    "sdvae_tc_bwd_w_supported": (C.c_int, [C.c_int] * 4),
+    "sdvae_spiralconv_bwd_w_tc": (C.c_int, [_c_fp] * 3 + [C.c_int] + [_c_fp] * 4 + [C.c_int] * 6 + [_c_fp]),
     "sdvae_spiralconv_bwd_w_workspace": (C.c_size_t, [C.c_longlong, C.c_int, C.c_int, C.c_int]),
     "sdvae_spiralconv_bwd_w": (C.c_int, [_c_fp] * 6 + [C.c_int] * 6 + [_c_fp]),
     "sdvae_dense_fwd": (C.c_int, [_c_fp] * 4 + [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, _c_fp]),
@@ -88,6 +90,7 @@ def load(build_if_missing: bool = False):
 _KERNELS_PER_CALL = {
     "spiralconv_fwd": 1, "weight_transpose": 1, "spiralconv_bwd_x": 1, "spiralconv_bwd_w": 3,
     "tc_pack_weights": 1, "spiralconv_fwd_tc": 1, "spiralconv_bwd_x_tc": 1,
+    "spiralconv_bwd_w_tc": 3,
     "dense_fwd": 1, "transpose2d": 1, "pool_ell_fwd": 1, "csr_rowsum": 1, "elu_fwd": 1,
     "elu_bwd": 1, "reparam_fwd": 1, "reparam_bwd": 1, "axpy3": 1, "swap": 1, "mse_lap_fwd": 3,
     "mse_lap_bwd": 1, "kl_fwd_bwd": 2, "lc_fwd_bwd": 3, "total_loss": 1, "adam_tick": 1,
@@ -222,6 +225,21 @@ def spiralconv_bwd_x_tc(dpre, plan, wimg_t, gate, dx, B, Vrows, Vdst, S, Cout, C
     if rc:
         _err(rc, "spiralconv_bwd_x_tc")
     add_launches(_KERNELS_PER_CALL["spiralconv_bwd_x_tc"])
+
+
+def tc_bwd_w_supported(S, Cin, Cout, rcap=128) -> bool:
+    return bool(load().sdvae_tc_bwd_w_supported(S, Cin, Cout, rcap))
+
+
+def spiralconv_bwd_w_tc(x, plan, dpre, dW, db, workspace, B, Vin, Vout, S, Cin, Cout):
+    """Weight / bias gradient on the tcgen05 path; ``plan`` is the layer's FORWARD tile plan."""
+    rc = load().sdvae_spiralconv_bwd_w_tc(_f(x, "x"), _i(plan.cnt, "plan.cnt"), _i(plan.src, "plan.src"),
+                                          plan.rcap, _f(dpre, "dpre"), _f(dW, "dW"), _fo(db, "db"),
+                                          _f(workspace, "workspace"), B, Vin, Vout, S, Cin, Cout,
+                                          _stream())
+    if rc:
+        _err(rc, "spiralconv_bwd_w_tc")
+    add_launches(_KERNELS_PER_CALL["spiralconv_bwd_w_tc"])
 
 
 def spiralconv_bwd_w_workspace(M, S, Cin, Cout) -> int:

@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "spiral_conv.cuh"
 #include "spiral_conv_umma.cuh"
+#include "spiral_conv_umma_bw.cuh"
 #include "pool_misc.cuh"
 #include "loss.cuh"
 
@@ -279,9 +280,64 @@ int sdvae_spiralconv_bwd_x_tc(const float* dpre, const int32_t* plan_cnt, const 
                    "spiralconv_bwd_x_tc: unsupported layer shape");
 }
 
+int sdvae_tc_bwd_w_supported(int S, int Cin, int Cout, int rcap) {
+    if (Cin != 32 || Cout < 1 || Cout > umma::kBwNT || S < 1 || S > 11) return 0;
+    if (rcap < 16 || rcap > umma::kMaxRcap || rcap % 16 != 0) return 0;
+    const long long budget = 226LL * 1024 - 2048 - 2 * umma::kGStage;
+    return budget / ((long long)rcap * 128) >= 7 ? 1 : 0;       // the phase-distance argument needs 7 raw stages
+}
+
+int sdvae_spiralconv_bwd_w_tc(const float* x, const int32_t* plan_cnt, const int32_t* plan_src, int rcap,
+                              const float* dpre, float* dW, float* db, void* workspace, int B, int Vin,
+                              int Vout, int S, int Cin, int Cout, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(x && plan_cnt && plan_src && dpre && dW && workspace, "spiralconv_bwd_w_tc: null pointer");
+    SDVAE_REQUIRE(B >= 0 && Vin > 0 && Vout > 0, "spiralconv_bwd_w_tc: bad shape");
+    SDVAE_REQUIRE((long long)B * Vin < 2147483647LL, "spiralconv_bwd_w_tc: B*Vin exceeds int32 rows");
+    SDVAE_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "spiralconv_bwd_w_tc: x must be 16-byte aligned");
+    if (!sdvae_tc_bwd_w_supported(S, Cin, Cout, rcap))
+        return set_error(SDVAE_ERR_UNSUPPORTED, "spiralconv_bwd_w_tc: unsupported layer shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int K = S * Cin;
+    if (B == 0) {
+        cudaMemsetAsync(dW, 0, sizeof(float) * Cout * K, st);
+        if (db) cudaMemsetAsync(db, 0, sizeof(float) * Cout, st);
+        return check_launch("bwd_w_tc memset");
+    }
+    umma::BwUmmaArgs a{};
+    a.in = x; a.plan_cnt = plan_cnt; a.plan_src = plan_src; a.g = dpre;
+    a.B = B; a.in_rows = Vin; a.out_rows = Vout; a.L = sdvae_tc_plan_tiles(Vout); a.S = S; a.rcap = rcap;
+    a.n_real = Cout; a.nraw = umma::kMaxRaw;
+    const long long ntiles = (long long)B * a.L;
+    const int grid = ntiles < kNumSMs ? (int)ntiles : kNumSMs;
+    a.part = static_cast<float*>(workspace);
+    a.part_b = a.part + (size_t)grid * Cout * K;
+    static int flush_tiles = 0;                // tiles per accumulator drain (tuning knob, default 2)
+    if (!flush_tiles) {
+        const char* e = getenv("SDVAE_BWW_FLUSH");
+        flush_tiles = e ? atoi(e) : 2;
+        if (flush_tiles < 1) flush_tiles = 1;
+    }
+    a.flush = flush_tiles;
+    cudaMemsetAsync(a.part, 0, sizeof(float) * (size_t)grid * (Cout * K + Cout), st);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(umma::bw_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_done = true;
+    }
+    const size_t smem = 1024 + 2 * (size_t)umma::kGStage + (size_t)a.nraw * rcap * 128 + 1024;
+    umma::bw_umma_kernel<<<grid, umma::kThreads, smem, st>>>(a);
+    int rc = check_launch("bw_umma_kernel");
+    if (rc) return rc;
+    const long long len = (long long)Cout * K;
+    split_reduce_kernel<<<blocks_for(len, 256), 256, 0, st>>>(a.part, dW, grid, len);
+    if (db) split_reduce_kernel<<<blocks_for(Cout, 256), 256, 0, st>>>(a.part_b, db, grid, Cout);
+    return check_launch("split_reduce_kernel");
+}
+
 size_t sdvae_spiralconv_bwd_w_workspace(long long M, int S, int Cin, int Cout) {
     long long rows; int nsplit;
     bw_split(M, &rows, &nsplit);
+    if (nsplit < kNumSMs) nsplit = kNumSMs;      // the tensor-core path keeps one partial per CTA (<= one per SM)
     return (size_t)nsplit * (size_t)Cout * ((size_t)S * Cin + 1) * sizeof(float);
 }
 

@@ -294,6 +294,12 @@ class TrainEngine:
         return z
 
     def _bwd_w(self, x, table, dpre, layer, B, Vin, Cin, Cout):
+        if self.use_tc and Cin == 32:
+            plan = table.plan_fwd()
+            if cabi.tc_bwd_w_supported(table.seq, Cin, Cout, plan.rcap):
+                cabi.spiralconv_bwd_w_tc(x, plan, dpre, self.g(layer.weight), self.g(layer.bias),
+                                         self.ws, B, Vin, table.n_rows, table.seq, Cin, Cout)
+                return
         cabi.spiralconv_bwd_w(x, table.idx, dpre, self.g(layer.weight), self.g(layer.bias), self.ws,
                               B, Vin, table.n_rows, table.seq, Cin, Cout)
 

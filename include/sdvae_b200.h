@@ -99,6 +99,15 @@ int sdvae_spiralconv_bwd_x_tc(const float* dpre, const int32_t* plan_cnt, const 
                               float* dx, int B, int Vrows, int Vdst, int S, int Cout, int Cin,
                               sdvae_stream_t stream);
 
+/* Weight gradient on the tensor cores, as sdvae_spiralconv_bwd_w (same workspace size), for
+ * C_in = 32, C_out <= 32.  (plan_cnt, plan_src, rcap) is the FORWARD tile plan of the layer's table
+ * (one source row per cell).  db comes from a row of ones in the A operand; partial sums per CTA are
+ * added in a fixed order.  Replaces: autograd of model.py:40 (grad_weight / grad_bias). */
+int sdvae_tc_bwd_w_supported(int S, int Cin, int Cout, int rcap);
+int sdvae_spiralconv_bwd_w_tc(const float* x, const int32_t* plan_cnt, const int32_t* plan_src, int rcap,
+                              const float* dpre, float* dW, float* db, void* workspace, int B, int Vin,
+                              int Vout, int S, int Cin, int Cout, sdvae_stream_t stream);
+
 /* dW[o, s*Cin+c] = sum_{b,v} dpre[b,v,o] * x[b, idx[v,s], c];  db[o] = sum_{b,v} dpre[b,v,o]
  * workspace: sdvae_spiralconv_bwd_w_workspace(...) bytes.  Split-M partial sums are added in a
  * fixed order.  db may be NULL.

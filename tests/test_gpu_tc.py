@@ -118,12 +118,73 @@ def test_tc_restricted_rows_forward_and_backward(cranio, orc):
     assert nerr(dx, x.grad) < TC_TOL
 
 
+@pytest.mark.parametrize('lvl,cout,B', [(1, 32, 3), (2, 32, 5), (0, 32, 2), (0, 3, 2), (3, 17, 4), (0, 32, 40)])
+def test_tc_weight_gradient_vs_fp64_autograd(cranio, orc, lvl, cout, B):
+    """dW, db of y = conv(x) on the tcgen05 path (C_in = 32) against fp64 autograd of the oracle;
+    deterministic (run twice, bit-identical).  B = 40 at level 0 gives every CTA several flush
+    groups (the accumulators are drained from TMEM every few tiles -- tensor-core accumulation
+    truncates, an undrained chain drifts past the tolerance)."""
+    from sdvae_b200 import cabi
+    from sdvae_b200.tables import spiral_table
+    cin = 32
+    idx = cranio.spiral_tensors()[lvl]
+    V, S = idx.shape
+    tab = spiral_table(idx.to(DEV))
+    plan = tab.plan_fwd()
+    assert cabi.tc_bwd_w_supported(S, cin, cout, plan.rcap)
+    x = rand((B, V, cin), 80 + lvl)
+    gy = rand((B, V, cout), 90 + lvl)
+    w = torch.zeros((cout, S * cin), dtype=torch.float64, requires_grad=True)
+    b = torch.zeros((cout,), dtype=torch.float64, requires_grad=True)
+    # fp64 reference in chunks of meshes (the materialised gather of the oracle is 9x the input)
+    for b0 in range(0, B, 8):
+        y = orc.spiral_conv(x[b0:b0 + 8].double(), idx, w, b)
+        y.backward(gy[b0:b0 + 8].double())
+    ws = torch.empty(cabi.spiralconv_bwd_w_workspace(B * V, S, cin, cout) // 4 + 4, device=DEV)
+    outs = []
+    for _ in range(2):
+        dW = torch.full((cout, S * cin), float('nan'), device=DEV)
+        db = torch.full((cout,), float('nan'), device=DEV)
+        cabi.spiralconv_bwd_w_tc(x.to(DEV), plan, gy.to(DEV), dW, db, ws, B, V, V, S, cin, cout)
+        outs.append((dW, db))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert nerr(outs[0][0], w.grad) < TC_TOL
+    assert nerr(outs[0][1], b.grad) < TC_TOL
+    # and against the fp32-FMA kernel of the same op
+    dW2 = torch.empty_like(outs[0][0]); db2 = torch.empty_like(outs[0][1])
+    cabi.spiralconv_bwd_w(x.to(DEV), tab.idx, gy.to(DEV), dW2, db2, ws, B, V, V, S, cin, cout)
+    assert nerr(outs[0][0], dW2) < TC_TOL
+
+
+def test_tc_weight_gradient_restricted_rows(cranio, orc):
+    """Encoder block: the gradient rows are the kept vertices only (restricted table plan)."""
+    from sdvae_b200 import cabi
+    from sdvae_b200.tables import pool_table, restricted_spiral_table
+    idx = cranio.spiral_tensors()[1]
+    down = cranio.down_tensors()[1]
+    sub = restricted_spiral_table(idx.to(DEV), pool_table(down.to(DEV)))
+    B, V, S, R = 3, idx.shape[0], idx.shape[1], sub.n_rows
+    x = rand((B, V, 32), 5)
+    gy = rand((B, R, 32), 6)
+    w = torch.zeros((32, S * 32), dtype=torch.float64, requires_grad=True)
+    b = torch.zeros((32,), dtype=torch.float64, requires_grad=True)
+    y = orc.pool_sparse(orc.spiral_conv(x.double(), idx, w, b), down.double())
+    y.backward(gy.double())
+    ws = torch.empty(cabi.spiralconv_bwd_w_workspace(B * R, S, 32, 32) // 4 + 4, device=DEV)
+    dW = torch.empty((32, S * 32), device=DEV); db = torch.empty((32,), device=DEV)
+    cabi.spiralconv_bwd_w_tc(x.to(DEV), sub.plan_fwd(), gy.to(DEV), dW, db, ws, B, V, R, S, 32, 32)
+    assert nerr(dW, w.grad) < TC_TOL
+    assert nerr(db, b.grad) < TC_TOL
+
+
 def test_tc_rejects_unsupported_shapes(cranio):
     from sdvae_b200 import cabi
     assert not cabi.tc_supported(9, 3, 32, 128)        # K = 27: stays on the FMA kernel
     assert not cabi.tc_supported(9, 32, 96, 128)       # N > 64
     assert not cabi.tc_supported(9, 64, 64, 128)       # weight image too large
     assert not cabi.tc_supported(9, 32, 32, 1024)      # plan stages more rows than the kernel supports
+    assert not cabi.tc_bwd_w_supported(9, 64, 32, 128)  # weight gradient: C_in = 32 only
+    assert not cabi.tc_bwd_w_supported(9, 32, 64, 128)  # ... and C_out <= 32
     w = torch.zeros((32, 27), device=DEV)
     with pytest.raises(RuntimeError):
         cabi.tc_pack_weights(w, torch.zeros(4096, device=DEV), 9, 3, 32, False)

@@ -96,6 +96,68 @@ int main(int argc, char** argv) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
 
+    if (strcmp(argv[1], "bww") == 0) {
+        // ---- weight gradient ------------------------------------------------------------------
+        std::vector<int> uptr((size_t)V * S + 1);
+        for (size_t i = 0; i <= (size_t)V * S; ++i) uptr[i] = (int)i;
+        DevPlan pl = make_plan(uptr, idx, V, S);
+        if (!sdvae_tc_bwd_w_supported(S, Cin, Cout, pl.rcap)) { printf("shape not supported by the tcgen05 dW path\n"); return 4; }
+        std::vector<float> x((size_t)B * V * Cin), gg((size_t)B * V * Cout);
+        for (auto& t : x) t = 1.5f * frand();
+        for (auto& t : gg) t = frand();
+        float* d_x = dev_copy(x);
+        float* d_g = dev_copy(gg);
+        const size_t nw = (size_t)Cout * S * Cin;
+        float *d_w0, *d_w1, *d_b0, *d_b1, *d_ws;
+        CK(cudaMalloc(&d_w0, nw * 4)); CK(cudaMalloc(&d_w1, nw * 4));
+        CK(cudaMalloc(&d_b0, Cout * 4)); CK(cudaMalloc(&d_b1, Cout * 4));
+        CK(cudaMemset(d_w1, 0xFF, nw * 4)); CK(cudaMemset(d_b1, 0xFF, Cout * 4));
+        CK(cudaMalloc(&d_ws, sdvae_spiralconv_bwd_w_workspace((long long)B * V, S, Cin, Cout)));
+        ABI(sdvae_spiralconv_bwd_w(d_x, d_idx, d_g, d_w0, d_b0, d_ws, B, V, V, S, Cin, Cout, st));
+        ABI(sdvae_spiralconv_bwd_w_tc(d_x, pl.cnt, pl.src, pl.rcap, d_g, d_w1, d_b1, d_ws, B, V, V, S, Cin, Cout, st));
+        CK(cudaDeviceSynchronize());
+        std::vector<float> w0(nw), w1(nw), b0(Cout), b1(Cout);
+        CK(cudaMemcpy(w0.data(), d_w0, nw * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(w1.data(), d_w1, nw * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(b0.data(), d_b0, Cout * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(b1.data(), d_b1, Cout * 4, cudaMemcpyDeviceToHost));
+        double maxref = 0, maxdiff = 0, bref = 0, bdiff = 0; size_t worst = 0;
+        for (size_t i = 0; i < nw; ++i) {
+            maxref = std::max(maxref, (double)fabsf(w0[i]));
+            const double d = fabs((double)w0[i] - (double)w1[i]);
+            if (!(d <= maxdiff)) { maxdiff = d; worst = i; }
+        }
+        for (int i = 0; i < Cout; ++i) { bref = std::max(bref, (double)fabsf(b0[i])); bdiff = std::max(bdiff, fabs((double)b0[i] - b1[i])); }
+        printf("dW tc vs fma: max|diff| %.3e  max|ref| %.3e  normwise %.3e (worst at %zu: %g vs %g);  db normwise %.3e\n",
+               maxdiff, maxref, maxdiff / maxref, worst, w1[worst], w0[worst], bdiff / bref);
+        // fp64 check of a few dW entries
+        double e_fma = 0, e_tc = 0, mref = 0;
+        for (int t = 0; t < 24; ++t) {
+            const int n = (int)(rnd() % Cout), k = (int)(rnd() % (S * Cin));
+            const int s = k / Cin, c = k % Cin;
+            double acc = 0;
+            for (int b = 0; b < B; ++b)
+                for (int v = 0; v < V; ++v)
+                    acc += (double)gg[((size_t)b * V + v) * Cout + n] * x[((size_t)b * V + idx[(size_t)v * S + s]) * Cin + c];
+            mref = std::max(mref, fabs(acc));
+            e_fma = std::max(e_fma, fabs(acc - w0[(size_t)n * S * Cin + k]));
+            e_tc = std::max(e_tc, fabs(acc - w1[(size_t)n * S * Cin + k]));
+        }
+        printf("vs fp64 (24 entries): fma %.3e  tc %.3e  (relative to max|ref| %.3e)\n", e_fma / mref, e_tc / mref, mref);
+        float ms0, ms1;
+        CK(cudaEventRecord(e0));
+        for (int i = 0; i < iters; ++i) ABI(sdvae_spiralconv_bwd_w(d_x, d_idx, d_g, d_w0, d_b0, d_ws, B, V, V, S, Cin, Cout, st));
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms0, e0, e1));
+        CK(cudaEventRecord(e0));
+        for (int i = 0; i < iters; ++i) ABI(sdvae_spiralconv_bwd_w_tc(d_x, pl.cnt, pl.src, pl.rcap, d_g, d_w1, d_b1, d_ws, B, V, V, S, Cin, Cout, st));
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms1, e0, e1));
+        const double flops = 2.0 * B * V * (double)S * Cin * Cout;
+        printf("time/launch: fma %.3f ms (%.1f TFLOP/s)   tc %.3f ms (%.1f TFLOP/s)   speedup %.2fx\n",
+               ms0 / iters, flops / (ms0 / iters) * 1e-9, ms1 / iters, flops / (ms1 / iters) * 1e-9, ms0 / ms1);
+        const bool ok = maxdiff / maxref < 2e-5 && bdiff / bref < 2e-5;
+        printf(ok ? "CHECK OK\n" : "CHECK FAILED\n");
+        return ok ? 0 : 5;
+    }
     if (!bwdx) {
         std::vector<int> uptr((size_t)V * S + 1);
         for (size_t i = 0; i <= (size_t)V * S; ++i) uptr[i] = (int)i;
