@@ -185,7 +185,7 @@ def tc_pack_weights(weight, wimg, S, Cin, Cout, transposed):
 
 def tc_plan_build(cell_ptr, cell_src, out_rows, S):
     """Host-side tile plan of a cell-form table (NumPy int32 arrays).  Returns
-    ``(cnt [L,S], src [L,S,rcap], cell [L,S,128], rcap)`` as NumPy arrays."""
+    ``(cnt [L,S], src [L,S,rcap/2] (packed), cell [L,S,128], rcap)`` as NumPy arrays."""
     import numpy as np
     lib = load()
     cell_ptr = np.ascontiguousarray(cell_ptr, np.int32)
@@ -196,9 +196,9 @@ def tc_plan_build(cell_ptr, cell_src, out_rows, S):
     mx = int(lib.sdvae_tc_plan_max_rows(cell_ptr.ctypes.data, out_rows, S))
     if mx < 0:
         raise RuntimeError("tc_plan_build: bad table")
-    rcap = max(16, (mx + 15) // 16 * 16)
+    rcap = max(32, (mx + 31) // 32 * 32)
     cnt = np.zeros((L, S), np.int32)
-    src = np.zeros((L, S, rcap), np.int32)
+    src = np.zeros((L, S, rcap // 2), np.int32)       # packed, two 16-bit rows per word
     cell = np.zeros((L, S, 128), np.int32)
     rc = lib.sdvae_tc_plan_build(cell_ptr.ctypes.data, cell_src.ctypes.data, out_rows, S, rcap,
                                  cnt.ctypes.data, src.ctypes.data, cell.ctypes.data)

@@ -99,14 +99,14 @@ static int tc_raw_stages(int S, int KS, int N, int rcap) {
 static bool tc_shape_ok(int S, int KS, int N, int rcap) {
     if (KS != 32 && KS != 64) return false;
     if (N < 1 || tc_tile_n(N) == 0 || S < 1) return false;
-    if (rcap < 16 || rcap > umma::kMaxRcap || rcap % 16 != 0) return false;
-    return tc_raw_stages(S, KS, N, rcap) >= 3;
+    if (rcap < 32 || rcap > umma::kMaxRcap || rcap % 32 != 0) return false;
+    return tc_raw_stages(S, KS, N, rcap) >= 3;      // NS <= NAST <= NRAW: fewer stages = fewer active splitter sets
 }
 
-template <int KS, int NT>
+template <int KS, int NT, bool UNIFORM>
 static int launch_umma(umma::UmmaArgs& ua, cudaStream_t st) {
     using Cfg = umma::UmmaCfg<KS, NT>;
-    auto kern = umma::gc_umma_kernel<KS, NT>;
+    auto kern = umma::gc_umma_kernel<KS, NT, UNIFORM>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -119,15 +119,16 @@ static int launch_umma(umma::UmmaArgs& ua, cudaStream_t st) {
     return check_launch("gc_umma_kernel");
 }
 
+template <bool UNIFORM>
 static int dispatch_umma(umma::UmmaArgs& ua, int KS, cudaStream_t st) {
     if (ua.B <= 0) return SDVAE_OK;
     const int NT = tc_tile_n(ua.n_real);
-    if (KS == 32 && NT == 16) return launch_umma<32, 16>(ua, st);
-    if (KS == 32 && NT == 32) return launch_umma<32, 32>(ua, st);
-    if (KS == 32 && NT == 64) return launch_umma<32, 64>(ua, st);
-    if (KS == 64 && NT == 16) return launch_umma<64, 16>(ua, st);
-    if (KS == 64 && NT == 32) return launch_umma<64, 32>(ua, st);
-    if (KS == 64 && NT == 64) return launch_umma<64, 64>(ua, st);
+    if (KS == 32 && NT == 16) return launch_umma<32, 16, UNIFORM>(ua, st);
+    if (KS == 32 && NT == 32) return launch_umma<32, 32, UNIFORM>(ua, st);
+    if (KS == 32 && NT == 64) return launch_umma<32, 64, UNIFORM>(ua, st);
+    if (KS == 64 && NT == 16) return launch_umma<64, 16, UNIFORM>(ua, st);
+    if (KS == 64 && NT == 32) return launch_umma<64, 32, UNIFORM>(ua, st);
+    if (KS == 64 && NT == 64) return launch_umma<64, 64, UNIFORM>(ua, st);
     return set_error(SDVAE_ERR_UNSUPPORTED, "tcgen05 path: unsupported layer shape");
 }
 
@@ -214,12 +215,12 @@ int sdvae_tc_plan_max_rows(const int32_t* cell_ptr, int out_rows, int S) {
 int sdvae_tc_plan_build(const int32_t* cell_ptr, const int32_t* cell_src, int out_rows, int S,
                         int rcap, int32_t* cnt, int32_t* src, int32_t* cell) {
     SDVAE_REQUIRE(cell_ptr && cell_src && cnt && src && cell, "tc_plan_build: null pointer");
-    SDVAE_REQUIRE(out_rows > 0 && S > 0 && rcap >= 16 && rcap % 16 == 0 && rcap <= umma::kMaxRcap, "tc_plan_build: bad shape");
+    SDVAE_REQUIRE(out_rows > 0 && S > 0 && rcap >= 32 && rcap % 32 == 0 && rcap <= umma::kMaxRcap, "tc_plan_build: bad shape");
     const int L = sdvae_tc_plan_tiles(out_rows);
+    int32_t rows[umma::kMaxRcap];
     for (int jt = 0; jt < L; ++jt)
         for (int s = 0; s < S; ++s) {
             int n = 0;
-            int32_t* srow = src + ((size_t)jt * S + s) * rcap;
             int32_t* crow = cell + ((size_t)jt * S + s) * umma::kBM;
             for (int lr = 0; lr < umma::kBM; ++lr) {
                 const int r = jt * umma::kBM + lr;
@@ -228,13 +229,26 @@ int sdvae_tc_plan_build(const int32_t* cell_ptr, const int32_t* cell_src, int ou
                     const int e0 = cell_ptr[(size_t)r * S + s], e1 = cell_ptr[(size_t)r * S + s + 1];
                     c = e1 - e0;
                     SDVAE_REQUIRE(c >= 0 && n + c <= rcap, "tc_plan_build: a (tile, slot) stages more rows than rcap");
-                    for (int e = e0; e < e1; ++e) srow[n + (e - e0)] = cell_src[e];
+                    for (int e = e0; e < e1; ++e) {
+                        SDVAE_REQUIRE(cell_src[e] >= 0 && cell_src[e] < 65536, "tc_plan_build: source row does not fit 16 bits");
+                        rows[n + (e - e0)] = cell_src[e];
+                    }
                 }
                 crow[lr] = (int32_t)((uint32_t)n | ((uint32_t)c << 16));
                 n += c;
             }
-            for (int e = n; e < rcap; ++e) srow[e] = 0;
+            for (int e = n; e < rcap; ++e) rows[e] = 0;
             cnt[(size_t)jt * S + s] = n;
+            // pack in loader-lane order (umma::plan_fetch): staged row e = 32*j + 4*t + rsub -> word
+            // 16*j + 4*rsub + (t >> 1), low half for even t
+            uint32_t* w = reinterpret_cast<uint32_t*>(src) + ((size_t)jt * S + s) * (rcap / 2);
+            for (int j = 0; 32 * j < rcap; ++j)
+                for (int rsub = 0; rsub < 4; ++rsub)
+                    for (int t = 0; t < 8; t += 2) {
+                        const uint32_t lo = (uint32_t)rows[32 * j + 4 * t + rsub];
+                        const uint32_t hi = (uint32_t)rows[32 * j + 4 * (t + 1) + rsub];
+                        w[16 * j + 4 * rsub + (t >> 1)] = lo | (hi << 16);
+                    }
         }
     return SDVAE_OK;
 }
@@ -242,8 +256,8 @@ int sdvae_tc_plan_build(const int32_t* cell_ptr, const int32_t* cell_src, int ou
 static int tc_conv(const float* in, const int32_t* plan_cnt, const int32_t* plan_src,
                    const int32_t* plan_cell, int rcap, const float* wimg, const float* bias,
                    const float* gate, float* out, int B, int in_rows, int out_rows, int S, int KS,
-                   int N, int epi, cudaStream_t st, const char* who) {
-    SDVAE_REQUIRE(in && plan_cnt && plan_src && plan_cell && wimg && out, "spiralconv tc: null pointer");
+                   int N, int epi, bool uniform, cudaStream_t st, const char* who) {
+    SDVAE_REQUIRE(in && plan_cnt && plan_src && (uniform || plan_cell) && wimg && out, "spiralconv tc: null pointer");
     SDVAE_REQUIRE(B >= 0 && in_rows > 0 && out_rows > 0 && S > 0 && KS > 0 && N > 0, "spiralconv tc: bad shape");
     SDVAE_REQUIRE((long long)B * in_rows < 2147483647LL, "spiralconv tc: B*rows exceeds int32");
     SDVAE_REQUIRE(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(wimg)) & 15) == 0,
@@ -259,7 +273,7 @@ static int tc_conv(const float* in, const int32_t* plan_cnt, const int32_t* plan
     ua.wimg = wimg; ua.bias = bias; ua.gate = gate; ua.out = out;
     ua.B = B; ua.in_rows = in_rows; ua.out_rows = out_rows; ua.L = sdvae_tc_plan_tiles(out_rows);
     ua.S = S; ua.rcap = rcap; ua.n_real = N; ua.ldo = N; ua.epi = epi;
-    return dispatch_umma(ua, KS, st);
+    return uniform ? dispatch_umma<true>(ua, KS, st) : dispatch_umma<false>(ua, KS, st);
 }
 
 int sdvae_spiralconv_fwd_tc(const float* x, const int32_t* plan_cnt, const int32_t* plan_src,
@@ -268,7 +282,7 @@ int sdvae_spiralconv_fwd_tc(const float* x, const int32_t* plan_cnt, const int32
                             sdvae_stream_t stream) {
     const int epi = act == SDVAE_ACT_ELU ? EPI_BIAS_ELU : EPI_BIAS;
     return tc_conv(x, plan_cnt, plan_src, plan_cell, rcap, wimg, bias, nullptr, y, B, Vin, Vout, S, Cin,
-                   Cout, epi, (cudaStream_t)stream, "spiralconv_fwd_tc: unsupported layer shape");
+                   Cout, epi, true, (cudaStream_t)stream, "spiralconv_fwd_tc: unsupported layer shape");
 }
 
 int sdvae_spiralconv_bwd_x_tc(const float* dpre, const int32_t* plan_cnt, const int32_t* plan_src,
@@ -276,13 +290,13 @@ int sdvae_spiralconv_bwd_x_tc(const float* dpre, const int32_t* plan_cnt, const 
                               float* dx, int B, int Vrows, int Vdst, int S, int Cout, int Cin,
                               sdvae_stream_t stream) {
     return tc_conv(dpre, plan_cnt, plan_src, plan_cell, rcap, wimg_t, nullptr, gate, dx, B, Vrows, Vdst, S,
-                   Cout, Cin, gate ? EPI_GATE : EPI_NONE, (cudaStream_t)stream,
+                   Cout, Cin, gate ? EPI_GATE : EPI_NONE, false, (cudaStream_t)stream,
                    "spiralconv_bwd_x_tc: unsupported layer shape");
 }
 
 int sdvae_tc_bwd_w_supported(int S, int Cin, int Cout, int rcap) {
     if (Cin != 32 || Cout < 1 || Cout > umma::kBwNT || S < 1 || S > 11) return 0;
-    if (rcap < 16 || rcap > umma::kMaxRcap || rcap % 16 != 0) return 0;
+    if (rcap < 32 || rcap > umma::kMaxRcap || rcap % 32 != 0) return 0;
     const long long budget = 226LL * 1024 - 2048 - 2 * umma::kGStage;
     return budget / ((long long)rcap * 128) >= 7 ? 1 : 0;       // the phase-distance argument needs 7 raw stages
 }
@@ -325,7 +339,7 @@ int sdvae_spiralconv_bwd_w_tc(const float* x, const int32_t* plan_cnt, const int
         attr_done = true;
     }
     const size_t smem = 1024 + 2 * (size_t)umma::kGStage + (size_t)a.nraw * rcap * 128 + 1024;
-    umma::bw_umma_kernel<<<grid, umma::kThreads, smem, st>>>(a);
+    umma::bw_umma_kernel<<<grid, umma::kBwThreads, smem, st>>>(a);
     int rc = check_launch("bw_umma_kernel");
     if (rc) return rc;
     const long long len = (long long)Cout * K;

@@ -17,13 +17,18 @@
 // rows of a mesh and every spiral slot, the list of source rows to stage and, per output row,
 // the [start, count) range of staged rows whose sum is that row's A-operand cell.
 //
-// Persistent, warp-specialised CTA (one per SM, 20 warps):
-//   warp 19      : TMEM allocation, MMA issue (one elected lane), tcgen05.commit -> mbarriers
+// Persistent, warp-specialised CTA (one per SM, 28 warps; register budgets moved between the
+// roles with setmaxnreg):
 //   warps 0..3   : epilogue: tcgen05.ld accumulator -> bias/ELU/ELU'-gate -> global
-//   warps 4..11  : splitters: staged rows (LDS.128, conflict-free through the 128B swizzle) -> in-order
-//                  sum -> hi/lo split in registers -> tcgen05.st into the TMEM A-operand ring
-//   warps 12..18 : loaders: cp.async 16 B (8 lanes per 128-byte row piece) into the raw shared-memory ring,
-//                  several chunks in flight (cp.async groups), no register staging
+//   warps 4..19  : splitters, four sets of four warps (warp % 4 = TMEM lane quarter), set k takes the chunks
+//                  g = k (mod 4): staged rows (LDS.128, conflict-free through the 128B swizzle) -> in-order
+//                  sum (backward plans) -> hi/lo split in registers -> tcgen05.st into the TMEM A ring.
+//                  ncu (profiles/r01_gc_umma_stalls.txt) showed this role latency-bound with two sets:
+//                  one instruction per ~13 clk per warp, nothing else above 55 % -- hence four sets and a
+//                  straight-line forward variant (one staged row per tile row, no cell table)
+//   warps 20..26 : loaders: cp.async 16 B (8 lanes per 128-byte row piece) into the raw shared-memory ring,
+//                  one chunk in flight per warp, no register staging
+//   warp 27      : TMEM allocation, MMA issue (one elected lane), tcgen05.commit -> mbarriers
 // A never passes through shared memory on its way into the MMA (TS form: A from TMEM, B from
 // shared memory), so no generic->async proxy fence sits on the gather path.  The weight image
 // (split and laid out by umma_pack_weights_kernel) stays resident in shared memory.
@@ -40,19 +45,24 @@ namespace sdvae {
 namespace umma {
 
 constexpr int kEpilogueWarps = 4;
-constexpr int kSplitWarps = 8;
+constexpr int kSplitSets = 4;
+constexpr int kSplitWarps = 4 * kSplitSets;
 constexpr int kLoadWarps = 7;
 constexpr int kFirstEpilogueWarp = 0;
 constexpr int kFirstSplitWarp = kFirstEpilogueWarp + kEpilogueWarps;      // 4
-constexpr int kFirstLoadWarp = kFirstSplitWarp + kSplitWarps;             // 12
-constexpr int kMmaWarp = kFirstLoadWarp + kLoadWarps;                     // 19: the issuer gets the highest warp id (scheduler priority)
-constexpr int kThreads = (kMmaWarp + 1) * 32;                             // 640
-constexpr int kLoadThreads = kLoadWarps * 32;                             // 224
-constexpr int kLoadRows = kLoadThreads / 8;                               // staged rows covered per pass (8 lanes per row)
+constexpr int kFirstLoadWarp = kFirstSplitWarp + kSplitWarps;             // 20
+constexpr int kMmaWarp = kFirstLoadWarp + kLoadWarps;                     // 27: the issuer gets the highest warp id
+constexpr int kThreads = (kMmaWarp + 1) * 32;                             // 896 -> 72 registers per thread at launch
+// setmaxnreg budgets per warpgroup: 128*56 + 512*80 + 256*64 = 64512 = 896*72
+#ifndef SDVAE_REGS_EPI
+#define SDVAE_REGS_EPI 56
+#define SDVAE_REGS_SPLIT 80
+#define SDVAE_REGS_LOAD 64
+#endif
+constexpr int kRegsEpilogue = SDVAE_REGS_EPI, kRegsSplit = SDVAE_REGS_SPLIT, kRegsLoad = SDVAE_REGS_LOAD;
 constexpr int kBM = 128;                  // rows per tile (UMMA M)
-constexpr int kAStages = 4;               // TMEM A-operand ring (64 columns each: 32 hi + 32 lo)
-constexpr int kAColBase = 256;            // TMEM columns [0,256): accumulators, [256,512): A ring
-constexpr int kTmemCols = 512;
+constexpr int kMaxAStages = 7;            // TMEM A-operand ring depth limit (64 columns each: 32 hi + 32 lo)
+constexpr int kTmemCols = 512;            // [0, 4*NT): two accumulators, [4*NT, 512): A ring
 constexpr int kMaxRcap = 192;             // staged rows per (tile, slot) the kernel supports
 constexpr int kMaxRaw = kLoadWarps;       // raw ring depth limit: loader warp w owns raw stage w
 constexpr uint32_t kSuspendHintNs = 100000;          // mbarrier.try_wait suspend-time hint
@@ -111,6 +121,14 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n.reg .b32 rx;\n.reg .pred px;\nelect.sync rx|px, 0xffffffff;\n@px mov.s32 %0, 1;\n}\n" : "+r"(pred));
     return pred != 0;
 }
+
+#ifdef SDVAE_NO_SETMAXNREG
+template <int N> __device__ __forceinline__ void reg_inc() {}
+template <int N> __device__ __forceinline__ void reg_dec() {}
+#else
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+#endif
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
@@ -179,6 +197,47 @@ __device__ __forceinline__ void split_tf32f(float x, float& hi, float& lo) {
 // byte offset of the 16-byte column q of row r inside a [rows x 128 B] SWIZZLE_128B tile
 __host__ __device__ __forceinline__ int sw128_off(int r, int q) { return r * 128 + ((q ^ (r & 7)) << 4); }
 
+// ---- loader: packed plan + cp.async issue ------------------------------------------------------
+// plan_src is PACKED: per (tile, slot) rcap/2 32-bit words (rcap a multiple of 32), two 16-bit source
+// rows per word, in the order the loader lanes consume them: lane (rsub = lane >> 3, q = lane & 7) copies
+// the 16-byte piece q of the staged rows e = 32*j + 4*t + rsub (t = 0..7) of every group j of 32 rows, and
+// finds those eight rows in the four consecutive words 16*j + 4*rsub + (t >> 1) (low half = even t): one
+// 16-byte load per lane and group, no shuffles, no per-lane predicates (entries past the count are row 0,
+// a valid address; their staged rows are never read).  Per cp.async that leaves: extract, one IMAD.WIDE,
+// LDGSTS -- the shuffle-based loader spent ~9 instructions per copy and bounded the kernel.
+template <int PV>
+struct PlanRegs { uint4 w[PV]; int n; };
+
+template <int PV>
+__device__ __forceinline__ void plan_fetch(PlanRegs<PV>& p, const int* plan_cnt, const int* plan_src,
+                                           int jt, int S, int s, int rcap, int rsub) {
+    p.n = __ldg(plan_cnt + jt * S + s);
+    const uint4* src = reinterpret_cast<const uint4*>(plan_src + ((size_t)jt * S + s) * (rcap >> 1)) + rsub;
+#pragma unroll
+    for (int j = 0; j < PV; ++j) p.w[j] = (32 * j < rcap) ? __ldg(src + 4 * j) : make_uint4(0u, 0u, 0u, 0u);
+}
+
+// dst0/dst1: shared address of staged row rsub, swizzled 16-byte column of the even / odd t rows;
+// base: global address of piece q of row 0; row_bytes: bytes per source row
+template <int PV>
+__device__ __forceinline__ void plan_issue(const PlanRegs<PV>& p, uint32_t dst0, uint32_t dst1,
+                                           const float* base, uint32_t row_bytes) {
+    const char* gb = reinterpret_cast<const char*>(base);
+#pragma unroll
+    for (int j = 0; j < PV; ++j) {
+        if (32 * j < p.n) {
+            const uint32_t w[4] = {p.w[j].x, p.w[j].y, p.w[j].z, p.w[j].w};
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const uint32_t row = (t & 1) ? (w[t >> 1] >> 16) : (w[t >> 1] & 0xffffu);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n"
+                             ::"r"(((t & 1) ? dst1 : dst0) + (uint32_t)(32 * j + 4 * t) * 128u),
+                               "l"(gb + (size_t)row * row_bytes));
+            }
+        }
+    }
+}
+
 // ---- weight image ----------------------------------------------------------------------------
 // img[chunk][j][32]:  j < NT -> hi part of W row j,  j >= NT -> lo part of row j-NT; rows >= n_real
 // are zero.  `transposed` selects the backward-to-input weight  Wt[c, s*Cout + o] = W[o, s*Cin + c]
@@ -220,7 +279,7 @@ __global__ void umma_pack_weights_kernel(const PackArgs a) {
 struct UmmaArgs {
     const float* in;          // [B, in_rows, KS]
     const int* plan_cnt;      // [L, S]            staged rows of (tile, slot)
-    const int* plan_src;      // [L, S, rcap]      source row (within the mesh) of each staged row
+    const int* plan_src;      // [L, S, rcap/2]    packed source rows of the staged rows (see plan_fetch)
     const int* plan_cell;     // [L, S, 128]       start | count << 16 : staged rows summed into tile row lr
     const float* wimg;        // packed weight image
     const float* bias;        // [n_real] or nullptr
@@ -232,8 +291,8 @@ struct UmmaArgs {
 };
 
 
-// Position of a CTA in its static schedule: chunk g = (tile iteration it, chunk ch of the tile),
-// kept incrementally so that the per-chunk role loops contain no integer division.
+// Position of a role in the CTA's static schedule: chunk g = (tile iteration, chunk ch of the tile),
+// kept incrementally (no integer division in the per-chunk loops).  `step` chunks per advance.
 struct ChunkCursor {
     int g, ch, b, jt, rs, as;
     uint32_t rph, aph;
@@ -243,12 +302,13 @@ struct ChunkCursor {
         b = (int)blockIdx.x / L; jt = (int)blockIdx.x - b * L;
         db = (int)gridDim.x / L; djt = (int)gridDim.x - db * L;       // tile stride, split into (mesh, tile-in-mesh)
     }
-    __device__ __forceinline__ void advance() {
-        ++g;
-        if (++rs == nraw) { rs = 0; rph ^= 1; }
-        if (++as == nast) { as = 0; aph ^= 1; }
-        if (++ch == nch) {
-            ch = 0; b += db; jt += djt;
+    __device__ __forceinline__ void advance(int step) {
+        g += step;
+        rs += step; while (rs >= nraw) { rs -= nraw; rph ^= 1; }
+        as += step; while (as >= nast) { as -= nast; aph ^= 1; }
+        ch += step;
+        while (ch >= nch) {
+            ch -= nch; b += db; jt += djt;
             if (jt >= L) { jt -= L; ++b; }
         }
     }
@@ -258,6 +318,8 @@ template <int KS, int NT>
 struct UmmaCfg {
     static constexpr int CPS = KS / 32;                  // 32-wide chunks per spiral slot
     static constexpr int B_CHUNK = 2 * NT * 128;
+    static constexpr int ACC_COLS = 4 * NT;              // two accumulators of 2*NT columns
+    static constexpr int MAX_AST = (kTmemCols - ACC_COLS) / 64 < kMaxAStages ? (kTmemCols - ACC_COLS) / 64 : kMaxAStages;
     static size_t b_bytes(int S) { return (size_t)S * CPS * B_CHUNK; }
     static int raw_stages(int S, int rcap) {
         const long long budget = 226LL * 1024 - 1024 /*align*/ - 1024 /*barriers*/ - (long long)b_bytes(S);
@@ -269,19 +331,23 @@ struct UmmaCfg {
     }
 };
 
-template <int KS, int NT>
+// UNIFORM: forward tile plan (staged row e of a (tile, slot) IS tile row e): the splitter needs no cell table
+template <int KS, int NT, bool UNIFORM>
 __global__ void __launch_bounds__(kThreads, 1)
 gc_umma_kernel(const UmmaArgs a) {
     using Cfg = UmmaCfg<KS, NT>;
-    constexpr int CPS = Cfg::CPS, B_CHUNK = Cfg::B_CHUNK;
-    static_assert(4 * NT <= kAColBase, "accumulators overlap the A ring");
+    constexpr int CPS = Cfg::CPS, B_CHUNK = Cfg::B_CHUNK, ACOL = Cfg::ACC_COLS;
     const int S = a.S;
     const int NCH = S * CPS;
     const int NRAW = a.nraw;
-    // TMEM A-ring depth.  The parity waits need every waiter within one phase of its barrier: a splitter
-    // runs at most NAST chunks ahead of the (in-order) MMA, so NAST <= NRAW keeps chunk g - NRAW loaded
-    // before anyone waits for chunk g on the same raw stage.
-    const int NAST = NRAW < kAStages ? NRAW : kAStages;
+    // TMEM A-ring depth and the number of active splitter sets.  The parity waits need every waiter within
+    // one phase of its barrier:
+    //  * a set handles every NS-th chunk, so before it waits for the MMAs of chunk g - NAST (a_empty) it has
+    //    seen those of chunk g - NS - NAST complete; NS <= NAST keeps that within one phase;
+    //  * once the MMAs of chunk g - NAST are done every chunk up to g - NAST has been loaded; NAST <= NRAW
+    //    then keeps the raw barrier of chunk g's stage at most one phase behind its waiter.
+    const int NAST = NRAW < Cfg::MAX_AST ? NRAW : Cfg::MAX_AST;
+    const int NS = NAST < kSplitSets ? NAST : kSplitSets;
     const int RAW_STAGE = a.rcap * 128;
 
     extern __shared__ uint8_t smem_raw[];
@@ -290,12 +356,12 @@ gc_umma_kernel(const UmmaArgs a) {
     uint8_t* B_s = smem;                                   // [NCH][2NT][128 B]   resident weight image
     uint8_t* R_s = B_s + (size_t)NCH * B_CHUNK;            // [NRAW][rcap][128 B] staged source rows (swizzled)
     uint64_t* bars = reinterpret_cast<uint64_t*>(R_s + (size_t)NRAW * RAW_STAGE);
-    uint64_t* raw_full = bars;                             // [NRAW]     loaders  -> splitters
-    uint64_t* raw_empty = bars + kMaxRaw;                  // [NRAW]     splitters -> loaders
-    uint64_t* a_full = bars + 2 * kMaxRaw;                 // [kAStages] splitters -> MMA
-    uint64_t* a_empty = a_full + kAStages;                 // [kAStages] MMA (commit) -> splitters
-    uint64_t* t_full = a_empty + kAStages;                 // [2]        MMA (commit) -> epilogue
-    uint64_t* t_empty = t_full + 2;                        // [2]        epilogue -> MMA
+    uint64_t* raw_full = bars;                             // [NRAW]  loaders   -> splitters
+    uint64_t* raw_empty = bars + kMaxRaw;                  // [NRAW]  splitters -> loaders
+    uint64_t* a_full = bars + 2 * kMaxRaw;                 // [NAST]  splitters -> MMA
+    uint64_t* a_empty = a_full + kMaxAStages;              // [NAST]  MMA (commit) -> splitters
+    uint64_t* t_full = a_empty + kMaxAStages;              // [2]     MMA (commit) -> epilogue
+    uint64_t* t_empty = t_full + 2;                        // [2]     epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -303,7 +369,7 @@ gc_umma_kernel(const UmmaArgs a) {
     // ---- one-time setup ---------------------------------------------------------------------
     if (tid == 0) {
         for (int i = 0; i < NRAW; ++i) { mbar_init(raw_full + i, 32); mbar_init(raw_empty + i, 128); }
-        for (int i = 0; i < kAStages; ++i) { mbar_init(a_full + i, 128); mbar_init(a_empty + i, 1); }
+        for (int i = 0; i < kMaxAStages; ++i) { mbar_init(a_full + i, 128); mbar_init(a_empty + i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, kEpilogueWarps * 32); }
         fence_barrier_init();
     }
@@ -329,41 +395,80 @@ gc_umma_kernel(const UmmaArgs a) {
     const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int G = my_tiles * NCH;                           // chunks this CTA processes
 
-    if (warp == kMmaWarp) {
-        // ================= MMA issuer =================
-        // the whole warp walks the schedule and waits on the barriers; one elected lane issues
-        constexpr uint32_t IDESC1 = idesc_tf32(kBM, 2 * NT);
-        constexpr uint32_t IDESC2 = idesc_tf32(kBM, NT);
-        const bool leader = elect_one();
-        const uint32_t b_base = smem_u32(B_s);
-        int as = 0; uint32_t aph = 0;
+    if (warp >= kFirstLoadWarp) {
+        reg_dec<kRegsLoad>();
+        if (warp == kMmaWarp) {
+            // ================= MMA issuer =================
+            // the whole warp walks the schedule and waits on the barriers; one elected lane issues
+            constexpr uint32_t IDESC1 = idesc_tf32(kBM, 2 * NT);
+            constexpr uint32_t IDESC2 = idesc_tf32(kBM, NT);
+            const bool leader = elect_one();
+            const uint32_t b_base = smem_u32(B_s);
+            int as = 0; uint32_t aph = 0;
 #pragma unroll 1
-        for (int it = 0; it < my_tiles; ++it) {
-            const int acc = it & 1;
-            mbar_wait(t_empty + acc, ((it >> 1) & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * NT);
-#pragma unroll 1
-            for (int ch = 0; ch < NCH; ++ch) {
-                mbar_wait(a_full + as, aph);
+            for (int it = 0; it < my_tiles; ++it) {
+                const int acc = it & 1;
+                mbar_wait(t_empty + acc, ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
-                if (leader) {
-                    const uint32_t a_hi = tmem_base + (uint32_t)(kAColBase + as * 64), a_lo = a_hi + 32;
-                    const uint32_t b_ch = b_base + ch * B_CHUNK;
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * NT);
+#pragma unroll 1
+                for (int ch = 0; ch < NCH; ++ch) {
+                    mbar_wait(a_full + as, aph);
+                    tc_fence_after();
+                    if (leader) {
+                        const uint32_t a_hi = tmem_base + (uint32_t)(ACOL + as * 64), a_lo = a_hi + 32;
+                        const uint32_t b_ch = b_base + ch * B_CHUNK;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t bd = smem_desc_sw128(b_ch + k * 32);
-                        umma_tf32_ts(d_tmem, a_hi + k * 8, bd, IDESC1, (ch | k) != 0);
-                        umma_tf32_ts(d_tmem, a_lo + k * 8, bd, IDESC2, 1u);
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t bd = smem_desc_sw128(b_ch + k * 32);
+                            umma_tf32_ts(d_tmem, a_hi + k * 8, bd, IDESC1, (ch | k) != 0);
+                            umma_tf32_ts(d_tmem, a_lo + k * 8, bd, IDESC2, 1u);
+                        }
+                        umma_commit(a_empty + as);
+                        if (ch == NCH - 1) umma_commit(t_full + acc);
                     }
-                    umma_commit(a_empty + as);
-                    if (ch == NCH - 1) umma_commit(t_full + acc);
+                    __syncwarp();
+                    if (++as == NAST) { as = 0; aph ^= 1; }
                 }
-                __syncwarp();
-                if (++as == NAST) { as = 0; aph ^= 1; }
+            }
+        } else {
+            // ================= loaders =================
+            // loader warp w (< NRAW) owns raw stage w and takes the chunks g = w (mod NRAW) whole: 4 staged rows
+            // per cp.async instruction (8 lanes x 16 B per row piece), the per-chunk bookkeeping is paid by one
+            // warp, and the warps together keep NRAW chunks in flight.  (One stage per warp also keeps every
+            // waiter within one phase of its mbarrier, which the parity wait requires.)
+            const int lw = warp - kFirstLoadWarp;
+            const int q = lane & 7, rsub = lane >> 3;
+            const uint32_t sw0 = (uint32_t)((q ^ rsub) << 4), sw1 = (uint32_t)((q ^ (rsub + 4)) << 4);
+            const uint32_t raw_base = smem_u32(R_s) + (uint32_t)rsub * 128u;
+            ChunkCursor cur(a, NCH, NRAW, NAST);
+            cur.advance(lw);
+            if (lw >= NRAW) cur.g = G;                                // more loader warps than stages: idle
+            // Forward plans stage <= 128 rows per chunk: their plan words are fetched one own-chunk ahead, so
+            // the issue loop never waits for them.  Backward plans (up to kMaxRcap rows) fetch at chunk start.
+            constexpr int PV = UNIFORM ? 4 : kMaxRcap / 32;
+            PlanRegs<PV> nxt;
+            if (UNIFORM && cur.g < G) plan_fetch(nxt, a.plan_cnt, a.plan_src, cur.jt, S, cur.ch / CPS, a.rcap, rsub);
+#pragma unroll 1
+            while (cur.g < G) {
+                PlanRegs<PV> now;
+                if (UNIFORM) now = nxt;
+                else plan_fetch(now, a.plan_cnt, a.plan_src, cur.jt, S, cur.ch / CPS, a.rcap, rsub);
+                const int rs = cur.rs, h = cur.ch % CPS;
+                const uint32_t rph = cur.rph;
+                const float* base = a.in + (size_t)cur.b * a.in_rows * KS + h * 32 + 4 * q;
+                cur.advance(NRAW);
+                if (UNIFORM && cur.g < G) plan_fetch(nxt, a.plan_cnt, a.plan_src, cur.jt, S, cur.ch / CPS, a.rcap, rsub);
+                mbar_wait(raw_empty + rs, rph ^ 1);
+                const uint32_t dst = raw_base + (uint32_t)rs * (uint32_t)RAW_STAGE;
+                plan_issue(now, dst + sw0, dst + sw1, base, KS * 4u);
+                cp_async_commit();
+                cp_async_wait<0>();
+                mbar_arrive(raw_full + rs);
             }
         }
     } else if (warp < kFirstSplitWarp) {
+        reg_dec<kRegsEpilogue>();
         // ================= epilogue =================
         const int q4 = warp & 3;                                  // TMEM lane quarter this warp may access
         const int EPI = a.epi;
@@ -372,10 +477,10 @@ gc_umma_kernel(const UmmaArgs a) {
         // NT >= 32: full-width rows, 16-byte accesses (the host checks n_real == NT and the alignments);
         // NT == 16: narrow outputs (e.g. the 3-channel output layer), scalar tail
         constexpr bool vec_ok = NT >= 32;
+        int b = (int)blockIdx.x / a.L, jt = (int)blockIdx.x - b * a.L;
+        const int db = (int)gridDim.x / a.L, djt = (int)gridDim.x - db * a.L;
 #pragma unroll 1
         for (int it = 0; it < my_tiles; ++it) {
-            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-            const int b = tile / a.L, jt = tile - b * a.L;
             const int acc = it & 1;
             mbar_wait(t_full + acc, (it >> 1) & 1);
             tc_fence_after();
@@ -439,99 +544,74 @@ gc_umma_kernel(const UmmaArgs a) {
                     }
                 }
             }
-        }
-    } else if (warp < kFirstLoadWarp) {
-        // ================= splitters =================
-        // warps 4..7 take the even chunks, warps 8..11 the odd ones; warp % 4 = TMEM lane quarter
-        const int set = (warp - kFirstSplitWarp) >> 2;
-        const int q4 = warp & 3;
-        const int lr = q4 * 32 + lane;                            // tile row owned by this thread
-        ChunkCursor cur(a, NCH, NRAW, NAST);                      // chunk being processed
-        ChunkCursor pre(a, NCH, NRAW, NAST);                      // chunk whose plan entry is prefetched
-        if (set) { cur.advance(); pre.advance(); }
-        auto cell_of = [&](const ChunkCursor& c) -> uint32_t {
-            return (uint32_t)__ldg(a.plan_cell + ((size_t)c.jt * S + c.ch / CPS) * kBM + lr);
-        };
-        uint32_t cell = cur.g < G ? cell_of(pre) : 0u;
-#pragma unroll 1
-        for (; cur.g < G; cur.advance(), cur.advance()) {
-            pre.advance(); pre.advance();
-            const uint32_t cell_next = pre.g < G ? cell_of(pre) : 0u;         // one own-chunk ahead
-            const int e0 = (int)(cell & 0xffffu), cnt = (int)(cell >> 16);
-            const int rs = cur.rs;
-            const int as = cur.as;
-            const uint32_t aph = cur.aph;
-
-            // Order matters: once the MMAs of chunk g - NAST are done (a_empty), every chunk up to g - NAST
-            // has been loaded, so the raw barrier of this stage is at most one phase behind this waiter.
-            mbar_wait(a_empty + as, aph ^ 1);
-            mbar_wait(raw_full + rs, cur.rph);
-            const uint8_t* stage = R_s + (size_t)rs * RAW_STAGE;
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
-#pragma unroll 1
-            for (int e = e0; e < e0 + cnt; ++e) {                 // in-order sum: deterministic scatter-add
-                const uint8_t* row = stage + e * 128;
-                const int x7 = e & 7;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 t = *reinterpret_cast<const float4*>(row + ((j ^ x7) << 4));
-                    v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
-                }
-            }
-            float lo[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { float h; split_tf32f(v[j], h, lo[j]); v[j] = h; }
-            tc_fence_after();
-            const uint32_t t_a = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(kAColBase + as * 64);
-            tmem_st32(t_a, v);
-            tmem_st32(t_a + 32, lo);
-            mbar_arrive(raw_empty + rs);          // the staged rows are in registers (consumed by the stores above)
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(a_full + as);
-            cell = cell_next;
+            b += db; jt += djt;
+            if (jt >= a.L) { jt -= a.L; ++b; }
         }
     } else {
-        // ================= loaders =================
-        // loader warp w (< NRAW) owns raw stage w and takes the chunks g = w (mod NRAW) whole: 4 staged rows
-        // per cp.async instruction (8 lanes x 16 B per row piece), the per-chunk bookkeeping is paid by one
-        // warp, and the warps together keep NRAW chunks in flight.  (One stage per warp also keeps every
-        // waiter within one phase of its mbarrier, which the parity wait requires.)
-        const int lw = warp - kFirstLoadWarp;
-        const int q = lane & 7, rsub = lane >> 3;
-        const uint32_t sw0 = (uint32_t)((q ^ rsub) << 4), sw1 = (uint32_t)((q ^ (rsub + 4)) << 4);
-        const uint32_t raw_base = smem_u32(R_s) + (uint32_t)rsub * 128u;
-        ChunkCursor cur(a, NCH, NRAW, NAST);
-        for (int i = 0; i < lw; ++i) cur.advance();
-        if (lw >= NRAW) cur.g = G;                                // more loader warps than stages: idle
+        reg_inc<kRegsSplit>();
+        // ================= splitters =================
+        const int set = (warp - kFirstSplitWarp) >> 2;            // chunks g = set (mod NS)
+        const int q4 = warp & 3;                                  // TMEM lane quarter
+        const int lr = q4 * 32 + lane;                            // tile row owned by this thread
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)ACOL;
+        if (set < NS) {
+            ChunkCursor cur(a, NCH, NRAW, NAST);                  // chunk being processed
+            cur.advance(set);
+            uint32_t cell = 0u;
+            if (!UNIFORM && cur.g < G)
+                cell = (uint32_t)__ldg(a.plan_cell + ((size_t)cur.jt * S + cur.ch / CPS) * kBM + lr);
 #pragma unroll 1
-        while (cur.g < G) {
-            const int s = cur.ch / CPS, h = cur.ch % CPS;
-            const int n = __ldg(a.plan_cnt + cur.jt * S + s);
-            const int* src = a.plan_src + ((size_t)cur.jt * S + s) * a.rcap + lane;   // entry 32*j + lane
-            int pv = __ldg(src);
-            mbar_wait(raw_empty + cur.rs, cur.rph ^ 1);
-            const uint32_t dst = raw_base + (uint32_t)cur.rs * (uint32_t)RAW_STAGE;
-            const float* base = a.in + (size_t)cur.b * a.in_rows * KS + h * 32 + 4 * q;
-#pragma unroll 1
-            for (int j = 0; 32 * j < n; ++j) {
-                const int pn = 32 * (j + 1) < n ? __ldg(src + 32 * (j + 1)) : 0;     // next 32 plan entries
+            while (cur.g < G) {
+                const int rs = cur.rs, as = cur.as;
+                const uint32_t rph = cur.rph, aph = cur.aph;
+                cur.advance(NS);
+                uint32_t cell_next = 0u;                          // one own-chunk ahead
+                if (!UNIFORM && cur.g < G)
+                    cell_next = (uint32_t)__ldg(a.plan_cell + ((size_t)cur.jt * S + cur.ch / CPS) * kBM + lr);
+                // Order matters (see NAST above): a_empty first, then the raw stage.
+                mbar_wait(a_empty + as, aph ^ 1);
+                mbar_wait(raw_full + rs, rph);
+                const uint8_t* stage = R_s + (size_t)rs * RAW_STAGE;
+                float v[32];
+                if (UNIFORM) {
+                    // rows past the end of the mesh were never staged: their A rows are garbage, and so are the
+                    // matching accumulator rows, which the epilogue never stores (MMA rows are independent)
+                    // (a stage holds rcap rows: small tables have rcap < 128, and rows >= rcap lie outside it)
+                    const uint8_t* row = stage + (lr < a.rcap ? lr : 0) * 128;
+                    const int x7 = lr & 7;
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    const int sr = __shfl_sync(0xffffffffu, pv, 4 * t + rsub);
-                    if (32 * j + 4 * t + rsub < n)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n"
-                                     ::"r"(dst + (uint32_t)(32 * j + 4 * t) * 128u + ((t & 1) ? sw1 : sw0)),
-                                       "l"(base + (size_t)sr * KS));
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 t = *reinterpret_cast<const float4*>(row + ((j ^ x7) << 4));
+                        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+                    }
+                } else {
+                    const int e0 = (int)(cell & 0xffffu), cnt = (int)(cell >> 16);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+#pragma unroll 1
+                    for (int e = e0; e < e0 + cnt; ++e) {             // in-order sum: deterministic scatter-add
+                        const uint8_t* row = stage + e * 128;
+                        const int x7 = e & 7;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 t = *reinterpret_cast<const float4*>(row + ((j ^ x7) << 4));
+                            v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+                        }
+                    }
                 }
-                pv = pn;
+                float lo[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { float h; split_tf32f(v[j], h, lo[j]); v[j] = h; }
+                tc_fence_after();
+                const uint32_t t_a = t_lane + (uint32_t)(as * 64);
+                tmem_st32(t_a, v);
+                tmem_st32(t_a + 32, lo);
+                mbar_arrive(raw_empty + rs);          // the staged rows are in registers (consumed by the stores above)
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(a_full + as);
+                cell = cell_next;
             }
-            cp_async_commit();
-            cp_async_wait<0>();
-            mbar_arrive(raw_full + cur.rs);
-            for (int i = 0; i < NRAW; ++i) cur.advance();
         }
     }
 

@@ -30,12 +30,20 @@ namespace sdvae {
 namespace umma {
 
 constexpr int kBwNT = 32;                 // output channels per tile (n_real <= 32)
+// warp roles of this kernel (20 warps): 0..3 g staging + drain, 4..11 splitters, 12..18 loaders, 19 MMA
+constexpr int kBwEpilogueWarps = 4;
+constexpr int kBwFirstSplitWarp = 4;
+constexpr int kBwFirstLoadWarp = 12;
+constexpr int kBwMmaWarp = 19;
+constexpr int kBwThreads = (kBwMmaWarp + 1) * 32;
+constexpr int kBwAStages = 4;             // TMEM A-operand ring (64 columns each: 32 hi + 32 lo)
+constexpr int kBwAColBase = 256;          // TMEM columns [0,192): two accumulator sets, [256,512): A ring
 constexpr int kGStage = 16 * 2048;        // 16 K-atoms x (hi atom + lo atom)
 
 struct BwUmmaArgs {
     const float* in;          // [B, in_rows, 32]
     const int* plan_cnt;      // [L, S]        forward tile plan: one staged row per tile row, in row order
-    const int* plan_src;      // [L, S, rcap]
+    const int* plan_src;      // [L, S, rcap/2]  packed (plan_fetch)
     const float* g;           // [B, out_rows, n_real]   gradient w.r.t. the pre-activation
     float* part;              // [grid, n_real, S*32]   zero-initialised by the caller
     float* part_b;            // [grid, n_real]         zero-initialised by the caller
@@ -61,7 +69,7 @@ __host__ __device__ constexpr uint32_t idesc_tf32_bmn(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kBwThreads, 1)
 bw_umma_kernel(const BwUmmaArgs a) {
     const int S = a.S;
     const int NRAW = a.nraw;
@@ -79,8 +87,8 @@ bw_umma_kernel(const BwUmmaArgs a) {
     uint64_t* raw_full = bars;
     uint64_t* raw_empty = bars + kMaxRaw;
     uint64_t* a_full = bars + 2 * kMaxRaw;
-    uint64_t* a_empty = a_full + kAStages;
-    uint64_t* g_full = a_empty + kAStages;                 // [2] g warps -> MMA
+    uint64_t* a_empty = a_full + kBwAStages;
+    uint64_t* g_full = a_empty + kBwAStages;                 // [2] g warps -> MMA
     uint64_t* g_empty = g_full + 2;                        // [2] MMA (commit) -> g warps
     uint64_t* done_bar = g_empty + 2;                      // [2] MMA (commit) -> drain, per accumulator set
     uint64_t* drained_bar = done_bar + 2;                  // [2] drain -> MMA: the set may be restarted
@@ -90,12 +98,12 @@ bw_umma_kernel(const BwUmmaArgs a) {
 
     if (tid == 0) {
         for (int i = 0; i < NRAW; ++i) { mbar_init(raw_full + i, 32); mbar_init(raw_empty + i, 128); }
-        for (int i = 0; i < kAStages; ++i) { mbar_init(a_full + i, 128); mbar_init(a_empty + i, 1); }
+        for (int i = 0; i < kBwAStages; ++i) { mbar_init(a_full + i, 128); mbar_init(a_empty + i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(g_full + i, 128); mbar_init(g_empty + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(done_bar + i, 1); mbar_init(drained_bar + i, kEpilogueWarps * 32); }
+        for (int i = 0; i < 2; ++i) { mbar_init(done_bar + i, 1); mbar_init(drained_bar + i, kBwEpilogueWarps * 32); }
         fence_barrier_init();
     }
-    if (warp == kMmaWarp) {
+    if (warp == kBwMmaWarp) {
         __syncwarp();
         tmem_alloc(tmem_slot, kTmemCols);
         tmem_relinquish();
@@ -111,7 +119,7 @@ bw_umma_kernel(const BwUmmaArgs a) {
     const int db = (int)gridDim.x / a.L, djt = (int)gridDim.x - db * a.L;
     const int T = a.flush;
 
-    if (warp == kMmaWarp) {
+    if (warp == kBwMmaWarp) {
         // ================= MMA issuer =================
         constexpr uint32_t IDESC = idesc_tf32_bmn(kBM, kBwNT);
         const bool leader = elect_one();
@@ -136,7 +144,7 @@ bw_umma_kernel(const BwUmmaArgs a) {
                 tc_fence_after();
                 if (leader) {
                     const uint32_t d_tmem = tmem_base + (uint32_t)((ab * NBLK + blk) * kBwNT);
-                    const uint32_t a_hi = tmem_base + (uint32_t)(kAColBase + as * 64), a_lo = a_hi + 32;
+                    const uint32_t a_hi = tmem_base + (uint32_t)(kBwAColBase + as * 64), a_lo = a_hi + 32;
                     const uint32_t g_t = g_base + gb * kGStage + r4 * 4 * 2048;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -153,11 +161,11 @@ bw_umma_kernel(const BwUmmaArgs a) {
                     }
                 }
                 __syncwarp();
-                if (++as == kAStages) { as = 0; aph ^= 1; }
+                if (++as == kBwAStages) { as = 0; aph ^= 1; }
             }
             if (last_of_group) { tf = 0; ++nfl; } else ++tf;
         }
-    } else if (warp < kFirstSplitWarp) {
+    } else if (warp < kBwFirstSplitWarp) {
         // ================= g staging (per tile), then the epilogue =================
         const int p = tid;                                        // 0..127
         int b = (int)blockIdx.x / a.L, jt = (int)blockIdx.x - b * a.L;
@@ -241,9 +249,9 @@ bw_umma_kernel(const BwUmmaArgs a) {
             tf = (tf == T - 1) ? 0 : tf + 1;
         }
         if (my_tiles > 0) drain(nfl);                             // the last group always ends with a flush
-    } else if (warp < kFirstLoadWarp) {
+    } else if (warp < kBwFirstLoadWarp) {
         // ================= splitters =================
-        const int set = (warp - kFirstSplitWarp) >> 2;            // set 0: even 32-row groups, set 1: odd
+        const int set = (warp - kBwFirstSplitWarp) >> 2;            // set 0: even 32-row groups, set 1: odd
         const int q4 = warp & 3;
         const int sw_lane = lane >> 2, w_lane = (lane & 3) * 4;
         int jt = (int)blockIdx.x % a.L;
@@ -274,7 +282,7 @@ bw_umma_kernel(const BwUmmaArgs a) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) { float h; split_tf32f(v[j], h, lo[j]); v[j] = h; }
                     tc_fence_after();
-                    const uint32_t t_a = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(kAColBase + as * 64);
+                    const uint32_t t_a = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(kBwAColBase + as * 64);
                     tmem_st32(t_a, v);
                     tmem_st32(t_a + 32, lo);
                     mbar_arrive(raw_empty + rs);
@@ -288,7 +296,7 @@ bw_umma_kernel(const BwUmmaArgs a) {
                         lo[j] = 0.f;
                     }
                     tc_fence_after();
-                    const uint32_t t_a = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(kAColBase + as * 64);
+                    const uint32_t t_a = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(kBwAColBase + as * 64);
                     tmem_st32(t_a, v);
                     tmem_st32(t_a + 32, lo);
                     tmem_st_wait();
@@ -297,16 +305,16 @@ bw_umma_kernel(const BwUmmaArgs a) {
                 tc_fence_before();
                 mbar_arrive(a_full + as);
                 as += 2;
-                if (as >= kAStages) { as -= kAStages; aph ^= 1; }
+                if (as >= kBwAStages) { as -= kBwAStages; aph ^= 1; }
             }
-            // CPT is a multiple of 4 = kAStages, so the (as, aph) sequence continues seamlessly into the next tile
+            // CPT is a multiple of 4 = kBwAStages, so the (as, aph) sequence continues seamlessly into the next tile
             rs0 += S;
             while (rs0 >= NRAW) { rs0 -= NRAW; rph0 ^= 1; }
             jt += djt; if (jt >= a.L) jt -= a.L;
         }
     } else {
         // ================= loaders (raw stage w owned by loader warp w; chunk = (tile, slot)) =================
-        const int lw = warp - kFirstLoadWarp;
+        const int lw = warp - kBwFirstLoadWarp;
         const int q = lane & 7, rsub = lane >> 3;
         const uint32_t sw0 = (uint32_t)((q ^ rsub) << 4), sw1 = (uint32_t)((q ^ (rsub + 4)) << 4);
         const uint32_t raw_base = smem_u32(R_s) + (uint32_t)rsub * 128u;
@@ -316,39 +324,28 @@ bw_umma_kernel(const BwUmmaArgs a) {
         while (sl >= S) { sl -= S; b += db; jt += djt; if (jt >= a.L) { jt -= a.L; ++b; } }
         uint32_t rph = 0;
         if (lw >= NRAW) g = G;
+        PlanRegs<4> nxt;                                           // forward plan: <= 128 staged rows
+        if (g < G) plan_fetch(nxt, a.plan_cnt, a.plan_src, jt, S, sl, a.rcap, rsub);
 #pragma unroll 1
         while (g < G) {
-            const int n = __ldg(a.plan_cnt + jt * S + sl);
-            const int* src = a.plan_src + ((size_t)jt * S + sl) * a.rcap + lane;
-            int pv = __ldg(src);
+            const PlanRegs<4> now = nxt;
+            const float* base = a.in + (size_t)b * a.in_rows * 32 + 4 * q;
+            g += NRAW; sl += NRAW;
+            while (sl >= S) { sl -= S; b += db; jt += djt; if (jt >= a.L) { jt -= a.L; ++b; } }
+            if (g < G) plan_fetch(nxt, a.plan_cnt, a.plan_src, jt, S, sl, a.rcap, rsub);
             mbar_wait(raw_empty + lw, rph ^ 1);
             const uint32_t dst = raw_base + (uint32_t)lw * (uint32_t)RAW_STAGE;
-            const float* base = a.in + (size_t)b * a.in_rows * 32 + 4 * q;
-#pragma unroll 1
-            for (int j = 0; 32 * j < n; ++j) {
-                const int pn = 32 * (j + 1) < n ? __ldg(src + 32 * (j + 1)) : 0;
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    const int sr = __shfl_sync(0xffffffffu, pv, 4 * t + rsub);
-                    if (32 * j + 4 * t + rsub < n)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n"
-                                     ::"r"(dst + (uint32_t)(32 * j + 4 * t) * 128u + ((t & 1) ? sw1 : sw0)),
-                                       "l"(base + (size_t)sr * 32));
-                }
-                pv = pn;
-            }
+            plan_issue(now, dst + sw0, dst + sw1, base, 128u);
             cp_async_commit();
             cp_async_wait<0>();
             mbar_arrive(raw_full + lw);
             rph ^= 1;
-            g += NRAW; sl += NRAW;
-            while (sl >= S) { sl -= S; b += db; jt += djt; if (jt >= a.L) { jt -= a.L; ++b; } }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == kMmaWarp) {
+    if (warp == kBwMmaWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }

@@ -144,7 +144,7 @@ class TilePlan:
     ``sdvae_tc_plan_build``): per tile of 128 output rows and spiral slot, the source rows
     to stage and, per output row, the range of staged rows summed into its cell."""
     cnt: torch.Tensor            # int32 [L, S]
-    src: torch.Tensor            # int32 [L, S, rcap]
+    src: torch.Tensor            # int32 [L, S, rcap/2]  two 16-bit source rows per word, loader-lane order
     cell: torch.Tensor           # int32 [L, S, 128]   start | count << 16
     rcap: int
     out_rows: int

@@ -78,7 +78,8 @@ int sdvae_spiralconv_bwd_x(const float* dpre, const int32_t* cell_ptr, const int
  * with cell_ptr[i] = i, cell_src = idx; the backward table is the inverse (cell_ptr, cell_src)
  * of sdvae_spiralconv_bwd_x.  Plan arrays, L = sdvae_tc_plan_tiles(out_rows) tiles of 128 rows:
  *   cnt  [L, S]        rows staged for (tile, slot)
- *   src  [L, S, rcap]  their source rows, rcap >= sdvae_tc_plan_max_rows(...) rounded up to 16
+ *   src  [L, S, rcap/2] their source rows (< 65536), two per 32-bit word, packed in the order the
+ *                      loader lanes consume them; rcap = sdvae_tc_plan_max_rows(...) rounded up to 32
  *   cell [L, S, 128]   start | count << 16 : staged rows summed (in order) into each tile row */
 int    sdvae_tc_supported(int S, int KS, int N, int rcap);
 size_t sdvae_tc_wimg_floats(int S, int KS, int N);
@@ -88,7 +89,9 @@ int sdvae_tc_plan_tiles(int out_rows);
 int sdvae_tc_plan_max_rows(const int32_t* cell_ptr, int out_rows, int S);
 int sdvae_tc_plan_build(const int32_t* cell_ptr, const int32_t* cell_src, int out_rows, int S,
                         int rcap, int32_t* cnt, int32_t* src, int32_t* cell);
-/* Replaces: model.py:27-41 + F.elu (model.py:68,84), as sdvae_spiralconv_fwd. */
+/* Replaces: model.py:27-41 + F.elu (model.py:68,84), as sdvae_spiralconv_fwd.  The plan must be the
+ * FORWARD plan of the layer's table (cell_ptr[i] = i: exactly one source row per cell, so staged row e of a
+ * (tile, slot) is tile row e); plan_cell is not read and may be NULL. */
 int sdvae_spiralconv_fwd_tc(const float* x, const int32_t* plan_cnt, const int32_t* plan_src,
                             const int32_t* plan_cell, int rcap, const float* wimg, const float* bias,
                             float* y, int B, int Vin, int Vout, int S, int Cin, int Cout, int act,

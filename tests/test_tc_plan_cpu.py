@@ -5,11 +5,25 @@ from sdvae_b200 import cabi
 from sdvae_b200.tables import inverse_cells
 
 
+def _unpack(packed, rcap):
+    """Undo the loader-lane packing (include/sdvae_b200.h): staged row e = 32*j + 4*t + rsub sits in word
+    16*j + 4*rsub + (t >> 1), low half for even t."""
+    w = packed.astype(np.uint32)
+    src = np.zeros(packed.shape[:2] + (rcap,), np.int64)
+    for j in range(rcap // 32):
+        for rsub in range(4):
+            for t in range(8):
+                word = w[:, :, 16 * j + 4 * rsub + (t >> 1)]
+                src[:, :, 32 * j + 4 * t + rsub] = (word >> 16) if (t & 1) else (word & 0xffff)
+    return src
+
+
 def _check_plan(cell_ptr, cell_src, out_rows, S):
-    cnt, src, cell, rcap = cabi.tc_plan_build(cell_ptr, cell_src, out_rows, S)
+    cnt, packed, cell, rcap = cabi.tc_plan_build(cell_ptr, cell_src, out_rows, S)
     L = (out_rows + 127) // 128
-    assert cnt.shape == (L, S) and src.shape == (L, S, rcap) and cell.shape == (L, S, 128)
-    assert rcap % 16 == 0 and cnt.max() <= rcap
+    assert cnt.shape == (L, S) and packed.shape == (L, S, rcap // 2) and cell.shape == (L, S, 128)
+    assert rcap % 32 == 0 and cnt.max() <= rcap
+    src = _unpack(packed, rcap)
     start = cell.astype(np.uint32) & 0xffff
     count = cell.astype(np.uint32) >> 16
     for jt in range(L):

@@ -55,7 +55,7 @@ struct DevPlan { int* cnt; int* src; int* cell; int rcap; };
 static DevPlan make_plan(const std::vector<int>& cell_ptr, const std::vector<int>& cell_src, int out_rows, int S) {
     const int L = sdvae_tc_plan_tiles(out_rows);
     const int mx = sdvae_tc_plan_max_rows(cell_ptr.data(), out_rows, S);
-    const int rcap = std::max(16, (mx + 15) / 16 * 16);
+    const int rcap = std::max(32, (mx + 31) / 32 * 32);
     std::vector<int> cnt((size_t)L * S), src((size_t)L * S * rcap), cell((size_t)L * S * 128);
     ABI(sdvae_tc_plan_build(cell_ptr.data(), cell_src.data(), out_rows, S, rcap, cnt.data(), src.data(), cell.data()));
     printf("plan: %d tiles/mesh, max staged rows %d (rcap %d)\n", L, mx, rcap);
