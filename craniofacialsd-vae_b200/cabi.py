@@ -39,6 +39,10 @@ _SIGNATURES = {
     "sdvae_spiralconv_bwd_x_tc": (C.c_int, [_c_fp] * 4 + [C.c_int] + [_c_fp] * 3 + [C.c_int] * 6 + [_c_fp]),
     "sdvae_tc_bwd_w_supported": (C.c_int, [C.c_int] * 4),
     "sdvae_spiralconv_bwd_w_tc": (C.c_int, [_c_fp] * 3 + [C.c_int] + [_c_fp] * 4 + [C.c_int] * 6 + [_c_fp]),
+    "sdvae_dense_tc": (C.c_int, [_c_fp] * 3 + [C.c_int] + [_c_fp] * 4 + [C.c_int] * 3 + [_c_fp]),
+    "sdvae_slot_pack": (C.c_int, [_c_fp] * 4 + [C.c_int] * 5 + [_c_fp]),
+    "sdvae_slot_weight": (C.c_int, [_c_fp, _c_fp] + [C.c_int] * 4 + [_c_fp]),
+    "sdvae_slot_grad": (C.c_int, [_c_fp] * 4 + [C.c_int] * 4 + [_c_fp]),
     "sdvae_spiralconv_bwd_w_workspace": (C.c_size_t, [C.c_longlong, C.c_int, C.c_int, C.c_int]),
     "sdvae_spiralconv_bwd_w": (C.c_int, [_c_fp] * 6 + [C.c_int] * 6 + [_c_fp]),
     "sdvae_dense_fwd": (C.c_int, [_c_fp] * 4 + [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, _c_fp]),
@@ -90,7 +94,7 @@ def load(build_if_missing: bool = False):
 _KERNELS_PER_CALL = {
     "spiralconv_fwd": 1, "weight_transpose": 1, "spiralconv_bwd_x": 1, "spiralconv_bwd_w": 3,
     "tc_pack_weights": 1, "spiralconv_fwd_tc": 1, "spiralconv_bwd_x_tc": 1,
-    "spiralconv_bwd_w_tc": 3,
+    "spiralconv_bwd_w_tc": 3, "dense_tc": 1, "slot_pack": 1, "slot_weight": 1, "slot_grad": 1,
     "dense_fwd": 1, "transpose2d": 1, "pool_ell_fwd": 1, "csr_rowsum": 1, "elu_fwd": 1,
     "elu_bwd": 1, "reparam_fwd": 1, "reparam_bwd": 1, "axpy3": 1, "swap": 1, "mse_lap_fwd": 3,
     "mse_lap_bwd": 1, "kl_fwd_bwd": 2, "lc_fwd_bwd": 3, "total_loss": 1, "adam_tick": 1,
@@ -138,6 +142,10 @@ def _i(t, name):
 
 def _fo(t: Optional[torch.Tensor], name):
     return None if t is None else _f(t, name)
+
+
+def _io(t: Optional[torch.Tensor], name):
+    return None if t is None else _i(t, name)
 
 
 # ---------------------------------------------------------------------------------
@@ -240,6 +248,40 @@ def spiralconv_bwd_w_tc(x, plan, dpre, dW, db, workspace, B, Vin, Vout, S, Cin, 
     if rc:
         _err(rc, "spiralconv_bwd_w_tc")
     add_launches(_KERNELS_PER_CALL["spiralconv_bwd_w_tc"])
+
+
+def dense_tc(x, plan, wimg, bias, gate, y, B, R, act):
+    """y[b, r, :] = epi(x[b, r, :32] Wd^T) on the tcgen05 path; ``plan`` = forward plan of the identity
+    table with R rows (S = 1)."""
+    rc = load().sdvae_dense_tc(_f(x, "x"), _i(plan.cnt, "plan.cnt"), _i(plan.src, "plan.src"), plan.rcap,
+                               _f(wimg, "wimg"), _fo(bias, "bias"), _fo(gate, "gate"), _f(y, "y"), B, R,
+                               act, _stream())
+    if rc:
+        _err(rc, "dense_tc")
+    add_launches(_KERNELS_PER_CALL["dense_tc"])
+
+
+def slot_pack(inp, cell_ptr, cell_src, out, B, Vin, R, S, Cn):
+    rc = load().sdvae_slot_pack(_f(inp, "in"), _io(cell_ptr, "cell_ptr"), _i(cell_src, "cell_src"),
+                                _f(out, "out"), B, Vin, R, S, Cn, _stream())
+    if rc:
+        _err(rc, "slot_pack")
+    add_launches(_KERNELS_PER_CALL["slot_pack"])
+
+
+def slot_weight(W, Wd, mode, N, S, Cn):
+    rc = load().sdvae_slot_weight(_f(W, "W"), _f(Wd, "Wd"), mode, N, S, Cn, _stream())
+    if rc:
+        _err(rc, "slot_weight")
+    add_launches(_KERNELS_PER_CALL["slot_weight"])
+
+
+def slot_grad(dWd, dbd, dW, db, mode, N, S, Cn):
+    rc = load().sdvae_slot_grad(_f(dWd, "dWd"), _fo(dbd, "dbd"), _f(dW, "dW"), _fo(db, "db"), mode, N, S,
+                                Cn, _stream())
+    if rc:
+        _err(rc, "slot_grad")
+    add_launches(_KERNELS_PER_CALL["slot_grad"])
 
 
 def spiralconv_bwd_w_workspace(M, S, Cin, Cout) -> int:

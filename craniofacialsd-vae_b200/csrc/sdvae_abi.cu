@@ -6,6 +6,7 @@
 #include "spiral_conv.cuh"
 #include "spiral_conv_umma.cuh"
 #include "spiral_conv_umma_bw.cuh"
+#include "slot_pack.cuh"
 #include "pool_misc.cuh"
 #include "loss.cuh"
 
@@ -292,6 +293,40 @@ int sdvae_spiralconv_bwd_x_tc(const float* dpre, const int32_t* plan_cnt, const 
     return tc_conv(dpre, plan_cnt, plan_src, plan_cell, rcap, wimg_t, nullptr, gate, dx, B, Vrows, Vdst, S,
                    Cout, Cin, gate ? EPI_GATE : EPI_NONE, false, (cudaStream_t)stream,
                    "spiralconv_bwd_x_tc: unsupported layer shape");
+}
+
+int sdvae_dense_tc(const float* x, const int32_t* plan_cnt, const int32_t* plan_src, int rcap,
+                   const float* wimg, const float* bias, const float* gate, float* y, int B, int R,
+                   int act, sdvae_stream_t stream) {
+    const int epi = gate ? EPI_GATE : (act == SDVAE_ACT_ELU ? EPI_BIAS_ELU : EPI_BIAS);
+    return tc_conv(x, plan_cnt, plan_src, nullptr, rcap, wimg, gate ? nullptr : bias, gate, y, B, R, R, 1, 32,
+                   32, epi, true, (cudaStream_t)stream, "dense_tc: unsupported shape");
+}
+
+int sdvae_slot_pack(const float* in, const int32_t* cell_ptr, const int32_t* cell_src, float* out, int B,
+                    int Vin, int R, int S, int C, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(in && cell_src && out, "slot_pack: null pointer");
+    SDVAE_REQUIRE(B >= 0 && Vin > 0 && R > 0 && S > 0 && C > 0 && S * C <= 32, "slot_pack: bad shape (S*C must be <= 32)");
+    if (B == 0) return SDVAE_OK;
+    const long long rows = (long long)B * R;
+    long long blocks = (rows + 7) / 8;                       // 8 warps (rows) per block
+    if (blocks > (long long)kNumSMs * 32) blocks = (long long)kNumSMs * 32;
+    slot_pack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, cell_ptr, cell_src, out, rows, R, Vin, S, C);
+    return check_launch("slot_pack_kernel");
+}
+
+int sdvae_slot_weight(const float* W, float* Wd, int mode, int N, int S, int C, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(W && Wd && (mode == 0 || mode == 1) && S > 0 && C > 0 && S * C <= 32 && N > 0 && N <= 32, "slot_weight: bad argument");
+    slot_weight_kernel<<<4, 256, 0, (cudaStream_t)stream>>>(W, Wd, mode, N, S, C);
+    return check_launch("slot_weight_kernel");
+}
+
+int sdvae_slot_grad(const float* dWd, const float* dbd, float* dW, float* db, int mode, int N, int S, int C,
+                    sdvae_stream_t stream) {
+    SDVAE_REQUIRE(dWd && dW && (mode == 0 || mode == 1) && S > 0 && C > 0 && S * C <= 32 && N > 0 && N <= 32, "slot_grad: bad argument");
+    SDVAE_REQUIRE(!db || dbd, "slot_grad: db without dbd");
+    slot_grad_kernel<<<4, 256, 0, (cudaStream_t)stream>>>(dWd, dbd, dW, db, mode, N, S, C);
+    return check_launch("slot_grad_kernel");
 }
 
 int sdvae_tc_bwd_w_supported(int S, int Cin, int Cout, int rcap) {

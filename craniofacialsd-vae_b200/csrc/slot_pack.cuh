@@ -1,0 +1,80 @@
+// Narrow-channel SpiralConv layers (C = 3: the first encoder block and the output layer of
+// model.py:104-136) through "slot packing".
+//
+// For a layer whose narrow side has C channels with S*C <= 32, the gathered operand of model.py:34
+// has only S*C (= 27) columns per vertex.  Materialising THAT (one 128-byte row per vertex, the same
+// size as a 32-channel activation row) is cheap, and it turns every pass of the layer into a DENSE
+// 32 x 32 contraction on the tcgen05 kernels with an identity tile plan (S = 1):
+//
+//   forward, narrow input    P[r, s*C + c] = x[idx[r, s], c]              y  = elu(P Wd^T + b)
+//   weight grad, narrow input                                             dW = dy^T P           (no gather of x)
+//   backward, narrow output  G[u, s*C + n] = sum_{v in cell(u,s)} dy[v,n] dx = (G Wd'^T) * elu'  (Wd'[c, j] = W[n, s*32+c])
+//   weight grad, narrow output                                            dW[n, s*32+c] = (G^T x)[s*C+n, c]
+//
+// instead of three gather-bound kernels that each move 9 x 128 bytes per vertex for 3 useful channels.
+#pragma once
+#include "common.cuh"
+
+namespace sdvae {
+
+// out[b, r, s*C + c] = sum_{e in cell(r, s)} in[b, src[e], c];  columns S*C .. 31 are zero.
+// cell_ptr == nullptr: cell(r, s) = { r*S + s } (forward table, cell_src = idx[R, S]).
+// One warp per output row (128-byte coalesced store); rows are summed in storage order.
+__global__ void slot_pack_kernel(const float* __restrict__ in, const int* __restrict__ cell_ptr,
+                                 const int* __restrict__ cell_src, float* __restrict__ out,
+                                 long long rows_total, int R, int Vin, int S, int C) {
+    const int lane = threadIdx.x & 31;
+    const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int s = lane / C, c = lane - s * C;
+    const bool live = lane < S * C;
+    for (long long m = w0; m < rows_total; m += nw) {
+        const long long b = m / R;
+        const int r = (int)(m - b * R);
+        float acc = 0.f;
+        if (live) {
+            const float* src = in + (size_t)b * Vin * C + c;
+            if (cell_ptr == nullptr) {
+                acc = __ldg(src + (size_t)__ldg(cell_src + (size_t)r * S + s) * C);
+            } else {
+                const int e0 = __ldg(cell_ptr + (size_t)r * S + s), e1 = __ldg(cell_ptr + (size_t)r * S + s + 1);
+                for (int e = e0; e < e1; ++e) acc = __fadd_rn(acc, __ldg(src + (size_t)__ldg(cell_src + e) * C));
+            }
+        }
+        out[(size_t)m * 32 + lane] = acc;
+    }
+}
+
+// Dense 32 x 32 weight of a slot-packed layer (rows n, columns k), from the layer's own weight:
+//   mode 0 (narrow input,  W [N, S*C])     Wd[n, k] = k < S*C ? W[n, k] : 0                      (n < N)
+//   mode 1 (narrow output, W [C, S*32])    Wd[c, j] = j < S*C ? W[j % C, (j / C)*32 + c] : 0
+__global__ void slot_weight_kernel(const float* __restrict__ W, float* __restrict__ Wd, int mode, int N, int S, int C) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 1024) return;
+    const int row = t >> 5, col = t & 31;
+    float v = 0.f;
+    if (col < S * C) {
+        if (mode == 0) { if (row < N) v = W[(size_t)row * S * C + col]; }
+        else v = W[(size_t)(col % C) * S * 32 + (col / C) * 32 + row];
+    }
+    Wd[t] = v;
+}
+
+// Scatter the dense 32 x 32 weight gradient (and bias gradient) of a slot-packed layer back:
+//   mode 0   dW[n, k] = dWd[n, k] (k < S*C, n < N),           db[n] = dbd[n]
+//   mode 1   dW[n, s*32 + c] = dWd[s*C + n, c] (n < C),       db[n] = dbd[n]   (slot 0 is the vertex itself)
+__global__ void slot_grad_kernel(const float* __restrict__ dWd, const float* __restrict__ dbd,
+                                 float* __restrict__ dW, float* __restrict__ db, int mode, int N, int S, int C) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 1024) return;
+    const int row = t >> 5, col = t & 31;
+    if (mode == 0) {
+        if (row < N && col < S * C) dW[(size_t)row * S * C + col] = dWd[t];
+        if (db && col == 0 && row < N) db[row] = dbd[row];
+    } else {
+        if (row < S * C) dW[(size_t)(row % C) * S * 32 + (row / C) * 32 + col] = dWd[t];
+        if (db && col == 0 && row < C) db[row] = dbd[row];
+    }
+}
+
+}  // namespace sdvae

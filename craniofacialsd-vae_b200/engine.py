@@ -37,7 +37,8 @@ import torch
 from . import cabi
 from .losses import LaplacianTable
 from .parallel import grid_rows, mean_loss_scale
-from .tables import PoolTable, SpiralTable, pool_table, restricted_spiral_table, spiral_table
+from .tables import (PoolTable, SpiralTable, identity_plan, pool_table, restricted_spiral_table,
+                     spiral_table)
 
 LOSS_KEYS = ['reconstruction', 'kl', 'latent_consistency', 'laplacian',
              'classification', 'classification_acc', 'tot']      # model_manager.py:150-154
@@ -212,6 +213,7 @@ class TrainEngine:
         """Per conv layer: tile plans + packed-weight buffers for the tcgen05 kernels, where
         the layer shape is supported.  Keys: ('f', name) forward, ('b', name) backward-to-input."""
         self.tc = {}
+        self.slot_en0 = self.slot_out = None
         if not self.use_tc:
             return
         m, L, C, S = self.model, self.L, self.C, self.S
@@ -237,12 +239,32 @@ class TrainEngine:
             add('b', 'de%d' % l, dec, self.full[l], self.cin_de[l], C[l + 1])
         out_layer = m.de_layers[L + 1].layer
         add('f', 'out', out_layer, self.full[0], C[1], C[0])
+        # Narrow layers (3 channels on one side, 32 on the other) through slot packing
+        # (csrc/slot_pack.cuh): the 27 gathered columns of a vertex are materialised once, every pass of
+        # the layer is then a dense 32 x 32 contraction on the tcgen05 kernels (identity plan, S = 1).
+        B, V = self.B, self.V
+        if S[0] * C[0] <= 32 and C[1] == 32 and cabi.tc_supported(1, 32, 32, 128):
+            R0 = self.sub[0].n_rows
+            self.slot_en0 = dict(plan=identity_plan(R0, self.dev), P=f(B * R0 * 32).view(B, R0, 32),
+                                 Wd=f(1024), wimg=f(cabi.tc_wimg_floats(1, 32, 32)),
+                                 dWd=f(1024), dbd=f(32))
+            self.slot_out = dict(plan=identity_plan(V[0], self.dev), G=f(B * V[0] * 32).view(B, V[0], 32),
+                                 Wd=f(1024), wimg=f(cabi.tc_wimg_floats(1, 32, 32)),
+                                 dWd=f(1024), dbd=f(32))
 
     def _pack_tc(self):
         """Re-pack every tensor-core weight image from the current weights (they change each step)."""
         for (kind, _), e in self.tc.items():
             cabi.tc_pack_weights(e['layer'].weight.data, e['wimg'], e['seq'], e['cin'], e['cout'],
                                  kind == 'b')
+        m, L, C, S = self.model, self.L, self.C, self.S
+        if self.slot_en0 is not None:
+            e = self.slot_en0
+            cabi.slot_weight(m.en_layers[0].conv.layer.weight.data, e['Wd'], 0, C[1], S[0], C[0])
+            cabi.tc_pack_weights(e['Wd'], e['wimg'], 1, 32, 32, False)
+            e = self.slot_out
+            cabi.slot_weight(m.de_layers[L + 1].layer.weight.data, e['Wd'], 1, C[0], S[0], C[0])
+            cabi.tc_pack_weights(e['Wd'], e['wimg'], 1, 32, 32, False)
 
     # ------------------------------------------------------------------ pieces
     def _conv(self, x, table, layer, out, act, B, Vin, Cin, Cout, name=None):
@@ -256,13 +278,20 @@ class TrainEngine:
 
     def forward(self, B=None):
         """x0 -> recon, z, mu, logvar (training mode)."""
-        m, L, V, C = self.model, self.L, self.V, self.C
+        m, L, V, C, S = self.model, self.L, self.V, self.C, self.S
         B = self.B if B is None else B
         self._pack_tc()
         x = self.x0
         for l in range(L):
-            self._conv(x, self.sub[l], m.en_layers[l].conv.layer, self.a[l], cabi.ACT_ELU,
-                       B, V[l], C[l], C[l + 1], name='en%d' % l)
+            if l == 0 and self.slot_en0 is not None:
+                e, sub = self.slot_en0, self.sub[0]
+                P = e['P'][:B]
+                cabi.slot_pack(x, None, sub.idx, P, B, V[0], sub.n_rows, S[0], C[0])
+                cabi.dense_tc(P, e['plan'], e['wimg'], m.en_layers[0].conv.layer.bias.data, None,
+                              self.a[0], B, sub.n_rows, cabi.ACT_ELU)
+            else:
+                self._conv(x, self.sub[l], m.en_layers[l].conv.layer, self.a[l], cabi.ACT_ELU,
+                           B, V[l], C[l], C[l + 1], name='en%d' % l)
             x = self.a[l]
         flat = x.view(B, V[L] * C[L])
         lin_mu = m.en_layers[-1]
@@ -346,11 +375,23 @@ class TrainEngine:
             cabi.mse_lap_bwd(self.recon, self.x0, None, None, None, None, self.drecon, B, V[0],
                              1.0, 0.0, scale, None)
         out_layer = m.de_layers[L + 1].layer
-        self._bwd_w(self.d[0], self.full[0], self.drecon, out_layer, B, V[0], C[1], C[0])
-        cabi.weight_transpose(out_layer.weight.data, self.wt_out, C[0], C[1], S[0])
         cp, cs = self.full[0].inverse()
-        cabi.spiralconv_bwd_x(self.drecon, cp, cs, self.wt_out, self.d[0], self.dd[0], B, V[0], V[0],
-                              S[0], C[0], C[1])
+        if self.slot_out is not None:
+            # G[u, s*3 + n] = sum of drecon over the vertices that gather u at slot s; then
+            # dd0 = (G Wd^T) * elu'(d0)  and  dW[n, s*32 + c] = (G^T d0)[s*3 + n, c] -- both dense
+            e = self.slot_out
+            G = e['G'][:B]
+            cabi.slot_pack(self.drecon, cp, cs, G, B, V[0], V[0], S[0], C[0])
+            cabi.dense_tc(G, e['plan'], e['wimg'], None, self.d[0], self.dd[0], B, V[0], cabi.ACT_NONE)
+            cabi.spiralconv_bwd_w_tc(self.d[0], e['plan'], G, e['dWd'].view(32, 32), e['dbd'], self.ws,
+                                     B, V[0], V[0], 1, 32, 32)
+            cabi.slot_grad(e['dWd'], e['dbd'], self.g(out_layer.weight), self.g(out_layer.bias), 1,
+                           C[0], S[0], C[0])
+        else:
+            self._bwd_w(self.d[0], self.full[0], self.drecon, out_layer, B, V[0], C[1], C[0])
+            cabi.weight_transpose(out_layer.weight.data, self.wt_out, C[0], C[1], S[0])
+            cabi.spiralconv_bwd_x(self.drecon, cp, cs, self.wt_out, self.d[0], self.dd[0], B, V[0], V[0],
+                                  S[0], C[0], C[1])
         for l in range(L):                               # deblock at level l, fine -> coarse
             layer = m.de_layers[L - l].conv.layer
             cin, cout = self.cin_de[l], C[l + 1]
@@ -412,7 +453,16 @@ class TrainEngine:
         for l in range(L - 1, -1, -1):
             layer = m.en_layers[l].conv.layer
             x_in = self.a[l - 1] if l > 0 else self.x0
-            self._bwd_w(x_in, self.sub[l], self.da[l], layer, B, V[l], C[l], C[l + 1])
+            if l == 0 and self.slot_en0 is not None:
+                # dW = da0^T P with the slot-packed input of the forward pass: no gather at all
+                e = self.slot_en0
+                R0 = self.sub[0].n_rows
+                cabi.spiralconv_bwd_w_tc(e['P'][:B], e['plan'], self.da[0], e['dWd'].view(32, 32), e['dbd'],
+                                         self.ws, B, R0, R0, 1, 32, 32)
+                cabi.slot_grad(e['dWd'], e['dbd'], self.g(layer.weight), self.g(layer.bias), 0,
+                               C[1], S[0], C[0])
+            else:
+                self._bwd_w(x_in, self.sub[l], self.da[l], layer, B, V[l], C[l], C[l + 1])
             e = self.tc.get(('b', 'en%d' % l)) if l > 0 else None
             if e is not None:
                 # input gradient of the fused block straight from the kept rows (inverse table of the

@@ -275,6 +275,21 @@ def pool_table(trans: torch.Tensor) -> PoolTable:
     return tab
 
 
+_identity_plans: Dict[Tuple[int, str], "TilePlan"] = {}
+
+
+def identity_plan(n_rows: int, device) -> "TilePlan":
+    """Forward tile plan of the identity table (S = 1, row r gathers row r): the dense 32-wide
+    contractions of the slot-packed narrow layers run on the tcgen05 kernels with it."""
+    k = (int(n_rows), str(device))
+    hit = _identity_plans.get(k)
+    if hit is None:
+        hit = TilePlan.build(np.arange(n_rows + 1, dtype=np.int32), np.arange(n_rows, dtype=np.int32),
+                             int(n_rows), 1, device)
+        _identity_plans[k] = hit
+    return hit
+
+
 def restricted_spiral_table(indices: torch.Tensor, pool: PoolTable) -> Optional[SpiralTable]:
     """Spiral table restricted to the rows a selection down-transform keeps, or None
     if ``pool`` is not a pure selection."""

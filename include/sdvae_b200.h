@@ -111,6 +111,28 @@ int sdvae_spiralconv_bwd_w_tc(const float* x, const int32_t* plan_cnt, const int
                               const float* dpre, float* dW, float* db, void* workspace, int B, int Vin,
                               int Vout, int S, int Cin, int Cout, sdvae_stream_t stream);
 
+/* ---- narrow-channel layers (C = 3: model.py:104-106 first encoder block, model.py:135-136 output
+ * layer) through slot packing: the S*C <= 32 gathered columns of a vertex are materialised once as a
+ * 128-byte row, after which every pass of the layer is a dense 32 x 32 contraction on the tcgen05
+ * kernels with an identity (S = 1) tile plan.
+ *   slot_pack   out[b, r, s*C + c] = sum_{e in cell(r,s)} in[b, cell_src[e], c], columns S*C..31 zero,
+ *               out is [B, R, 32]; cell_ptr == NULL: forward table, cell_src = idx[R, S]
+ *               (replaces the index_select of model.py:34 for this layer; bit-exact: storage-order sums)
+ *   slot_weight Wd[32,32] from the layer weight: mode 0 (narrow input, W [N, S*C]): zero-padded copy;
+ *               mode 1 (narrow output, W [C, S*32]): Wd[c, s*C + n] = W[n, s*32 + c]
+ *   slot_grad   the inverse scatter of a dense [32,32] weight gradient (+ bias gradient) into dW / db
+ *   dense_tc    y[b, r, :] = epi(x[b, r, :32] Wd^T): wimg = sdvae_tc_pack_weights(Wd, S=1, 32, 32, 0),
+ *               plan = forward plan of the identity table (S = 1, R rows); gate != NULL: y *= elu'(gate)
+ *               (no bias), else bias + optional ELU. */
+int sdvae_slot_pack(const float* in, const int32_t* cell_ptr, const int32_t* cell_src, float* out, int B,
+                    int Vin, int R, int S, int C, sdvae_stream_t stream);
+int sdvae_slot_weight(const float* W, float* Wd, int mode, int N, int S, int C, sdvae_stream_t stream);
+int sdvae_slot_grad(const float* dWd, const float* dbd, float* dW, float* db, int mode, int N, int S, int C,
+                    sdvae_stream_t stream);
+int sdvae_dense_tc(const float* x, const int32_t* plan_cnt, const int32_t* plan_src, int rcap,
+                   const float* wimg, const float* bias, const float* gate, float* y, int B, int R,
+                   int act, sdvae_stream_t stream);
+
 /* dW[o, s*Cin+c] = sum_{b,v} dpre[b,v,o] * x[b, idx[v,s], c];  db[o] = sum_{b,v} dpre[b,v,o]
  * workspace: sdvae_spiralconv_bwd_w_workspace(...) bytes.  Split-M partial sums are added in a
  * fixed order.  db may be NULL.

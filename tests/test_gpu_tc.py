@@ -177,6 +177,87 @@ def test_tc_weight_gradient_restricted_rows(cranio, orc):
     assert nerr(db, b.grad) < TC_TOL
 
 
+def test_slot_pack_is_bit_exact(cranio):
+    """slot_pack = the gather of model.py:34 restricted to S*C <= 32 columns, forward table and inverse
+    (cell) table; index work and storage-order sums are bit-exact against torch on the same inputs."""
+    from sdvae_b200 import cabi
+    from sdvae_b200.tables import spiral_table
+    idx = cranio.spiral_tensors()[1]
+    V, S = idx.shape
+    B, Cn = 3, 3
+    tab = spiral_table(idx.to(DEV))
+    x = rand((B, V, Cn), 7)
+    out = torch.full((B, V, 32), float('nan'), device=DEV)
+    cabi.slot_pack(x.to(DEV), None, tab.idx, out, B, V, V, S, Cn)
+    want = torch.zeros(B, V, 32)
+    want[:, :, :S * Cn] = x[:, idx.reshape(-1)].reshape(B, V, S * Cn)
+    assert torch.equal(out.cpu(), want)
+    # inverse table: G[u, s*C + n] = sum over the rows v with idx[v, s] = u, in ascending v
+    cp, cs = tab.inverse()
+    cabi.slot_pack(x.to(DEV), cp, cs, out, B, V, V, S, Cn)
+    want = torch.zeros(B, V, S, Cn)
+    for v in range(V):                      # ascending v = storage order of the inverse cells
+        for s_ in range(S):
+            want[:, idx[v, s_], s_] += x[:, v]
+    got = out.cpu()
+    assert torch.equal(got[:, :, :S * Cn], want.reshape(B, V, S * Cn))
+    assert not got[:, :, S * Cn:].any()
+
+
+@pytest.mark.parametrize('lvl,B', [(2, 3), (0, 2)])
+def test_slot_packed_narrow_layers_vs_fp64_autograd(cranio, orc, lvl, B):
+    """3 -> 32 (first encoder block) and 32 -> 3 (output layer) SpiralConv through slot packing + dense
+    tcgen05 contractions: forward, input gradient (ELU' gate fused) and weight / bias gradients."""
+    from sdvae_b200 import cabi
+    from sdvae_b200.tables import identity_plan, spiral_table
+    idx = cranio.spiral_tensors()[lvl]
+    V, S = idx.shape
+    tab = spiral_table(idx.to(DEV))
+    plan = identity_plan(V, DEV)
+    Wd = torch.empty(1024, device=DEV); wimg = torch.empty(cabi.tc_wimg_floats(1, 32, 32), device=DEV)
+    dWd = torch.empty(32, 32, device=DEV); dbd = torch.empty(32, device=DEV)
+    ws = torch.empty(cabi.spiralconv_bwd_w_workspace(B * V, 1, 32, 32) // 4 + 4, device=DEV)
+    # ---- narrow input: y = elu(conv(x)), dW, db
+    x = rand((B, V, 3), 11)
+    w = rand((32, S * 3), 12, 0.3).double().requires_grad_(True)
+    b = rand((32,), 13, 0.1).double().requires_grad_(True)
+    gy = rand((B, V, 32), 14)
+    pre = orc.spiral_conv(x.double(), idx, w, b)
+    y64 = orc.elu(pre)
+    pre.backward(gy.double())
+    P = torch.empty(B, V, 32, device=DEV)
+    cabi.slot_pack(x.to(DEV), None, tab.idx, P, B, V, V, S, 3)
+    cabi.slot_weight(w.detach().float().to(DEV), Wd, 0, 32, S, 3)
+    cabi.tc_pack_weights(Wd, wimg, 1, 32, 32, False)
+    y = torch.full((B, V, 32), float('nan'), device=DEV)
+    cabi.dense_tc(P, plan, wimg, b.detach().float().to(DEV), None, y, B, V, cabi.ACT_ELU)
+    assert nerr(y, y64) < TC_TOL
+    dW = torch.full((32, S * 3), float('nan'), device=DEV); db = torch.full((32,), float('nan'), device=DEV)
+    cabi.spiralconv_bwd_w_tc(P, plan, gy.to(DEV), dWd, dbd, ws, B, V, V, 1, 32, 32)
+    cabi.slot_grad(dWd, dbd, dW, db, 0, 32, S, 3)
+    assert nerr(dW, w.grad) < TC_TOL and nerr(db, b.grad) < TC_TOL
+    # ---- narrow output: r = conv(elu(u)); du (gated), dW, db
+    u = rand((B, V, 32), 21).double().requires_grad_(True)
+    w2 = rand((3, S * 32), 22, 0.1).double().requires_grad_(True)
+    b2 = torch.zeros(3, dtype=torch.float64, requires_grad=True)
+    gr = rand((B, V, 3), 23)
+    d0 = orc.elu(u)
+    orc.spiral_conv(d0, idx, w2, b2).backward(gr.double())
+    cp, cs = tab.inverse()
+    G = torch.empty(B, V, 32, device=DEV)
+    cabi.slot_pack(gr.to(DEV), cp, cs, G, B, V, V, S, 3)
+    cabi.slot_weight(w2.detach().float().to(DEV), Wd, 1, 3, S, 3)
+    cabi.tc_pack_weights(Wd, wimg, 1, 32, 32, False)
+    d0f = d0.detach().float().to(DEV).contiguous()
+    du = torch.full((B, V, 32), float('nan'), device=DEV)
+    cabi.dense_tc(G, plan, wimg, None, d0f, du, B, V, cabi.ACT_NONE)
+    assert nerr(du, u.grad) < TC_TOL
+    dW2 = torch.full((3, S * 32), float('nan'), device=DEV); db2 = torch.full((3,), float('nan'), device=DEV)
+    cabi.spiralconv_bwd_w_tc(d0f, plan, G, dWd, dbd, ws, B, V, V, 1, 32, 32)
+    cabi.slot_grad(dWd, dbd, dW2, db2, 1, 3, S, 3)
+    assert nerr(dW2, w2.grad) < TC_TOL and nerr(db2, b2.grad) < TC_TOL
+
+
 def test_tc_rejects_unsupported_shapes(cranio):
     from sdvae_b200 import cabi
     assert not cabi.tc_supported(9, 3, 32, 128)        # K = 27: stays on the FMA kernel
