@@ -114,6 +114,7 @@ static int launch_umma(umma::UmmaArgs& ua, cudaStream_t st) {
         attr_done = true;
     }
     ua.nraw = Cfg::raw_stages(ua.S, ua.rcap);
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SDVAE_DBG"); dbg = e ? atoi(e) : 0; } ua.dbg = dbg; }
     const long long ntiles = (long long)ua.B * ua.L;
     const int grid = ntiles < kNumSMs ? (int)ntiles : kNumSMs;
     kern<<<grid, umma::kThreads, Cfg::smem_bytes(ua.S, ua.rcap, ua.nraw), st>>>(ua);
@@ -174,6 +175,11 @@ int sdvae_spiralconv_bwd_x(const float* dpre, const int32_t* cell_ptr, const int
     a.M = (long long)B * Vdst; a.in_rows = Vrows; a.Vout = Vdst; a.S = S;
     a.ldw = S * Cout; a.ldo = Cin; a.n_real = Cin;
     return dispatch_gc<true>(a, Cout, gate ? EPI_GATE : EPI_NONE, (cudaStream_t)stream);
+}
+
+/* tuning aid (not part of the product interface): cycle counters written by CTA 0 when SDVAE_DBG has bit 32 */
+int sdvae_debug_read_prof(long long* host64) {
+    return cudaMemcpyFromSymbol(host64, umma::g_prof, 64 * sizeof(long long)) == cudaSuccess ? 0 : 2;
 }
 
 int sdvae_tc_supported(int S, int KS, int N, int rcap) { return tc_shape_ok(S, KS, N, rcap) ? 1 : 0; }
@@ -309,8 +315,10 @@ int sdvae_slot_pack(const float* in, const int32_t* cell_ptr, const int32_t* cel
     SDVAE_REQUIRE(B >= 0 && Vin > 0 && R > 0 && S > 0 && C > 0 && S * C <= 32, "slot_pack: bad shape (S*C must be <= 32)");
     if (B == 0) return SDVAE_OK;
     const long long rows = (long long)B * R;
-    long long blocks = (rows + 7) / 8;                       // 8 warps (rows) per block
-    if (blocks > (long long)kNumSMs * 32) blocks = (long long)kNumSMs * 32;
+    // one warp per row, no grid-stride cap: a row is three dependent loads (cell range, source row, value),
+    // so the kernel lives on the number of rows in flight
+    long long blocks = (rows + 8 * kSlotRows - 1) / (8 * kSlotRows);      // 8 warps x kSlotRows rows per block
+    if (blocks > 0x7fffffffLL) blocks = 0x7fffffffLL;
     slot_pack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, cell_ptr, cell_src, out, rows, R, Vin, S, C);
     return check_launch("slot_pack_kernel");
 }

@@ -19,7 +19,9 @@ namespace sdvae {
 
 // out[b, r, s*C + c] = sum_{e in cell(r, s)} in[b, src[e], c];  columns S*C .. 31 are zero.
 // cell_ptr == nullptr: cell(r, s) = { r*S + s } (forward table, cell_src = idx[R, S]).
-// One warp per output row (128-byte coalesced store); rows are summed in storage order.
+// One warp per output row (128-byte coalesced store); rows are summed in storage order.  A row is a chain of
+// three dependent loads (cell range -> source row -> value), so each warp keeps kSlotRows rows in flight.
+constexpr int kSlotRows = 4;
 __global__ void slot_pack_kernel(const float* __restrict__ in, const int* __restrict__ cell_ptr,
                                  const int* __restrict__ cell_src, float* __restrict__ out,
                                  long long rows_total, int R, int Vin, int S, int C) {
@@ -28,20 +30,34 @@ __global__ void slot_pack_kernel(const float* __restrict__ in, const int* __rest
     const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
     const int s = lane / C, c = lane - s * C;
     const bool live = lane < S * C;
-    for (long long m = w0; m < rows_total; m += nw) {
-        const long long b = m / R;
-        const int r = (int)(m - b * R);
-        float acc = 0.f;
-        if (live) {
-            const float* src = in + (size_t)b * Vin * C + c;
-            if (cell_ptr == nullptr) {
-                acc = __ldg(src + (size_t)__ldg(cell_src + (size_t)r * S + s) * C);
-            } else {
-                const int e0 = __ldg(cell_ptr + (size_t)r * S + s), e1 = __ldg(cell_ptr + (size_t)r * S + s + 1);
-                for (int e = e0; e < e1; ++e) acc = __fadd_rn(acc, __ldg(src + (size_t)__ldg(cell_src + e) * C));
+    for (long long m0 = w0 * kSlotRows; m0 < rows_total; m0 += nw * kSlotRows) {
+        int e0[kSlotRows], e1[kSlotRows];
+        const float* src[kSlotRows];
+#pragma unroll
+        for (int i = 0; i < kSlotRows; ++i) {
+            const long long m = m0 + i;
+            e0[i] = e1[i] = 0;
+            src[i] = in;
+            if (live && m < rows_total) {
+                const long long b = m / R;
+                const int r = (int)(m - b * R);
+                src[i] = in + (size_t)b * Vin * C + c;
+                if (cell_ptr == nullptr) { e0[i] = r * S + s; e1[i] = e0[i] + 1; }
+                else { e0[i] = __ldg(cell_ptr + (size_t)r * S + s); e1[i] = __ldg(cell_ptr + (size_t)r * S + s + 1); }
             }
         }
-        out[(size_t)m * 32 + lane] = acc;
+        int v0[kSlotRows];
+#pragma unroll
+        for (int i = 0; i < kSlotRows; ++i) v0[i] = e0[i] < e1[i] ? __ldg(cell_src + e0[i]) : -1;
+        float acc[kSlotRows];
+#pragma unroll
+        for (int i = 0; i < kSlotRows; ++i) acc[i] = v0[i] >= 0 ? __ldg(src[i] + (size_t)v0[i] * C) : 0.f;
+#pragma unroll
+        for (int i = 0; i < kSlotRows; ++i)                       // cells with more than one row (inverse tables)
+            for (int e = e0[i] + 1; e < e1[i]; ++e) acc[i] = __fadd_rn(acc[i], __ldg(src[i] + (size_t)__ldg(cell_src + e) * C));
+#pragma unroll
+        for (int i = 0; i < kSlotRows; ++i)
+            if (m0 + i < rows_total) out[(size_t)(m0 + i) * 32 + lane] = acc[i];
     }
 }
 

@@ -67,6 +67,10 @@ constexpr int kMaxRcap = 192;             // staged rows per (tile, slot) the ke
 constexpr int kMaxRaw = kLoadWarps;       // raw ring depth limit: loader warp w owns raw stage w
 constexpr uint32_t kSuspendHintNs = 100000;          // mbarrier.try_wait suspend-time hint
 constexpr int kSpinLimit = 1 << 22;                 // failed try_waits before a stuck wait traps
+#ifndef SDVAE_BACKOFF_NS
+#define SDVAE_BACKOFF_NS 100
+#endif
+constexpr unsigned kBackoffNs = SDVAE_BACKOFF_NS;    // sleep between polls of the relaxed waits
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -76,6 +80,14 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// One arrival per WARP (after a warp-level sync) instead of one per thread.  A sleeping waiter is woken by
+// every arrival on the CTA's barriers; with per-thread arrivals (128 per hand-off) the waiting warps of the
+// weight-gradient kernel executed 40 wake-up / re-check rounds per wait -- half of all issued instructions
+// (profiles/r01_bw_umma_stalls.txt).
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
 }
 // try_wait with a suspend-time hint: a waiting warp sleeps in hardware until the phase completes (or
 // the hint expires) instead of re-polling -- with 21 warps per CTA a polling loop would take issue
@@ -96,6 +108,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > kSpinLimit) __trap();
     }
+}
+// The same for the roles that have slack (loaders, splitters, epilogue): a failed try_wait comes back after
+// ~40 clk whatever the suspend hint says, and with 20+ warps of a CTA polling, the re-check rounds took
+// half of the SM's issue slots from the warps that had work (ncu: 199 M instructions for 8.6 k tiles, 150 M
+// of them in wait loops).  Back off between polls; the MMA warp keeps the tight loop.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    int spins = 0;
+    do {
+        __nanosleep(kBackoffNs);
+        if (++spins > kSpinLimit) __trap();
+    } while (!mbar_try_wait(bar, parity));
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -178,6 +202,24 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---- tuning instrumentation, compiled in with -DSDVAE_TUNING only (it costs 5-8 % when present) -------
+// SDVAE_DBG bits: 1 no copies, 2 no staged-row reads, 4 no MMAs, 8 no epilogue math/stores, 16 no split/STTM,
+// 32 per-role wait-cycle counters of CTA 0 (sdvae_debug_read_prof), 64/128/256 MMA-thread micro-ablations.
+#ifdef SDVAE_TUNING
+constexpr bool kTuning = true;
+#else
+constexpr bool kTuning = false;
+#endif
+#define SDVAE_DBG_ON(args, bit) (::sdvae::umma::kTuning && ((args).dbg & (bit)) != 0)
+__device__ long long g_prof[64];
+struct WaitClock {
+    long long acc; bool on;
+    __device__ __forceinline__ WaitClock(bool on_) : acc(0), on(on_) {}
+    template <class F> __device__ __forceinline__ void timed(F&& f) {
+        if (on) { const long long t0 = clock64(); f(); acc += clock64() - t0; } else f();
+    }
+};
 
 // ---- descriptors -----------------------------------------------------------------------------
 // Shared-memory matrix descriptor, K-major, SWIZZLE_128B, 8-row atoms 1024 B apart.
@@ -288,6 +330,7 @@ struct UmmaArgs {
     int B, in_rows, out_rows, L, S, rcap;
     int n_real, ldo, epi;
     int nraw;                 // raw ring depth (= active loader warps)
+    int dbg;                  // ablation switches for tuning runs (SDVAE_DBG): 1 no copies, 2 no staged-row reads, 4 no MMAs
 };
 
 
@@ -368,9 +411,9 @@ gc_umma_kernel(const UmmaArgs a) {
 
     // ---- one-time setup ---------------------------------------------------------------------
     if (tid == 0) {
-        for (int i = 0; i < NRAW; ++i) { mbar_init(raw_full + i, 32); mbar_init(raw_empty + i, 128); }
-        for (int i = 0; i < kMaxAStages; ++i) { mbar_init(a_full + i, 128); mbar_init(a_empty + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, kEpilogueWarps * 32); }
+        for (int i = 0; i < NRAW; ++i) { mbar_init(raw_full + i, 1); mbar_init(raw_empty + i, 4); }
+        for (int i = 0; i < kMaxAStages; ++i) { mbar_init(a_full + i, 4); mbar_init(a_empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, kEpilogueWarps); }
         fence_barrier_init();
     }
     if (warp == kMmaWarp) {
@@ -399,38 +442,52 @@ gc_umma_kernel(const UmmaArgs a) {
         reg_dec<kRegsLoad>();
         if (warp == kMmaWarp) {
             // ================= MMA issuer =================
-            // the whole warp walks the schedule and waits on the barriers; one elected lane issues
-            constexpr uint32_t IDESC1 = idesc_tf32(kBM, 2 * NT);
-            constexpr uint32_t IDESC2 = idesc_tf32(kBM, NT);
-            const bool leader = elect_one();
-            const uint32_t b_base = smem_u32(B_s);
-            int as = 0; uint32_t aph = 0;
+            // ONE elected thread walks the schedule.  Its per-chunk instruction stream is the serial spine of
+            // the kernel (with every other role ablated the kernel still took 324 clk per chunk, all of it this
+            // loop: ~70 mostly uniform-datapath instructions per chunk, each waiting for the previous one), so:
+            // no per-chunk warp sync, shared-memory descriptors by one 32-bit add from a precomputed base, and
+            // the readiness of the NEXT chunk is polled before the MMAs of the current one are issued, which
+            // hides the ~90 clk try_wait round trip behind them.
+            if (elect_one()) {
+                constexpr uint32_t IDESC1 = idesc_tf32(kBM, 2 * NT);
+                constexpr uint32_t IDESC2 = idesc_tf32(kBM, NT);
+                const uint64_t desc0 = smem_desc_sw128(smem_u32(B_s));
+                const uint32_t desc_hi = (uint32_t)(desc0 >> 32), desc_lo0 = (uint32_t)desc0;
+                const bool no_mma = SDVAE_DBG_ON(a, 4);
+                int as = 0; uint32_t aph = 0;
+                const bool prof = SDVAE_DBG_ON(a, 32) && blockIdx.x == 0;
+                WaitClock w_afull(prof), w_tempty(prof);
+                const long long t_begin = prof ? clock64() : 0;
+                bool ready = my_tiles > 0 && mbar_try_wait(a_full, 0u);
 #pragma unroll 1
-            for (int it = 0; it < my_tiles; ++it) {
-                const int acc = it & 1;
-                mbar_wait(t_empty + acc, ((it >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * NT);
+                for (int it = 0; it < my_tiles; ++it) {
+                    const int acc = it & 1;
+                    w_tempty.timed([&] { mbar_wait(t_empty + acc, ((it >> 1) & 1) ^ 1); });
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * NT);
 #pragma unroll 1
-                for (int ch = 0; ch < NCH; ++ch) {
-                    mbar_wait(a_full + as, aph);
-                    tc_fence_after();
-                    if (leader) {
+                    for (int ch = 0; ch < NCH; ++ch) {
+                        if (!ready) w_afull.timed([&] { mbar_wait(a_full + as, aph); });
+                        if (!SDVAE_DBG_ON(a, 128)) tc_fence_after();
                         const uint32_t a_hi = tmem_base + (uint32_t)(ACOL + as * 64), a_lo = a_hi + 32;
-                        const uint32_t b_ch = b_base + ch * B_CHUNK;
+                        const uint32_t dl = desc_lo0 + (uint32_t)(ch * (B_CHUNK >> 4));
+                        uint64_t* const my_empty = a_empty + as;
+                        if (++as == NAST) { as = 0; aph ^= 1; }
+                        ready = !SDVAE_DBG_ON(a, 256) && (ch + 1 < NCH || it + 1 < my_tiles) && mbar_try_wait(a_full + as, aph);
+                        if (!no_mma) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t bd = smem_desc_sw128(b_ch + k * 32);
-                            umma_tf32_ts(d_tmem, a_hi + k * 8, bd, IDESC1, (ch | k) != 0);
-                            umma_tf32_ts(d_tmem, a_lo + k * 8, bd, IDESC2, 1u);
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(dl + 2u * k);
+                                umma_tf32_ts(d_tmem, a_hi + k * 8, bd, IDESC1, (ch | k) != 0);
+                                umma_tf32_ts(d_tmem, a_lo + k * 8, bd, IDESC2, 1u);
+                            }
                         }
-                        umma_commit(a_empty + as);
-                        if (ch == NCH - 1) umma_commit(t_full + acc);
+                        if SDVAE_DBG_ON(a, 64) { mbar_arrive(my_empty); if (ch == NCH - 1) mbar_arrive(t_full + acc); }
+                        else { umma_commit(my_empty); if (ch == NCH - 1) umma_commit(t_full + acc); }
                     }
-                    __syncwarp();
-                    if (++as == NAST) { as = 0; aph ^= 1; }
                 }
+                if (prof) { g_prof[0] = clock64() - t_begin; g_prof[1] = w_afull.acc; g_prof[2] = w_tempty.acc; g_prof[3] = G; }
             }
+            __syncwarp();
         } else {
             // ================= loaders =================
             // loader warp w (< NRAW) owns raw stage w and takes the chunks g = w (mod NRAW) whole: 4 staged rows
@@ -447,25 +504,32 @@ gc_umma_kernel(const UmmaArgs a) {
             // Forward plans stage <= 128 rows per chunk: their plan words are fetched one own-chunk ahead, so
             // the issue loop never waits for them.  Backward plans (up to kMaxRcap rows) fetch at chunk start.
             constexpr int PV = UNIFORM ? 4 : kMaxRcap / 32;
+            const bool prof = SDVAE_DBG_ON(a, 32) && blockIdx.x == 0 && lw == 0;
+            WaitClock w_rempty(prof), w_copy(prof), w_plan(prof);
+            const long long t_begin = prof ? clock64() : 0;
             PlanRegs<PV> nxt;
             if (UNIFORM && cur.g < G) plan_fetch(nxt, a.plan_cnt, a.plan_src, cur.jt, S, cur.ch / CPS, a.rcap, rsub);
 #pragma unroll 1
             while (cur.g < G) {
                 PlanRegs<PV> now;
-                if (UNIFORM) now = nxt;
-                else plan_fetch(now, a.plan_cnt, a.plan_src, cur.jt, S, cur.ch / CPS, a.rcap, rsub);
+                w_plan.timed([&] {
+                    if (UNIFORM) now = nxt;
+                    else plan_fetch(now, a.plan_cnt, a.plan_src, cur.jt, S, cur.ch / CPS, a.rcap, rsub);
+                    if (prof && now.n < 0) g_prof[63] = now.w[0].x;      // force the loads to have landed
+                });
                 const int rs = cur.rs, h = cur.ch % CPS;
                 const uint32_t rph = cur.rph;
                 const float* base = a.in + (size_t)cur.b * a.in_rows * KS + h * 32 + 4 * q;
                 cur.advance(NRAW);
                 if (UNIFORM && cur.g < G) plan_fetch(nxt, a.plan_cnt, a.plan_src, cur.jt, S, cur.ch / CPS, a.rcap, rsub);
-                mbar_wait(raw_empty + rs, rph ^ 1);
+                w_rempty.timed([&] { mbar_wait_relaxed(raw_empty + rs, rph ^ 1); });
                 const uint32_t dst = raw_base + (uint32_t)rs * (uint32_t)RAW_STAGE;
-                plan_issue(now, dst + sw0, dst + sw1, base, KS * 4u);
+                if (!SDVAE_DBG_ON(a, 1)) plan_issue(now, dst + sw0, dst + sw1, base, KS * 4u);
                 cp_async_commit();
-                cp_async_wait<0>();
-                mbar_arrive(raw_full + rs);
+                w_copy.timed([&] { cp_async_wait<0>(); });
+                warp_arrive(raw_full + rs, lane);
             }
+            if (prof && lane == 0) { g_prof[8] = clock64() - t_begin; g_prof[9] = w_rempty.acc; g_prof[10] = w_copy.acc; g_prof[11] = w_plan.acc; }
         }
     } else if (warp < kFirstSplitWarp) {
         reg_dec<kRegsEpilogue>();
@@ -479,10 +543,13 @@ gc_umma_kernel(const UmmaArgs a) {
         constexpr bool vec_ok = NT >= 32;
         int b = (int)blockIdx.x / a.L, jt = (int)blockIdx.x - b * a.L;
         const int db = (int)gridDim.x / a.L, djt = (int)gridDim.x - db * a.L;
+        const bool prof = SDVAE_DBG_ON(a, 32) && blockIdx.x == 0 && warp == 0;
+        WaitClock w_tfull(prof);
+        const long long t_begin = prof ? clock64() : 0;
 #pragma unroll 1
         for (int it = 0; it < my_tiles; ++it) {
             const int acc = it & 1;
-            mbar_wait(t_full + acc, (it >> 1) & 1);
+            w_tfull.timed([&] { mbar_wait_relaxed(t_full + acc, (it >> 1) & 1); });
             tc_fence_after();
             const int r = jt * kBM + q4 * 32 + lane;              // row inside the mesh
             const bool row_ok = r < a.out_rows;
@@ -496,9 +563,9 @@ gc_umma_kernel(const UmmaArgs a) {
                 tmem_ld_wait();
                 if (c0 + 16 >= NT) {            // last read of this accumulator: hand it back to the MMA warp
                     tc_fence_before();
-                    mbar_arrive(t_empty + acc);
+                    warp_arrive(t_empty + acc, lane);
                 }
-                if (!row_ok) continue;
+                if (!row_ok || SDVAE_DBG_ON(a, 8)) continue;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] += d2[j];
                 float* orow = a.out + m * ldo + c0;
@@ -547,6 +614,7 @@ gc_umma_kernel(const UmmaArgs a) {
             b += db; jt += djt;
             if (jt >= a.L) { jt -= a.L; ++b; }
         }
+        if (prof && lane == 0) { g_prof[16] = clock64() - t_begin; g_prof[17] = w_tfull.acc; }
     } else {
         reg_inc<kRegsSplit>();
         // ================= splitters =================
@@ -557,6 +625,9 @@ gc_umma_kernel(const UmmaArgs a) {
         if (set < NS) {
             ChunkCursor cur(a, NCH, NRAW, NAST);                  // chunk being processed
             cur.advance(set);
+            const bool prof = SDVAE_DBG_ON(a, 32) && blockIdx.x == 0 && warp == kFirstSplitWarp;
+            WaitClock w_aempty(prof), w_rfull(prof), w_st(prof);
+            const long long t_begin = prof ? clock64() : 0;
             uint32_t cell = 0u;
             if (!UNIFORM && cur.g < G)
                 cell = (uint32_t)__ldg(a.plan_cell + ((size_t)cur.jt * S + cur.ch / CPS) * kBM + lr);
@@ -569,11 +640,14 @@ gc_umma_kernel(const UmmaArgs a) {
                 if (!UNIFORM && cur.g < G)
                     cell_next = (uint32_t)__ldg(a.plan_cell + ((size_t)cur.jt * S + cur.ch / CPS) * kBM + lr);
                 // Order matters (see NAST above): a_empty first, then the raw stage.
-                mbar_wait(a_empty + as, aph ^ 1);
-                mbar_wait(raw_full + rs, rph);
+                w_aempty.timed([&] { mbar_wait_relaxed(a_empty + as, aph ^ 1); });
+                w_rfull.timed([&] { mbar_wait_relaxed(raw_full + rs, rph); });
                 const uint8_t* stage = R_s + (size_t)rs * RAW_STAGE;
                 float v[32];
-                if (UNIFORM) {
+                if SDVAE_DBG_ON(a, 2) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = (float)(lr + j);
+                } else if (UNIFORM) {
                     // rows past the end of the mesh were never staged: their A rows are garbage, and so are the
                     // matching accumulator rows, which the epilogue never stores (MMA rows are independent)
                     // (a stage holds rcap rows: small tables have rcap < 128, and rows >= rcap lie outside it)
@@ -599,6 +673,7 @@ gc_umma_kernel(const UmmaArgs a) {
                         }
                     }
                 }
+                if (!SDVAE_DBG_ON(a, 16)) {
                 float lo[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) { float h; split_tf32f(v[j], h, lo[j]); v[j] = h; }
@@ -606,12 +681,14 @@ gc_umma_kernel(const UmmaArgs a) {
                 const uint32_t t_a = t_lane + (uint32_t)(as * 64);
                 tmem_st32(t_a, v);
                 tmem_st32(t_a + 32, lo);
-                mbar_arrive(raw_empty + rs);          // the staged rows are in registers (consumed by the stores above)
-                tmem_st_wait();
+                }
+                warp_arrive(raw_empty + rs, lane);    // the staged rows are in registers (consumed by the stores above)
+                w_st.timed([&] { tmem_st_wait(); });
                 tc_fence_before();
-                mbar_arrive(a_full + as);
+                warp_arrive(a_full + as, lane);
                 cell = cell_next;
             }
+            if (prof && lane == 0) { g_prof[24] = clock64() - t_begin; g_prof[25] = w_aempty.acc; g_prof[26] = w_rfull.acc; g_prof[27] = w_st.acc; }
         }
     }
 

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../include/sdvae_b200.h"
+extern "C" int sdvae_debug_read_prof(long long* host64);
 
 #define CK(x)                                                                          \
     do {                                                                               \
@@ -50,6 +51,16 @@ static T* dev_copy(const std::vector<T>& h) {
     return d;
 }
 
+
+static void print_prof() {
+    if (!getenv("SDVAE_DBG") || !(atoi(getenv("SDVAE_DBG")) & 32)) return;
+    long long pr[64];
+    sdvae_debug_read_prof(pr);
+    printf("prof (CTA 0, cycles)  chunks %lld\n  mma      total %lld  wait a_full %lld  wait t_empty %lld\n"
+           "  loader0  total %lld  wait raw_empty %lld  wait copies %lld  wait plan %lld\n"
+           "  epilogue total %lld  wait t_full %lld\n  split0   total %lld  wait a_empty %lld  wait raw_full %lld  wait tmem st %lld\n",
+           pr[3], pr[0], pr[1], pr[2], pr[8], pr[9], pr[10], pr[11], pr[16], pr[17], pr[24], pr[25], pr[26], pr[27]);
+}
 
 struct DevPlan { int* cnt; int* src; int* cell; int rcap; };
 static DevPlan make_plan(const std::vector<int>& cell_ptr, const std::vector<int>& cell_src, int out_rows, int S) {
@@ -213,6 +224,7 @@ int main(int argc, char** argv) {
         for (int i = 0; i < iters; ++i) ABI(sdvae_spiralconv_fwd_tc(d_x, pl.cnt, pl.src, pl.cell, pl.rcap, d_img, d_bias, d_y1, B, V, V, S, Cin, Cout, flag, st));
         CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms1, e0, e1));
         const double flops = 2.0 * B * V * (double)S * Cin * Cout, bytes = 4.0 * B * V * (double)(Cin + Cout);
+        print_prof();
         printf("time/launch: fma %.3f ms (%.1f TFLOP/s, %.0f GB/s alg)   tc %.3f ms (%.1f TFLOP/s, %.0f GB/s alg)   speedup %.2fx\n",
                ms0 / iters, flops / (ms0 / iters) * 1e-9, bytes / (ms0 / iters) * 1e-6,
                ms1 / iters, flops / (ms1 / iters) * 1e-9, bytes / (ms1 / iters) * 1e-6, ms0 / ms1);
@@ -290,6 +302,7 @@ int main(int argc, char** argv) {
     for (int i = 0; i < iters; ++i) ABI(sdvae_spiralconv_bwd_x_tc(d_dpre, pl.cnt, pl.src, pl.cell, pl.rcap, d_img, g, d_dx1, B, V, V, S, Cout, Cin, st));
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms1, e0, e1));
     const double flops = 2.0 * B * V * (double)S * Cin * Cout;
+    print_prof();
     printf("time/launch: fma %.3f ms (%.1f TFLOP/s)   tc %.3f ms (%.1f TFLOP/s)   speedup %.2fx\n",
            ms0 / iters, flops / (ms0 / iters) * 1e-9, ms1 / iters, flops / (ms1 / iters) * 1e-9, ms0 / ms1);
     const bool ok = maxdiff / maxref < 2e-5 && bad == 0;
