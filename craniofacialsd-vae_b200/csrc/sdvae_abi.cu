@@ -314,6 +314,21 @@ int sdvae_slot_pack(const float* in, const int32_t* cell_ptr, const int32_t* cel
     SDVAE_REQUIRE(in && cell_src && out, "slot_pack: null pointer");
     SDVAE_REQUIRE(B >= 0 && Vin > 0 && R > 0 && S > 0 && C > 0 && S * C <= 32, "slot_pack: bad shape (S*C must be <= 32)");
     if (B == 0) return SDVAE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t in_bytes = (size_t)Vin * C * sizeof(float);
+    if (in_bytes <= 220 * 1024) {            // the mesh's narrow input fits in shared memory
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(slot_pack_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            attr_done = true;
+        }
+        int parts = 1;                         // split meshes into row ranges until the grid fills the SMs evenly
+        while ((long long)B * parts < 4LL * kNumSMs && parts < 16 && R / (parts * 2) >= 256) parts *= 2;
+        const long long items = (long long)B * parts;
+        const int grid = items < kNumSMs ? (int)items : kNumSMs;
+        slot_pack_smem_kernel<<<grid, 1024, in_bytes, st>>>(in, cell_ptr, cell_src, out, B, parts, R, Vin, S, C);
+        return check_launch("slot_pack_smem_kernel");
+    }
     const long long rows = (long long)B * R;
     // one warp per row, no grid-stride cap: a row is three dependent loads (cell range, source row, value),
     // so the kernel lives on the number of rows in flight

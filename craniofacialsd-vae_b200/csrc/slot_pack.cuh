@@ -61,6 +61,64 @@ __global__ void slot_pack_kernel(const float* __restrict__ in, const int* __rest
     }
 }
 
+// The same operation with the whole narrow input of one mesh ([Vin, C], 204 KB for the craniofacial
+// template) resident in shared memory: the 12-byte gathers then cost shared-memory wavefronts instead of
+// one 32-byte L2 sector each (the global version moves ~5x its useful bytes and ran at 0.7 ms for 256
+// meshes; this one is bound by the 128-byte row stores).  Work item = (mesh, row range); every item
+// loads its mesh.  1024 threads, one warp per output row, kSlotRows rows in flight per warp.
+__global__ void __launch_bounds__(1024, 1)
+slot_pack_smem_kernel(const float* __restrict__ in, const int* __restrict__ cell_ptr,
+                      const int* __restrict__ cell_src, float* __restrict__ out,
+                      int B, int parts, int R, int Vin, int S, int C) {
+    extern __shared__ float xs[];                               // [Vin * C]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s = lane / C, c = lane - s * C;
+    const bool live = lane < S * C;
+    const int n4 = (Vin * C) >> 2, tail = (Vin * C) & 3;
+    const int rows_per_part = (R + parts - 1) / parts;
+    for (int item = blockIdx.x; item < B * parts; item += gridDim.x) {
+        const int b = item / parts, part = item - b * parts;
+        const float* src = in + (size_t)b * Vin * C;
+        __syncthreads();                                        // previous item's reads are done
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            for (int i = threadIdx.x; i < n4; i += blockDim.x) cp_async16(xs + 4 * i, src + 4 * i);
+            if (threadIdx.x < tail) xs[4 * n4 + threadIdx.x] = __ldg(src + 4 * n4 + threadIdx.x);
+            cp_async_commit();
+            cp_async_wait<0>();
+        } else {
+            for (int i = threadIdx.x; i < Vin * C; i += blockDim.x) xs[i] = __ldg(src + i);
+        }
+        __syncthreads();
+        const int r_begin = part * rows_per_part;
+        const int r_end = min(R, r_begin + rows_per_part);
+        float* o = out + (size_t)b * R * 32;
+        for (int r0 = r_begin + warp * kSlotRows; r0 < r_end; r0 += 32 * kSlotRows) {
+            int e0[kSlotRows], e1[kSlotRows];
+#pragma unroll
+            for (int i = 0; i < kSlotRows; ++i) {
+                const int r = r0 + i;
+                e0[i] = e1[i] = 0;
+                if (live && r < r_end) {
+                    if (cell_ptr == nullptr) { e0[i] = r * S + s; e1[i] = e0[i] + 1; }
+                    else { e0[i] = __ldg(cell_ptr + (size_t)r * S + s); e1[i] = __ldg(cell_ptr + (size_t)r * S + s + 1); }
+                }
+            }
+            int v0[kSlotRows];
+#pragma unroll
+            for (int i = 0; i < kSlotRows; ++i) v0[i] = e0[i] < e1[i] ? __ldg(cell_src + e0[i]) : -1;
+            float acc[kSlotRows];
+#pragma unroll
+            for (int i = 0; i < kSlotRows; ++i) acc[i] = v0[i] >= 0 ? xs[v0[i] * C + c] : 0.f;
+#pragma unroll
+            for (int i = 0; i < kSlotRows; ++i)
+                for (int e = e0[i] + 1; e < e1[i]; ++e) acc[i] = __fadd_rn(acc[i], xs[__ldg(cell_src + e) * C + c]);
+#pragma unroll
+            for (int i = 0; i < kSlotRows; ++i)
+                if (r0 + i < r_end) o[(size_t)(r0 + i) * 32 + lane] = acc[i];
+        }
+    }
+}
+
 // Dense 32 x 32 weight of a slot-packed layer (rows n, columns k), from the layer's own weight:
 //   mode 0 (narrow input,  W [N, S*C])     Wd[n, k] = k < S*C ? W[n, k] : 0                      (n < N)
 //   mode 1 (narrow output, W [C, S*32])    Wd[c, j] = j < S*C ? W[j % C, (j / C)*32 + c] : 0

@@ -177,12 +177,18 @@ def test_tc_weight_gradient_restricted_rows(cranio, orc):
     assert nerr(db, b.grad) < TC_TOL
 
 
-def test_slot_pack_is_bit_exact(cranio):
+@pytest.mark.parametrize('case', ['template-level-1', 'large-random'])
+def test_slot_pack_is_bit_exact(cranio, case):
     """slot_pack = the gather of model.py:34 restricted to S*C <= 32 columns, forward table and inverse
-    (cell) table; index work and storage-order sums are bit-exact against torch on the same inputs."""
+    (cell) table; index work and storage-order sums are bit-exact against torch on the same inputs.
+    'large-random': 19 000 vertices x 3 channels do not fit in shared memory -> the global-gather kernel."""
     from sdvae_b200 import cabi
     from sdvae_b200.tables import spiral_table
-    idx = cranio.spiral_tensors()[1]
+    if case == 'template-level-1':
+        idx = cranio.spiral_tensors()[1]
+    else:
+        rs = np.random.RandomState(3)
+        idx = torch.from_numpy(np.concatenate([np.arange(19000)[:, None], rs.randint(0, 19000, (19000, 8))], 1))
     V, S = idx.shape
     B, Cn = 3, 3
     tab = spiral_table(idx.to(DEV))
@@ -196,9 +202,10 @@ def test_slot_pack_is_bit_exact(cranio):
     cp, cs = tab.inverse()
     cabi.slot_pack(x.to(DEV), cp, cs, out, B, V, V, S, Cn)
     want = torch.zeros(B, V, S, Cn)
+    idx_l = idx.tolist()
     for v in range(V):                      # ascending v = storage order of the inverse cells
         for s_ in range(S):
-            want[:, idx[v, s_], s_] += x[:, v]
+            want[:, idx_l[v][s_], s_] += x[:, v]
     got = out.cpu()
     assert torch.equal(got[:, :, :S * Cn], want.reshape(B, V, S * Cn))
     assert not got[:, :, S * Cn:].any()
