@@ -494,6 +494,11 @@ int sdvae_pool_ell_fwd(const float* x, const int32_t* col, const float* val, flo
                      ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     const long long total = (long long)B * Vout * (vec ? C / 4 : C);
     if (total == 0) return SDVAE_OK;
+    if (vec && B >= kPoolMeshes) {
+        const long long tb = (long long)((B + kPoolMeshes - 1) / kPoolMeshes) * Vout * (C / 4);
+        pool_ell_fwd_batch_kernel<<<blocks_for(tb, 256), 256, 0, st>>>(x, col, val, out, tb, B, Vin, Vout, Wd, C);
+        return check_launch("pool_ell_fwd_batch_kernel");
+    }
     if (vec) pool_ell_fwd_kernel<true><<<blocks_for(total, 256), 256, 0, st>>>(x, col, val, out, total, Vin, Vout, Wd, C);
     else pool_ell_fwd_kernel<false><<<blocks_for(total, 256), 256, 0, st>>>(x, col, val, out, total, Vin, Vout, Wd, C);
     return check_launch("pool_ell_fwd_kernel");
@@ -510,6 +515,11 @@ int sdvae_csr_rowsum(const float* dy, const int32_t* ptr, const int32_t* src, co
                      (!gate || (reinterpret_cast<uintptr_t>(gate) & 15) == 0);
     const long long total = (long long)B * Vdst * (vec ? C / 4 : C);
     if (total == 0) return SDVAE_OK;
+    if (vec && B >= kPoolMeshes) {
+        const long long tb = (long long)((B + kPoolMeshes - 1) / kPoolMeshes) * Vdst * (C / 4);
+        csr_rowsum_batch_kernel<<<blocks_for(tb, 256), 256, 0, st>>>(dy, ptr, src, val, gate, dx, tb, B, Vsrc, Vdst, C);
+        return check_launch("csr_rowsum_batch_kernel");
+    }
     if (vec) csr_rowsum_kernel<true><<<blocks_for(total, 256), 256, 0, st>>>(dy, ptr, src, val, gate, dx, total, Vsrc, Vdst, C);
     else csr_rowsum_kernel<false><<<blocks_for(total, 256), 256, 0, st>>>(dy, ptr, src, val, gate, dx, total, Vsrc, Vdst, C);
     return check_launch("csr_rowsum_kernel");

@@ -87,13 +87,13 @@ def test_spiralconv_2d_input_and_errors(cranio, golden):
         conv(x.double().to(DEV))
 
 
-@pytest.mark.parametrize('lvl,C', [(0, 32), (1, 32), (2, 64), (3, 64), (3, 5)])
-def test_pool_up_down_bit_exact_forward(cranio, orc, lvl, C):
-    """Pool keeps the reference's storage-order, mul-then-add arithmetic -> identical bits."""
+@pytest.mark.parametrize('lvl,C,B', [(0, 32, 3), (0, 32, 6), (1, 32, 5), (2, 64, 3), (3, 64, 9), (3, 5, 3)])
+def test_pool_up_down_bit_exact_forward(cranio, orc, lvl, C, B):
+    """Pool keeps the reference's storage-order, mul-then-add arithmetic -> identical bits.
+    B >= 4 runs the several-meshes-per-thread kernels (with a ragged last group), B = 3 the plain ones."""
     from sdvae_b200.model import Pool
     up, down = cranio.up_tensors()[lvl], cranio.down_tensors()[lvl]
     Vf, Vc = up.shape
-    B = 3
     xc = rand((B, Vc, C), 5)
     xf = rand((B, Vf, C), 6)
     for trans, x in ((up, xc), (down, xf)):
