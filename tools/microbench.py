@@ -1,0 +1,197 @@
+#!/usr/bin/env python
+"""SpiralConv + Pool micro-benchmark sweep (BASELINE.json configs[4]).
+
+Every encoder/decoder layer of craniofacial.yaml x {forward, backward-to-input, weight gradient} and every
+Pool level x {forward, backward}, at several batch sizes, through the C ABI, timed with CUDA events on the
+launching stream.  Each timed iteration works on a different one of several input/output buffer sets
+whose total size exceeds the 126 MB L2 (so no iteration finds its inputs cached).  Reports milliseconds,
+the ALGORITHMIC bytes per launch (4*(Vin*Cin + Vout*Cout) per mesh for a conv,
+4*C*(rows_read + Vout) for a pool), the achieved GB/s against MEASURED_PEAKS.json's HBM figure, and the
+effective TFLOP/s.  Output: a Markdown table on stdout (committed under profiles/).
+
+usage: python tools/microbench.py [--batches 1,16,256,1024] [--iters 10]"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+DEV = 'cuda:0'
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        return float(json.load(open(p))['hbm_gbs']), 'measured'
+    return 6650.0, 'fallback'
+
+
+def timeit(fn, sets, iters):
+    """fn(k) runs the launch on buffer set k.  Returns average ms per launch."""
+    for k in range(min(3, sets)):
+        fn(k % sets)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i % sets)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def nsets(bytes_per_set):
+    return int(max(2, min(8, (300 << 20) // max(1, bytes_per_set) + 1)))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--batches', default='1,16,256,1024')
+    ap.add_argument('--iters', type=int, default=10)
+    args = ap.parse_args()
+    from sdvae_b200 import cabi, fixtures as fx
+    from sdvae_b200.tables import identity_plan, pool_table, restricted_spiral_table, spiral_table
+    cabi.load()
+    tabs = fx.craniofacial_tables()
+    sp = [s.to(DEV) for s in tabs.spiral_tensors()]
+    dn = [d.to(DEV) for d in tabs.down_tensors()]
+    up = [u.to(DEV) for u in tabs.up_tensors()]
+    V = tabs.num_vertices
+    peak, src = hbm_peak()
+    f = lambda *shape: torch.randn(shape, device=DEV, dtype=torch.float32)
+    print('# SpiralConv / Pool micro-benchmark (craniofacial.yaml layers, 1 x B200)\n')
+    print('HBM peak %.1f GB/s (%s); algorithmic bytes per SURVEY.md 8(d); inputs rotate through buffer sets > L2.\n' % (peak, src))
+    print('| op | layer | B | path | ms | alg MB | GB/s | frac of HBM peak | TFLOP/s |')
+    print('|---|---|---|---|---|---|---|---|---|')
+
+    def row(op, layer, B, path, ms, alg_bytes, flops):
+        gbs = alg_bytes / ms * 1e-6
+        print('| %s | %s | %d | %s | %.4f | %.1f | %.0f | %.3f | %.1f |' %
+              (op, layer, B, path, ms, alg_bytes / 1e6, gbs, gbs / peak, flops / ms * 1e-9))
+
+    # (name, level, restricted to kept rows?, Cin, Cout, act)
+    convs = [('en0 3->32 @17039 (kept rows)', 0, True, 3, 32), ('en1 32->32 @4260 (kept rows)', 1, True, 32, 32),
+             ('en2 32->32 @1065 (kept rows)', 2, True, 32, 32), ('en3 32->64 @267 (kept rows)', 3, True, 32, 64),
+             ('de1 64->64 @267', 3, False, 64, 64), ('de2 64->32 @1065', 2, False, 64, 32),
+             ('de3 32->32 @4260', 1, False, 32, 32), ('de4 32->32 @17039', 0, False, 32, 32),
+             ('de5 32->3 @17039', 0, False, 32, 3)]
+    for B in [int(b) for b in args.batches.split(',')]:
+        for name, lvl, restricted, cin, cout in convs:
+            full = spiral_table(sp[lvl])
+            tab = restricted_spiral_table(sp[lvl], pool_table(dn[lvl])) if restricted else full
+            Vin, R, S = V[lvl], tab.n_rows, tab.seq
+            alg = 4.0 * B * (Vin * cin + R * cout)
+            flops = 2.0 * B * R * S * cin * cout
+            ns = nsets(int(alg))
+            xs = [f(B, Vin, cin) for _ in range(ns)]
+            ys = [f(B, R, cout) for _ in range(ns)]
+            w = f(cout, S * cin) * 0.05
+            b = f(cout) * 0.1
+            act = cabi.ACT_NONE if cout == 3 else cabi.ACT_ELU
+            # forward
+            plan = tab.plan_fwd()
+            if cin in (32, 64) and cabi.tc_supported(S, cin, cout, plan.rcap):
+                wimg = torch.empty(cabi.tc_wimg_floats(S, cin, cout), device=DEV)
+                cabi.tc_pack_weights(w, wimg, S, cin, cout, False)
+                ms = timeit(lambda k: cabi.spiralconv_fwd_tc(xs[k], plan, wimg, b, ys[k], B, Vin, R, S, cin, cout, act), ns, args.iters)
+                row('conv fwd', name, B, 'tcgen05 3xTF32', ms, alg, flops)
+            elif S * cin <= 32 and cout == 32:
+                P = torch.empty(B, R, 32, device=DEV)
+                Wd = torch.empty(1024, device=DEV)
+                wimg = torch.empty(cabi.tc_wimg_floats(1, 32, 32), device=DEV)
+                cabi.slot_weight(w, Wd, 0, cout, S, cin)
+                cabi.tc_pack_weights(Wd, wimg, 1, 32, 32, False)
+                ip = identity_plan(R, DEV)
+
+                def fwd_slot(k):
+                    cabi.slot_pack(xs[k], None, tab.idx, P, B, Vin, R, S, cin)
+                    cabi.dense_tc(P, ip, wimg, b, None, ys[k], B, R, act)
+                ms = timeit(fwd_slot, ns, args.iters)
+                row('conv fwd', name, B, 'slot-pack + dense tcgen05', ms, alg, flops)
+            else:
+                ms = timeit(lambda k: cabi.spiralconv_fwd(xs[k], tab.idx, w, b, ys[k], B, Vin, R, S, cin, cout, act), ns, args.iters)
+                row('conv fwd', name, B, 'fp32 FMA', ms, alg, flops)
+            # weight gradient (reads x and dy, writes dW)
+            ws = torch.empty(cabi.spiralconv_bwd_w_workspace(B * R, S, cin, cout) // 4 + 4, device=DEV)
+            dW, db = torch.empty(cout, S * cin, device=DEV), torch.empty(cout, device=DEV)
+            dWd, dbd = torch.empty(32, 32, device=DEV), torch.empty(32, device=DEV)
+            if S * cin <= 32 and cout == 32:
+                # the engine's path: dW = dy^T P with the slot-packed input P of the forward pass
+                ipR = identity_plan(R, DEV)
+                Pk = torch.randn(B, R, 32, device=DEV)
+
+                def dw_slot_in(k):
+                    cabi.spiralconv_bwd_w_tc(Pk, ipR, ys[k], dWd, dbd, ws, B, R, R, 1, 32, 32)
+                    cabi.slot_grad(dWd, dbd, dW, db, 0, cout, S, cin)
+                ms = timeit(dw_slot_in, ns, args.iters)
+                row('conv dW', name, B, 'dense tcgen05 on slot-packed P', ms, alg, flops)
+            elif S * cout <= 32 and cin == 32:
+                # the engine's path: dW[n, s*32+c] = (G^T x)[s*3+n, c], G shared with the input-gradient pass
+                ipV = identity_plan(Vin, DEV)
+                Gk = torch.randn(B, Vin, 32, device=DEV)
+
+                def dw_slot_out(k):
+                    cabi.spiralconv_bwd_w_tc(xs[k], ipV, Gk, dWd, dbd, ws, B, Vin, Vin, 1, 32, 32)
+                    cabi.slot_grad(dWd, dbd, dW, db, 1, cout, S, cout)
+                ms = timeit(dw_slot_out, ns, args.iters)
+                row('conv dW', name, B, 'dense tcgen05 on slot-packed G (G from the dx pass)', ms, alg, flops)
+            elif cin == 32 and cabi.tc_bwd_w_supported(S, cin, cout, plan.rcap):
+                ms = timeit(lambda k: cabi.spiralconv_bwd_w_tc(xs[k], plan, ys[k], dW, db, ws, B, Vin, R, S, cin, cout), ns, args.iters)
+                row('conv dW', name, B, 'tcgen05 3xTF32', ms, alg, flops)
+            else:
+                ms = timeit(lambda k: cabi.spiralconv_bwd_w(xs[k], tab.idx, ys[k], dW, db, ws, B, Vin, R, S, cin, cout), ns, args.iters)
+                row('conv dW', name, B, 'fp32 FMA', ms, alg, flops)
+            # backward to input (reads dy, writes dx)
+            if cin == 3:
+                continue                                   # the first layer has no input gradient
+            pb = tab.plan_bwd()
+            if cabi.tc_supported(S, cout, cin, pb.rcap):
+                wimg_t = torch.empty(cabi.tc_wimg_floats(S, cout, cin), device=DEV)
+                cabi.tc_pack_weights(w, wimg_t, S, cin, cout, True)
+                ms = timeit(lambda k: cabi.spiralconv_bwd_x_tc(ys[k], pb, wimg_t, None, xs[k], B, R, Vin, S, cout, cin), ns, args.iters)
+                row('conv dx', name, B, 'tcgen05 3xTF32', ms, alg, flops)
+            elif S * cout <= 32 and cin == 32:
+                G = torch.empty(B, Vin, 32, device=DEV)
+                Wd = torch.empty(1024, device=DEV)
+                wimg = torch.empty(cabi.tc_wimg_floats(1, 32, 32), device=DEV)
+                cabi.slot_weight(w, Wd, 1, cout, S, cout)
+                cabi.tc_pack_weights(Wd, wimg, 1, 32, 32, False)
+                ip = identity_plan(Vin, DEV)
+                cp, cs = tab.inverse()
+
+                def bwd_slot(k):
+                    cabi.slot_pack(ys[k], cp, cs, G, B, R, Vin, S, cout)
+                    cabi.dense_tc(G, ip, wimg, None, None, xs[k], B, Vin, cabi.ACT_NONE)
+                ms = timeit(bwd_slot, ns, args.iters)
+                row('conv dx', name, B, 'slot-pack + dense tcgen05', ms, alg, flops)
+            else:
+                wt = torch.empty(cin, S * cout, device=DEV)
+                cabi.weight_transpose(w, wt, cout, cin, S)
+                cp, cs = tab.inverse()
+                ms = timeit(lambda k: cabi.spiralconv_bwd_x(ys[k], cp, cs, wt, None, xs[k], B, R, Vin, S, cout, cin), ns, args.iters)
+                row('conv dx', name, B, 'fp32 FMA', ms, alg, flops)
+            del xs, ys
+        # pools: up-sampling (3 nnz / row) forward and backward; the down-sampling selections are fused
+        # into the encoder convolutions (computed at the kept rows only) and have no launch of their own
+        for lvl, C in ((3, 64), (2, 64), (1, 32), (0, 32)):
+            pt = pool_table(up[lvl])
+            Vf, Vc = V[lvl], V[lvl + 1]
+            alg = 4.0 * B * C * (Vc + Vf)
+            flops = 2.0 * B * 3 * Vf * C
+            ns = nsets(int(alg))
+            xc = [f(B, Vc, C) for _ in range(ns)]
+            xf = [f(B, Vf, C) for _ in range(ns)]
+            ms = timeit(lambda k: cabi.pool_ell_fwd(xc[k], pt.ell_col, pt.ell_val, xf[k], B, Vc, Vf, pt.width, C), ns, args.iters)
+            row('pool up fwd', '%d->%d C%d' % (Vc, Vf, C), B, 'ELL gather', ms, alg, flops)
+            ms = timeit(lambda k: cabi.csr_rowsum(xf[k], pt.t_ptr, pt.t_row, pt.t_val, None, xc[k], B, Vf, Vc, C), ns, args.iters)
+            row('pool up bwd', '%d->%d C%d' % (Vf, Vc, C), B, 'transposed CSR', ms, alg, flops)
+            del xc, xf
+        torch.cuda.empty_cache()
+
+
+if __name__ == '__main__':
+    main()
