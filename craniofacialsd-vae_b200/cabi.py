@@ -35,8 +35,9 @@ _SIGNATURES = {
     "sdvae_tc_plan_tiles": (C.c_int, [C.c_int]),
     "sdvae_tc_plan_max_rows": (C.c_int, [_c_fp, C.c_int, C.c_int]),
     "sdvae_tc_plan_build": (C.c_int, [_c_fp, _c_fp, C.c_int, C.c_int, C.c_int, _c_fp, _c_fp, _c_fp]),
-    "sdvae_spiralconv_fwd_tc": (C.c_int, [_c_fp] * 4 + [C.c_int] + [_c_fp] * 3 + [C.c_int] * 7 + [_c_fp]),
-    "sdvae_spiralconv_bwd_x_tc": (C.c_int, [_c_fp] * 4 + [C.c_int] + [_c_fp] * 3 + [C.c_int] * 6 + [_c_fp]),
+    "sdvae_tc_pack_weights_part": (C.c_int, [_c_fp, _c_fp] + [C.c_int] * 6 + [_c_fp]),
+    "sdvae_spiralconv_fwd_tc": (C.c_int, [_c_fp] * 4 + [C.c_int] + [_c_fp] * 3 + [C.c_int] * 8 + [_c_fp]),
+    "sdvae_spiralconv_bwd_x_tc": (C.c_int, [_c_fp] * 4 + [C.c_int] + [_c_fp] * 3 + [C.c_int] * 7 + [_c_fp]),
     "sdvae_tc_bwd_w_supported": (C.c_int, [C.c_int] * 4),
     "sdvae_spiralconv_bwd_w_tc": (C.c_int, [_c_fp] * 3 + [C.c_int] + [_c_fp] * 4 + [C.c_int] * 6 + [_c_fp]),
     "sdvae_dense_tc": (C.c_int, [_c_fp] * 3 + [C.c_int] + [_c_fp] * 4 + [C.c_int] * 3 + [_c_fp]),
@@ -183,9 +184,12 @@ def tc_wimg_floats(S, KS, N) -> int:
     return int(load().sdvae_tc_wimg_floats(S, KS, N))
 
 
-def tc_pack_weights(weight, wimg, S, Cin, Cout, transposed):
-    rc = load().sdvae_tc_pack_weights(_f(weight, "weight"), _f(wimg, "wimg"), S, Cin, Cout,
-                                      1 if transposed else 0, _stream())
+def tc_pack_weights(weight, wimg, S, Cin, Cout, transposed, n0=0, n_cnt=None):
+    """Packed weight image of output channels [n0, n0 + n_cnt) (input channels if ``transposed``)."""
+    if n_cnt is None:
+        n_cnt = (Cin if transposed else Cout) - n0
+    rc = load().sdvae_tc_pack_weights_part(_f(weight, "weight"), _f(wimg, "wimg"), S, Cin, Cout,
+                                           1 if transposed else 0, n0, n_cnt, _stream())
     if rc:
         _err(rc, "tc_pack_weights")
     add_launches(_KERNELS_PER_CALL["tc_pack_weights"])
@@ -215,21 +219,23 @@ def tc_plan_build(cell_ptr, cell_src, out_rows, S):
     return cnt, src, cell, rcap
 
 
-def spiralconv_fwd_tc(x, plan, wimg, bias, y, B, Vin, Vout, S, Cin, Cout, act):
+def spiralconv_fwd_tc(x, plan, wimg, bias, y, B, Vin, Vout, S, Cin, Cout, act, ldy=0):
+    """``ldy`` > Cout: ``y`` (and ``bias``) start at the first of Cout consecutive output channels of a wider
+    [.., ldy] tensor (a flat view sliced at that channel)."""
     rc = load().sdvae_spiralconv_fwd_tc(_f(x, "x"), _i(plan.cnt, "plan.cnt"), _i(plan.src, "plan.src"),
                                         _i(plan.cell, "plan.cell"), plan.rcap, _f(wimg, "wimg"),
                                         _fo(bias, "bias"), _f(y, "y"), B, Vin, Vout, S, Cin, Cout,
-                                        act, _stream())
+                                        act, ldy, _stream())
     if rc:
         _err(rc, "spiralconv_fwd_tc")
     add_launches(_KERNELS_PER_CALL["spiralconv_fwd_tc"])
 
 
-def spiralconv_bwd_x_tc(dpre, plan, wimg_t, gate, dx, B, Vrows, Vdst, S, Cout, Cin):
+def spiralconv_bwd_x_tc(dpre, plan, wimg_t, gate, dx, B, Vrows, Vdst, S, Cout, Cin, lddx=0):
     rc = load().sdvae_spiralconv_bwd_x_tc(_f(dpre, "dpre"), _i(plan.cnt, "plan.cnt"),
                                           _i(plan.src, "plan.src"), _i(plan.cell, "plan.cell"),
                                           plan.rcap, _f(wimg_t, "wimg_t"), _fo(gate, "gate"),
-                                          _f(dx, "dx"), B, Vrows, Vdst, S, Cout, Cin, _stream())
+                                          _f(dx, "dx"), B, Vrows, Vdst, S, Cout, Cin, lddx, _stream())
     if rc:
         _err(rc, "spiralconv_bwd_x_tc")
     add_launches(_KERNELS_PER_CALL["spiralconv_bwd_x_tc"])

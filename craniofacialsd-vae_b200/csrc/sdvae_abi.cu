@@ -191,12 +191,21 @@ size_t sdvae_tc_wimg_floats(int S, int KS, int N) {
 
 int sdvae_tc_pack_weights(const float* W, float* wimg, int S, int Cin, int Cout, int transposed,
                           sdvae_stream_t stream) {
+    return sdvae_tc_pack_weights_part(W, wimg, S, Cin, Cout, transposed, 0, transposed ? Cin : Cout, stream);
+}
+
+int sdvae_tc_pack_weights_part(const float* W, float* wimg, int S, int Cin, int Cout, int transposed,
+                               int n0, int n_cnt, sdvae_stream_t stream) {
     SDVAE_REQUIRE(W && wimg && S > 0 && Cin > 0 && Cout > 0, "tc_pack_weights: bad argument");
-    const int KS = transposed ? Cout : Cin, N = transposed ? Cin : Cout;
+    const int KS = transposed ? Cout : Cin, Nfull = transposed ? Cin : Cout, N = n_cnt;
+    SDVAE_REQUIRE(n0 >= 0 && n_cnt > 0 && n0 + n_cnt <= Nfull, "tc_pack_weights: bad output-channel range");
     if (!tc_shape_ok(S, KS, N, 128)) return set_error(SDVAE_ERR_UNSUPPORTED, "tc_pack_weights: unsupported layer shape");
     SDVAE_REQUIRE((reinterpret_cast<uintptr_t>(wimg) & 15) == 0, "tc_pack_weights: wimg must be 16-byte aligned");
     umma::PackArgs a;
-    a.W = W; a.img = wimg; a.NT = tc_tile_n(N); a.KS = KS; a.S = S; a.n_real = N; a.ldw = S * Cin;
+    // rows n0 .. n0+n_cnt of the (transposed) weight: forward W[n, k] -> offset n0 rows; transposed
+    // Wt[c, s*Cout + o] = W[o, s*Cin + c] -> offset n0 columns
+    a.W = transposed ? W + n0 : W + (size_t)n0 * S * Cin;
+    a.img = wimg; a.NT = tc_tile_n(N); a.KS = KS; a.S = S; a.n_real = N; a.ldw = S * Cin;
     a.transposed = transposed ? 1 : 0; a.cin = Cin;
     const long long total = (long long)S * (KS / 32) * 2 * a.NT * 32;
     umma::umma_pack_weights_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a);
@@ -263,7 +272,7 @@ int sdvae_tc_plan_build(const int32_t* cell_ptr, const int32_t* cell_src, int ou
 static int tc_conv(const float* in, const int32_t* plan_cnt, const int32_t* plan_src,
                    const int32_t* plan_cell, int rcap, const float* wimg, const float* bias,
                    const float* gate, float* out, int B, int in_rows, int out_rows, int S, int KS,
-                   int N, int epi, bool uniform, cudaStream_t st, const char* who) {
+                   int N, int ldo, int epi, bool uniform, cudaStream_t st, const char* who) {
     SDVAE_REQUIRE(in && plan_cnt && plan_src && (uniform || plan_cell) && wimg && out, "spiralconv tc: null pointer");
     SDVAE_REQUIRE(B >= 0 && in_rows > 0 && out_rows > 0 && S > 0 && KS > 0 && N > 0, "spiralconv tc: bad shape");
     SDVAE_REQUIRE((long long)B * in_rows < 2147483647LL, "spiralconv tc: B*rows exceeds int32");
@@ -273,31 +282,31 @@ static int tc_conv(const float* in, const int32_t* plan_cnt, const int32_t* plan
     if (tc_tile_n(N) >= 32) {       // full-width tiles use 16-byte epilogue accesses
         const uintptr_t al = reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias) |
                              reinterpret_cast<uintptr_t>(gate);
-        if (N != tc_tile_n(N) || (al & 15) != 0) return set_error(SDVAE_ERR_UNSUPPORTED, who);
+        if (N != tc_tile_n(N) || (al & 15) != 0 || (ldo > 0 && ldo % 4 != 0)) return set_error(SDVAE_ERR_UNSUPPORTED, who);
     }
     umma::UmmaArgs ua{};
     ua.in = in; ua.plan_cnt = plan_cnt; ua.plan_src = plan_src; ua.plan_cell = plan_cell;
     ua.wimg = wimg; ua.bias = bias; ua.gate = gate; ua.out = out;
     ua.B = B; ua.in_rows = in_rows; ua.out_rows = out_rows; ua.L = sdvae_tc_plan_tiles(out_rows);
-    ua.S = S; ua.rcap = rcap; ua.n_real = N; ua.ldo = N; ua.epi = epi;
+    ua.S = S; ua.rcap = rcap; ua.n_real = N; ua.ldo = ldo > 0 ? ldo : N; ua.epi = epi;
     return uniform ? dispatch_umma<true>(ua, KS, st) : dispatch_umma<false>(ua, KS, st);
 }
 
 int sdvae_spiralconv_fwd_tc(const float* x, const int32_t* plan_cnt, const int32_t* plan_src,
                             const int32_t* plan_cell, int rcap, const float* wimg, const float* bias,
                             float* y, int B, int Vin, int Vout, int S, int Cin, int Cout, int act,
-                            sdvae_stream_t stream) {
+                            int ldy, sdvae_stream_t stream) {
     const int epi = act == SDVAE_ACT_ELU ? EPI_BIAS_ELU : EPI_BIAS;
     return tc_conv(x, plan_cnt, plan_src, plan_cell, rcap, wimg, bias, nullptr, y, B, Vin, Vout, S, Cin,
-                   Cout, epi, true, (cudaStream_t)stream, "spiralconv_fwd_tc: unsupported layer shape");
+                   Cout, ldy, epi, true, (cudaStream_t)stream, "spiralconv_fwd_tc: unsupported layer shape");
 }
 
 int sdvae_spiralconv_bwd_x_tc(const float* dpre, const int32_t* plan_cnt, const int32_t* plan_src,
                               const int32_t* plan_cell, int rcap, const float* wimg_t, const float* gate,
                               float* dx, int B, int Vrows, int Vdst, int S, int Cout, int Cin,
-                              sdvae_stream_t stream) {
+                              int lddx, sdvae_stream_t stream) {
     return tc_conv(dpre, plan_cnt, plan_src, plan_cell, rcap, wimg_t, nullptr, gate, dx, B, Vrows, Vdst, S,
-                   Cout, Cin, gate ? EPI_GATE : EPI_NONE, false, (cudaStream_t)stream,
+                   Cout, Cin, lddx, gate ? EPI_GATE : EPI_NONE, false, (cudaStream_t)stream,
                    "spiralconv_bwd_x_tc: unsupported layer shape");
 }
 
@@ -306,7 +315,7 @@ int sdvae_dense_tc(const float* x, const int32_t* plan_cnt, const int32_t* plan_
                    int act, sdvae_stream_t stream) {
     const int epi = gate ? EPI_GATE : (act == SDVAE_ACT_ELU ? EPI_BIAS_ELU : EPI_BIAS);
     return tc_conv(x, plan_cnt, plan_src, nullptr, rcap, wimg, gate ? nullptr : bias, gate, y, B, R, R, 1, 32,
-                   32, epi, true, (cudaStream_t)stream, "dense_tc: unsupported shape");
+                   32, 0, epi, true, (cudaStream_t)stream, "dense_tc: unsupported shape");
 }
 
 int sdvae_slot_pack(const float* in, const int32_t* cell_ptr, const int32_t* cell_src, float* out, int B,
@@ -353,7 +362,8 @@ int sdvae_slot_grad(const float* dWd, const float* dbd, float* dW, float* db, in
 }
 
 int sdvae_tc_bwd_w_supported(int S, int Cin, int Cout, int rcap) {
-    if (Cin != 32 || Cout < 1 || Cout > umma::kBwNT || S < 1 || S > 11) return 0;
+    // C_in in 32-channel passes, C_out in passes of <= 32; 32*S + 1 accumulator rows in <= 3 blocks of 128
+    if ((Cin != 32 && Cin != 64) || Cout < 1 || Cout > 64 || S < 1 || S > 11) return 0;
     if (rcap < 32 || rcap > umma::kMaxRcap || rcap % 32 != 0) return 0;
     const long long budget = 226LL * 1024 - 2048 - 2 * umma::kGStage;
     return budget / ((long long)rcap * 128) >= 7 ? 1 : 0;       // the phase-distance argument needs 7 raw stages
@@ -376,13 +386,13 @@ int sdvae_spiralconv_bwd_w_tc(const float* x, const int32_t* plan_cnt, const int
         return check_launch("bwd_w_tc memset");
     }
     umma::BwUmmaArgs a{};
-    a.in = x; a.plan_cnt = plan_cnt; a.plan_src = plan_src; a.g = dpre;
+    a.plan_cnt = plan_cnt; a.plan_src = plan_src;
     a.B = B; a.in_rows = Vin; a.out_rows = Vout; a.L = sdvae_tc_plan_tiles(Vout); a.S = S; a.rcap = rcap;
-    a.n_real = Cout; a.nraw = umma::kMaxRaw;
+    a.nraw = umma::kMaxRaw;
     const long long ntiles = (long long)B * a.L;
     const int grid = ntiles < kNumSMs ? (int)ntiles : kNumSMs;
-    a.part = static_cast<float*>(workspace);
-    a.part_b = a.part + (size_t)grid * Cout * K;
+    float* part = static_cast<float*>(workspace);               // [grid, Cout, K]
+    float* part_b = part + (size_t)grid * Cout * K;             // [grid, Cout]
     static int flush_tiles = 0;                // tiles per accumulator drain (tuning knob, default 2)
     if (!flush_tiles) {
         const char* e = getenv("SDVAE_BWW_FLUSH");
@@ -390,19 +400,30 @@ int sdvae_spiralconv_bwd_w_tc(const float* x, const int32_t* plan_cnt, const int
         if (flush_tiles < 1) flush_tiles = 1;
     }
     a.flush = flush_tiles;
-    cudaMemsetAsync(a.part, 0, sizeof(float) * (size_t)grid * (Cout * K + Cout), st);
+    a.in_ld = Cin; a.g_ld = Cout; a.part_ld = K; a.part_cta = Cout * K; a.partb_cta = Cout;
+    cudaMemsetAsync(part, 0, sizeof(float) * (size_t)grid * (Cout * K + Cout), st);
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(umma::bw_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_done = true;
     }
     const size_t smem = 1024 + 2 * (size_t)umma::kGStage + (size_t)a.nraw * rcap * 128 + 1024;
-    umma::bw_umma_kernel<<<grid, umma::kBwThreads, smem, st>>>(a);
-    int rc = check_launch("bw_umma_kernel");
-    if (rc) return rc;
+    // one pass per (32 input channels, <= 32 output channels); the bias gradient comes from the first
+    // input-channel pass only (its row of ones)
+    for (int c0 = 0; c0 < Cin; c0 += 32)
+        for (int n0 = 0; n0 < Cout; n0 += umma::kBwNT) {
+            a.in = x + c0;
+            a.g = dpre + n0;
+            a.n_real = Cout - n0 < umma::kBwNT ? Cout - n0 : umma::kBwNT;
+            a.part = part + (size_t)n0 * K + c0;
+            a.part_b = c0 == 0 ? part_b + n0 : nullptr;
+            umma::bw_umma_kernel<<<grid, umma::kBwThreads, smem, st>>>(a);
+            int rc = check_launch("bw_umma_kernel");
+            if (rc) return rc;
+        }
     const long long len = (long long)Cout * K;
-    split_reduce_kernel<<<blocks_for(len, 256), 256, 0, st>>>(a.part, dW, grid, len);
-    if (db) split_reduce_kernel<<<blocks_for(Cout, 256), 256, 0, st>>>(a.part_b, db, grid, Cout);
+    split_reduce_kernel<<<blocks_for(len, 256), 256, 0, st>>>(part, dW, grid, len);
+    if (db) split_reduce_kernel<<<blocks_for(Cout, 256), 256, 0, st>>>(part_b, db, grid, Cout);
     return check_launch("split_reduce_kernel");
 }
 

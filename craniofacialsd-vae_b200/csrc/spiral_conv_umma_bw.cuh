@@ -41,12 +41,15 @@ constexpr int kBwAColBase = 256;          // TMEM columns [0,192): two accumulat
 constexpr int kGStage = 16 * 2048;        // 16 K-atoms x (hi atom + lo atom)
 
 struct BwUmmaArgs {
-    const float* in;          // [B, in_rows, 32]
+    const float* in;          // [B, in_rows, in_ld], the 32 channels of this pass start at `in`
     const int* plan_cnt;      // [L, S]        forward tile plan: one staged row per tile row, in row order
     const int* plan_src;      // [L, S, rcap/2]  packed (plan_fetch)
-    const float* g;           // [B, out_rows, n_real]   gradient w.r.t. the pre-activation
-    float* part;              // [grid, n_real, S*32]   zero-initialised by the caller
-    float* part_b;            // [grid, n_real]         zero-initialised by the caller
+    const float* g;           // [B, out_rows, g_ld]     gradient w.r.t. the pre-activation, n_real columns from `g`
+    float* part;              // per-CTA partial dW, zero-initialised by the caller: element (n, s, c) of CTA k at
+                              //   part[k*part_cta + n*part_ld + s*in_ld + c]   (the caller offsets `part` to the
+                              //   first output channel / input channel of this pass)
+    float* part_b;            // per-CTA partial db at part_b[k*partb_cta + n], or nullptr (no bias from this pass)
+    int in_ld, g_ld, part_ld, part_cta, partb_cta;
     int B, in_rows, out_rows, L, S, rcap, n_real, nraw;
     int flush;                // tiles per accumulator drain (>= 1)
 };
@@ -170,11 +173,11 @@ bw_umma_kernel(const BwUmmaArgs a) {
         const int p = tid;                                        // 0..127
         int b = (int)blockIdx.x / a.L, jt = (int)blockIdx.x - b * a.L;
         const int n_real = a.n_real;
-        const bool vec = (n_real == kBwNT) && ((reinterpret_cast<uintptr_t>(a.g) & 15) == 0);
+        const bool vec = (n_real == kBwNT) && ((reinterpret_cast<uintptr_t>(a.g) & 15) == 0) && (a.g_ld % 4 == 0);
         // ---- drain f: D[(s,c), n] += into the partial dW[n, s*32 + c], ones row -> partial db[n] ----
         const int q4 = warp & 3;
-        float* P = a.part + (size_t)blockIdx.x * n_real * K;
-        float* Pb = a.part_b + (size_t)blockIdx.x * n_real;
+        float* P = a.part + (size_t)blockIdx.x * a.part_cta;
+        float* Pb = a.part_b ? a.part_b + (size_t)blockIdx.x * a.partb_cta : nullptr;
         auto drain = [&](int f) {
             const int ab = f & 1;
             mbar_wait(done_bar + ab, (uint32_t)((f >> 1) & 1));
@@ -191,8 +194,9 @@ bw_umma_kernel(const BwUmmaArgs a) {
                     tc_fence_before();
                     mbar_arrive(drained_bar + ab);
                 }
-                float* dst = row < K ? P + row : (row == ONES_ROW ? Pb : nullptr);
-                const size_t ld = row < K ? (size_t)K : (size_t)1;
+                // M row = s*32 + c -> column s*in_ld + c of the layer's [n, S*C_in] weight gradient
+                float* dst = row < K ? P + (row >> 5) * a.in_ld + (row & 31) : (row == ONES_ROW ? Pb : nullptr);
+                const size_t ld = row < K ? (size_t)a.part_ld : (size_t)1;
                 if (dst) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
@@ -208,13 +212,13 @@ bw_umma_kernel(const BwUmmaArgs a) {
             const int gb = it & 1;
             uint8_t* gs = G_s + gb * kGStage;
             const int nvalid = min(kBM, a.out_rows - jt * kBM);
-            const float* gt = a.g + ((size_t)b * a.out_rows + (size_t)jt * kBM) * n_real;
+            const float* gt = a.g + ((size_t)b * a.out_rows + (size_t)jt * kBM) * a.g_ld;
             float4 v[8];
             if (vec) {                                            // 8 lanes per row, coalesced 16-byte loads
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int m = (p >> 3) + 16 * i;
-                    v[i] = m < nvalid ? ldg4(gt + (size_t)m * kBwNT + 4 * (p & 7)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[i] = m < nvalid ? ldg4(gt + (size_t)m * a.g_ld + 4 * (p & 7)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             } else {                                              // narrow rows: thread = row, scalar loads
 #pragma unroll
@@ -223,7 +227,7 @@ bw_umma_kernel(const BwUmmaArgs a) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int n = 4 * i + j;
-                        t[j] = (p < nvalid && n < n_real) ? __ldg(gt + (size_t)p * n_real + n) : 0.f;
+                        t[j] = (p < nvalid && n < n_real) ? __ldg(gt + (size_t)p * a.g_ld + n) : 0.f;
                     }
                     v[i] = make_float4(t[0], t[1], t[2], t[3]);
                 }
@@ -329,13 +333,13 @@ bw_umma_kernel(const BwUmmaArgs a) {
 #pragma unroll 1
         while (g < G) {
             const PlanRegs<4> now = nxt;
-            const float* base = a.in + (size_t)b * a.in_rows * 32 + 4 * q;
+            const float* base = a.in + (size_t)b * a.in_rows * a.in_ld + 4 * q;
             g += NRAW; sl += NRAW;
             while (sl >= S) { sl -= S; b += db; jt += djt; if (jt >= a.L) { jt -= a.L; ++b; } }
             if (g < G) plan_fetch(nxt, a.plan_cnt, a.plan_src, jt, S, sl, a.rcap, rsub);
             mbar_wait(raw_empty + lw, rph ^ 1);
             const uint32_t dst = raw_base + (uint32_t)lw * (uint32_t)RAW_STAGE;
-            plan_issue(now, dst + sw0, dst + sw1, base, 128u);
+            plan_issue(now, dst + sw0, dst + sw1, base, (uint32_t)a.in_ld * 4u);
             cp_async_commit();
             cp_async_wait<0>();
             mbar_arrive(raw_full + lw);

@@ -224,10 +224,19 @@ class TrainEngine:
                 plan, ks, n = table.plan_fwd(), cin, cout
             else:
                 plan, ks, n = table.plan_bwd(), cout, cin
-            if ks not in (32, 64) or not cabi.tc_supported(table.seq, ks, n, plan.rcap):
+            if ks not in (32, 64):
+                return
+            # output channels in one pass, or (64 -> 64: the weight image of all 64 does not fit in shared
+            # memory next to the rings) in two passes of 32, each writing its columns of the output
+            if cabi.tc_supported(table.seq, ks, n, plan.rcap):
+                parts = [(0, n)]
+            elif n == 64 and cabi.tc_supported(table.seq, ks, 32, plan.rcap):
+                parts = [(0, 32), (32, 32)]
+            else:
                 return
             self.tc[(kind, name)] = dict(layer=layer, plan=plan, cin=cin, cout=cout, seq=table.seq,
-                                         wimg=f(cabi.tc_wimg_floats(table.seq, ks, n)))
+                                         parts=[(n0, nc, f(cabi.tc_wimg_floats(table.seq, ks, nc)))
+                                                for n0, nc in parts])
 
         for l in range(L):
             enc = m.en_layers[l].conv.layer
@@ -255,8 +264,9 @@ class TrainEngine:
     def _pack_tc(self):
         """Re-pack every tensor-core weight image from the current weights (they change each step)."""
         for (kind, _), e in self.tc.items():
-            cabi.tc_pack_weights(e['layer'].weight.data, e['wimg'], e['seq'], e['cin'], e['cout'],
-                                 kind == 'b')
+            for n0, nc, wimg in e['parts']:
+                cabi.tc_pack_weights(e['layer'].weight.data, wimg, e['seq'], e['cin'], e['cout'],
+                                     kind == 'b', n0, nc)
         m, L, C, S = self.model, self.L, self.C, self.S
         if self.slot_en0 is not None:
             e = self.slot_en0
@@ -270,8 +280,11 @@ class TrainEngine:
     def _conv(self, x, table, layer, out, act, B, Vin, Cin, Cout, name=None):
         e = self.tc.get(('f', name))
         if e is not None:
-            cabi.spiralconv_fwd_tc(x, e['plan'], e['wimg'], layer.bias.data, out, B, Vin,
-                                   table.n_rows, table.seq, Cin, Cout, act)
+            for n0, nc, wimg in e['parts']:
+                full = nc == Cout
+                cabi.spiralconv_fwd_tc(x, e['plan'], wimg, layer.bias.data[n0:],
+                                       out if full else out.view(-1)[n0:], B, Vin, table.n_rows,
+                                       table.seq, Cin, nc, act, 0 if full else Cout)
             return
         cabi.spiralconv_fwd(x, table.idx, layer.weight.data, layer.bias.data, out, B, Vin,
                             table.n_rows, table.seq, Cin, Cout, act)
@@ -323,7 +336,7 @@ class TrainEngine:
         return z
 
     def _bwd_w(self, x, table, dpre, layer, B, Vin, Cin, Cout):
-        if self.use_tc and Cin == 32:
+        if self.use_tc and Cin in (32, 64):
             plan = table.plan_fwd()
             if cabi.tc_bwd_w_supported(table.seq, Cin, Cout, plan.rcap):
                 cabi.spiralconv_bwd_w_tc(x, plan, dpre, self.g(layer.weight), self.g(layer.bias),
@@ -398,8 +411,11 @@ class TrainEngine:
             self._bwd_w(self.u[l], self.full[l], self.dd[l], layer, B, V[l], cin, cout)
             e = self.tc.get(('b', 'de%d' % l))
             if e is not None:
-                cabi.spiralconv_bwd_x_tc(self.dd[l], e['plan'], e['wimg'], None, self.du[l], B, V[l],
-                                         V[l], S[l], cout, cin)
+                for n0, nc, wimg in e['parts']:
+                    full = nc == cin
+                    cabi.spiralconv_bwd_x_tc(self.dd[l], e['plan'], wimg, None,
+                                             self.du[l] if full else self.du[l].view(-1)[n0:], B, V[l],
+                                             V[l], S[l], cout, nc, 0 if full else cin)
             else:
                 cabi.weight_transpose(layer.weight.data, self.wt[l], cout, cin, S[l])
                 cp, cs = self.full[l].inverse()
@@ -467,8 +483,13 @@ class TrainEngine:
             if e is not None:
                 # input gradient of the fused block straight from the kept rows (inverse table of the
                 # restricted spiral table), ELU' of the previous block fused in the epilogue
-                cabi.spiralconv_bwd_x_tc(self.da[l], e['plan'], e['wimg'], self.a[l - 1], self.da[l - 1],
-                                         B, self.sub[l].n_rows, V[l], S[l], C[l + 1], C[l])
+                for n0, nc, wimg in e['parts']:
+                    full = nc == C[l]
+                    cabi.spiralconv_bwd_x_tc(self.da[l], e['plan'], wimg,
+                                             self.a[l - 1] if full else self.a[l - 1].view(-1)[n0:],
+                                             self.da[l - 1] if full else self.da[l - 1].view(-1)[n0:],
+                                             B, self.sub[l].n_rows, V[l], S[l], C[l + 1], nc,
+                                             0 if full else C[l])
             elif l > 0:
                 K = S[l] * C[l]
                 cabi.transpose2d(layer.weight.data, self.wT[l], C[l + 1], K)

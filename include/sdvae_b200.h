@@ -85,25 +85,31 @@ int    sdvae_tc_supported(int S, int KS, int N, int rcap);
 size_t sdvae_tc_wimg_floats(int S, int KS, int N);
 int sdvae_tc_pack_weights(const float* W, float* wimg, int S, int Cin, int Cout, int transposed,
                           sdvae_stream_t stream);
+/* The same for output channels [n0, n0 + n_cnt) only (input channels for the transposed weight): a layer
+ * whose full weight image does not fit in shared memory (64 -> 64) runs as two 32-channel passes, each
+ * writing its columns of the output through ldy / lddx below. */
+int sdvae_tc_pack_weights_part(const float* W, float* wimg, int S, int Cin, int Cout, int transposed,
+                               int n0, int n_cnt, sdvae_stream_t stream);
 int sdvae_tc_plan_tiles(int out_rows);
 int sdvae_tc_plan_max_rows(const int32_t* cell_ptr, int out_rows, int S);
 int sdvae_tc_plan_build(const int32_t* cell_ptr, const int32_t* cell_src, int out_rows, int S,
                         int rcap, int32_t* cnt, int32_t* src, int32_t* cell);
 /* Replaces: model.py:27-41 + F.elu (model.py:68,84), as sdvae_spiralconv_fwd.  The plan must be the
  * FORWARD plan of the layer's table (cell_ptr[i] = i: exactly one source row per cell, so staged row e of a
- * (tile, slot) is tile row e); plan_cell is not read and may be NULL. */
+ * (tile, slot) is tile row e); plan_cell is not read and may be NULL.  ldy: floats between output rows
+ * (0 = Cout); with ldy > Cout, y points at the first of Cout consecutive columns of a wider tensor. */
 int sdvae_spiralconv_fwd_tc(const float* x, const int32_t* plan_cnt, const int32_t* plan_src,
                             const int32_t* plan_cell, int rcap, const float* wimg, const float* bias,
-                            float* y, int B, int Vin, int Vout, int S, int Cin, int Cout, int act,
+                            float* y, int B, int Vin, int Vout, int S, int Cin, int Cout, int act, int ldy,
                             sdvae_stream_t stream);
 /* Replaces: autograd of model.py:34,40 w.r.t. the input, as sdvae_spiralconv_bwd_x. */
 int sdvae_spiralconv_bwd_x_tc(const float* dpre, const int32_t* plan_cnt, const int32_t* plan_src,
                               const int32_t* plan_cell, int rcap, const float* wimg_t, const float* gate,
-                              float* dx, int B, int Vrows, int Vdst, int S, int Cout, int Cin,
+                              float* dx, int B, int Vrows, int Vdst, int S, int Cout, int Cin, int lddx,
                               sdvae_stream_t stream);
 
 /* Weight gradient on the tensor cores, as sdvae_spiralconv_bwd_w (same workspace size), for
- * C_in = 32, C_out <= 32.  (plan_cnt, plan_src, rcap) is the FORWARD tile plan of the layer's table
+ * C_in in {32, 64}, C_out <= 64 (passes of 32 x <= 32 channels).  (plan_cnt, plan_src, rcap) is the FORWARD tile plan of the layer's table
  * (one source row per cell).  db comes from a row of ones in the A operand; partial sums per CTA are
  * added in a fixed order.  Replaces: autograd of model.py:40 (grad_weight / grad_bias). */
 int sdvae_tc_bwd_w_supported(int S, int Cin, int Cout, int rcap);

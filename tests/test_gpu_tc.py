@@ -89,6 +89,42 @@ def test_tc_backward_to_input_vs_fp64_autograd(cranio, orc, lvl, cin, cout, gate
     assert nerr(outs[0], u.grad) < TC_TOL
 
 
+@pytest.mark.parametrize('gated', [False, True])
+def test_tc_wide_layer_in_two_passes(cranio, orc, gated):
+    """64 -> 64 (de1 of craniofacial.yaml): the weight image of all 64 output channels does not fit in
+    shared memory, so forward and backward-to-input run as two passes of 32 output channels, each writing
+    its columns of the [.., 64] result (ldy / lddx)."""
+    from sdvae_b200 import cabi
+    from sdvae_b200.tables import spiral_table
+    lvl, cin, cout, B = 3, 64, 64, 3
+    idx = cranio.spiral_tensors()[lvl]
+    V, S = idx.shape
+    tab = spiral_table(idx.to(DEV))
+    assert not cabi.tc_supported(S, cin, cout, 128) and cabi.tc_supported(S, cin, 32, 128)
+    u = rand((B, V, cin), 41).double().requires_grad_(True)
+    w = rand((cout, S * cin), 42, (2.0 / (S * cin)) ** 0.5)
+    b = rand((cout,), 43, 0.1)
+    gy = rand((B, V, cout), 44)
+    x = orc.elu(u) if gated else u
+    y64 = orc.elu(orc.spiral_conv(x, idx, w.double(), b.double()))
+    pre = orc.spiral_conv(x, idx, w.double(), b.double())
+    pre.backward(gy.double())
+    xf = x.detach().float().to(DEV).contiguous()
+    y = torch.full((B, V, cout), float('nan'), device=DEV)
+    wimg = torch.empty(cabi.tc_wimg_floats(S, cin, 32), device=DEV)
+    for n0 in (0, 32):
+        cabi.tc_pack_weights(w.to(DEV), wimg, S, cin, cout, False, n0, 32)
+        cabi.spiralconv_fwd_tc(xf, tab.plan_fwd(), wimg, b.to(DEV)[n0:], y.view(-1)[n0:], B, V, V, S, cin, 32, 1, cout)
+    assert nerr(y, y64) < TC_TOL
+    dx = torch.full((B, V, cin), float('nan'), device=DEV)
+    gate = xf if gated else None
+    for n0 in (0, 32):
+        cabi.tc_pack_weights(w.to(DEV), wimg, S, cin, cout, True, n0, 32)
+        cabi.spiralconv_bwd_x_tc(gy.to(DEV), tab.plan_bwd(), wimg, None if gate is None else gate.view(-1)[n0:],
+                                 dx.view(-1)[n0:], B, V, V, S, cout, 32, cin)
+    assert nerr(dx, u.grad) < TC_TOL
+
+
 def test_tc_restricted_rows_forward_and_backward(cranio, orc):
     """Fused encoder block on the tensor cores: conv only at the kept vertices, and the input
     gradient straight from those rows (inverse of the restricted table)."""
@@ -118,20 +154,20 @@ def test_tc_restricted_rows_forward_and_backward(cranio, orc):
     assert nerr(dx, x.grad) < TC_TOL
 
 
-@pytest.mark.parametrize('lvl,cout,B', [(1, 32, 3), (2, 32, 5), (0, 32, 2), (0, 3, 2), (3, 17, 4), (0, 32, 40)])
-def test_tc_weight_gradient_vs_fp64_autograd(cranio, orc, lvl, cout, B):
+@pytest.mark.parametrize('lvl,cin,cout,B', [(1, 32, 32, 3), (2, 32, 32, 5), (0, 32, 32, 2), (0, 32, 3, 2), (3, 32, 17, 4),
+                                            (0, 32, 32, 40), (3, 32, 64, 4), (2, 64, 32, 3), (3, 64, 64, 5), (3, 64, 40, 2)])
+def test_tc_weight_gradient_vs_fp64_autograd(cranio, orc, lvl, cin, cout, B):
     """dW, db of y = conv(x) on the tcgen05 path (C_in = 32) against fp64 autograd of the oracle;
     deterministic (run twice, bit-identical).  B = 40 at level 0 gives every CTA several flush
     groups (the accumulators are drained from TMEM every few tiles -- tensor-core accumulation
     truncates, an undrained chain drifts past the tolerance)."""
     from sdvae_b200 import cabi
     from sdvae_b200.tables import spiral_table
-    cin = 32
     idx = cranio.spiral_tensors()[lvl]
     V, S = idx.shape
     tab = spiral_table(idx.to(DEV))
     plan = tab.plan_fwd()
-    assert cabi.tc_bwd_w_supported(S, cin, cout, plan.rcap)
+    assert cabi.tc_bwd_w_supported(S, cin, cout, plan.rcap)      # 64 channels: passes of 32 x <= 32
     x = rand((B, V, cin), 80 + lvl)
     gy = rand((B, V, cout), 90 + lvl)
     w = torch.zeros((cout, S * cin), dtype=torch.float64, requires_grad=True)
@@ -271,8 +307,8 @@ def test_tc_rejects_unsupported_shapes(cranio):
     assert not cabi.tc_supported(9, 32, 96, 128)       # N > 64
     assert not cabi.tc_supported(9, 64, 64, 128)       # weight image too large
     assert not cabi.tc_supported(9, 32, 32, 1024)      # plan stages more rows than the kernel supports
-    assert not cabi.tc_bwd_w_supported(9, 64, 32, 128)  # weight gradient: C_in = 32 only
-    assert not cabi.tc_bwd_w_supported(9, 32, 64, 128)  # ... and C_out <= 32
+    assert not cabi.tc_bwd_w_supported(9, 48, 32, 128)  # weight gradient: C_in in {32, 64}
+    assert not cabi.tc_bwd_w_supported(9, 32, 96, 128)  # ... and C_out <= 64
     w = torch.zeros((32, 27), device=DEV)
     with pytest.raises(RuntimeError):
         cabi.tc_pack_weights(w, torch.zeros(4096, device=DEV), 9, 3, 32, False)

@@ -184,7 +184,7 @@ int main(int argc, char** argv) {
         CK(cudaMalloc(&d_img, sdvae_tc_wimg_floats(S, Cin, Cout) * 4));
         ABI(sdvae_spiralconv_fwd(d_x, d_idx, d_W, d_bias, d_y0, B, V, V, S, Cin, Cout, flag, st));
         ABI(sdvae_tc_pack_weights(d_W, d_img, S, Cin, Cout, 0, st));
-        ABI(sdvae_spiralconv_fwd_tc(d_x, pl.cnt, pl.src, pl.cell, pl.rcap, d_img, d_bias, d_y1, B, V, V, S, Cin, Cout, flag, st));
+        ABI(sdvae_spiralconv_fwd_tc(d_x, pl.cnt, pl.src, pl.cell, pl.rcap, d_img, d_bias, d_y1, B, V, V, S, Cin, Cout, flag, 0, st));
         CK(cudaDeviceSynchronize());
         std::vector<float> y0(ny), y1(ny);
         CK(cudaMemcpy(y0.data(), d_y0, ny * 4, cudaMemcpyDeviceToHost));
@@ -221,7 +221,7 @@ int main(int argc, char** argv) {
         for (int i = 0; i < iters; ++i) ABI(sdvae_spiralconv_fwd(d_x, d_idx, d_W, d_bias, d_y0, B, V, V, S, Cin, Cout, flag, st));
         CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms0, e0, e1));
         CK(cudaEventRecord(e0));
-        for (int i = 0; i < iters; ++i) ABI(sdvae_spiralconv_fwd_tc(d_x, pl.cnt, pl.src, pl.cell, pl.rcap, d_img, d_bias, d_y1, B, V, V, S, Cin, Cout, flag, st));
+        for (int i = 0; i < iters; ++i) ABI(sdvae_spiralconv_fwd_tc(d_x, pl.cnt, pl.src, pl.cell, pl.rcap, d_img, d_bias, d_y1, B, V, V, S, Cin, Cout, flag, 0, st));
         CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms1, e0, e1));
         const double flops = 2.0 * B * V * (double)S * Cin * Cout, bytes = 4.0 * B * V * (double)(Cin + Cout);
         print_prof();
@@ -262,7 +262,7 @@ int main(int argc, char** argv) {
     ABI(sdvae_weight_transpose(d_W, d_wt, Cout, Cin, S, st));
     ABI(sdvae_spiralconv_bwd_x(d_dpre, d_cp, d_cs, d_wt, g, d_dx0, B, V, V, S, Cout, Cin, st));
     ABI(sdvae_tc_pack_weights(d_W, d_img, S, Cin, Cout, 1, st));
-    ABI(sdvae_spiralconv_bwd_x_tc(d_dpre, pl.cnt, pl.src, pl.cell, pl.rcap, d_img, g, d_dx1, B, V, V, S, Cout, Cin, st));
+    ABI(sdvae_spiralconv_bwd_x_tc(d_dpre, pl.cnt, pl.src, pl.cell, pl.rcap, d_img, g, d_dx1, B, V, V, S, Cout, Cin, 0, st));
     CK(cudaDeviceSynchronize());
     std::vector<float> x0(nx), x1(nx);
     CK(cudaMemcpy(x0.data(), d_dx0, nx * 4, cudaMemcpyDeviceToHost));
@@ -299,7 +299,7 @@ int main(int argc, char** argv) {
     for (int i = 0; i < iters; ++i) ABI(sdvae_spiralconv_bwd_x(d_dpre, d_cp, d_cs, d_wt, g, d_dx0, B, V, V, S, Cout, Cin, st));
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms0, e0, e1));
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < iters; ++i) ABI(sdvae_spiralconv_bwd_x_tc(d_dpre, pl.cnt, pl.src, pl.cell, pl.rcap, d_img, g, d_dx1, B, V, V, S, Cout, Cin, st));
+    for (int i = 0; i < iters; ++i) ABI(sdvae_spiralconv_bwd_x_tc(d_dpre, pl.cnt, pl.src, pl.cell, pl.rcap, d_img, g, d_dx1, B, V, V, S, Cout, Cin, 0, st));
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms1, e0, e1));
     const double flops = 2.0 * B * V * (double)S * Cin * Cout;
     print_prof();
