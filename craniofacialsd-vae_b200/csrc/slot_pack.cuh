@@ -92,8 +92,11 @@ slot_pack_smem_kernel(const float* __restrict__ in, const int* __restrict__ cell
         const int r_begin = part * rows_per_part;
         const int r_end = min(R, r_begin + rows_per_part);
         float* o = out + (size_t)b * R * 32;
-        for (int r0 = r_begin + warp * kSlotRows; r0 < r_end; r0 += 32 * kSlotRows) {
-            int e0[kSlotRows], e1[kSlotRows];
+        // A row is a chain cell range -> first source row -> shared-memory value.  The two index loads are
+        // software-pipelined two and one iterations ahead (each iteration = kSlotRows rows per warp), so the
+        // loop body never waits a full L2 round trip for them.
+        const int step = 32 * kSlotRows;
+        auto load_range = [&](int r0, int (&e0)[kSlotRows], int (&e1)[kSlotRows]) {
 #pragma unroll
             for (int i = 0; i < kSlotRows; ++i) {
                 const int r = r0 + i;
@@ -103,9 +106,23 @@ slot_pack_smem_kernel(const float* __restrict__ in, const int* __restrict__ cell
                     else { e0[i] = __ldg(cell_ptr + (size_t)r * S + s); e1[i] = __ldg(cell_ptr + (size_t)r * S + s + 1); }
                 }
             }
-            int v0[kSlotRows];
+        };
+        auto load_first = [&](const int (&e0)[kSlotRows], const int (&e1)[kSlotRows], int (&v0)[kSlotRows]) {
 #pragma unroll
             for (int i = 0; i < kSlotRows; ++i) v0[i] = e0[i] < e1[i] ? __ldg(cell_src + e0[i]) : -1;
+        };
+        int a0[kSlotRows], a1[kSlotRows];                       // ranges of the iteration after next
+        int b0[kSlotRows], b1[kSlotRows], bv[kSlotRows];        // ranges + first source row of the next iteration
+        const int r_first = r_begin + warp * kSlotRows;
+        load_range(r_first, b0, b1);
+        load_first(b0, b1, bv);
+        load_range(r_first + step, a0, a1);
+        for (int r0 = r_first; r0 < r_end; r0 += step) {
+            int e0[kSlotRows], e1[kSlotRows], v0[kSlotRows];
+#pragma unroll
+            for (int i = 0; i < kSlotRows; ++i) { e0[i] = b0[i]; e1[i] = b1[i]; v0[i] = bv[i]; b0[i] = a0[i]; b1[i] = a1[i]; }
+            load_first(b0, b1, bv);
+            load_range(r0 + 2 * step, a0, a1);
             float acc[kSlotRows];
 #pragma unroll
             for (int i = 0; i < kSlotRows; ++i) acc[i] = v0[i] >= 0 ? xs[v0[i] * C + c] : 0.f;
