@@ -28,6 +28,7 @@ gradient arenas reproduces the single-GPU gradient.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
 
@@ -89,7 +90,11 @@ class TrainEngine:
         self.lap = laplacian if cfg.laplacian_weight > 0 else None
         self.latent_regions = [tuple(int(t) for t in r) for r in latent_regions]
         self.use_lc = cfg.latent_consistency_weight > 0
-        self.use_graph = use_graph and self.world == 1
+        # The data-parallel step is captured too (NCCL collectives are graph-capturable; the side stream that
+        # carries the bucket all-reduces forks from and joins back into the capture stream).  At 8 GPUs the
+        # step is 5 ms, and ~130 eager launches through ctypes were a visible part of it.
+        # SDVAE_DP_GRAPH=0 keeps multi-GPU steps eager.
+        self.use_graph = use_graph and (self.world == 1 or os.environ.get('SDVAE_DP_GRAPH', '1') != '0')
         self.use_tc = bool(use_tc)
         self._graphs: Dict[int, torch.cuda.CUDAGraph] = {}
         self.fixed_eps: Optional[torch.Tensor] = None

@@ -6,7 +6,8 @@
 
 Every rank runs one DP training step of the craniofacial model on its rows of the bs x bs swap
 grid; rank 0 additionally runs the same step on ONE GPU with the whole grid and compares the
-all-reduced gradient arena, the seven losses and the updated parameters."""
+all-reduced gradient arena, the seven losses and the updated parameters.
+DP_CHECK_GRAPH=1 runs the data-parallel step from a captured CUDA graph (as bench.py does)."""
 import os
 import sys
 
@@ -43,7 +44,8 @@ def main():
         model.load_state_dict({k: v.to(dev) for k, v in params.items()})
         lt = losses.LaplacianTable.build(*tabs.lap, tabs.num_vertices[0], dev)
         return TrainEngine(model, lt, [r[1] for r in tabs.regions],
-                           [lat[k] for k in tabs.region_keys()], cfg, process_group=pg, use_graph=False)
+                           [lat[k] for k in tabs.region_keys()], cfg, process_group=pg,
+                           use_graph=(pg is not None and os.environ.get('DP_CHECK_GRAPH') == '1'))
 
     rng = np.random.RandomState(1)
     x = torch.from_numpy(rng.randn(bs, tabs.num_vertices[0], 3).astype(np.float32)).to(dev)
@@ -71,9 +73,14 @@ def main():
         print("losses dp  ", got)
         print("losses 1gpu", want)
         ok = gerr < 5e-5 and lerr < 5e-5
+    # release the captured step graphs (they hold NCCL work) before any further eager collective / teardown
+    del eng
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
     flag = torch.tensor([1 if ok else 0], device=dev)
-    dist.broadcast(flag, 0)
-    dist.barrier()
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    torch.cuda.synchronize()
     dist.destroy_process_group()
     if int(flag.item()) != 1:
         raise SystemExit("dp_check FAILED")
