@@ -335,7 +335,7 @@ int sdvae_slot_pack(const float* in, const int32_t* cell_ptr, const int32_t* cel
         while ((long long)B * parts < 4LL * kNumSMs && parts < 16 && R / (parts * 2) >= 256) parts *= 2;
         const long long items = (long long)B * parts;
         const int grid = items < kNumSMs ? (int)items : kNumSMs;
-        slot_pack_smem_kernel<<<grid, 1024, in_bytes, st>>>(in, cell_ptr, cell_src, out, B, parts, R, Vin, S, C);
+        slot_pack_smem_kernel<<<grid, 1024, in_bytes + 16, st>>>(in, cell_ptr, cell_src, out, B, parts, R, Vin, S, C);
         return check_launch("slot_pack_smem_kernel");
     }
     const long long rows = (long long)B * R;

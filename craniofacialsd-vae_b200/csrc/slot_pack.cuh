@@ -70,46 +70,49 @@ __global__ void __launch_bounds__(1024, 1)
 slot_pack_smem_kernel(const float* __restrict__ in, const int* __restrict__ cell_ptr,
                       const int* __restrict__ cell_src, float* __restrict__ out,
                       int B, int parts, int R, int Vin, int S, int C) {
-    extern __shared__ float xs[];                               // [Vin * C]
+    extern __shared__ float xs_raw[];                           // [4 + Vin * C]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int s = lane / C, c = lane - s * C;
     const bool live = lane < S * C;
-    const int n4 = (Vin * C) >> 2, tail = (Vin * C) & 3;
+    const int s = live ? lane / C : 0, c = live ? lane - s * C : 0;     // dead lanes shadow (slot 0, channel 0)
+    const int n = Vin * C;
     const int rows_per_part = (R + parts - 1) / parts;
     for (int item = blockIdx.x; item < B * parts; item += gridDim.x) {
         const int b = item / parts, part = item - b * parts;
-        const float* src = in + (size_t)b * Vin * C;
+        const float* src = in + (size_t)b * n;
+        // a mesh of 3-channel rows starts at any 4-byte phase: keep the 16-byte phase of the source in shared
+        // memory (element i at xs[i], xs = xs_raw + phase) so that all but <= 3 + 3 elements move as 16-byte
+        // cp.async; the rest as 4-byte cp.async.  Nothing on this path waits per element.
+        const int phase = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3);
+        float* xs = xs_raw + phase;
+        const int head = (4 - phase) & 3;                        // elements before the first aligned 16 bytes
+        const int n4 = (n - head) >> 2, tail0 = head + 4 * n4;
         __syncthreads();                                        // previous item's reads are done
-        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-            for (int i = threadIdx.x; i < n4; i += blockDim.x) cp_async16(xs + 4 * i, src + 4 * i);
-            if (threadIdx.x < tail) xs[4 * n4 + threadIdx.x] = __ldg(src + 4 * n4 + threadIdx.x);
-            cp_async_commit();
-            cp_async_wait<0>();
-        } else {
-            for (int i = threadIdx.x; i < Vin * C; i += blockDim.x) xs[i] = __ldg(src + i);
-        }
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) cp_async16(xs + head + 4 * i, src + head + 4 * i);
+        if (threadIdx.x < head) cp_async4(xs + threadIdx.x, src + threadIdx.x);
+        if (tail0 + (int)threadIdx.x < n) cp_async4(xs + tail0 + threadIdx.x, src + tail0 + threadIdx.x);
+        cp_async_commit();
+        cp_async_wait<0>();
         __syncthreads();
         const int r_begin = part * rows_per_part;
         const int r_end = min(R, r_begin + rows_per_part);
         float* o = out + (size_t)b * R * 32;
-        // A row is a chain cell range -> first source row -> shared-memory value.  The two index loads are
-        // software-pipelined two and one iterations ahead (each iteration = kSlotRows rows per warp), so the
-        // loop body never waits a full L2 round trip for them.
+        // A row is a chain cell range -> first source row -> shared-memory value.  Every load is UNCONDITIONAL
+        // on a clamped index (a conditional load compiles to a branch that waits for its predicate's data, which
+        // serialised the rows of a warp: 5 us per 128 rows), and the two index loads run two and one iterations
+        // ahead of their use.
         const int step = 32 * kSlotRows;
         auto load_range = [&](int r0, int (&e0)[kSlotRows], int (&e1)[kSlotRows]) {
 #pragma unroll
             for (int i = 0; i < kSlotRows; ++i) {
-                const int r = r0 + i;
-                e0[i] = e1[i] = 0;
-                if (live && r < r_end) {
-                    if (cell_ptr == nullptr) { e0[i] = r * S + s; e1[i] = e0[i] + 1; }
-                    else { e0[i] = __ldg(cell_ptr + (size_t)r * S + s); e1[i] = __ldg(cell_ptr + (size_t)r * S + s + 1); }
-                }
+                const int r = min(r0 + i, R - 1);
+                if (cell_ptr == nullptr) { e0[i] = r * S + s; e1[i] = e0[i] + 1; }
+                else { e0[i] = __ldg(cell_ptr + (size_t)r * S + s); e1[i] = __ldg(cell_ptr + (size_t)r * S + s + 1); }
             }
         };
         auto load_first = [&](const int (&e0)[kSlotRows], const int (&e1)[kSlotRows], int (&v0)[kSlotRows]) {
 #pragma unroll
-            for (int i = 0; i < kSlotRows; ++i) v0[i] = e0[i] < e1[i] ? __ldg(cell_src + e0[i]) : -1;
+            for (int i = 0; i < kSlotRows; ++i)                 // an empty cell reads the entry before it (unused)
+                v0[i] = __ldg(cell_src + (e0[i] < e1[i] ? e0[i] : max(e0[i] - 1, 0)));
         };
         int a0[kSlotRows], a1[kSlotRows];                       // ranges of the iteration after next
         int b0[kSlotRows], b1[kSlotRows], bv[kSlotRows];        // ranges + first source row of the next iteration
@@ -125,10 +128,14 @@ slot_pack_smem_kernel(const float* __restrict__ in, const int* __restrict__ cell
             load_range(r0 + 2 * step, a0, a1);
             float acc[kSlotRows];
 #pragma unroll
-            for (int i = 0; i < kSlotRows; ++i) acc[i] = v0[i] >= 0 ? xs[v0[i] * C + c] : 0.f;
+            for (int i = 0; i < kSlotRows; ++i) {
+                const float v = xs[v0[i] * C + c];
+                acc[i] = (live && e0[i] < e1[i]) ? v : 0.f;
+            }
 #pragma unroll
-            for (int i = 0; i < kSlotRows; ++i)
-                for (int e = e0[i] + 1; e < e1[i]; ++e) acc[i] = __fadd_rn(acc[i], xs[__ldg(cell_src + e) * C + c]);
+            for (int i = 0; i < kSlotRows; ++i)                   // cells with more than one row (inverse tables)
+                if (live)
+                    for (int e = e0[i] + 1; e < e1[i]; ++e) acc[i] = __fadd_rn(acc[i], xs[__ldg(cell_src + e) * C + c]);
 #pragma unroll
             for (int i = 0; i < kSlotRows; ++i)
                 if (r0 + i < r_end) o[(size_t)(r0 + i) * 32 + lane] = acc[i];
