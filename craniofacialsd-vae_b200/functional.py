@@ -7,12 +7,52 @@ saved in ``ctx`` and the stream current on that thread -- no module state.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
 
 from . import cabi
-from .tables import PoolTable, SpiralTable, pool_table, spiral_table
+from .tables import PoolTable, SpiralTable, identity_plan, pool_table, spiral_table
+
+# The SpiralConv passes run on the tcgen05 tensor-core kernels (error-compensated 3xTF32, results within
+# 1e-5 of fp64 per layer, tests/test_gpu_tc.py) wherever the layer shape is supported, and on the fp32-FMA
+# kernels otherwise.  ``set_tensor_cores(False)`` (or SDVAE_NO_TC=1) keeps everything on the FMA kernels.
+_USE_TC = os.environ.get('SDVAE_NO_TC', '0') != '1'
+
+
+def set_tensor_cores(flag: bool) -> None:
+    global _USE_TC
+    _USE_TC = bool(flag)
+
+
+def tensor_cores_enabled() -> bool:
+    return _USE_TC
+
+
+def _f32(*shape, like):
+    return torch.empty(shape, device=like.device, dtype=torch.float32)
+
+
+def _aligned(*ts) -> bool:
+    return all(t is None or t.data_ptr() % 16 == 0 for t in ts)
+
+
+def _tc_parts(S, ks, n, rcap):
+    """Output-channel passes of a tensor-core convolution: all at once, two passes of 32 for 64 -> 64
+    (the weight image of all 64 does not fit in shared memory), or None (unsupported shape)."""
+    if ks not in (32, 64):
+        return None
+    if cabi.tc_supported(S, ks, n, rcap):
+        return [(0, n)]
+    if n == 64 and cabi.tc_supported(S, ks, 32, rcap):
+        return [(0, 32), (32, 32)]
+    return None
+
+
+def _slot_ok(S, narrow, wide) -> bool:
+    """3-channel side slot-packed into a dense 32 x 32 contraction (csrc/slot_pack.cuh)."""
+    return S * narrow <= 32 and wide == 32 and cabi.tc_supported(1, 32, 32, 128)
 
 
 def _prep(x: torch.Tensor, name: str) -> torch.Tensor:
@@ -32,20 +72,43 @@ class SpiralConvFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, table: SpiralTable, act: int):
         B, Vin, Cin = x.shape
         Cout = weight.shape[0]
-        y = torch.empty((B, table.n_rows, Cout), device=x.device, dtype=torch.float32)
-        cabi.spiralconv_fwd(x, table.idx, weight, bias, y, B, Vin, table.n_rows, table.seq,
-                            Cin, Cout, act)
+        R, S = table.n_rows, table.seq
+        y = torch.empty((B, R, Cout), device=x.device, dtype=torch.float32)
+        packed = None                       # slot-packed input of a 3-channel first layer, kept for dW
+        done = False
+        if _USE_TC and B > 0 and _aligned(x, weight, bias):
+            plan = table.plan_fwd()
+            parts = _tc_parts(S, Cin, Cout, plan.rcap)
+            if parts is not None:
+                for n0, nc in parts:
+                    wimg = _f32(cabi.tc_wimg_floats(S, Cin, nc), like=x)
+                    cabi.tc_pack_weights(weight, wimg, S, Cin, Cout, False, n0, nc)
+                    full = nc == Cout
+                    cabi.spiralconv_fwd_tc(x, plan, wimg, None if bias is None else bias[n0:],
+                                           y if full else y.view(-1)[n0:], B, Vin, R, S, Cin, nc, act,
+                                           0 if full else Cout)
+                done = True
+            elif _slot_ok(S, Cin, Cout):
+                packed = _f32(B, R, 32, like=x)
+                cabi.slot_pack(x, None, table.idx, packed, B, Vin, R, S, Cin)
+                wd, wimg = _f32(1024, like=x), _f32(cabi.tc_wimg_floats(1, 32, 32), like=x)
+                cabi.slot_weight(weight, wd, 0, Cout, S, Cin)
+                cabi.tc_pack_weights(wd, wimg, 1, 32, 32, False)
+                cabi.dense_tc(packed, identity_plan(R, x.device), wimg, bias, None, y, B, R, act)
+                done = True
+        if not done:
+            cabi.spiralconv_fwd(x, table.idx, weight, bias, y, B, Vin, R, S, Cin, Cout, act)
         ctx.table, ctx.act = table, act
         ctx.has_bias = bias is not None
-        ctx.save_for_backward(x, weight, y if act == cabi.ACT_ELU else None)
+        ctx.save_for_backward(x, weight, y if act == cabi.ACT_ELU else None, packed)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight, y = ctx.saved_tensors
+        x, weight, y, packed = ctx.saved_tensors
         table: SpiralTable = ctx.table
         B, Vin, Cin = x.shape
-        Cout, S = weight.shape[0], table.seq
+        Cout, S, R = weight.shape[0], table.seq, table.n_rows
         dy = dy.contiguous()
         if ctx.act == cabi.ACT_ELU:
             dpre = torch.empty_like(dy)
@@ -53,15 +116,57 @@ class SpiralConvFn(torch.autograd.Function):
         else:
             dpre = dy
         dx = dw = db = None
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+        want_w = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
+        want_x = ctx.needs_input_grad[0]
+        tc = _USE_TC and B > 0 and _aligned(x, weight, dpre)
+        if want_w:
             dw = torch.empty_like(weight)
             db = torch.empty(Cout, device=x.device, dtype=torch.float32) if ctx.has_bias else None
-            ws = torch.empty(cabi.spiralconv_bwd_w_workspace(B * table.n_rows, S, Cin, Cout) // 4 + 4,
+            ws = torch.empty(cabi.spiralconv_bwd_w_workspace(B * max(R, Vin), S, max(Cin, 32), max(Cout, 32)) // 4 + 4,
                              device=x.device, dtype=torch.float32)
-            cabi.spiralconv_bwd_w(x, table.idx, dpre, dw, db, ws, B, Vin, table.n_rows, S, Cin, Cout)
-        if ctx.needs_input_grad[0]:
+        if tc and _slot_ok(S, Cout, Cin) and (want_w or want_x):
+            # 3-channel OUTPUT layer: G[u, s*C + n] = sum of dpre over the rows that gather u at slot s, then
+            # dW = (G^T x) re-indexed and dx = G Wd^T -- two dense 32 x 32 contractions
+            cell_ptr, cell_src = table.inverse()
+            G = _f32(B, Vin, 32, like=x)
+            cabi.slot_pack(dpre, cell_ptr, cell_src, G, B, R, Vin, S, Cout)
+            ident = identity_plan(Vin, x.device)
+            if want_w:
+                dwd, dbd = _f32(32, 32, like=x), _f32(32, like=x)
+                cabi.spiralconv_bwd_w_tc(x, ident, G, dwd, dbd, ws, B, Vin, Vin, 1, 32, 32)
+                cabi.slot_grad(dwd, dbd, dw, db, 1, Cout, S, Cout)
+                want_w = False
+            if want_x:
+                wd, wimg = _f32(1024, like=x), _f32(cabi.tc_wimg_floats(1, 32, 32), like=x)
+                cabi.slot_weight(weight, wd, 1, Cout, S, Cout)
+                cabi.tc_pack_weights(wd, wimg, 1, 32, 32, False)
+                dx = torch.empty_like(x)
+                cabi.dense_tc(G, ident, wimg, None, None, dx, B, Vin, cabi.ACT_NONE)
+                want_x = False
+        if want_w:
+            if tc and packed is not None:
+                # 3-channel INPUT layer: dW = dpre^T P with the slot-packed input of the forward pass
+                dwd, dbd = _f32(32, 32, like=x), _f32(32, like=x)
+                cabi.spiralconv_bwd_w_tc(packed, identity_plan(R, x.device), dpre, dwd, dbd, ws, B, R, R, 1, 32, 32)
+                cabi.slot_grad(dwd, dbd, dw, db, 0, Cout, S, Cin)
+            elif tc and cabi.tc_bwd_w_supported(S, Cin, Cout, table.plan_fwd().rcap):
+                cabi.spiralconv_bwd_w_tc(x, table.plan_fwd(), dpre, dw, db, ws, B, Vin, R, S, Cin, Cout)
+            else:
+                cabi.spiralconv_bwd_w(x, table.idx, dpre, dw, db, ws, B, Vin, R, S, Cin, Cout)
+        if want_x:
             dx = torch.empty_like(x)
-            if table.n_rows * 2 <= Vin:
+            parts = _tc_parts(S, Cout, Cin, table.plan_bwd().rcap) if tc else None
+            if parts is not None:
+                # inverse-table plan (of the row-restricted table for a fused encoder block): deterministic
+                # scatter-add as an in-order sum inside the A-operand cells
+                plan = table.plan_bwd()
+                for n0, nc in parts:
+                    wimg = _f32(cabi.tc_wimg_floats(S, Cout, nc), like=x)
+                    cabi.tc_pack_weights(weight, wimg, S, Cin, Cout, True, n0, nc)
+                    full = nc == Cin
+                    cabi.spiralconv_bwd_x_tc(dpre, plan, wimg, None, dx if full else dx.view(-1)[n0:], B, R, Vin,
+                                             S, Cout, nc, 0 if full else Cin)
+            elif table.n_rows * 2 <= Vin:
                 # row-restricted (fused encoder block): per-slot gradients, then an
                 # owner-computes row sum -- no work on the vertices that were dropped
                 K = S * Cin

@@ -15,6 +15,24 @@ def samp(t, stride=97):
     return t.detach().reshape(-1)[::stride].cpu()
 
 
+# The drop-in modules run their SpiralConv passes on the tcgen05 kernels by default (error-compensated
+# 3xTF32; per-layer bar 1e-5 vs fp64 in test_gpu_tc.py).  Through the whole network the stated bars are
+# NET_TOL on outputs / latents and TC_GRAD_TOL on gradients; with the tensor cores switched off the
+# fp32-FMA bars (TOL, 5*TOL) apply.
+NET_TOL = {False: TOL, True: 5e-5}
+GRAD_TOL = {False: 5 * TOL, True: 1e-4}
+LOSS_RTOL = {False: 2e-5, True: 1e-4}
+
+
+@pytest.fixture(params=[False, True], ids=['fma', 'tcgen05'])
+def tc_mode(request):
+    from sdvae_b200 import functional
+    before = functional.tensor_cores_enabled()
+    functional.set_tensor_cores(request.param)
+    yield request.param
+    functional.set_tensor_cores(before)
+
+
 @pytest.fixture(scope='module')
 def case_a(golden, cranio):
     from oracle import sdvae_oracle as orc
@@ -26,14 +44,15 @@ def case_a(golden, cranio):
     return net, params, model, x2, xa, key
 
 
-def test_eval_forward_vs_reference_golden(golden, case_a):
+def test_eval_forward_vs_reference_golden(golden, case_a, tc_mode):
     _, _, model, _, xa, _ = case_a
+    tol = NET_TOL[tc_mode]
     model.eval()
     with torch.no_grad():
         rec, z, mu, lv = model(xa.to(DEV))
-    assert nerr(rec[0], golden['A_eval_recon0']) < TOL
-    assert nerr(samp(rec), golden['A_eval_recon_sample']) < TOL
-    assert nerr(mu, golden['A_eval_mu']) < TOL and nerr(lv, golden['A_eval_logvar']) < TOL
+    assert nerr(rec[0], golden['A_eval_recon0']) < tol
+    assert nerr(samp(rec), golden['A_eval_recon_sample']) < tol
+    assert nerr(mu, golden['A_eval_mu']) < tol and nerr(lv, golden['A_eval_logvar']) < tol
     assert torch.equal(z, mu)
     enc = model.encode(xa.to(DEV))[0]
     assert torch.equal(enc, mu)
@@ -41,7 +60,7 @@ def test_eval_forward_vs_reference_golden(golden, case_a):
     assert torch.equal(dec, rec)
 
 
-def test_train_step_autograd_vs_reference_golden(golden, case_a, cranio, monkeypatch):
+def test_train_step_autograd_vs_reference_golden(golden, case_a, cranio, monkeypatch, tc_mode):
     """The reference's _do_iteration composition (model_manager.py:281-315) on the drop-in
     modules: losses and all 24 gradients against the reference's own numbers."""
     from sdvae_b200 import losses
@@ -52,7 +71,7 @@ def test_train_step_autograd_vs_reference_golden(golden, case_a, cranio, monkeyp
     monkeypatch.setattr(torch, 'randn_like', lambda t: eps)
     x = xa.to(DEV)
     rec, z, mu, lv = model(x)
-    assert nerr(z, golden['A_train_z']) < TOL
+    assert nerr(z, golden['A_train_z']) < NET_TOL[tc_mode]
     lt = losses.LaplacianTable.from_sparse(cranio.laplacian_tensor(DEV))
     region = cranio.latent_regions(75)[key]
     l_rec = losses.mse_loss(rec, x)
@@ -63,13 +82,13 @@ def test_train_step_autograd_vs_reference_golden(golden, case_a, cranio, monkeyp
     tot.backward()
     ref = golden['A_losses']
     for got, want in zip((l_rec, l_kl, l_lc, l_lap, tot), ref):
-        assert float(got) == pytest.approx(float(want), rel=2e-5)
+        assert float(got) == pytest.approx(float(want), rel=LOSS_RTOL[tc_mode])
     for k, p in model.named_parameters():
         g = p.grad
         if 'A_grad/' + k in golden:
-            assert nerr(g, golden['A_grad/' + k]) < 5 * TOL, k
+            assert nerr(g, golden['A_grad/' + k]) < GRAD_TOL[tc_mode], k
         else:
-            assert nerr(samp(g), golden['A_grad_sample/' + k]) < 5 * TOL, k
+            assert nerr(samp(g), golden['A_grad_sample/' + k]) < GRAD_TOL[tc_mode], k
 
 
 def test_small_ae_model_vs_reference_golden(golden):
