@@ -17,8 +17,11 @@ preallocated buffers, without autograd:
   overlapping the rest of backward; Adam is one launch over the arena;
 * the seven loss scalars come back in ONE 28-byte D2H copy (the reference issues
   seven ``.item()`` syncs, model_manager.py:320-326);
-* on a single GPU the whole step is replayed from a CUDA graph (one per swapped
-  region, since the region's latent slice is a kernel argument).
+* the whole step -- data-parallel collectives included -- is replayed from a CUDA graph
+  (one per swapped region, since the region's latent slice is a kernel argument);
+* every SpiralConv pass runs on the tcgen05 tensor-core kernels (``use_tc``): wide layers
+  through tile plans of the spiral / inverse tables, the two 3-channel layers slot-packed
+  into dense 32 x 32 contractions (csrc/slot_pack.cuh), 64 -> 64 layers in two passes.
 
 Data parallelism: rank r owns rows ``[r*bs/N, (r+1)*bs/N)`` of the
 ``bs x bs`` swap grid.  Mean losses are normalised by the GLOBAL counts, the
