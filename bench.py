@@ -296,7 +296,7 @@ def run_ours(args):
                          if on_tc else "fp32-FMA contraction: compute-bound on the FMA pipe "
                          "(peak %.1f TFLOP/s)" % (148 * 128 * 2 * 1.965e9 / 1e12))}
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # reported baseline: rank 0 at N = 1 only
         rate, sec = cpu_step_rate(tabs, net, params, args.ref_bs, 5, 2, args.seed)
         cpu = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                "sample": "5 steps (2 warm-up) of the same training step on %d swapped meshes (bs=%d), "
