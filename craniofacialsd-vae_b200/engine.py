@@ -260,7 +260,7 @@ class TrainEngine:
         # (csrc/slot_pack.cuh): the 27 gathered columns of a vertex are materialised once, every pass of
         # the layer is then a dense 32 x 32 contraction on the tcgen05 kernels (identity plan, S = 1).
         B, V = self.B, self.V
-        if S[0] * C[0] <= 32 and C[1] == 32 and cabi.tc_supported(1, 32, 32, 128):
+        if S[0] * C[0] <= 32 and C[1] == 32 and V[0] < 65536 and cabi.tc_supported(1, 32, 32, 128):
             R0 = self.sub[0].n_rows
             self.slot_en0 = dict(plan=identity_plan(R0, self.dev), P=f(B * R0 * 32).view(B, R0, 32),
                                  Wd=f(1024), wimg=f(cabi.tc_wimg_floats(1, 32, 32)),

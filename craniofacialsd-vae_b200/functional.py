@@ -50,9 +50,10 @@ def _tc_parts(S, ks, n, rcap):
     return None
 
 
-def _slot_ok(S, narrow, wide) -> bool:
-    """3-channel side slot-packed into a dense 32 x 32 contraction (csrc/slot_pack.cuh)."""
-    return S * narrow <= 32 and wide == 32 and cabi.tc_supported(1, 32, 32, 128)
+def _slot_ok(S, narrow, wide, rows) -> bool:
+    """3-channel side slot-packed into a dense 32 x 32 contraction (csrc/slot_pack.cuh); ``rows`` = rows of
+    the dense problem (identity tile plans carry 16-bit rows)."""
+    return S * narrow <= 32 and wide == 32 and rows < 65536 and cabi.tc_supported(1, 32, 32, 128)
 
 
 def _prep(x: torch.Tensor, name: str) -> torch.Tensor:
@@ -88,7 +89,7 @@ class SpiralConvFn(torch.autograd.Function):
                                            y if full else y.view(-1)[n0:], B, Vin, R, S, Cin, nc, act,
                                            0 if full else Cout)
                 done = True
-            elif _slot_ok(S, Cin, Cout):
+            elif _slot_ok(S, Cin, Cout, R):
                 packed = _f32(B, R, 32, like=x)
                 cabi.slot_pack(x, None, table.idx, packed, B, Vin, R, S, Cin)
                 wd, wimg = _f32(1024, like=x), _f32(cabi.tc_wimg_floats(1, 32, 32), like=x)
@@ -124,7 +125,7 @@ class SpiralConvFn(torch.autograd.Function):
             db = torch.empty(Cout, device=x.device, dtype=torch.float32) if ctx.has_bias else None
             ws = torch.empty(cabi.spiralconv_bwd_w_workspace(B * max(R, Vin), S, max(Cin, 32), max(Cout, 32)) // 4 + 4,
                              device=x.device, dtype=torch.float32)
-        if tc and _slot_ok(S, Cout, Cin) and (want_w or want_x):
+        if tc and _slot_ok(S, Cout, Cin, Vin) and (want_w or want_x):
             # 3-channel OUTPUT layer: G[u, s*C + n] = sum of dpre over the rows that gather u at slot s, then
             # dW = (G^T x) re-indexed and dx = G Wd^T -- two dense 32 x 32 contractions
             cell_ptr, cell_src = table.inverse()

@@ -151,6 +151,16 @@ class TilePlan:
     seq: int
 
     @staticmethod
+    def try_build(cell_ptr, cell_src, out_rows: int, seq: int, device) -> "TilePlan":
+        """``build``, or the ``NO_PLAN`` marker (empty arrays, ``rcap == 0``) when the table is outside what
+        the tensor-core kernels support."""
+        try:
+            return TilePlan.build(cell_ptr, cell_src, out_rows, seq, device)
+        except RuntimeError:
+            z = torch.zeros(1, dtype=torch.int32, device=device)
+            return TilePlan(z, z, z, 0, int(out_rows), int(seq))
+
+    @staticmethod
     def build(cell_ptr: np.ndarray, cell_src: np.ndarray, out_rows: int, seq: int, device) -> "TilePlan":
         from . import cabi
         cnt, src, cell, rcap = cabi.tc_plan_build(cell_ptr, cell_src, out_rows, seq)
@@ -190,18 +200,23 @@ class SpiralTable:
         return self._inv_flat
 
     def plan_fwd(self) -> "TilePlan":
-        """Tile plan of the forward gather (one source row per cell: cell_ptr[i] = i)."""
+        """Tile plan of the forward gather (one source row per cell: cell_ptr[i] = i).  A table the
+        tensor-core kernels cannot take (>= 65536 source rows: plans carry 16-bit rows) gets the
+        ``NO_PLAN`` marker (``rcap == 0``); every ``*_supported`` query rejects it, so callers fall
+        back to the fp32-FMA kernels."""
         if self._plan_fwd is None:
             n = self.n_rows * self.seq
-            self._plan_fwd = TilePlan.build(np.arange(n + 1, dtype=np.int32), self._np_idx.ravel(),
-                                            self.n_rows, self.seq, self.idx.device)
+            self._plan_fwd = TilePlan.try_build(np.arange(n + 1, dtype=np.int32), self._np_idx.ravel(),
+                                                self.n_rows, self.seq, self.idx.device)
         return self._plan_fwd
 
     def plan_bwd(self) -> "TilePlan":
-        """Tile plan of the backward-to-input gather (inverse table, rows = source vertices)."""
+        """Tile plan of the backward-to-input gather (inverse table, rows = source vertices); ``NO_PLAN``
+        marker as for ``plan_fwd`` (also when one (tile, slot) cell group stages more rows than the kernels'
+        ring stage holds)."""
         if self._plan_bwd is None:
             ptr, src = inverse_cells(self._np_idx, self.n_src)
-            self._plan_bwd = TilePlan.build(ptr, src, self.n_src, self.seq, self.idx.device)
+            self._plan_bwd = TilePlan.try_build(ptr, src, self.n_src, self.seq, self.idx.device)
         return self._plan_bwd
 
     def restrict(self, kept: np.ndarray) -> "SpiralTable":

@@ -74,3 +74,22 @@ def test_shape_support_matrix():
     assert cabi.tc_supported(9, 32, 3, 128) and cabi.tc_supported(9, 64, 32, 160)
     assert not cabi.tc_supported(9, 3, 32, 128) and not cabi.tc_supported(9, 32, 128, 128)
     assert cabi.tc_wimg_floats(9, 32, 32) == 9 * 2 * 32 * 32
+
+
+def test_identity_plan_for_slot_packed_layers():
+    """S = 1 identity table (row r gathers row r): the plan the dense 32 x 32 contractions of the slot-packed
+    3-channel layers run with."""
+    R = 300
+    rcap = _check_plan(np.arange(R + 1, dtype=np.int32), np.arange(R, dtype=np.int32), R, 1)
+    assert rcap == 128
+    cnt, packed, cell, _ = cabi.tc_plan_build(np.arange(R + 1, dtype=np.int32), np.arange(R, dtype=np.int32), R, 1)
+    assert cnt.ravel().tolist() == [128, 128, 44]
+    assert np.array_equal(_unpack(packed, 128)[0, 0], np.arange(128))
+
+
+def test_plan_rejects_rows_that_do_not_fit_16_bits():
+    import pytest
+    ptr = np.arange(5, dtype=np.int32)
+    src = np.array([0, 1, 70000, 3], dtype=np.int32)      # packed plans carry 16-bit source rows
+    with pytest.raises(RuntimeError):
+        cabi.tc_plan_build(ptr, src, 4, 1)
