@@ -93,9 +93,9 @@ def load(build_if_missing: bool = False):
 
 # kernels launched per ABI call (for bench.py's `gpu_launches`)
 _KERNELS_PER_CALL = {
-    "spiralconv_fwd": 1, "weight_transpose": 1, "spiralconv_bwd_x": 1, "spiralconv_bwd_w": 3,
+    "spiralconv_fwd": 1, "weight_transpose": 1, "spiralconv_bwd_x": 1, "spiralconv_bwd_w": 2,
     "tc_pack_weights": 1, "spiralconv_fwd_tc": 1, "spiralconv_bwd_x_tc": 1,
-    "spiralconv_bwd_w_tc": 3, "dense_tc": 1, "slot_pack": 1, "slot_weight": 1, "slot_grad": 1,
+    "spiralconv_bwd_w_tc": 2, "dense_tc": 1, "slot_pack": 1, "slot_weight": 1, "slot_grad": 1,
     "dense_fwd": 1, "transpose2d": 1, "pool_ell_fwd": 1, "csr_rowsum": 1, "elu_fwd": 1,
     "elu_bwd": 1, "reparam_fwd": 1, "reparam_bwd": 1, "axpy3": 1, "swap": 1, "mse_lap_fwd": 3,
     "mse_lap_bwd": 1, "kl_fwd_bwd": 2, "lc_fwd_bwd": 3, "total_loss": 1, "adam_tick": 1,
@@ -253,7 +253,7 @@ def spiralconv_bwd_w_tc(x, plan, dpre, dW, db, workspace, B, Vin, Vout, S, Cin, 
                                           _stream())
     if rc:
         _err(rc, "spiralconv_bwd_w_tc")
-    add_launches(_KERNELS_PER_CALL["spiralconv_bwd_w_tc"])
+    add_launches((Cin // 32) * ((Cout + 31) // 32) + 1)      # one bw_umma_kernel per 32 x <=32 pass + the reduction
 
 
 def dense_tc(x, plan, wimg, bias, gate, y, B, R, act):

@@ -422,8 +422,7 @@ int sdvae_spiralconv_bwd_w_tc(const float* x, const int32_t* plan_cnt, const int
             if (rc) return rc;
         }
     const long long len = (long long)Cout * K;
-    split_reduce_kernel<<<blocks_for(len, 256), 256, 0, st>>>(part, dW, grid, len);
-    if (db) split_reduce_kernel<<<blocks_for(Cout, 256), 256, 0, st>>>(part_b, db, grid, Cout);
+    split_reduce2_kernel<<<blocks_for(len + Cout, 64), 256, 0, st>>>(part, part_b, dW, db, grid, len, Cout);
     return check_launch("split_reduce_kernel");
 }
 
@@ -468,8 +467,7 @@ int sdvae_spiralconv_bwd_w(const float* x, const int32_t* idx, const float* dpre
     }
     if (rc) return rc;
     const long long len = (long long)Cout * K;
-    split_reduce_kernel<<<blocks_for(len, 256), 256, 0, st>>>(a.part, dW, nsplit, len);
-    if (db) split_reduce_kernel<<<blocks_for(Cout, 256), 256, 0, st>>>(a.part_b, db, nsplit, Cout);
+    split_reduce2_kernel<<<blocks_for(len + Cout, 64), 256, 0, st>>>(a.part, a.part_b, dW, db, nsplit, len, Cout);
     return check_launch("split_reduce_kernel");
 }
 
