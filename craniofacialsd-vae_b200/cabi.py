@@ -35,6 +35,7 @@ _SIGNATURES = {
     "sdvae_tc_plan_tiles": (C.c_int, [C.c_int]),
     "sdvae_tc_plan_max_rows": (C.c_int, [_c_fp, C.c_int, C.c_int]),
     "sdvae_tc_plan_build": (C.c_int, [_c_fp, _c_fp, C.c_int, C.c_int, C.c_int, _c_fp, _c_fp, _c_fp]),
+    "sdvae_tc_pack_weights_batch": (C.c_int, [_c_fp, C.c_int, _c_fp]),
     "sdvae_tc_pack_weights_part": (C.c_int, [_c_fp, _c_fp] + [C.c_int] * 6 + [_c_fp]),
     "sdvae_spiralconv_fwd_tc": (C.c_int, [_c_fp] * 4 + [C.c_int] + [_c_fp] * 3 + [C.c_int] * 8 + [_c_fp]),
     "sdvae_spiralconv_bwd_x_tc": (C.c_int, [_c_fp] * 4 + [C.c_int] + [_c_fp] * 3 + [C.c_int] * 7 + [_c_fp]),
@@ -193,6 +194,31 @@ def tc_pack_weights(weight, wimg, S, Cin, Cout, transposed, n0=0, n_cnt=None):
     if rc:
         _err(rc, "tc_pack_weights")
     add_launches(_KERNELS_PER_CALL["tc_pack_weights"])
+
+
+class PackEntry(C.Structure):
+    """``sdvae_pack_entry`` of include/sdvae_b200.h."""
+    _fields_ = [("W", C.c_void_p), ("wimg", C.c_void_p), ("S", C.c_int), ("Cin", C.c_int),
+                ("Cout", C.c_int), ("transposed", C.c_int), ("n0", C.c_int), ("n_cnt", C.c_int)]
+
+
+def tc_pack_table(entries, device) -> torch.Tensor:
+    """Device table for ``tc_pack_weights_batch`` from ``(weight, wimg, S, Cin, Cout, transposed, n0,
+    n_cnt)`` tuples.  The tensors must outlive the table (it holds raw pointers)."""
+    arr = (PackEntry * len(entries))()
+    for i, (w, img, S, Cin, Cout, tr, n0, nc) in enumerate(entries):
+        arr[i] = PackEntry(_f(w, "weight"), _f(img, "wimg"), S, Cin, Cout, 1 if tr else 0, n0, nc)
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8) if len(entries) else torch.zeros(0, dtype=torch.uint8)
+    return host.to(device)
+
+
+def tc_pack_weights_batch(table: torch.Tensor, n: int):
+    if n == 0:
+        return
+    rc = load().sdvae_tc_pack_weights_batch(_chk(table, torch.uint8, "table"), n, _stream())
+    if rc:
+        _err(rc, "tc_pack_weights_batch")
+    add_launches(1)
 
 
 def tc_plan_build(cell_ptr, cell_src, out_rows, S):

@@ -212,6 +212,17 @@ int sdvae_tc_pack_weights_part(const float* W, float* wimg, int S, int Cin, int 
     return check_launch("umma_pack_weights_kernel");
 }
 
+int sdvae_tc_pack_weights_batch(const sdvae_pack_entry* entries, int n, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(entries && n >= 0, "tc_pack_weights_batch: bad argument");
+    static_assert(sizeof(sdvae_pack_entry) == sizeof(umma::PackEntry), "pack entry layouts differ");
+    if (n == 0) return SDVAE_OK;
+    // the caller validated every entry when it built the table (sdvae_tc_supported); 32 blocks x 256 threads
+    // cover the largest image (64 x 576 weights -> 2 x 64 x 576 floats) in a few strides
+    umma::umma_pack_weights_batch_kernel<<<dim3(32, (unsigned)n), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const umma::PackEntry*>(entries));
+    return check_launch("umma_pack_weights_batch_kernel");
+}
+
 int sdvae_tc_plan_tiles(int out_rows) { return (out_rows + umma::kBM - 1) / umma::kBM; }
 
 int sdvae_tc_plan_max_rows(const int32_t* cell_ptr, int out_rows, int S) {

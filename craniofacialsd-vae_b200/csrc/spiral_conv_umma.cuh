@@ -317,6 +317,42 @@ __global__ void umma_pack_weights_kernel(const PackArgs a) {
     }
 }
 
+// Batched form: blockIdx.y selects the image; entries live in device memory (layout = sdvae_pack_entry).
+struct PackEntry { const float* W; float* img; int S, Cin, Cout, transposed, n0, n_cnt; };
+
+__device__ __forceinline__ int pack_tile_n(int N) { return N <= 16 ? 16 : (N <= 32 ? 32 : 64); }
+
+__global__ void umma_pack_weights_batch_kernel(const PackEntry* __restrict__ entries) {
+    const PackEntry e = entries[blockIdx.y];
+    PackArgs a;
+    a.KS = e.transposed ? e.Cout : e.Cin;
+    a.W = e.transposed ? e.W + e.n0 : e.W + (size_t)e.n0 * e.S * e.Cin;
+    a.img = e.img; a.NT = pack_tile_n(e.n_cnt); a.S = e.S; a.n_real = e.n_cnt; a.ldw = e.S * e.Cin;
+    a.transposed = e.transposed; a.cin = e.Cin;
+    const int K = a.S * a.KS;
+    const int total = (K / 32) * 2 * a.NT * 32;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int kk = t & 31;
+        const int j = (t >> 5) % (2 * a.NT);
+        const int ch = (t >> 5) / (2 * a.NT);
+        const int n = j % a.NT, part = j / a.NT;
+        const int k = ch * 32 + kk;
+        float w = 0.f;
+        if (n < a.n_real) {
+            if (!a.transposed) {
+                w = a.W[(size_t)n * a.ldw + k];
+            } else {
+                const int s = k / a.KS, o = k - s * a.KS;
+                w = a.W[(size_t)o * a.ldw + s * a.cin + n];
+            }
+        }
+        float hi, lo;
+        split_tf32f(w, hi, lo);
+        const int off = ch * (2 * a.NT * 128) + sw128_off(j, kk >> 2) + (kk & 3) * 4;
+        a.img[off >> 2] = part ? lo : hi;
+    }
+}
+
 // ---- main kernel -----------------------------------------------------------------------------
 struct UmmaArgs {
     const float* in;          // [B, in_rows, KS]

@@ -221,6 +221,7 @@ class TrainEngine:
         """Per conv layer: tile plans + packed-weight buffers for the tcgen05 kernels, where
         the layer shape is supported.  Keys: ('f', name) forward, ('b', name) backward-to-input."""
         self.tc = {}
+        self._pack_table = None
         self.slot_en0 = self.slot_out = None
         if not self.use_tc:
             return
@@ -271,18 +272,22 @@ class TrainEngine:
 
     def _pack_tc(self):
         """Re-pack every tensor-core weight image from the current weights (they change each step)."""
-        for (kind, _), e in self.tc.items():
-            for n0, nc, wimg in e['parts']:
-                cabi.tc_pack_weights(e['layer'].weight.data, wimg, e['seq'], e['cin'], e['cout'],
-                                     kind == 'b', n0, nc)
         m, L, C, S = self.model, self.L, self.C, self.S
         if self.slot_en0 is not None:
-            e = self.slot_en0
-            cabi.slot_weight(m.en_layers[0].conv.layer.weight.data, e['Wd'], 0, C[1], S[0], C[0])
-            cabi.tc_pack_weights(e['Wd'], e['wimg'], 1, 32, 32, False)
-            e = self.slot_out
-            cabi.slot_weight(m.de_layers[L + 1].layer.weight.data, e['Wd'], 1, C[0], S[0], C[0])
-            cabi.tc_pack_weights(e['Wd'], e['wimg'], 1, 32, 32, False)
+            cabi.slot_weight(m.en_layers[0].conv.layer.weight.data, self.slot_en0['Wd'], 0, C[1], S[0], C[0])
+            cabi.slot_weight(m.de_layers[L + 1].layer.weight.data, self.slot_out['Wd'], 1, C[0], S[0], C[0])
+        if self._pack_table is None:
+            # one launch for every image: the weights live in the flat arena and the images are persistent,
+            # so a device table of raw pointers stays valid for the life of the engine
+            ents = []
+            for (kind, _), e in self.tc.items():
+                for n0, nc, wimg in e['parts']:
+                    ents.append((e['layer'].weight.data, wimg, e['seq'], e['cin'], e['cout'], kind == 'b', n0, nc))
+            if self.slot_en0 is not None:
+                for e in (self.slot_en0, self.slot_out):
+                    ents.append((e['Wd'], e['wimg'], 1, 32, 32, False, 0, 32))
+            self._pack_table = (cabi.tc_pack_table(ents, self.dev), len(ents))
+        cabi.tc_pack_weights_batch(*self._pack_table)
 
     # ------------------------------------------------------------------ pieces
     def _conv(self, x, table, layer, out, act, B, Vin, Cin, Cout, name=None):

@@ -85,6 +85,14 @@ int    sdvae_tc_supported(int S, int KS, int N, int rcap);
 size_t sdvae_tc_wimg_floats(int S, int KS, int N);
 int sdvae_tc_pack_weights(const float* W, float* wimg, int S, int Cin, int Cout, int transposed,
                           sdvae_stream_t stream);
+/* Several weight images in ONE launch (the images of a training step are re-packed every step; one launch
+ * instead of ~20 three-microsecond ones).  `entries` is a DEVICE array of n sdvae_pack_entry. */
+typedef struct {
+    const float* W;     /* layer weight [Cout, S*Cin] */
+    float* wimg;        /* destination image, sdvae_tc_wimg_floats(S, KS, n_cnt) floats */
+    int S, Cin, Cout, transposed, n0, n_cnt;
+} sdvae_pack_entry;
+int sdvae_tc_pack_weights_batch(const sdvae_pack_entry* entries, int n, sdvae_stream_t stream);
 /* The same for output channels [n0, n0 + n_cnt) only (input channels for the transposed weight): a layer
  * whose full weight image does not fit in shared memory (64 -> 64) runs as two 32-channel passes, each
  * writing its columns of the output through ldy / lddx below. */
