@@ -696,10 +696,19 @@ gc_umma_kernel(const UmmaArgs a) {
                     }
                 } else {
                     const int e0 = (int)(cell & 0xffffu), cnt = (int)(cell >> 16);
+                    {   // first row of the cell: plain copy (most cells hold exactly one row); empty cells read
+                        // staged row 0 and keep zeros
+                        const uint8_t* row = stage + (cnt > 0 ? e0 : 0) * 128;
+                        const int x7 = (cnt > 0 ? e0 : 0) & 7;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 t = *reinterpret_cast<const float4*>(row + ((j ^ x7) << 4));
+                            v[4 * j] = cnt > 0 ? t.x : 0.f; v[4 * j + 1] = cnt > 0 ? t.y : 0.f;
+                            v[4 * j + 2] = cnt > 0 ? t.z : 0.f; v[4 * j + 3] = cnt > 0 ? t.w : 0.f;
+                        }
+                    }
 #pragma unroll 1
-                    for (int e = e0; e < e0 + cnt; ++e) {             // in-order sum: deterministic scatter-add
+                    for (int e = e0 + 1; e < e0 + cnt; ++e) {         // in-order sum: deterministic scatter-add
                         const uint8_t* row = stage + e * 128;
                         const int x7 = e & 7;
 #pragma unroll
