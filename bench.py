@@ -106,28 +106,25 @@ class ClockSampler:
 
 
 def build_problem(dev, bs, seed):
-    from oracle import sdvae_oracle as orc   # only for deterministic weight init (xavier_params)
+    """Tables, the drop-in model on ``dev`` (seeded xavier init), the synthetic un-swapped batch and the
+    sequence of swapped regions.  No oracle on this path."""
     from sdvae_b200 import fixtures as fx
-    from sdvae_b200.model import Model
     tabs = fx.craniofacial_tables()
-    sp, dn, up = tabs.spiral_tensors(), tabs.down_tensors(), tabs.up_tensors()
-    net = orc.Net(3, CHANNELS, LATENT, sp, dn, up, False, True)
-    params = orc.xavier_params(net.param_shapes(), seed=seed)
-    model = None
-    if dev is not None:
-        model = Model(3, CHANNELS, LATENT, [s.to(dev) for s in sp], [d.to(dev) for d in dn],
-                      [u.to(dev) for u in up], False, True).to(dev)
-        model.load_state_dict({k: v.to(dev) for k, v in params.items()})
+    model = fx.build_model(tabs, 3, CHANNELS, LATENT, False, True, seed, dev) if dev is not None else None
     rng = np.random.RandomState(seed)
     x = torch.from_numpy(rng.randn(bs, tabs.num_vertices[0], 3).astype(np.float32))
     regions = [int(r) for r in rng.randint(0, len(tabs.regions), 4096)]
-    return tabs, net, params, model, x, regions
+    return tabs, model, x, regions
 
 
-def cpu_step_rate(tabs, net, params, bs, steps, warmup, seed):
-    """The reference's _do_iteration on host cores via the oracle port (swap included)."""
+def cpu_step_rate(tabs, bs, steps, warmup, seed):
+    """CPU-baseline leg (the one place bench.py executes oracle/): the reference's _do_iteration on host cores
+    via the oracle port (swap included), with its own seeded xavier weights."""
     from oracle import sdvae_oracle as orc
     torch.set_num_threads(os.cpu_count() or 1)
+    sp, dn, up = tabs.spiral_tensors(), tabs.down_tensors(), tabs.up_tensors()
+    net = orc.Net(3, CHANNELS, LATENT, sp, dn, up, False, True)
+    params = orc.xavier_params(net.param_shapes(), seed=seed)
     w = dict(kl=1e-4, lc=0.5, lap=0.1, eta1=0.5, eta2=0.5)
     trainer = orc.Trainer(net, params, tuple(torch.from_numpy(a) for a in tabs.lap), w, lr=1e-4)
     rng = np.random.RandomState(seed)
@@ -151,8 +148,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    tabs, net, params, _, _, _ = build_problem(None, args.ref_bs, args.seed)
-    rate, sec = cpu_step_rate(tabs, net, params, args.ref_bs, args.steps, args.warmup, args.seed)
+    tabs, _, _, _ = build_problem(None, args.ref_bs, args.seed)
+    rate, sec = cpu_step_rate(tabs, args.ref_bs, args.steps, args.warmup, args.seed)
     cores = os.cpu_count() or 1
     sample = ("%d steps of the craniofacial.yaml step on %d swapped meshes (bs=%d), fp32, "
               "oracle port of model.py/model_manager.py on torch-CPU" % (args.steps, args.ref_bs ** 2, args.ref_bs))
@@ -210,7 +207,7 @@ def run_ours(args):
     from sdvae_b200.engine import StepConfig, TrainEngine
 
     bs = args.bs
-    tabs, net, params, model, x_host, regions = build_problem(dev, bs, args.seed)
+    tabs, model, x_host, regions = build_problem(dev, bs, args.seed)
     cfg = StepConfig(batch_size=bs)
     lt = losses.LaplacianTable.build(*tabs.lap, tabs.num_vertices[0], dev)
     lat = tabs.latent_regions(LATENT)
@@ -297,7 +294,7 @@ def run_ours(args):
                          "(peak %.1f TFLOP/s)" % (148 * 128 * 2 * 1.965e9 / 1e12))}
     cpu = None
     if not args.no_cpu_baseline and world == 1:      # reported baseline: rank 0 at N = 1 only
-        rate, sec = cpu_step_rate(tabs, net, params, args.ref_bs, 5, 2, args.seed)
+        rate, sec = cpu_step_rate(tabs, args.ref_bs, 5, 2, args.seed)
         cpu = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                "sample": "5 steps (2 warm-up) of the same training step on %d swapped meshes (bs=%d), "
                          "oracle port on torch-CPU, all host threads" % (args.ref_bs ** 2, args.ref_bs),

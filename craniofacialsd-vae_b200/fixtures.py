@@ -435,3 +435,35 @@ def craniofacial_tables() -> MeshTables:
     if not os.path.exists(p):
         raise FileNotFoundError(p + ' is missing; run tools/make_golden.py where /root/reference exists')
     return MeshTables.load_npz(p)
+
+
+def build_model(tabs: "MeshTables", in_channels, out_channels, latent_size, pre_z_sigmoid, is_vae,
+                seed: int, device, bias_scale: float = 0.05):
+    """The drop-in ``Model`` for these tables on ``device`` with a seeded initialisation: the reference's
+    xavier-uniform weights (model.py:139-144) and small random biases (all-zero biases would hide bias
+    handling in benchmarks and checks).  Deterministic for a given seed, identical on every rank."""
+    from .model import Model
+    sp = [s.to(device) for s in tabs.spiral_tensors()]
+    dn = [d.to(device) for d in tabs.down_tensors()]
+    up = [u.to(device) for u in tabs.up_tensors()]
+    gen = torch.Generator().manual_seed(int(seed))
+    model = Model(in_channels, out_channels, latent_size, sp, dn, up, pre_z_sigmoid, is_vae)
+    with torch.no_grad():
+        for name, p in sorted(model.named_parameters()):
+            if p.dim() >= 2:
+                bound = (6.0 / (p.shape[0] + p.shape[1])) ** 0.5
+                p.copy_((torch.rand(p.shape, generator=gen) * 2 - 1) * bound)
+            else:
+                p.copy_(torch.randn(p.shape, generator=gen) * bias_scale)
+    return model.to(device)
+
+
+def swap_features_torch(x: torch.Tensor, feature_vertices) -> torch.Tensor:
+    """``[bs, V, C] -> [bs*bs, V, C]``: element i*bs + j is base mesh i with the feature's vertices taken from
+    mesh j (swap_batch_transform.py:27-38), by plain indexing -- input preparation for tools."""
+    bs = x.shape[0]
+    out = x.unsqueeze(1).repeat(1, bs, 1, 1)                 # [i, j] = x[i]
+    idx = torch.as_tensor(feature_vertices, dtype=torch.long, device=x.device)
+    out[:, :, idx] = x[:, idx].unsqueeze(0).expand(bs, bs, idx.numel(), x.shape[2])
+    return out.reshape(bs * bs, x.shape[1], x.shape[2])
+

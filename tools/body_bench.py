@@ -36,11 +36,10 @@ def main():
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
         pg = dist.group.WORLD
-    from _util import build_pair
     from sdvae_b200 import fixtures as fx, losses
     from sdvae_b200.engine import StepConfig, TrainEngine
     tabs = fx.synthetic_tables(6890, 3, seq_length=9, n_regions=11, seed=0, name='body-synthetic')
-    _, _, model = build_pair(tabs, 3, [32, 32, 64], 33, False, False, 3, dev)
+    model = fx.build_model(tabs, 3, [32, 32, 64], 33, False, False, 3, dev)
     cfg = StepConfig(batch_size=args.bs, kl_weight=0.0, latent_consistency_weight=1.0, laplacian_weight=1.0)
     lt = losses.LaplacianTable.build(*tabs.lap, tabs.num_vertices[0], dev)
     lat = tabs.latent_regions(33)

@@ -25,23 +25,16 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    from oracle import sdvae_oracle as orc
     from sdvae_b200 import fixtures as fx, losses
     from sdvae_b200.engine import StepConfig, TrainEngine
-    from sdvae_b200.model import Model
 
     tabs = fx.craniofacial_tables()
-    sp, dn, up = tabs.spiral_tensors(), tabs.down_tensors(), tabs.up_tensors()
-    shapes = orc.Net(3, [32, 32, 32, 64], 75, sp, dn, up, False, True).param_shapes()
-    params = orc.xavier_params(shapes, seed=5, bias_scale=0.05)
     bs = 2 * world
     cfg = StepConfig(batch_size=bs, lr=1e-3)
     lat = tabs.latent_regions(75)
 
     def make(pg):
-        model = Model(3, [32, 32, 32, 64], 75, [s.to(dev) for s in sp], [d.to(dev) for d in dn],
-                      [u.to(dev) for u in up], False, True).to(dev)
-        model.load_state_dict({k: v.to(dev) for k, v in params.items()})
+        model = fx.build_model(tabs, 3, [32, 32, 32, 64], 75, False, True, 5, dev)     # same seed on every rank
         lt = losses.LaplacianTable.build(*tabs.lap, tabs.num_vertices[0], dev)
         return TrainEngine(model, lt, [r[1] for r in tabs.regions],
                            [lat[k] for k in tabs.region_keys()], cfg, process_group=pg,

@@ -20,8 +20,6 @@ DEV = 'cuda:0'
 
 
 def main():
-    from _util import build_pair
-    from oracle import sdvae_oracle as orc
     from sdvae_b200 import fixtures as fx, functional, losses
     tabs = fx.craniofacial_tables()
     lat = tabs.latent_regions(75)
@@ -33,11 +31,11 @@ def main():
     for bs in sides:
         rng = np.random.RandomState(0)
         x0 = torch.from_numpy(rng.randn(bs, tabs.num_vertices[0], 3).astype(np.float32))
-        x = orc.swap_features(x0, torch.from_numpy(tabs.regions[3][1])).to(DEV)      # [bs^2, V, 3]
+        x = fx.swap_features_torch(x0, tabs.regions[3][1]).to(DEV)                 # [bs^2, V, 3]
         region = lat[keys[3]]
         for use_tc in (False, True):
             functional.set_tensor_cores(use_tc)
-            _, _, model = build_pair(tabs, 3, [32, 32, 32, 64], 75, False, True, 7, DEV)
+            model = fx.build_model(tabs, 3, [32, 32, 32, 64], 75, False, True, 7, DEV)
             model.train()
             opt = torch.optim.Adam(model.parameters(), lr=1e-4)
 

@@ -33,10 +33,9 @@ def gpu_time(fn, n=10):
 
 
 def main():
-    from _util import build_pair
     from sdvae_b200 import fixtures as fx
     tabs = fx.craniofacial_tables()
-    net, params, model = build_pair(tabs, 3, [32, 32, 32, 64], 75, False, True, 0, DEV)
+    model = fx.build_model(tabs, 3, [32, 32, 32, 64], 75, False, True, 0, DEV)
     model.eval()
     V = tabs.num_vertices[0]
     print('| op | batch | where | ms | meshes/s |')
@@ -51,6 +50,11 @@ def main():
             ms = gpu_time(lambda: model.decode(z))
             print('| decode (generate) | %d | 1xB200, drop-in model.py (tcgen05) | %.3f | %.0f |' % (B, ms, B / ms * 1e3))
     if '--no-cpu' not in sys.argv:
+        # CPU-baseline leg: the oracle port of model.py with the same weights, on this box's host cores
+        from oracle import sdvae_oracle as orc
+        sp, dn, up = tabs.spiral_tensors(), tabs.down_tensors(), tabs.up_tensors()
+        net = orc.Net(3, [32, 32, 32, 64], 75, sp, dn, up, False, True)
+        params = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
         torch.set_num_threads(os.cpu_count() or 1)
         x = torch.randn(8, V, 3)
         ts = []

@@ -17,7 +17,7 @@ def nerr(a, b):
 
 
 def main():
-    from _util import build_pair, rand
+    from _util import rand
     from sdvae_b200 import fixtures as fx, losses
     from sdvae_b200.engine import StepConfig, TrainEngine
     dev = 'cuda:0'
@@ -25,7 +25,7 @@ def main():
     bs = int(sys.argv[1]) if len(sys.argv) > 1 else 2
     engs = []
     for use_tc in (False, True):
-        _, _, model = build_pair(tabs, 3, [32, 32, 32, 64], 75, False, True, 77, dev)
+        model = fx.build_model(tabs, 3, [32, 32, 32, 64], 75, False, True, 77, dev)
         lt = losses.LaplacianTable.build(*tabs.lap, tabs.num_vertices[0], dev)
         lat = tabs.latent_regions(75)
         eng = TrainEngine(model, lt, [r[1] for r in tabs.regions], [lat[k] for k in tabs.region_keys()],
