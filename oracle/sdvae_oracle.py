@@ -2,9 +2,10 @@
 
 A functional restatement, in plain CPU PyTorch, of the reference's mesh
 encoder/decoder path.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
-``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import this
-module, and only as the checker or the timed CPU baseline.  Nothing under
-``craniofacialsd-vae_b200/`` imports it.
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` (plus the CPU-baseline
+column of ``tools/infer_bench.py`` and the fixture generator ``tools/make_golden.py``)
+may import this module, and only as the checker or the timed CPU baseline.  Nothing
+under ``craniofacialsd-vae_b200/`` imports it.
 
 Every function cites the reference lines it follows (paths are relative to the
 reference checkout).  Pinning: the reference has **no** golden vectors or tests
