@@ -117,7 +117,8 @@ static int launch_umma(umma::UmmaArgs& ua, cudaStream_t st) {
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SDVAE_DBG"); dbg = e ? atoi(e) : 0; } ua.dbg = dbg; }
     const long long ntiles = (long long)ua.B * ua.L;
     const int grid = ntiles < kNumSMs ? (int)ntiles : kNumSMs;
-    kern<<<grid, umma::kThreads, Cfg::smem_bytes(ua.S, ua.rcap, ua.nraw), st>>>(ua);
+    ua.ostage = (UNIFORM && Cfg::out_stage(ua.S, ua.rcap)) ? 1 : 0;
+    kern<<<grid, umma::kThreads, Cfg::smem_bytes(ua.S, ua.rcap, ua.nraw, ua.ostage != 0), st>>>(ua);
     return check_launch("gc_umma_kernel");
 }
 

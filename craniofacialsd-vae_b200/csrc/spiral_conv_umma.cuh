@@ -65,6 +65,8 @@ constexpr int kMaxAStages = 7;            // TMEM A-operand ring depth limit (64
 constexpr int kTmemCols = 512;            // [0, 4*NT): two accumulators, [4*NT, 512): A ring
 constexpr int kMaxRcap = 192;             // staged rows per (tile, slot) the kernel supports
 constexpr int kMaxRaw = kLoadWarps;       // raw ring depth limit: loader warp w owns raw stage w
+constexpr int kOutRowBytes = 144;         // output staging: 128-byte rows padded to 144 B (conflict-free both ways)
+constexpr int kOutStageBytes = kBM * kOutRowBytes;
 constexpr uint32_t kSuspendHintNs = 100000;          // mbarrier.try_wait suspend-time hint
 constexpr int kSpinLimit = 1 << 22;                 // failed try_waits before a stuck wait traps
 #ifndef SDVAE_BACKOFF_NS
@@ -366,6 +368,7 @@ struct UmmaArgs {
     int B, in_rows, out_rows, L, S, rcap;
     int n_real, ldo, epi;
     int nraw;                 // raw ring depth (= active loader warps)
+    int ostage;               // 1: epilogue stages output rows in shared memory (coalesced stores); NT == 32 only
     int dbg;                  // ablation switches for tuning runs (SDVAE_DBG): 1 no copies, 2 no staged-row reads, 4 no MMAs
 };
 
@@ -405,8 +408,14 @@ struct UmmaCfg {
         long long st = budget / ((long long)rcap * 128);
         return (int)(st > kMaxRaw ? kMaxRaw : st);
     }
-    static size_t smem_bytes(int S, int rcap, int nraw) {
-        return 1024 + b_bytes(S) + (size_t)nraw * rcap * 128 + 1024;
+    // the output staging tile is used when it fits WITHOUT shortening the raw ring
+    static bool out_stage(int S, int rcap) {
+        if (NT != 32) return false;
+        const long long budget = 226LL * 1024 - 2048 - (long long)b_bytes(S) - kOutStageBytes;
+        return budget / ((long long)rcap * 128) >= kMaxRaw;
+    }
+    static size_t smem_bytes(int S, int rcap, int nraw, bool ostage) {
+        return 1024 + b_bytes(S) + (size_t)nraw * rcap * 128 + (ostage ? kOutStageBytes : 0) + 1024;
     }
 };
 
@@ -434,7 +443,8 @@ gc_umma_kernel(const UmmaArgs a) {
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
     uint8_t* B_s = smem;                                   // [NCH][2NT][128 B]   resident weight image
     uint8_t* R_s = B_s + (size_t)NCH * B_CHUNK;            // [NRAW][rcap][128 B] staged source rows (swizzled)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(R_s + (size_t)NRAW * RAW_STAGE);
+    uint8_t* O_s = R_s + (size_t)NRAW * RAW_STAGE;         // [128][144 B] output staging (a.ostage only)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(O_s + (a.ostage ? kOutStageBytes : 0));
     uint64_t* raw_full = bars;                             // [NRAW]  loaders   -> splitters
     uint64_t* raw_empty = bars + kMaxRaw;                  // [NRAW]  splitters -> loaders
     uint64_t* a_full = bars + 2 * kMaxRaw;                 // [NAST]  splitters -> MMA
@@ -577,6 +587,9 @@ gc_umma_kernel(const UmmaArgs a) {
         // NT >= 32: full-width rows, 16-byte accesses (the host checks n_real == NT and the alignments);
         // NT == 16: narrow outputs (e.g. the 3-channel output layer), scalar tail
         constexpr bool vec_ok = NT >= 32;
+        // output staging is compiled into the forward (uniform) instantiations only: the backward plans stage up to
+        // 192 rows per chunk and leave no room for it, and the extra code cost the ragged kernel 10 %
+        constexpr bool kCanStage = NT == 32 && UNIFORM;
         int b = (int)blockIdx.x / a.L, jt = (int)blockIdx.x - b * a.L;
         const int db = (int)gridDim.x / a.L, djt = (int)gridDim.x - db * a.L;
         const bool prof = SDVAE_DBG_ON(a, 32) && blockIdx.x == 0 && warp == 0;
@@ -601,7 +614,7 @@ gc_umma_kernel(const UmmaArgs a) {
                     tc_fence_before();
                     warp_arrive(t_empty + acc, lane);
                 }
-                if (!row_ok || SDVAE_DBG_ON(a, 8)) continue;
+                if (!row_ok || SDVAE_DBG_ON(a, 8)) continue;      // (rows past the mesh: nothing staged, nothing stored)
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] += d2[j];
                 float* orow = a.out + m * ldo + c0;
@@ -632,9 +645,17 @@ gc_umma_kernel(const UmmaArgs a) {
                             v[j + 2] *= elu_grad_from_out(gt.z); v[j + 3] *= elu_grad_from_out(gt.w);
                         }
                     }
+                    if (kCanStage && a.ostage) {
+                        // row-per-thread 16-byte global stores touch 32 lines per instruction; stage the row in
+                        // shared memory instead and store 4 whole rows per instruction below
+                        float4* srow = reinterpret_cast<float4*>(O_s + (q4 * 32 + lane) * kOutRowBytes + c0 * 4);
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        *reinterpret_cast<float4*>(orow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        for (int j = 0; j < 16; j += 4) srow[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4)
+                            *reinterpret_cast<float4*>(orow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
                 } else {
                     // narrow / unaligned outputs (e.g. the 3-channel output layer): scalar tail
 #pragma unroll
@@ -646,6 +667,20 @@ gc_umma_kernel(const UmmaArgs a) {
                         }
                     }
                 }
+            }
+            if (kCanStage && a.ostage && !SDVAE_DBG_ON(a, 8)) {
+                // coalesced write-out of this warp's 32 rows: lane -> (row 4k + lane/8, 16-byte piece lane%8)
+                __syncwarp();
+                const int piece = lane & 7;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int lr2 = q4 * 32 + 4 * k + (lane >> 3);
+                    const float4 t = *reinterpret_cast<const float4*>(O_s + lr2 * kOutRowBytes + piece * 16);
+                    const int r2 = jt * kBM + lr2;
+                    if (r2 < a.out_rows)
+                        *reinterpret_cast<float4*>(a.out + ((size_t)b * a.out_rows + r2) * ldo + piece * 4) = t;
+                }
+                __syncwarp();
             }
             b += db; jt += djt;
             if (jt >= a.L) { jt -= a.L; ++b; }
