@@ -280,16 +280,17 @@ def run_ours(args):
     kname = ("gc_umma_kernel<32,32,uniform> (tcgen05, 3xTF32)" if on_tc else "gc_tile_kernel<32,32> (fp32 FMA)")
     # DRAM traffic of this kernel per launch from the ncu --set full capture of the same launch
     # (profiles/r01_de4_fwd_full_metrics_final.txt: dram__bytes_read.sum + dram__bytes_write.sum =
-    # 2.234 + 2.189 GB at 1024 meshes), scaled to this run's mesh count; null off the captured path.
-    traffic = (2.233760e9 + 2.188867e9) * eng.B / 1024.0 if on_tc else None
+    # 2.234 + 2.193 GB at 1024 meshes), scaled to this run's mesh count; null off the captured path.
+    traffic = (2.233842e9 + 2.192886e9) * eng.B / 1024.0 if on_tc else None
     roofline = {"bound": "hbm", "kernel": "%s de4 SpiralConv+ELU fwd [%d x 17039 x 288 x 32]" % (kname, eng.B),
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                 "kernel_ms": ksec * 1e3, "effective_tflops": flops / ksec / 1e12,
                 "note": ("tensor-core contraction (error-compensated 3xTF32, fp32-level parity). DRAM traffic = "
                          "algorithmic bytes (no re-reads); the kernel is bound by the L2->SM gather of 9 neighbour "
-                         "rows per vertex (6.2 TB/s L2->SM in the ncu capture, ~8 TB/s measured ceiling for "
-                         "128-byte row gathers) and by the single MMA-issuing thread, not by HBM"
+                         "rows per vertex (7.0 TB/s L2->SM in the ncu capture, ~8 TB/s measured ceiling for "
+                         "128-byte row gathers), by instruction issue (76 % of issue slots) and by the single "
+                         "MMA-issuing thread, not by HBM"
                          if on_tc else "fp32-FMA contraction: compute-bound on the FMA pipe "
                          "(peak %.1f TFLOP/s)" % (148 * 128 * 2 * 1.965e9 / 1e12))}
     cpu = None
