@@ -312,3 +312,24 @@ def test_tc_rejects_unsupported_shapes(cranio):
     w = torch.zeros((32, 27), device=DEV)
     with pytest.raises(RuntimeError):
         cabi.tc_pack_weights(w, torch.zeros(4096, device=DEV), 9, 3, 32, False)
+
+
+def test_large_table_falls_back_to_fma_kernels(orc):
+    """Tile plans carry 16-bit source rows: a table with >= 65536 vertices gets the NO_PLAN marker and the
+    drop-in SpiralConv runs on the fp32-FMA kernels instead of raising."""
+    from sdvae_b200 import functional
+    from sdvae_b200.model import SpiralConv
+    from sdvae_b200.tables import spiral_table
+    V, S = 70000, 9
+    rs = np.random.RandomState(1)
+    idx = torch.from_numpy(np.concatenate([np.arange(V)[:, None], rs.randint(0, V, (V, S - 1))], 1))
+    tab = spiral_table(idx.to(DEV))
+    assert tab.plan_fwd().rcap == 0 and tab.plan_bwd().rcap == 0
+    assert functional.tensor_cores_enabled()
+    conv = SpiralConv(32, 32, idx.to(DEV)).to(DEV)
+    x = rand((1, V, 32), 3).to(DEV).requires_grad_(True)
+    y = conv(x)
+    y.sum().backward()
+    want = orc.spiral_conv(x.detach().cpu().double(), idx, conv.layer.weight.detach().cpu().double(),
+                           conv.layer.bias.detach().cpu().double())
+    assert nerr(y, want) < 1e-5 and x.grad is not None and conv.layer.weight.grad is not None
