@@ -50,6 +50,9 @@ _SIGNATURES = {
     "sdvae_dense_fwd": (C.c_int, [_c_fp] * 4 + [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, _c_fp]),
     "sdvae_transpose2d": (C.c_int, [_c_fp, _c_fp, C.c_int, C.c_int, _c_fp]),
     "sdvae_pool_ell_fwd": (C.c_int, [_c_fp] * 4 + [C.c_int] * 5 + [_c_fp]),
+    "sdvae_pool_stage_tile": (C.c_int, []),
+    "sdvae_pool_stage_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "sdvae_pool_ell_fwd_staged": (C.c_int, [_c_fp] * 5 + [C.c_int] * 7 + [_c_fp]),
     "sdvae_csr_rowsum": (C.c_int, [_c_fp] * 6 + [C.c_int] * 4 + [_c_fp]),
     "sdvae_elu_fwd": (C.c_int, [_c_fp, _c_fp, C.c_longlong, _c_fp]),
     "sdvae_elu_bwd": (C.c_int, [_c_fp, _c_fp, _c_fp, C.c_longlong, _c_fp]),
@@ -97,7 +100,7 @@ _KERNELS_PER_CALL = {
     "spiralconv_fwd": 1, "weight_transpose": 1, "spiralconv_bwd_x": 1, "spiralconv_bwd_w": 2,
     "tc_pack_weights": 1, "spiralconv_fwd_tc": 1, "spiralconv_bwd_x_tc": 1,
     "spiralconv_bwd_w_tc": 2, "dense_tc": 1, "slot_pack": 1, "slot_weight": 1, "slot_grad": 1,
-    "dense_fwd": 1, "transpose2d": 1, "pool_ell_fwd": 1, "csr_rowsum": 1, "elu_fwd": 1,
+    "dense_fwd": 1, "transpose2d": 1, "pool_ell_fwd": 1, "pool_ell_fwd_staged": 1, "csr_rowsum": 1, "elu_fwd": 1,
     "elu_bwd": 1, "reparam_fwd": 1, "reparam_bwd": 1, "axpy3": 1, "swap": 1, "mse_lap_fwd": 3,
     "mse_lap_bwd": 1, "kl_fwd_bwd": 2, "lc_fwd_bwd": 3, "total_loss": 1, "adam_tick": 1,
     "adam_step": 1,
@@ -350,6 +353,33 @@ def pool_ell_fwd(x, col, val, out, B, Vin, Vout, Wd, Cc):
     if rc:
         _err(rc, "pool_ell_fwd")
     add_launches(_KERNELS_PER_CALL["pool_ell_fwd"])
+
+
+def pool_stage_supported(Cc: int, Wd: int, ucap: int) -> bool:
+    return bool(load().sdvae_pool_stage_supported(int(Cc), int(Wd), int(ucap)))
+
+
+def pool_ell_fwd_staged(x, plan, out, B, Vin, Vout, Wd, Cc):
+    """``plan``: tables.PoolStagePlan (tile_ptr, stage_src, ent, T, ucap)."""
+    rc = load().sdvae_pool_ell_fwd_staged(_f(x, "x"), _i(plan.tile_ptr, "tile_ptr"),
+                                          _i(plan.stage_src, "stage_src"), _i(plan.ent, "ent"),
+                                          _f(out, "out"), B, Vin, Vout, Wd, Cc, plan.T, plan.ucap,
+                                          _stream())
+    if rc:
+        _err(rc, "pool_ell_fwd_staged")
+    add_launches(_KERNELS_PER_CALL["pool_ell_fwd_staged"])
+
+
+POOL_STAGE_MIN_MESHES = 32      # below this the ring of staged meshes never fills; the L2 gather is faster
+
+
+def pool_fwd(x, table, out, B, Vin, Cc):
+    """Pool forward through the staged kernel when the table has a usable stage plan, else the ELL gather."""
+    plan = table.stage_plan() if B >= POOL_STAGE_MIN_MESHES else None
+    if plan is not None and pool_stage_supported(Cc, table.width, plan.ucap):
+        pool_ell_fwd_staged(x, plan, out, B, Vin, table.n_rows, table.width, Cc)
+    else:
+        pool_ell_fwd(x, table.ell_col, table.ell_val, out, B, Vin, table.n_rows, table.width, Cc)
 
 
 def csr_rowsum(dy, ptr, src, val, gate, dx, B, Vsrc, Vdst, Cc):

@@ -2,6 +2,7 @@
 // checks, template selection, launches.  Build:
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
 #include "../../include/sdvae_b200.h"
+#include <algorithm>
 #include "common.cuh"
 #include "spiral_conv.cuh"
 #include "spiral_conv_umma.cuh"
@@ -135,6 +136,55 @@ static int dispatch_umma(umma::UmmaArgs& ua, int KS, cudaStream_t st) {
     return set_error(SDVAE_ERR_UNSUPPORTED, "tcgen05 path: unsupported layer shape");
 }
 
+template <int CQ, int WD, int NST>
+static int launch_pool_staged_n(const float* x, const int32_t* tile_ptr, const int32_t* stage_src,
+                                const int32_t* ent, float* out, int B, int Vin, int Vout, int ucap,
+                                cudaStream_t st) {
+    auto kern = pool_ell_fwd_staged_kernel<CQ, WD, NST>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_done = true;
+    }
+    const size_t smem = (size_t)NST * ucap * CQ * 16;
+    const int L = (Vout + kPoolTile - 1) / kPoolTile;
+    // meshes per CTA (MG): runs long enough to amortise the ring's fill, and a CTA count that fills whole
+    // waves of the resident CTAs (a wave lasts ~MG mesh-tiles: minimise waves x MG)
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (226 * 1024) / (smem + 1024)));
+    const long long slots = (long long)kNumSMs * per_sm;
+    int MG = 1;
+    long long best = -1;
+    for (int mg = std::min(B, 2 * NST); mg <= std::min(B, 48); ++mg) {
+        const long long ctas = (long long)L * ((B + mg - 1) / mg);
+        const long long cost = ((ctas + slots - 1) / slots) * (mg + NST);      // + fill per CTA
+        if (best < 0 || cost < best) { best = cost; MG = mg; }
+    }
+    const long long grid = (long long)L * ((B + MG - 1) / MG);
+    kern<<<(unsigned)grid, kPoolStageThreads, smem, st>>>(x, tile_ptr, stage_src,
+                                                          reinterpret_cast<const int2*>(ent), out, B, Vin,
+                                                          Vout, L, ucap, MG);
+    return check_launch("pool_ell_fwd_staged_kernel");
+}
+
+// ring depth: 128-byte rows (C = 32) run 3 CTAs per SM with 3 stages (measured 0.456 ms against 0.468 ms with
+// 4 stages / 2 CTAs at 1024 meshes, level 0); 256-byte rows (C = 64, 2 CTAs per SM either way) want the deeper ring
+template <int CQ, int WD>
+static int launch_pool_staged(const float* x, const int32_t* tile_ptr, const int32_t* stage_src,
+                              const int32_t* ent, float* out, int B, int Vin, int Vout, int ucap,
+                              cudaStream_t st) {
+    return launch_pool_staged_n<CQ, WD, pool_stages_for(CQ)>(x, tile_ptr, stage_src, ent, out, B, Vin, Vout, ucap, st);
+}
+
+template <int CQ>
+static int launch_pool_staged_w(const float* x, const int32_t* tile_ptr, const int32_t* stage_src,
+                                const int32_t* ent, float* out, int B, int Vin, int Vout, int Wd, int ucap,
+                                cudaStream_t st) {
+    switch (Wd) {
+        case 2: return launch_pool_staged<CQ, 2>(x, tile_ptr, stage_src, ent, out, B, Vin, Vout, ucap, st);
+        case 3: return launch_pool_staged<CQ, 3>(x, tile_ptr, stage_src, ent, out, B, Vin, Vout, ucap, st);
+        default: return launch_pool_staged<CQ, 4>(x, tile_ptr, stage_src, ent, out, B, Vin, Vout, ucap, st);
+    }
+}
 }  // namespace sdvae
 
 using namespace sdvae;
@@ -535,6 +585,29 @@ int sdvae_pool_ell_fwd(const float* x, const int32_t* col, const float* val, flo
     return check_launch("pool_ell_fwd_kernel");
 }
 
+int sdvae_pool_stage_tile(void) { return kPoolTile; }
+
+int sdvae_pool_stage_supported(int C, int Wd, int ucap) {
+    return (C == 32 || C == 64) && Wd >= 2 && Wd <= 4 && ucap > 0 &&
+           ucap * (C / 4) <= kPoolMaxIssue * kPoolStageThreads &&
+           (long long)pool_stages_for(C / 4) * ucap * C * 4 <= 200 * 1024 ? 1 : 0;
+}
+
+int sdvae_pool_ell_fwd_staged(const float* x, const int32_t* tile_ptr, const int32_t* stage_src,
+                              const int32_t* ent, float* out, int B, int Vin, int Vout, int Wd, int C,
+                              int T, int ucap, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(x && tile_ptr && stage_src && ent && out, "pool_ell_fwd_staged: null pointer");
+    SDVAE_REQUIRE(B >= 0 && Vin > 0 && Vout > 0, "pool_ell_fwd_staged: bad shape");
+    SDVAE_REQUIRE(T == kPoolTile, "pool_ell_fwd_staged: the plan's tile must be sdvae_pool_stage_tile() rows");
+    SDVAE_REQUIRE(sdvae_pool_stage_supported(C, Wd, ucap), "pool_ell_fwd_staged: unsupported C / width / staged rows per tile (see sdvae_pool_stage_supported)");
+    SDVAE_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(ent) & 7) == 0, "pool_ell_fwd_staged: misaligned pointer");
+    if (B == 0) return SDVAE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 32) return launch_pool_staged_w<8>(x, tile_ptr, stage_src, ent, out, B, Vin, Vout, Wd, ucap, st);
+    return launch_pool_staged_w<16>(x, tile_ptr, stage_src, ent, out, B, Vin, Vout, Wd, ucap, st);
+}
+
 int sdvae_csr_rowsum(const float* dy, const int32_t* ptr, const int32_t* src, const float* val,
                      const float* gate, float* dx, int B, int Vsrc, int Vdst, int C,
                      sdvae_stream_t stream) {
@@ -546,6 +619,14 @@ int sdvae_csr_rowsum(const float* dy, const int32_t* ptr, const int32_t* src, co
                      (!gate || (reinterpret_cast<uintptr_t>(gate) & 15) == 0);
     const long long total = (long long)B * Vdst * (vec ? C / 4 : C);
     if (total == 0) return SDVAE_OK;
+    if (vec && (C == 32 || C == 64) && B >= 2 * (128 / C)) {
+        // one output row per warp (uniform trip count): C/4 lanes x 128/C meshes, kPoolMeshes more in registers
+        const int MW = (128 / C) * kPoolMeshes;
+        const long long warps = (long long)((B + MW - 1) / MW) * Vdst;
+        if (C == 32) csr_rowsum_warp_kernel<8><<<blocks_for(warps * 32, 256), 256, 0, st>>>(dy, ptr, src, val, gate, dx, warps, B, Vsrc, Vdst);
+        else csr_rowsum_warp_kernel<16><<<blocks_for(warps * 32, 256), 256, 0, st>>>(dy, ptr, src, val, gate, dx, warps, B, Vsrc, Vdst);
+        return check_launch("csr_rowsum_warp_kernel");
+    }
     if (vec && B >= kPoolMeshes) {
         const long long tb = (long long)((B + kPoolMeshes - 1) / kPoolMeshes) * Vdst * (C / 4);
         csr_rowsum_batch_kernel<<<blocks_for(tb, 256), 256, 0, st>>>(dy, ptr, src, val, gate, dx, tb, B, Vsrc, Vdst, C);

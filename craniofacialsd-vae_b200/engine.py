@@ -339,8 +339,7 @@ class TrainEngine:
         x = self.h
         for l in range(L - 1, -1, -1):
             up = self.up[l]
-            cabi.pool_ell_fwd(x, up.ell_col, up.ell_val, self.u[l], B, V[l + 1], V[l], up.width,
-                              self.cin_de[l])
+            cabi.pool_fwd(x, up, self.u[l], B, V[l + 1], self.cin_de[l])
             self._conv(self.u[l], self.full[l], m.de_layers[L - l].conv.layer, self.d[l],
                        cabi.ACT_ELU, B, V[l], self.cin_de[l], C[l + 1], name='de%d' % l)
             x = self.d[l]

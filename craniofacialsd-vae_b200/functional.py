@@ -211,8 +211,7 @@ class PoolFn(torch.autograd.Function):
     def forward(ctx, x, table: PoolTable):
         B, Vin, C = x.shape
         out = torch.empty((B, table.n_rows, C), device=x.device, dtype=torch.float32)
-        cabi.pool_ell_fwd(x, table.ell_col, table.ell_val, out, B, Vin, table.n_rows,
-                          table.width, C)
+        cabi.pool_fwd(x, table, out, B, Vin, C)
         ctx.table = table
         return out
 

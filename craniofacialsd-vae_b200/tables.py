@@ -117,6 +117,40 @@ def transposed_csr(row: np.ndarray, col: np.ndarray, val: np.ndarray, n_cols: in
             np.asarray(val, np.float32)[order].copy())
 
 
+POOL_STAGE_TILE = 128          # output rows per tile of the staged Pool forward (= sdvae_pool_stage_tile())
+
+
+def pool_stage_plan(ell_col: np.ndarray, ell_val: np.ndarray, tile: int = POOL_STAGE_TILE):
+    """Stage plan of the shared-memory Pool forward (include/sdvae_b200.h, ``sdvae_pool_ell_fwd_staged``).
+
+    For every tile of ``tile`` consecutive output rows: the ascending list of DISTINCT source rows its ELL
+    entries read.  Returns ``(tile_ptr [L+1], stage_src [sum], ent [n_rows, W, 2], ucap)`` where
+    ``ent[r, j] = (position of ell_col[r, j] in the list of r's tile, or -1 for padding; bits of ell_val[r, j])``.
+    Entry order inside a row is untouched (the reference adds in storage order, model.py:53-54)."""
+    ell_col = np.asarray(ell_col, np.int32)
+    ell_val = np.asarray(ell_val, np.float32)
+    n_rows, width = ell_col.shape
+    n_tiles = (n_rows + tile - 1) // tile
+    tile_ptr = np.zeros(n_tiles + 1, np.int64)
+    ent = np.empty((n_rows, width, 2), np.int32)
+    ent[:, :, 1] = ell_val.view(np.int32)
+    lists = []
+    for t in range(n_tiles):
+        blk = ell_col[t * tile:(t + 1) * tile]
+        valid = blk >= 0
+        uniq = np.unique(blk[valid])
+        loc = np.full(blk.shape, -1, np.int32)
+        loc[valid] = np.searchsorted(uniq, blk[valid]).astype(np.int32)
+        ent[t * tile:(t + 1) * tile, :, 0] = loc
+        lists.append(uniq.astype(np.int32))
+        tile_ptr[t + 1] = tile_ptr[t] + uniq.size
+    stage_src = np.concatenate(lists) if lists else np.zeros(0, np.int32)
+    if stage_src.size == 0:
+        stage_src = np.zeros(1, np.int32)
+    ucap = int(np.diff(tile_ptr).max()) if n_tiles else 0
+    return tile_ptr.astype(np.int32), stage_src, ent, ucap
+
+
 def selection_columns(row, col, val, n_rows) -> Optional[np.ndarray]:
     """If the matrix is a pure row selection (exactly one entry per row, value 1.0)
     return ``kept[r] = col of row r``; otherwise ``None``."""
@@ -226,6 +260,16 @@ class SpiralTable:
 
 
 @dataclass
+class PoolStagePlan:
+    """Device copy of ``pool_stage_plan``."""
+    tile_ptr: torch.Tensor       # int32 [L + 1]
+    stage_src: torch.Tensor      # int32 [tile_ptr[L]]
+    ent: torch.Tensor            # int32 [n_rows, W, 2]
+    T: int
+    ucap: int
+
+
+@dataclass
 class PoolTable:
     """Device copies of one sparse transform: ELL forward rows, transposed CSR."""
     n_rows: int
@@ -237,6 +281,22 @@ class PoolTable:
     t_row: torch.Tensor          # int32 [nnz]
     t_val: torch.Tensor          # fp32  [nnz]
     kept: Optional[np.ndarray]   # selection columns or None
+    _stage: Optional[object] = None
+
+    def stage_plan(self) -> Optional[PoolStagePlan]:
+        """Stage plan of the shared-memory forward, built on first use; ``None`` when staging cannot pay
+        (a tile reads at least as many distinct source rows as it has entries, e.g. selection matrices)."""
+        if self._stage is None:
+            ec = self.ell_col.cpu().numpy()
+            tp, ss, ent, ucap = pool_stage_plan(ec, self.ell_val.cpu().numpy())
+            entries = int((ec >= 0).sum())
+            if ucap == 0 or int(tp[-1]) * 2 > entries:
+                self._stage = False
+            else:
+                dev = self.ell_col.device
+                self._stage = PoolStagePlan(_dev(tp, dev), _dev(ss, dev), _dev(ent, dev),
+                                            POOL_STAGE_TILE, ucap)
+        return self._stage or None
 
     @staticmethod
     def build(row, col, val, shape, device) -> "PoolTable":

@@ -173,6 +173,20 @@ int sdvae_transpose2d(const float* in, float* out, int R, int C, sdvae_stream_t 
 int sdvae_pool_ell_fwd(const float* x, const int32_t* col, const float* val, float* out, int B,
                        int Vin, int Vout, int Wd, int C, sdvae_stream_t stream);
 
+/* The same result (bit-identical: same products, same order of additions) with the DISTINCT source
+ * rows of every tile of T = sdvae_pool_stage_tile() consecutive output rows staged once per mesh in
+ * shared memory; the plan is built on the host from the ELL rows (tables.pool_stage_plan):
+ *   tile_ptr [L+1], L = ceil(Vout/T); stage_src [tile_ptr[L]]: source rows of tile t, ascending;
+ *   ent [Vout,Wd,2] int32: {position of the entry's source row in its tile's list or -1, fp32 value bits}
+ *   ucap = max rows staged by a tile.  Supported (sdvae_pool_stage_supported) for C in {32, 64},
+ *   2 <= Wd <= 4, when the ring of stage buffers fits shared memory; otherwise call sdvae_pool_ell_fwd.
+ * Replaces: model.py:50-55, as above. */
+int sdvae_pool_stage_tile(void);
+int sdvae_pool_stage_supported(int C, int Wd, int ucap);
+int sdvae_pool_ell_fwd_staged(const float* x, const int32_t* tile_ptr, const int32_t* stage_src,
+                              const int32_t* ent, float* out, int B, int Vin, int Vout, int Wd, int C,
+                              int T, int ucap, sdvae_stream_t stream);
+
 /* dx[b,k,:] = gate * sum_{e in [ptr[k],ptr[k+1])} val[e] * dy[b, src[e], :]
  * CSR of the TRANSPOSED matrix, entries in storage order; val NULL = all ones; gate NULL = none.
  * Replaces: autograd of model.py:53-54 (scatter_add / index_select backward, atomics). */

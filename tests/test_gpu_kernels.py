@@ -111,6 +111,48 @@ def test_pool_up_down_bit_exact_forward(cranio, orc, lvl, C, B):
     assert torch.equal(rt.cpu(), xc)
 
 
+@pytest.mark.parametrize('lvl,C,B', [(0, 32, 19), (1, 32, 37), (2, 64, 21), (3, 64, 5), (0, 32, 1)])
+def test_pool_staged_forward_equals_ell_gather_bitwise(cranio, lvl, C, B):
+    """The shared-memory-staged forward keeps the ELL kernel's arithmetic and order: identical bits
+    (several meshes per CTA, ragged last mesh group, last tile shorter than T)."""
+    from sdvae_b200 import cabi
+    from sdvae_b200.tables import pool_table
+    up = cranio.up_tensors()[lvl].to(DEV)
+    pt = pool_table(up)
+    plan = pt.stage_plan()
+    assert plan is not None and cabi.pool_stage_supported(C, pt.width, plan.ucap)
+    Vf, Vc = up.shape
+    x = rand((B, Vc, C), 11).to(DEV)
+    a = torch.empty(B, Vf, C, device=DEV)
+    b = torch.full_like(a, float('nan'))
+    cabi.pool_ell_fwd(x, pt.ell_col, pt.ell_val, a, B, Vc, Vf, pt.width, C)
+    cabi.pool_ell_fwd_staged(x, plan, b, B, Vc, Vf, pt.width, C)
+    assert torch.equal(a, b)
+    assert plan.T == cabi.load().sdvae_pool_stage_tile()
+    # selection matrices (down-transforms) have nothing to stage: no plan, ELL path
+    assert pool_table(cranio.down_tensors()[lvl].to(DEV)).stage_plan() is None
+
+
+@pytest.mark.parametrize('lvl,C,B', [(0, 32, 19), (1, 32, 8), (2, 64, 21), (3, 64, 4)])
+@pytest.mark.parametrize('gated', [False, True])
+def test_csr_rowsum_row_per_warp_equals_row_per_thread_bitwise(cranio, lvl, C, B, gated):
+    """Pool backward: the row-per-warp kernel (large B) against the one-mesh-per-thread kernel (B = 1 calls)."""
+    from sdvae_b200 import cabi
+    from sdvae_b200.tables import pool_table
+    up = cranio.up_tensors()[lvl].to(DEV)
+    pt = pool_table(up)
+    Vf, Vc = up.shape
+    dy = rand((B, Vf, C), 12).to(DEV)
+    gate = rand((B, Vc, C), 13).to(DEV) if gated else None
+    a = torch.full((B, Vc, C), float('nan'), device=DEV)
+    b = torch.empty_like(a)
+    cabi.csr_rowsum(dy, pt.t_ptr, pt.t_row, pt.t_val, gate, a, B, Vf, Vc, C)
+    for m in range(B):
+        cabi.csr_rowsum(dy[m:m + 1], pt.t_ptr, pt.t_row, pt.t_val, None if gate is None else gate[m:m + 1],
+                        b[m:m + 1], 1, Vf, Vc, C)
+    assert torch.equal(a, b)
+
+
 def test_pool_empty_rows_and_ragged_width():
     from sdvae_b200.model import Pool
     ind = torch.tensor([[2, 0, 2, 2], [1, 3, 0, 2]])

@@ -120,3 +120,23 @@ def test_cpu_tensors_are_rejected(cranio):
         conv(torch.randn(1, 2, 267, 3))
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         Pool(torch.randn(2, 67, 4), cranio.up_tensors()[3])
+
+
+def test_pool_stage_plan_reproduces_ell_columns():
+    """Stage plan of the shared-memory Pool forward: per tile the ascending distinct source rows, entries
+    re-addressed into that list, values and entry order untouched."""
+    from sdvae_b200 import fixtures as fx, tables as tb
+    tabs = fx.craniofacial_tables()
+    for trans in list(tabs.up_tensors()) + list(tabs.down_tensors()):
+        ind = trans._indices().numpy()
+        ec, ev = tb.ell_from_coo(ind[0], ind[1], trans._values().numpy(), trans.shape[0], trans.shape[1])
+        for T in (32, tb.POOL_STAGE_TILE):
+            tp, ss, ent, ucap = tb.pool_stage_plan(ec, ev, T)
+            assert tp[0] == 0 and ucap == np.diff(tp).max() and np.array_equal(ent[:, :, 1].view(np.float32), ev)
+            for t in range(len(tp) - 1):
+                lst = ss[tp[t]:tp[t + 1]]
+                assert np.all(np.diff(lst) > 0)                        # distinct, ascending
+                blk, loc = ec[t * T:(t + 1) * T], ent[t * T:(t + 1) * T, :, 0]
+                assert np.array_equal(loc >= 0, blk >= 0)
+                assert np.array_equal(lst[loc[loc >= 0]], blk[blk >= 0])
+                assert set(lst.tolist()) == set(blk[blk >= 0].tolist())

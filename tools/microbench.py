@@ -52,6 +52,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--batches', default='1,16,256,1024')
     ap.add_argument('--iters', type=int, default=10)
+    ap.add_argument('--only', default='', help="'pool' or 'conv': run only that half of the sweep")
     args = ap.parse_args()
     from sdvae_b200 import cabi, fixtures as fx
     from sdvae_b200.tables import identity_plan, pool_table, restricted_spiral_table, spiral_table
@@ -80,7 +81,7 @@ def main():
              ('de3 32->32 @4260', 1, False, 32, 32), ('de4 32->32 @17039', 0, False, 32, 32),
              ('de5 32->3 @17039', 0, False, 32, 3)]
     for B in [int(b) for b in args.batches.split(',')]:
-        for name, lvl, restricted, cin, cout in convs:
+        for name, lvl, restricted, cin, cout in ([] if args.only == 'pool' else convs):
             full = spiral_table(sp[lvl])
             tab = restricted_spiral_table(sp[lvl], pool_table(dn[lvl])) if restricted else full
             Vin, R, S = V[lvl], tab.n_rows, tab.seq
@@ -177,7 +178,7 @@ def main():
             del xs, ys
         # pools: up-sampling (3 nnz / row) forward and backward; the down-sampling selections are fused
         # into the encoder convolutions (computed at the kept rows only) and have no launch of their own
-        for lvl, C in ((3, 64), (2, 64), (1, 32), (0, 32)):
+        for lvl, C in ([] if args.only == 'conv' else [(3, 64), (2, 64), (1, 32), (0, 32)]):
             pt = pool_table(up[lvl])
             Vf, Vc = V[lvl], V[lvl + 1]
             alg = 4.0 * B * C * (Vc + Vf)
@@ -186,9 +187,13 @@ def main():
             xc = [f(B, Vc, C) for _ in range(ns)]
             xf = [f(B, Vf, C) for _ in range(ns)]
             ms = timeit(lambda k: cabi.pool_ell_fwd(xc[k], pt.ell_col, pt.ell_val, xf[k], B, Vc, Vf, pt.width, C), ns, args.iters)
-            row('pool up fwd', '%d->%d C%d' % (Vc, Vf, C), B, 'ELL gather', ms, alg, flops)
+            row('pool up fwd', '%d->%d C%d' % (Vc, Vf, C), B, 'ELL gather (L2)', ms, alg, flops)
+            plan = pt.stage_plan()
+            if plan is not None and cabi.pool_stage_supported(C, pt.width, plan.ucap):
+                ms = timeit(lambda k: cabi.pool_ell_fwd_staged(xc[k], plan, xf[k], B, Vc, Vf, pt.width, C), ns, args.iters)
+                row('pool up fwd', '%d->%d C%d' % (Vc, Vf, C), B, 'ELL, tile source rows staged in smem', ms, alg, flops)
             ms = timeit(lambda k: cabi.csr_rowsum(xf[k], pt.t_ptr, pt.t_row, pt.t_val, None, xc[k], B, Vf, Vc, C), ns, args.iters)
-            row('pool up bwd', '%d->%d C%d' % (Vf, Vc, C), B, 'transposed CSR', ms, alg, flops)
+            row('pool up bwd', '%d->%d C%d' % (Vf, Vc, C), B, 'transposed CSR, row per warp', ms, alg, flops)
             del xc, xf
         torch.cuda.empty_cache()
 
