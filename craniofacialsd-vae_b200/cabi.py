@@ -50,6 +50,9 @@ _SIGNATURES = {
     "sdvae_dense_fwd": (C.c_int, [_c_fp] * 4 + [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, _c_fp]),
     "sdvae_transpose2d": (C.c_int, [_c_fp, _c_fp, C.c_int, C.c_int, _c_fp]),
     "sdvae_pool_ell_fwd": (C.c_int, [_c_fp] * 4 + [C.c_int] * 5 + [_c_fp]),
+    "sdvae_narrow_out_bwd_supported": (C.c_int, [C.c_int] * 4),
+    "sdvae_narrow_out_bwd_workspace": (C.c_size_t, [C.c_int, C.c_int]),
+    "sdvae_narrow_out_bwd": (C.c_int, [_c_fp] * 10 + [C.c_int] * 7 + [_c_fp]),
     "sdvae_pool_stage_tile": (C.c_int, []),
     "sdvae_pool_stage_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "sdvae_pool_ell_fwd_staged": (C.c_int, [_c_fp] * 5 + [C.c_int] * 7 + [_c_fp]),
@@ -100,7 +103,7 @@ _KERNELS_PER_CALL = {
     "spiralconv_fwd": 1, "weight_transpose": 1, "spiralconv_bwd_x": 1, "spiralconv_bwd_w": 2,
     "tc_pack_weights": 1, "spiralconv_fwd_tc": 1, "spiralconv_bwd_x_tc": 1,
     "spiralconv_bwd_w_tc": 2, "dense_tc": 1, "slot_pack": 1, "slot_weight": 1, "slot_grad": 1,
-    "dense_fwd": 1, "transpose2d": 1, "pool_ell_fwd": 1, "pool_ell_fwd_staged": 1, "csr_rowsum": 1, "elu_fwd": 1,
+    "dense_fwd": 1, "transpose2d": 1, "narrow_out_bwd": 2, "pool_ell_fwd": 1, "pool_ell_fwd_staged": 1, "csr_rowsum": 1, "elu_fwd": 1,
     "elu_bwd": 1, "reparam_fwd": 1, "reparam_bwd": 1, "axpy3": 1, "swap": 1, "mse_lap_fwd": 3,
     "mse_lap_bwd": 1, "kl_fwd_bwd": 2, "lc_fwd_bwd": 3, "total_loss": 1, "adam_tick": 1,
     "adam_step": 1,
@@ -355,6 +358,26 @@ def pool_ell_fwd(x, col, val, out, B, Vin, Vout, Wd, Cc):
     add_launches(_KERNELS_PER_CALL["pool_ell_fwd"])
 
 
+def narrow_out_bwd_supported(R: int, S: int, Cin: int, Cout: int) -> bool:
+    return bool(load().sdvae_narrow_out_bwd_supported(int(R), int(S), int(Cin), int(Cout)))
+
+
+def narrow_out_bwd_workspace(S: int, Cout: int) -> int:
+    return int(load().sdvae_narrow_out_bwd_workspace(int(S), int(Cout)))
+
+
+def narrow_out_bwd(dy, x, cell_ptr, cell_src, cell_pack, W, dx, dW, db, ws, B, R, Vin, S, Cin, Cout, gated):
+    """Fused backward of the 32 -> 3 output layer (dx, dW, db; any of them may be None)."""
+    if ws.numel() * 4 < narrow_out_bwd_workspace(S, Cout):
+        raise RuntimeError("sdvae_b200: narrow_out_bwd workspace too small")
+    rc = load().sdvae_narrow_out_bwd(_f(dy, "dy"), _f(x, "x"), _i(cell_ptr, "cell_ptr"), _i(cell_src, "cell_src"),
+                                     _i(cell_pack, "cell_pack"), _f(W, "W"), _fo(dx, "dx"), _fo(dW, "dW"), _fo(db, "db"), _f(ws, "ws"),
+                                     B, R, Vin, S, Cin, Cout, 1 if gated else 0, _stream())
+    if rc:
+        _err(rc, "narrow_out_bwd")
+    add_launches(_KERNELS_PER_CALL["narrow_out_bwd"])
+
+
 def pool_stage_supported(Cc: int, Wd: int, ucap: int) -> bool:
     return bool(load().sdvae_pool_stage_supported(int(Cc), int(Wd), int(ucap)))
 
@@ -370,7 +393,7 @@ def pool_ell_fwd_staged(x, plan, out, B, Vin, Vout, Wd, Cc):
     add_launches(_KERNELS_PER_CALL["pool_ell_fwd_staged"])
 
 
-POOL_STAGE_MIN_MESHES = 32      # below this the ring of staged meshes never fills; the L2 gather is faster
+POOL_STAGE_MIN_MESHES = 8       # below this the ring of staged meshes never fills; the L2 gather is as fast
 
 
 def pool_fwd(x, table, out, B, Vin, Cc):

@@ -9,6 +9,7 @@
 #include "spiral_conv_umma_bw.cuh"
 #include "slot_pack.cuh"
 #include "pool_misc.cuh"
+#include "narrow_conv.cuh"
 #include "loss.cuh"
 
 namespace sdvae {
@@ -583,6 +584,50 @@ int sdvae_pool_ell_fwd(const float* x, const int32_t* col, const float* val, flo
     if (vec) pool_ell_fwd_kernel<true><<<blocks_for(total, 256), 256, 0, st>>>(x, col, val, out, total, Vin, Vout, Wd, C);
     else pool_ell_fwd_kernel<false><<<blocks_for(total, 256), 256, 0, st>>>(x, col, val, out, total, Vin, Vout, Wd, C);
     return check_launch("pool_ell_fwd_kernel");
+}
+
+/* ---- narrow-output layer backward (narrow_conv.cuh) ------------------------------------------ */
+int sdvae_narrow_out_bwd_supported(int R, int S, int Cin, int Cout) {
+    if (!(S == 9 && Cout == 3 && Cin == 32 && R > 0 && R * Cout < 0xffff)) return 0;      // cell_pack: 16-bit offsets
+    return NarrowCfg<9, 3>::smem_bytes(R) <= 227 * 1024 ? 1 : 0;
+}
+
+size_t sdvae_narrow_out_bwd_workspace(int S, int Cout) {
+    return sizeof(float) * (size_t)kNumSMs * ((size_t)S * Cout * 32 + 32);
+}
+
+int sdvae_narrow_out_bwd(const float* dy, const float* x, const int32_t* cell_ptr, const int32_t* cell_src,
+                         const int32_t* cell_pack, const float* W, float* dx, float* dW, float* db, void* workspace, int B, int R,
+                         int Vin, int S, int Cin, int Cout, int gated, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(dy && x && cell_ptr && cell_src && cell_pack && W && workspace, "narrow_out_bwd: null pointer");
+    SDVAE_REQUIRE((reinterpret_cast<uintptr_t>(cell_pack) & 7) == 0, "narrow_out_bwd: cell_pack must be 8-byte aligned");
+    SDVAE_REQUIRE(B >= 0 && Vin > 0, "narrow_out_bwd: bad shape");
+    SDVAE_REQUIRE(sdvae_narrow_out_bwd_supported(R, S, Cin, Cout), "narrow_out_bwd: unsupported shape (see sdvae_narrow_out_bwd_supported)");
+    cudaStream_t st = (cudaStream_t)stream;
+    using Cfg = NarrowCfg<9, 3>;
+    float* part = static_cast<float*>(workspace);
+    int grid = 0;
+    if (B > 0) {
+        auto kern = narrow_out_bwd_kernel<9, 3>;
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            attr_done = true;
+        }
+        int parts = 1;                         // split meshes into row ranges until the grid fills the SMs evenly
+        while ((long long)B * parts < 4LL * kNumSMs && parts < 16 && Vin / (parts * 2) >= 256) parts *= 2;
+        const long long items = (long long)B * parts;
+        grid = items < kNumSMs ? (int)items : kNumSMs;
+        kern<<<grid, kNarrowThreads, Cfg::smem_bytes(R), st>>>(dy, x, cell_ptr, cell_src, cell_pack, W, dx, part, B, parts, R,
+                                                               Vin, gated, (int)Cfg::main_floats(R));
+        const int rc = check_launch("narrow_out_bwd_kernel");
+        if (rc) return rc;
+    }
+    if (dW || db) {
+        narrow_out_reduce_kernel<<<blocks_for(Cfg::PART, 256), 256, 0, st>>>(part, grid, dW, db, S, Cout);
+        return check_launch("narrow_out_reduce_kernel");
+    }
+    return SDVAE_OK;
 }
 
 int sdvae_pool_stage_tile(void) { return kPoolTile; }

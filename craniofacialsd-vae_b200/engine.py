@@ -223,6 +223,7 @@ class TrainEngine:
         self.tc = {}
         self._pack_table = None
         self.slot_en0 = self.slot_out = None
+        self.narrow_out_ws = None
         if not self.use_tc:
             return
         m, L, C, S = self.model, self.L, self.C, self.S
@@ -266,16 +267,23 @@ class TrainEngine:
             self.slot_en0 = dict(plan=identity_plan(R0, self.dev), P=f(B * R0 * 32).view(B, R0, 32),
                                  Wd=f(1024), wimg=f(cabi.tc_wimg_floats(1, 32, 32)),
                                  dWd=f(1024), dbd=f(32))
-            self.slot_out = dict(plan=identity_plan(V[0], self.dev), G=f(B * V[0] * 32).view(B, V[0], 32),
+            # Output layer backward (32 -> 3) fused on the FMA units (csrc/narrow_conv.cuh): G stays on the SM
+            # and is never materialised
+            narrow = cabi.narrow_out_bwd_supported(V[0], S[0], C[1], C[0])
+            self.slot_out = dict(plan=identity_plan(V[0], self.dev),
+                                 G=None if narrow else f(B * V[0] * 32).view(B, V[0], 32),
                                  Wd=f(1024), wimg=f(cabi.tc_wimg_floats(1, 32, 32)),
                                  dWd=f(1024), dbd=f(32))
+            if narrow:
+                self.narrow_out_ws = f(cabi.narrow_out_bwd_workspace(S[0], C[0]) // 4)
 
     def _pack_tc(self):
         """Re-pack every tensor-core weight image from the current weights (they change each step)."""
         m, L, C, S = self.model, self.L, self.C, self.S
         if self.slot_en0 is not None:
             cabi.slot_weight(m.en_layers[0].conv.layer.weight.data, self.slot_en0['Wd'], 0, C[1], S[0], C[0])
-            cabi.slot_weight(m.de_layers[L + 1].layer.weight.data, self.slot_out['Wd'], 1, C[0], S[0], C[0])
+            if self.narrow_out_ws is None:
+                cabi.slot_weight(m.de_layers[L + 1].layer.weight.data, self.slot_out['Wd'], 1, C[0], S[0], C[0])
         if self._pack_table is None:
             # one launch for every image: the weights live in the flat arena and the images are persistent,
             # so a device table of raw pointers stays valid for the life of the engine
@@ -284,7 +292,7 @@ class TrainEngine:
                 for n0, nc, wimg in e['parts']:
                     ents.append((e['layer'].weight.data, wimg, e['seq'], e['cin'], e['cout'], kind == 'b', n0, nc))
             if self.slot_en0 is not None:
-                for e in (self.slot_en0, self.slot_out):
+                for e in (self.slot_en0,) + ((self.slot_out,) if self.narrow_out_ws is None else ()):
                     ents.append((e['Wd'], e['wimg'], 1, 32, 32, False, 0, 32))
             self._pack_table = (cabi.tc_pack_table(ents, self.dev), len(ents))
         cabi.tc_pack_weights_batch(*self._pack_table)
@@ -401,7 +409,12 @@ class TrainEngine:
                              1.0, 0.0, scale, None)
         out_layer = m.de_layers[L + 1].layer
         cp, cs = self.full[0].inverse()
-        if self.slot_out is not None:
+        if self.narrow_out_ws is not None:
+            # dd0 = (G Wd^T) * elu'(d0), dW and db from one pass over drecon and d0 (G in registers)
+            cabi.narrow_out_bwd(self.drecon, self.d[0], cp, cs, self.full[0].inverse_packed(), out_layer.weight.data, self.dd[0],
+                                self.g(out_layer.weight), self.g(out_layer.bias), self.narrow_out_ws,
+                                B, V[0], V[0], S[0], C[1], C[0], True)
+        elif self.slot_out is not None:
             # G[u, s*3 + n] = sum of drecon over the vertices that gather u at slot s; then
             # dd0 = (G Wd^T) * elu'(d0)  and  dW[n, s*32 + c] = (G^T d0)[s*3 + n, c] -- both dense
             e = self.slot_out

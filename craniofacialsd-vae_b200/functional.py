@@ -125,7 +125,16 @@ class SpiralConvFn(torch.autograd.Function):
             db = torch.empty(Cout, device=x.device, dtype=torch.float32) if ctx.has_bias else None
             ws = torch.empty(cabi.spiralconv_bwd_w_workspace(B * max(R, Vin), S, max(Cin, 32), max(Cout, 32)) // 4 + 4,
                              device=x.device, dtype=torch.float32)
-        if tc and _slot_ok(S, Cout, Cin, Vin) and (want_w or want_x):
+        if tc and (want_w or want_x) and cabi.narrow_out_bwd_supported(R, S, Cin, Cout):
+            # 3-channel OUTPUT layer, fused (csrc/narrow_conv.cuh): dx, dW, db from one pass over dpre and x
+            cell_ptr, cell_src = table.inverse()
+            nws = _f32(cabi.narrow_out_bwd_workspace(S, Cout) // 4, like=x)
+            if want_x:
+                dx = torch.empty_like(x)
+            cabi.narrow_out_bwd(dpre, x, cell_ptr, cell_src, table.inverse_packed(), weight, dx, dw if want_w else None,
+                                db if want_w else None, nws, B, R, Vin, S, Cin, Cout, False)
+            want_w = want_x = False
+        elif tc and _slot_ok(S, Cout, Cin, Vin) and (want_w or want_x):
             # 3-channel OUTPUT layer: G[u, s*C + n] = sum of dpre over the rows that gather u at slot s, then
             # dW = (G^T x) re-indexed and dx = G Wd^T -- two dense 32 x 32 contractions
             cell_ptr, cell_src = table.inverse()

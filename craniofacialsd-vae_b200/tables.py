@@ -68,6 +68,30 @@ def inverse_cells(idx: np.ndarray, n_src: int) -> Tuple[np.ndarray, np.ndarray]:
     return ptr.astype(np.int32), rows[order].astype(np.int32)
 
 
+def pack_cells16(cell_ptr: np.ndarray, cell_src: np.ndarray, n_rows: int, width: int) -> np.ndarray:
+    """First four source rows of every cell as 16-bit fields of an 8-byte word (``sdvae_narrow_out_bwd``'s
+    ``cell_pack``): ``[n_cells, 2] int32``.  Field k = ELEMENT OFFSET ``row * width`` of row k of the cell inside a
+    ``[n_rows, width]`` mesh; an absent row is ``n_rows * width`` (the kernel keeps a zero pad there), and
+    ``0xFFFF`` in the fourth field marks a cell with more than four rows (the kernel reads rows 4.. from the
+    CSR).  ``n_rows * width`` must be below ``0xFFFF``."""
+    ptr = np.asarray(cell_ptr, np.int64)
+    src = np.asarray(cell_src, np.int64)
+    pad = int(n_rows) * int(width)
+    if pad >= 0xFFFF or (src.size and src.max() >= n_rows):
+        raise IndexError('pack_cells16: row offsets must fit 16 bits')
+    n = ptr.size - 1
+    cnt = np.diff(ptr)
+    f = np.full((n, 4), pad, np.uint32)
+    for k in range(4):
+        m = cnt > k
+        f[m, k] = src[ptr[:-1][m] + k] * width
+    f[cnt > 4, 3] = 0xFFFF
+    out = np.empty((n, 2), np.uint32)
+    out[:, 0] = f[:, 0] | (f[:, 1] << 16)
+    out[:, 1] = f[:, 2] | (f[:, 3] << 16)
+    return out.view(np.int32)
+
+
 def inverse_rows_flat(idx: np.ndarray, n_src: int) -> Tuple[np.ndarray, np.ndarray]:
     """Inverse table as a CSR over input vertices whose entries are flat
     ``r*S + s`` positions (ascending): ``dx[u] = sum_e G[flat_e]`` scatters the
@@ -212,6 +236,7 @@ class SpiralTable:
     _np_idx: np.ndarray
     _inv: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
     _inv_flat: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+    _inv_pack: Optional[dict] = None
     _plan_fwd: Optional["TilePlan"] = None
     _plan_bwd: Optional["TilePlan"] = None
 
@@ -226,6 +251,15 @@ class SpiralTable:
             ptr, src = inverse_cells(self._np_idx, self.n_src)
             self._inv = (_dev(ptr, self.idx.device), _dev(src, self.idx.device))
         return self._inv
+
+    def inverse_packed(self, width: int = 3) -> torch.Tensor:
+        """``pack_cells16`` of the inverse table for ``width``-channel rows, on the device."""
+        if self._inv_pack is None:
+            self._inv_pack = {}
+        if width not in self._inv_pack:
+            ptr, src = inverse_cells(self._np_idx, self.n_src)
+            self._inv_pack[width] = _dev(pack_cells16(ptr, src, self.n_rows, width), self.idx.device)
+        return self._inv_pack[width]
 
     def inverse_flat(self):
         if self._inv_flat is None:

@@ -165,6 +165,26 @@ int sdvae_dense_fwd(const float* in, const float* W, const float* bias, float* o
 /* out[c, r] = in[r, c] */
 int sdvae_transpose2d(const float* in, float* out, int R, int C, sdvae_stream_t stream);
 
+/* ---- narrow-output layer (32 -> 3, model.py:135-136): the whole backward in one pass --------------
+ * G[u, s*Cout + n] = sum_{v in cell(u,s)} dy[b, v, n]   (cell_ptr [Vin*S+1], cell_src: the inverse spiral table
+ *                                                         in cell-CSR form, rows ascending inside a cell)
+ * dx[b,u,c] = (gated ? elu'(x[b,u,c]) : 1) * sum_j G[u,j] * W[j % Cout, (j / Cout)*32 + c]
+ * dW[n, s*32+c] = sum_{b,u} G[u, s*Cout+n] * x[b,u,c];   db[n] = sum_{b,v} dy[b,v,n]
+ * cell_pack [Vin*S, 2] int32: the first four rows of every cell as 16-bit fields (low half first) holding the
+ *   element offset row*Cout; R*Cout = no row; 0xFFFF in the fourth field = the cell has more rows, read from
+ *   cell_ptr/cell_src from its 4th on (tables.pack_cells16 builds it; needs R*Cout < 0xFFFF).
+ * dy [B,R,Cout], x / dx [B,Vin,32] (x = the layer's input; with gated = 1 it is also the ELU output whose
+ * derivative gates dx).  dx, dW, db may each be NULL.  workspace: sdvae_narrow_out_bwd_workspace bytes.
+ * Deterministic (fixed summation orders).  Supported for S = 9, Cin = 32, Cout = 3 while one mesh of dy fits
+ * shared memory (sdvae_narrow_out_bwd_supported); otherwise use the slot-packed or generic entry points.
+ * Replaces: autograd of model.py:34,40 for the output layer (index_select backward = index_add_ atomics,
+ * grad_weight GEMM over the materialised gather). */
+int sdvae_narrow_out_bwd_supported(int R, int S, int Cin, int Cout);
+size_t sdvae_narrow_out_bwd_workspace(int S, int Cout);
+int sdvae_narrow_out_bwd(const float* dy, const float* x, const int32_t* cell_ptr, const int32_t* cell_src,
+                         const int32_t* cell_pack, const float* W, float* dx, float* dW, float* db, void* workspace, int B, int R,
+                         int Vin, int S, int Cin, int Cout, int gated, sdvae_stream_t stream);
+
 /* ---- Pool --------------------------------------------------------------------------------- */
 
 /* out[b,r,:] = sum_{j<Wd, col[r,j]>=0} val[r,j] * x[b, col[r,j], :]   (entries in storage order,

@@ -301,6 +301,47 @@ def test_slot_packed_narrow_layers_vs_fp64_autograd(cranio, orc, lvl, B):
     assert nerr(dW2, w2.grad) < TC_TOL and nerr(db2, b2.grad) < TC_TOL
 
 
+@pytest.mark.parametrize('lvl,B', [(2, 3), (0, 2), (0, 21), (1, 37)])
+@pytest.mark.parametrize('gated', [False, True])
+def test_fused_narrow_output_backward_vs_fp64_autograd(cranio, orc, lvl, B, gated):
+    """32 -> 3 output layer, whole backward in one fp32-FMA pass (csrc/narrow_conv.cuh): input gradient (with
+    and without the ELU' gate), weight and bias gradients against fp64 autograd of the oracle; deterministic;
+    dx / dW / db individually optional.  B = 21 / 37: several meshes per CTA and row-range parts."""
+    from sdvae_b200 import cabi
+    from sdvae_b200.tables import spiral_table
+    idx = cranio.spiral_tensors()[lvl]
+    V, S = idx.shape
+    tab = spiral_table(idx.to(DEV))
+    assert cabi.narrow_out_bwd_supported(V, S, 32, 3)
+    u = rand((B, V, 32), 21).double().requires_grad_(True)
+    w2 = rand((3, S * 32), 22, 0.1).double().requires_grad_(True)
+    b2 = torch.zeros(3, dtype=torch.float64, requires_grad=True)
+    gr = rand((B, V, 3), 23)
+    d0 = orc.elu(u) if gated else u
+    orc.spiral_conv(d0, idx, w2, b2).backward(gr.double())
+    cp, cs = tab.inverse()
+    d0f = d0.detach().float().to(DEV).contiguous()
+    wf = w2.detach().float().to(DEV)
+    ws = torch.empty(cabi.narrow_out_bwd_workspace(S, 3) // 4, device=DEV)
+
+    def run(want_dx=True, want_w=True):
+        du = torch.full((B, V, 32), float('nan'), device=DEV) if want_dx else None
+        dW = torch.full((3, S * 32), float('nan'), device=DEV) if want_w else None
+        db = torch.full((3,), float('nan'), device=DEV) if want_w else None
+        cabi.narrow_out_bwd(gr.to(DEV), d0f, cp, cs, tab.inverse_packed(), wf, du, dW, db, ws, B, V, V, S, 32, 3, gated)
+        return du, dW, db
+    du, dW, db = run()
+    assert nerr(du, u.grad) < TC_TOL
+    assert nerr(dW, w2.grad) < TC_TOL and nerr(db, b2.grad) < TC_TOL
+    du2, dW2, db2 = run()
+    assert torch.equal(du, du2) and torch.equal(dW, dW2) and torch.equal(db, db2)
+    du3, _, _ = run(want_w=False)
+    _, dW3, db3 = run(want_dx=False)
+    assert torch.equal(du, du3) and torch.equal(dW, dW3) and torch.equal(db, db3)
+    assert not cabi.narrow_out_bwd_supported(V, S, 64, 3) and not cabi.narrow_out_bwd_supported(V, S, 32, 4)
+    assert not cabi.narrow_out_bwd_supported(30000, S, 32, 3)          # dy of one mesh must fit shared memory
+
+
 def test_tc_rejects_unsupported_shapes(cranio):
     from sdvae_b200 import cabi
     assert not cabi.tc_supported(9, 3, 32, 128)        # K = 27: stays on the FMA kernel

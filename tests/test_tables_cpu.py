@@ -140,3 +140,27 @@ def test_pool_stage_plan_reproduces_ell_columns():
                 assert np.array_equal(loc >= 0, blk >= 0)
                 assert np.array_equal(lst[loc[loc >= 0]], blk[blk >= 0])
                 assert set(lst.tolist()) == set(blk[blk >= 0].tolist())
+
+
+def test_pack_cells16_first_rows_and_overflow_marker():
+    """``cell_pack`` of the fused output-layer backward: first four rows of each cell as 16-bit element offsets
+    row*3, ``n_rows*3`` = none (zero pad), 0xFFFF in the fourth field = longer cell (rest read from the CSR)."""
+    from sdvae_b200 import fixtures as fx, tables as tb
+    idx = fx.craniofacial_tables().spiral_tensors()[0].numpy()
+    V = idx.shape[0]
+    ptr, src = tb.inverse_cells(idx, V)
+    pk = tb.pack_cells16(ptr, src, V, 3).view(np.uint32)
+    f = np.stack([pk[:, 0] & 0xFFFF, pk[:, 0] >> 16, pk[:, 1] & 0xFFFF, pk[:, 1] >> 16], 1).astype(np.int64)
+    cnt = np.diff(ptr)
+    assert cnt.max() > 4                                   # the template has cells that overflow
+    for k in range(4):
+        has = cnt > k
+        if k == 3:
+            assert np.all(f[cnt > 4, 3] == 0xFFFF)
+            has = cnt == 4
+            assert np.all(f[cnt < 4, 3] == V * 3)
+        else:
+            assert np.all(f[~has, k] == V * 3)
+        assert np.array_equal(f[has, k], 3 * src[ptr[:-1][has] + k])
+    with pytest.raises(IndexError):
+        tb.pack_cells16(np.array([0, 1]), np.array([0]), 30000, 3)

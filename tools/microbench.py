@@ -52,6 +52,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--batches', default='1,16,256,1024')
     ap.add_argument('--iters', type=int, default=10)
+    ap.add_argument('--layer', default='', help='substring of the conv layer names to run')
     ap.add_argument('--only', default='', help="'pool' or 'conv': run only that half of the sweep")
     args = ap.parse_args()
     from sdvae_b200 import cabi, fixtures as fx
@@ -81,7 +82,7 @@ def main():
              ('de3 32->32 @4260', 1, False, 32, 32), ('de4 32->32 @17039', 0, False, 32, 32),
              ('de5 32->3 @17039', 0, False, 32, 3)]
     for B in [int(b) for b in args.batches.split(',')]:
-        for name, lvl, restricted, cin, cout in ([] if args.only == 'pool' else convs):
+        for name, lvl, restricted, cin, cout in ([] if args.only == 'pool' else [c for c in convs if args.layer in c[0]]):
             full = spiral_table(sp[lvl])
             tab = restricted_spiral_table(sp[lvl], pool_table(dn[lvl])) if restricted else full
             Vin, R, S = V[lvl], tab.n_rows, tab.seq
@@ -169,6 +170,15 @@ def main():
                     cabi.dense_tc(G, ip, wimg, None, None, xs[k], B, Vin, cabi.ACT_NONE)
                 ms = timeit(bwd_slot, ns, args.iters)
                 row('conv dx', name, B, 'slot-pack + dense tcgen05', ms, alg, flops)
+                del G
+                if cabi.narrow_out_bwd_supported(R, S, cin, cout):
+                    nws = torch.empty(cabi.narrow_out_bwd_workspace(S, cout) // 4, device=DEV)
+                    dxo = torch.empty(B, Vin, cin, device=DEV)
+                    cpk = tab.inverse_packed()
+                    ms = timeit(lambda k: cabi.narrow_out_bwd(ys[k], xs[k], cp, cs, cpk, w, dxo, dW, db, nws, B, R, Vin, S, cin, cout, True), ns, args.iters)
+                    # reads dy and x, writes dx: one more activation-sized tensor than the dx pass alone
+                    row('conv dx+dW+db', name, B, 'fused fp32 FMA, dy resident in smem, G in registers', ms, alg + 4.0 * B * Vin * cin, 2 * flops)
+                    del dxo
             else:
                 wt = torch.empty(cin, S * cout, device=DEV)
                 cabi.weight_transpose(w, wt, cout, cin, S)
