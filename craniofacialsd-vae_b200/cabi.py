@@ -53,6 +53,9 @@ _SIGNATURES = {
     "sdvae_narrow_out_bwd_supported": (C.c_int, [C.c_int] * 4),
     "sdvae_narrow_out_bwd_workspace": (C.c_size_t, [C.c_int, C.c_int]),
     "sdvae_narrow_out_bwd": (C.c_int, [_c_fp] * 10 + [C.c_int] * 7 + [_c_fp]),
+    "sdvae_narrow_out_fwd_tile": (C.c_int, []),
+    "sdvae_narrow_out_fwd_supported": (C.c_int, [C.c_int] * 4),
+    "sdvae_narrow_out_fwd": (C.c_int, [_c_fp] * 7 + [C.c_int] * 8 + [_c_fp]),
     "sdvae_pool_stage_tile": (C.c_int, []),
     "sdvae_pool_stage_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "sdvae_pool_ell_fwd_staged": (C.c_int, [_c_fp] * 5 + [C.c_int] * 7 + [_c_fp]),
@@ -103,7 +106,7 @@ _KERNELS_PER_CALL = {
     "spiralconv_fwd": 1, "weight_transpose": 1, "spiralconv_bwd_x": 1, "spiralconv_bwd_w": 2,
     "tc_pack_weights": 1, "spiralconv_fwd_tc": 1, "spiralconv_bwd_x_tc": 1,
     "spiralconv_bwd_w_tc": 2, "dense_tc": 1, "slot_pack": 1, "slot_weight": 1, "slot_grad": 1,
-    "dense_fwd": 1, "transpose2d": 1, "narrow_out_bwd": 2, "pool_ell_fwd": 1, "pool_ell_fwd_staged": 1, "csr_rowsum": 1, "elu_fwd": 1,
+    "dense_fwd": 1, "transpose2d": 1, "narrow_out_bwd": 2, "narrow_out_fwd": 1, "pool_ell_fwd": 1, "pool_ell_fwd_staged": 1, "csr_rowsum": 1, "elu_fwd": 1,
     "elu_bwd": 1, "reparam_fwd": 1, "reparam_bwd": 1, "axpy3": 1, "swap": 1, "mse_lap_fwd": 3,
     "mse_lap_bwd": 1, "kl_fwd_bwd": 2, "lc_fwd_bwd": 3, "total_loss": 1, "adam_tick": 1,
     "adam_step": 1,
@@ -356,6 +359,20 @@ def pool_ell_fwd(x, col, val, out, B, Vin, Vout, Wd, Cc):
     if rc:
         _err(rc, "pool_ell_fwd")
     add_launches(_KERNELS_PER_CALL["pool_ell_fwd"])
+
+
+def narrow_out_fwd_supported(S: int, Cin: int, Cout: int, ucap: int) -> bool:
+    return bool(load().sdvae_narrow_out_fwd_supported(int(S), int(Cin), int(Cout), int(ucap)))
+
+
+def narrow_out_fwd(x, plan, W, bias, out, B, Vin, Vout, S, Cin, Cout):
+    """32 -> 3 SpiralConv forward (no activation); ``plan``: tables.GatherStagePlan of the spiral table."""
+    rc = load().sdvae_narrow_out_fwd(_f(x, "x"), _i(plan.tile_ptr, "tile_ptr"), _i(plan.stage_src, "stage_src"),
+                                     _i(plan.loc, "loc"), _f(W, "W"), _fo(bias, "bias"), _f(out, "out"),
+                                     B, Vin, Vout, S, Cin, Cout, plan.T, plan.ucap, _stream())
+    if rc:
+        _err(rc, "narrow_out_fwd")
+    add_launches(_KERNELS_PER_CALL["narrow_out_fwd"])
 
 
 def narrow_out_bwd_supported(R: int, S: int, Cin: int, Cout: int) -> bool:

@@ -16,6 +16,7 @@
 // Deterministic: fixed summation orders, per-CTA partials reduced in CTA order by narrow_out_reduce_kernel.
 #pragma once
 #include "common.cuh"
+#include "pool_misc.cuh"
 
 namespace sdvae {
 
@@ -194,6 +195,124 @@ __global__ void narrow_out_reduce_kernel(const float* __restrict__ part, int npa
         if (dW) dW[(size_t)(j % NO) * S * 32 + (j / NO) * 32 + c] = t;
     } else if (db && idx - J * 32 < NO) {
         db[idx - J * 32] = t;
+    }
+}
+
+
+// ---- narrow-output layer forward (32 -> 3) ------------------------------------------------------------
+//   y[b, v, n] = bias[n] + sum_{s, c} W[n, s*32 + c] * x[b, idx[v, s], c]                      (model.py:27-41)
+// On the tensor-core kernel this layer cost as much as a 32 -> 32 layer (it is bound by the gather of 9 x 128
+// bytes per vertex through L2, for 3 outputs).  Here the DISTINCT source rows of a tile of kNarrowTile output
+// rows are staged once per mesh in shared memory (the plan and the cp.async ring of pool_ell_fwd_staged_kernel:
+// 3.5 rows per output row instead of 9), the 8 lanes of an output row read whole staged rows (conflict-free
+// LDS.128, 4 channels each) and do the 9 x 4 x 3 FMAs against weights held in registers; a 3-step shuffle tree
+// adds the 8 partial sums.  Deterministic (fixed orders).
+constexpr int kNarrowFwdThreads = 256;
+constexpr int kNarrowTile = 64;           // output rows per tile (= tables.NARROW_FWD_TILE)
+constexpr int kNarrowMinStages = 3, kNarrowMaxStages = 5;   // cp.async ring depth: as deep as shared memory allows
+constexpr int kNarrowMaxIssue = 12;       // cp.async per thread and mesh: ucap * 8 <= 12 * 256
+
+template <int S, int NO, int NST>
+__global__ void __launch_bounds__(kNarrowFwdThreads, 1)
+narrow_out_fwd_kernel(const float* __restrict__ x, const int* __restrict__ tile_ptr,
+                      const int* __restrict__ stage_src, const int* __restrict__ loc_tab,
+                      const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ out,
+                      int B, int Vin, int Vout, int L, int ucap, int MG) {
+    constexpr int CQ = 8;                                        // 16-byte pieces of a 32-channel row
+    constexpr int PASSES = kNarrowTile * CQ / kNarrowFwdThreads; // output rows per thread and mesh
+    constexpr int RSTEP = kNarrowFwdThreads / CQ;
+    extern __shared__ float4 nf_stage[];                         // [NST][ucap * CQ]
+    const int tile = (int)blockIdx.x % L, grp = (int)blockIdx.x / L;
+    const int m0 = grp * MG, m1 = min(B, m0 + MG);
+    if (m0 >= m1) return;
+    const int u0 = __ldg(tile_ptr + tile), U = __ldg(tile_ptr + tile + 1) - u0;
+    const int r0 = tile * kNarrowTile;
+    const int tid = threadIdx.x, q = tid % CQ, lr0 = tid / CQ;
+    const size_t mesh_in = (size_t)Vin * CQ;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const int stage_f4 = ucap * CQ;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(nf_stage);
+
+    int src_off[kNarrowMaxIssue];
+#pragma unroll
+    for (int i = 0; i < kNarrowMaxIssue; ++i) {
+        const int p = tid + i * kNarrowFwdThreads;
+        src_off[i] = p < U * CQ ? __ldg(stage_src + u0 + p / CQ) * CQ + q : -1;
+    }
+    uint32_t loc[PASSES][S];                                     // byte offset of (staged row, piece q) in a stage
+#pragma unroll
+    for (int k = 0; k < PASSES; ++k) {
+        const int r = min(r0 + lr0 + k * RSTEP, Vout - 1);       // rows past the end shadow the last row (not stored)
+#pragma unroll
+        for (int s = 0; s < S; ++s) loc[k][s] = (uint32_t)(__ldg(loc_tab + (size_t)r * S + s) * CQ + q) * 16u;
+    }
+    float w[S][4][NO];                                           // W[n, s*32 + 4q + i]
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int n = 0; n < NO; ++n) w[s][i][n] = __ldg(W + (size_t)n * S * 32 + s * 32 + 4 * q + i);
+    const float bq = (bias != nullptr && q < NO) ? __ldg(bias + q) : 0.f;
+
+    auto issue = [&](int m, int buf) {
+        if (m < m1) {
+            const float4* xm = x4 + (size_t)m * mesh_in;
+            float4* dst = nf_stage + (size_t)buf * stage_f4 + tid;
+#pragma unroll
+            for (int i = 0; i < kNarrowMaxIssue; ++i)
+                if (src_off[i] >= 0) cp_async16(dst + i * kNarrowFwdThreads, xm + src_off[i]);
+        }
+        cp_async_commit();
+    };
+
+#pragma unroll
+    for (int st = 0; st < NST - 1; ++st) issue(m0 + st, st);
+    int buf = 0;
+    for (int m = m0; m < m1; ++m) {
+        issue(m + NST - 1, buf == 0 ? NST - 1 : buf - 1);
+        cp_async_wait<NST - 1>();
+        __syncthreads();
+        const uint32_t st = sbase + (uint32_t)(buf * stage_f4) * 16u;
+        float acc[PASSES][NO];
+#pragma unroll
+        for (int k = 0; k < PASSES; ++k)
+#pragma unroll
+            for (int n = 0; n < NO; ++n) acc[k][n] = 0.f;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+#pragma unroll
+            for (int k = 0; k < PASSES; ++k) {
+                const float4 v = lds128(st + loc[k][s]);
+#pragma unroll
+                for (int n = 0; n < NO; ++n) {
+                    acc[k][n] = fmaf(v.x, w[s][0][n], acc[k][n]);
+                    acc[k][n] = fmaf(v.y, w[s][1][n], acc[k][n]);
+                    acc[k][n] = fmaf(v.z, w[s][2][n], acc[k][n]);
+                    acc[k][n] = fmaf(v.w, w[s][3][n], acc[k][n]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < PASSES; ++k) {
+#pragma unroll
+            for (int n = 0; n < NO; ++n) {
+                float a = acc[k][n];
+                a += __shfl_xor_sync(0xffffffffu, a, 1);
+                a += __shfl_xor_sync(0xffffffffu, a, 2);
+                a += __shfl_xor_sync(0xffffffffu, a, 4);
+                acc[k][n] = a;
+            }
+            const int r = r0 + lr0 + k * RSTEP;
+            if (q < NO && r < Vout) {
+                float o = acc[k][0];
+#pragma unroll
+                for (int n = 1; n < NO; ++n) o = q == n ? acc[k][n] : o;
+                out[((size_t)m * Vout + r) * NO + q] = o + bq;
+            }
+        }
+        __syncthreads();
+        buf = buf + 1 == NST ? 0 : buf + 1;
     }
 }
 

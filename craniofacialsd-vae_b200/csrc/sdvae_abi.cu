@@ -137,6 +137,19 @@ static int dispatch_umma(umma::UmmaArgs& ua, int KS, cudaStream_t st) {
     return set_error(SDVAE_ERR_UNSUPPORTED, "tcgen05 path: unsupported layer shape");
 }
 
+// Meshes per CTA (MG) of the staged kernels: runs long enough to amortise the ring's fill, and a CTA count that
+// fills whole waves of the resident CTAs (a wave lasts ~MG mesh-tiles: minimise waves x (MG + fill)).
+static int pick_mesh_group(int B, int L, long long slots, int nst) {
+    int MG = 1;
+    long long best = -1;
+    for (int mg = std::min(B, 2 * nst); mg <= std::min(B, 48); ++mg) {
+        const long long ctas = (long long)L * ((B + mg - 1) / mg);
+        const long long cost = ((ctas + slots - 1) / slots) * (mg + nst);
+        if (best < 0 || cost < best) { best = cost; MG = mg; }
+    }
+    return MG;
+}
+
 template <int CQ, int WD, int NST>
 static int launch_pool_staged_n(const float* x, const int32_t* tile_ptr, const int32_t* stage_src,
                                 const int32_t* ent, float* out, int B, int Vin, int Vout, int ucap,
@@ -149,17 +162,8 @@ static int launch_pool_staged_n(const float* x, const int32_t* tile_ptr, const i
     }
     const size_t smem = (size_t)NST * ucap * CQ * 16;
     const int L = (Vout + kPoolTile - 1) / kPoolTile;
-    // meshes per CTA (MG): runs long enough to amortise the ring's fill, and a CTA count that fills whole
-    // waves of the resident CTAs (a wave lasts ~MG mesh-tiles: minimise waves x MG)
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (226 * 1024) / (smem + 1024)));
-    const long long slots = (long long)kNumSMs * per_sm;
-    int MG = 1;
-    long long best = -1;
-    for (int mg = std::min(B, 2 * NST); mg <= std::min(B, 48); ++mg) {
-        const long long ctas = (long long)L * ((B + mg - 1) / mg);
-        const long long cost = ((ctas + slots - 1) / slots) * (mg + NST);      // + fill per CTA
-        if (best < 0 || cost < best) { best = cost; MG = mg; }
-    }
+    const int MG = pick_mesh_group(B, L, (long long)kNumSMs * per_sm, NST);
     const long long grid = (long long)L * ((B + MG - 1) / MG);
     kern<<<(unsigned)grid, kPoolStageThreads, smem, st>>>(x, tile_ptr, stage_src,
                                                           reinterpret_cast<const int2*>(ent), out, B, Vin,
@@ -628,6 +632,41 @@ int sdvae_narrow_out_bwd(const float* dy, const float* x, const int32_t* cell_pt
         return check_launch("narrow_out_reduce_kernel");
     }
     return SDVAE_OK;
+}
+
+int sdvae_narrow_out_fwd_tile(void) { return kNarrowTile; }
+
+int sdvae_narrow_out_fwd_supported(int S, int Cin, int Cout, int ucap) {
+    return S == 9 && Cin == 32 && Cout == 3 && ucap > 0 && ucap * 8 <= kNarrowMaxIssue * kNarrowFwdThreads &&
+           (long long)kNarrowMinStages * ucap * 128 <= 220 * 1024 ? 1 : 0;
+}
+
+int sdvae_narrow_out_fwd(const float* x, const int32_t* tile_ptr, const int32_t* stage_src, const int32_t* loc,
+                         const float* W, const float* bias, float* out, int B, int Vin, int Vout, int S, int Cin,
+                         int Cout, int T, int ucap, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(x && tile_ptr && stage_src && loc && W && out, "narrow_out_fwd: null pointer");
+    SDVAE_REQUIRE(B >= 0 && Vin > 0 && Vout > 0, "narrow_out_fwd: bad shape");
+    SDVAE_REQUIRE(T == kNarrowTile, "narrow_out_fwd: the plan's tile must be sdvae_narrow_out_fwd_tile() rows");
+    SDVAE_REQUIRE(sdvae_narrow_out_fwd_supported(S, Cin, Cout, ucap), "narrow_out_fwd: unsupported shape (see sdvae_narrow_out_fwd_supported)");
+    SDVAE_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "narrow_out_fwd: x must be 16-byte aligned");
+    if (B == 0) return SDVAE_OK;
+    int nst = (int)((220LL * 1024) / ((long long)ucap * 128));
+    nst = std::max(kNarrowMinStages, std::min(kNarrowMaxStages, nst));
+    { static int env = -1; if (env < 0) { const char* e = getenv("SDVAE_NARROW_STAGES"); env = e ? atoi(e) : 0; }
+      if (env >= kNarrowMinStages && env <= nst) nst = env; }
+    auto kern = nst == 5 ? narrow_out_fwd_kernel<9, 3, 5> : nst == 4 ? narrow_out_fwd_kernel<9, 3, 4> : narrow_out_fwd_kernel<9, 3, 3>;
+    static bool attr_done[8] = {false};
+    if (!attr_done[nst]) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_done[nst] = true;
+    }
+    const size_t smem = (size_t)nst * ucap * 128;
+    const int L = (Vout + kNarrowTile - 1) / kNarrowTile;
+    const int MG = pick_mesh_group(B, L, kNumSMs, nst);          // one CTA per SM (registers)
+    const long long grid = (long long)L * ((B + MG - 1) / MG);
+    kern<<<(unsigned)grid, kNarrowFwdThreads, smem, (cudaStream_t)stream>>>(x, tile_ptr, stage_src, loc, W, bias, out,
+                                                                            B, Vin, Vout, L, ucap, MG);
+    return check_launch("narrow_out_fwd_kernel");
 }
 
 int sdvae_pool_stage_tile(void) { return kPoolTile; }

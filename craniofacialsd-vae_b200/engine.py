@@ -224,6 +224,7 @@ class TrainEngine:
         self._pack_table = None
         self.slot_en0 = self.slot_out = None
         self.narrow_out_ws = None
+        self.narrow_out_plan = None
         if not self.use_tc:
             return
         m, L, C, S = self.model, self.L, self.C, self.S
@@ -276,6 +277,9 @@ class TrainEngine:
                                  dWd=f(1024), dbd=f(32))
             if narrow:
                 self.narrow_out_ws = f(cabi.narrow_out_bwd_workspace(S[0], C[0]) // 4)
+        sp = self.full[0].stage_plan()
+        if self.full[0].n_rows == V[0] and cabi.narrow_out_fwd_supported(S[0], C[1], C[0], sp.ucap):
+            self.narrow_out_plan = sp
 
     def _pack_tc(self):
         """Re-pack every tensor-core weight image from the current weights (they change each step)."""
@@ -351,8 +355,13 @@ class TrainEngine:
             self._conv(self.u[l], self.full[l], m.de_layers[L - l].conv.layer, self.d[l],
                        cabi.ACT_ELU, B, V[l], self.cin_de[l], C[l + 1], name='de%d' % l)
             x = self.d[l]
-        self._conv(x, self.full[0], m.de_layers[L + 1].layer, self.recon, cabi.ACT_NONE,
-                   B, V[0], C[1], C[0], name='out')
+        out_layer = m.de_layers[L + 1].layer
+        if self.narrow_out_plan is not None:
+            # 32 -> 3 on the FMA units over shared-memory-staged source rows (csrc/narrow_conv.cuh)
+            cabi.narrow_out_fwd(x, self.narrow_out_plan, out_layer.weight.data, out_layer.bias.data, self.recon,
+                                B, V[0], V[0], S[0], C[1], C[0])
+        else:
+            self._conv(x, self.full[0], out_layer, self.recon, cabi.ACT_NONE, B, V[0], C[1], C[0], name='out')
         return z
 
     def _bwd_w(self, x, table, dpre, layer, B, Vin, Cin, Cout):

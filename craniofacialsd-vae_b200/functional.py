@@ -77,7 +77,12 @@ class SpiralConvFn(torch.autograd.Function):
         y = torch.empty((B, R, Cout), device=x.device, dtype=torch.float32)
         packed = None                       # slot-packed input of a 3-channel first layer, kept for dW
         done = False
-        if _USE_TC and B > 0 and _aligned(x, weight, bias):
+        if _USE_TC and B > 0 and _aligned(x, weight, bias) and act == cabi.ACT_NONE and Cout == 3 and Cin == 32 \
+                and S == 9 and cabi.narrow_out_fwd_supported(S, Cin, Cout, table.stage_plan().ucap):
+            # 3-channel OUTPUT layer: fp32 FMA over shared-memory-staged source rows (csrc/narrow_conv.cuh)
+            cabi.narrow_out_fwd(x, table.stage_plan(), weight, bias, y, B, Vin, R, S, Cin, Cout)
+            done = True
+        elif _USE_TC and B > 0 and _aligned(x, weight, bias):
             plan = table.plan_fwd()
             parts = _tc_parts(S, Cin, Cout, plan.rcap)
             if parts is not None:

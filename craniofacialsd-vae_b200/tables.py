@@ -141,38 +141,49 @@ def transposed_csr(row: np.ndarray, col: np.ndarray, val: np.ndarray, n_cols: in
             np.asarray(val, np.float32)[order].copy())
 
 
+NARROW_FWD_TILE = 64           # output rows per tile of the staged 32 -> 3 forward (= sdvae_narrow_out_fwd_tile())
 POOL_STAGE_TILE = 128          # output rows per tile of the staged Pool forward (= sdvae_pool_stage_tile())
 
 
-def pool_stage_plan(ell_col: np.ndarray, ell_val: np.ndarray, tile: int = POOL_STAGE_TILE):
-    """Stage plan of the shared-memory Pool forward (include/sdvae_b200.h, ``sdvae_pool_ell_fwd_staged``).
-
-    For every tile of ``tile`` consecutive output rows: the ascending list of DISTINCT source rows its ELL
-    entries read.  Returns ``(tile_ptr [L+1], stage_src [sum], ent [n_rows, W, 2], ucap)`` where
-    ``ent[r, j] = (position of ell_col[r, j] in the list of r's tile, or -1 for padding; bits of ell_val[r, j])``.
-    Entry order inside a row is untouched (the reference adds in storage order, model.py:53-54)."""
-    ell_col = np.asarray(ell_col, np.int32)
-    ell_val = np.asarray(ell_val, np.float32)
-    n_rows, width = ell_col.shape
+def gather_stage_plan(cols: np.ndarray, tile: int):
+    """Stage plan of a gather table ``cols [n_rows, W]`` (-1 = padding) for the shared-memory-staged kernels:
+    for every tile of ``tile`` consecutive rows the ascending list of DISTINCT source rows it reads.  Returns
+    ``(tile_ptr [L+1], stage_src [sum], loc [n_rows, W], ucap)`` with ``loc[r, j]`` = position of ``cols[r, j]``
+    in the list of r's tile (-1 for padding) and ``ucap`` the longest list."""
+    cols = np.asarray(cols, np.int32)
+    n_rows = cols.shape[0]
     n_tiles = (n_rows + tile - 1) // tile
     tile_ptr = np.zeros(n_tiles + 1, np.int64)
-    ent = np.empty((n_rows, width, 2), np.int32)
-    ent[:, :, 1] = ell_val.view(np.int32)
+    loc = np.full(cols.shape, -1, np.int32)
     lists = []
     for t in range(n_tiles):
-        blk = ell_col[t * tile:(t + 1) * tile]
+        blk = cols[t * tile:(t + 1) * tile]
         valid = blk >= 0
         uniq = np.unique(blk[valid])
-        loc = np.full(blk.shape, -1, np.int32)
-        loc[valid] = np.searchsorted(uniq, blk[valid]).astype(np.int32)
-        ent[t * tile:(t + 1) * tile, :, 0] = loc
+        lt = np.full(blk.shape, -1, np.int32)
+        lt[valid] = np.searchsorted(uniq, blk[valid]).astype(np.int32)
+        loc[t * tile:(t + 1) * tile] = lt
         lists.append(uniq.astype(np.int32))
         tile_ptr[t + 1] = tile_ptr[t] + uniq.size
     stage_src = np.concatenate(lists) if lists else np.zeros(0, np.int32)
     if stage_src.size == 0:
         stage_src = np.zeros(1, np.int32)
     ucap = int(np.diff(tile_ptr).max()) if n_tiles else 0
-    return tile_ptr.astype(np.int32), stage_src, ent, ucap
+    return tile_ptr.astype(np.int32), stage_src, loc, ucap
+
+
+def pool_stage_plan(ell_col: np.ndarray, ell_val: np.ndarray, tile: int = POOL_STAGE_TILE):
+    """Stage plan of the shared-memory Pool forward (include/sdvae_b200.h, ``sdvae_pool_ell_fwd_staged``):
+    ``gather_stage_plan`` of the ELL columns, with each entry's position and value interleaved:
+    ``(tile_ptr [L+1], stage_src [sum], ent [n_rows, W, 2], ucap)``,
+    ``ent[r, j] = (position of ell_col[r, j] in the list of r's tile, or -1 for padding; bits of ell_val[r, j])``.
+    Entry order inside a row is untouched (the reference adds in storage order, model.py:53-54)."""
+    ell_val = np.asarray(ell_val, np.float32)
+    tile_ptr, stage_src, loc, ucap = gather_stage_plan(ell_col, tile)
+    ent = np.empty(loc.shape + (2,), np.int32)
+    ent[:, :, 0] = loc
+    ent[:, :, 1] = ell_val.view(np.int32)
+    return tile_ptr, stage_src, ent, ucap
 
 
 def selection_columns(row, col, val, n_rows) -> Optional[np.ndarray]:
@@ -237,6 +248,7 @@ class SpiralTable:
     _inv: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
     _inv_flat: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
     _inv_pack: Optional[dict] = None
+    _stage: Optional[dict] = None
     _plan_fwd: Optional["TilePlan"] = None
     _plan_bwd: Optional["TilePlan"] = None
 
@@ -260,6 +272,16 @@ class SpiralTable:
             ptr, src = inverse_cells(self._np_idx, self.n_src)
             self._inv_pack[width] = _dev(pack_cells16(ptr, src, self.n_rows, width), self.idx.device)
         return self._inv_pack[width]
+
+    def stage_plan(self, tile: int = NARROW_FWD_TILE) -> GatherStagePlan:
+        """``gather_stage_plan`` of this table (forward gather), on the device."""
+        if self._stage is None:
+            self._stage = {}
+        if tile not in self._stage:
+            tp, ss, loc, ucap = gather_stage_plan(self._np_idx, tile)
+            dev = self.idx.device
+            self._stage[tile] = GatherStagePlan(_dev(tp, dev), _dev(ss, dev), _dev(loc, dev), int(tile), ucap)
+        return self._stage[tile]
 
     def inverse_flat(self):
         if self._inv_flat is None:
@@ -291,6 +313,16 @@ class SpiralTable:
         """Table of the rows in ``kept`` only (fused conv + selection pooling)."""
         return SpiralTable.build(self._np_idx[np.asarray(kept, np.int64)], self.n_src,
                                  self.idx.device)
+
+
+@dataclass
+class GatherStagePlan:
+    """Device copy of ``gather_stage_plan`` of a spiral table."""
+    tile_ptr: torch.Tensor       # int32 [L + 1]
+    stage_src: torch.Tensor      # int32 [tile_ptr[L]]
+    loc: torch.Tensor            # int32 [n_rows, S]
+    T: int
+    ucap: int
 
 
 @dataclass

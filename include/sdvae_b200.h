@@ -185,6 +185,18 @@ int sdvae_narrow_out_bwd(const float* dy, const float* x, const int32_t* cell_pt
                          const int32_t* cell_pack, const float* W, float* dx, float* dW, float* db, void* workspace, int B, int R,
                          int Vin, int S, int Cin, int Cout, int gated, sdvae_stream_t stream);
 
+/* Forward of the same layer, y[b,v,n] = bias[n] + sum_{s,c} W[n, s*32+c] * x[b, idx[v,s], c], with the DISTINCT
+ * source rows of every tile of T = sdvae_narrow_out_fwd_tile() output rows staged once per mesh in shared
+ * memory (plan: tables.gather_stage_plan on the spiral table: tile_ptr [L+1], stage_src [tile_ptr[L]] ascending
+ * source rows per tile, loc [Vout,S] = position of idx[v,s] in its tile's list, ucap = max rows per tile).
+ * fp32 FMA, deterministic.  x [B,Vin,32], out [B,Vout,3]; bias may be NULL.
+ * Replaces: model.py:27-41 for de_layers[-1] (index_select -> [B, V*S, Cin] gather -> Linear). */
+int sdvae_narrow_out_fwd_tile(void);
+int sdvae_narrow_out_fwd_supported(int S, int Cin, int Cout, int ucap);
+int sdvae_narrow_out_fwd(const float* x, const int32_t* tile_ptr, const int32_t* stage_src, const int32_t* loc,
+                         const float* W, const float* bias, float* out, int B, int Vin, int Vout, int S, int Cin,
+                         int Cout, int T, int ucap, sdvae_stream_t stream);
+
 /* ---- Pool --------------------------------------------------------------------------------- */
 
 /* out[b,r,:] = sum_{j<Wd, col[r,j]>=0} val[r,j] * x[b, col[r,j], :]   (entries in storage order,

@@ -342,6 +342,35 @@ def test_fused_narrow_output_backward_vs_fp64_autograd(cranio, orc, lvl, B, gate
     assert not cabi.narrow_out_bwd_supported(30000, S, 32, 3)          # dy of one mesh must fit shared memory
 
 
+@pytest.mark.parametrize('lvl,B', [(2, 3), (0, 2), (0, 21), (1, 37), (3, 1)])
+@pytest.mark.parametrize('with_bias', [True, False])
+def test_staged_narrow_output_forward_vs_fp64_oracle(cranio, orc, lvl, B, with_bias):
+    """32 -> 3 output layer forward on the FMA units over shared-memory-staged source rows
+    (csrc/narrow_conv.cuh): against the oracle in fp64; deterministic; last tile shorter than the tile size,
+    several meshes per CTA with a ragged last group."""
+    from sdvae_b200 import cabi
+    from sdvae_b200.tables import spiral_table
+    idx = cranio.spiral_tensors()[lvl]
+    V, S = idx.shape
+    tab = spiral_table(idx.to(DEV))
+    plan = tab.stage_plan()
+    assert plan.T == cabi.load().sdvae_narrow_out_fwd_tile()
+    assert cabi.narrow_out_fwd_supported(S, 32, 3, plan.ucap)
+    x = rand((B, V, 32), 31)
+    w = rand((3, S * 32), 32, 0.1)
+    b = rand((3,), 33, 0.5) if with_bias else None
+    y64 = orc.spiral_conv(x.double(), idx, w.double(), None if b is None else b.double())
+    outs = []
+    for _ in range(2):
+        y = torch.full((B, V, 3), float('nan'), device=DEV)
+        cabi.narrow_out_fwd(x.to(DEV), plan, w.to(DEV), None if b is None else b.to(DEV), y, B, V, V, S, 32, 3)
+        outs.append(y)
+    assert nerr(outs[0], y64) < TC_TOL
+    assert torch.equal(outs[0], outs[1])
+    assert not cabi.narrow_out_fwd_supported(S, 64, 3, plan.ucap) and not cabi.narrow_out_fwd_supported(S, 32, 4, plan.ucap)
+    assert not cabi.narrow_out_fwd_supported(S, 32, 3, 100000)
+
+
 def test_tc_rejects_unsupported_shapes(cranio):
     from sdvae_b200 import cabi
     assert not cabi.tc_supported(9, 3, 32, 128)        # K = 27: stays on the FMA kernel

@@ -96,6 +96,10 @@ def main():
             act = cabi.ACT_NONE if cout == 3 else cabi.ACT_ELU
             # forward
             plan = tab.plan_fwd()
+            if cin == 32 and cout == 3 and cabi.narrow_out_fwd_supported(S, cin, cout, tab.stage_plan().ucap):
+                sp_ = tab.stage_plan()
+                ms = timeit(lambda k: cabi.narrow_out_fwd(xs[k], sp_, w, b, ys[k], B, Vin, R, S, cin, cout), ns, args.iters)
+                row('conv fwd', name, B, 'fp32 FMA, tile source rows staged in smem', ms, alg, flops)
             if cin in (32, 64) and cabi.tc_supported(S, cin, cout, plan.rcap):
                 wimg = torch.empty(cabi.tc_wimg_floats(S, cin, cout), device=DEV)
                 cabi.tc_pack_weights(w, wimg, S, cin, cout, False)
