@@ -53,6 +53,10 @@ _SIGNATURES = {
     "sdvae_narrow_out_bwd_supported": (C.c_int, [C.c_int] * 4),
     "sdvae_narrow_out_bwd_workspace": (C.c_size_t, [C.c_int, C.c_int]),
     "sdvae_narrow_out_bwd": (C.c_int, [_c_fp] * 10 + [C.c_int] * 7 + [_c_fp]),
+    "sdvae_narrow_in_supported": (C.c_int, [C.c_int] * 4),
+    "sdvae_narrow_in_bwd_w_workspace": (C.c_size_t, [C.c_int, C.c_int]),
+    "sdvae_narrow_in_fwd": (C.c_int, [_c_fp] * 5 + [C.c_int] * 7 + [_c_fp]),
+    "sdvae_narrow_in_bwd_w": (C.c_int, [_c_fp] * 6 + [C.c_int] * 6 + [_c_fp]),
     "sdvae_narrow_out_fwd_tile": (C.c_int, []),
     "sdvae_narrow_out_fwd_supported": (C.c_int, [C.c_int] * 4),
     "sdvae_narrow_out_fwd": (C.c_int, [_c_fp] * 7 + [C.c_int] * 8 + [_c_fp]),
@@ -106,7 +110,7 @@ _KERNELS_PER_CALL = {
     "spiralconv_fwd": 1, "weight_transpose": 1, "spiralconv_bwd_x": 1, "spiralconv_bwd_w": 2,
     "tc_pack_weights": 1, "spiralconv_fwd_tc": 1, "spiralconv_bwd_x_tc": 1,
     "spiralconv_bwd_w_tc": 2, "dense_tc": 1, "slot_pack": 1, "slot_weight": 1, "slot_grad": 1,
-    "dense_fwd": 1, "transpose2d": 1, "narrow_out_bwd": 2, "narrow_out_fwd": 1, "pool_ell_fwd": 1, "pool_ell_fwd_staged": 1, "csr_rowsum": 1, "elu_fwd": 1,
+    "dense_fwd": 1, "transpose2d": 1, "narrow_out_bwd": 2, "narrow_out_fwd": 1, "narrow_in_fwd": 1, "narrow_in_bwd_w": 2, "pool_ell_fwd": 1, "pool_ell_fwd_staged": 1, "csr_rowsum": 1, "elu_fwd": 1,
     "elu_bwd": 1, "reparam_fwd": 1, "reparam_bwd": 1, "axpy3": 1, "swap": 1, "mse_lap_fwd": 3,
     "mse_lap_bwd": 1, "kl_fwd_bwd": 2, "lc_fwd_bwd": 3, "total_loss": 1, "adam_tick": 1,
     "adam_step": 1,
@@ -359,6 +363,33 @@ def pool_ell_fwd(x, col, val, out, B, Vin, Vout, Wd, Cc):
     if rc:
         _err(rc, "pool_ell_fwd")
     add_launches(_KERNELS_PER_CALL["pool_ell_fwd"])
+
+
+def narrow_in_supported(Vin: int, S: int, Cin: int, Cout: int) -> bool:
+    return bool(load().sdvae_narrow_in_supported(int(Vin), int(S), int(Cin), int(Cout)))
+
+
+def narrow_in_bwd_w_workspace(S: int, Cin: int) -> int:
+    return int(load().sdvae_narrow_in_bwd_w_workspace(int(S), int(Cin)))
+
+
+def narrow_in_fwd(x, idx, W, bias, y, B, Vin, R, S, Cin, Cout, act):
+    """3 -> 32 SpiralConv forward (+ ELU) with the mesh's input resident in shared memory."""
+    rc = load().sdvae_narrow_in_fwd(_f(x, "x"), _i(idx, "idx"), _f(W, "W"), _fo(bias, "bias"), _f(y, "y"),
+                                    B, Vin, R, S, Cin, Cout, act, _stream())
+    if rc:
+        _err(rc, "narrow_in_fwd")
+    add_launches(_KERNELS_PER_CALL["narrow_in_fwd"])
+
+
+def narrow_in_bwd_w(x, idx, dpre, dW, db, ws, B, Vin, R, S, Cin, Cout):
+    if ws.numel() * 4 < narrow_in_bwd_w_workspace(S, Cin):
+        raise RuntimeError("sdvae_b200: narrow_in_bwd_w workspace too small")
+    rc = load().sdvae_narrow_in_bwd_w(_f(x, "x"), _i(idx, "idx"), _f(dpre, "dpre"), _fo(dW, "dW"), _fo(db, "db"),
+                                      _f(ws, "ws"), B, Vin, R, S, Cin, Cout, _stream())
+    if rc:
+        _err(rc, "narrow_in_bwd_w")
+    add_launches(_KERNELS_PER_CALL["narrow_in_bwd_w"])
 
 
 def narrow_out_fwd_supported(S: int, Cin: int, Cout: int, ucap: int) -> bool:

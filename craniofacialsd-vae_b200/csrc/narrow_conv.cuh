@@ -316,4 +316,149 @@ narrow_out_fwd_kernel(const float* __restrict__ x, const int* __restrict__ tile_
     }
 }
 
+
+// ---- narrow-INPUT layer (3 -> 32, the first encoder block, model.py:104-110) ----------------------------
+//   forward      y[b, r, o] = act( bias[o] + sum_j P[b, r, j] * W[o, j] ),  P[b, r, s*CI + c] = x[b, idx[r, s], c]
+//   weight grad  dW[o, j] = sum_{b, r} dpre[b, r, o] * P[b, r, j],   db[o] = sum_{b, r} dpre[b, r, o]
+// with the mesh's whole input ([Vin, 3]: 204 KB) resident in shared memory, as in narrow_out_bwd_kernel: lane j
+// gathers its value of P (one coalesced index load, one LDS), the J = 27 values reach every lane through a
+// warp-private shared-memory row, and lane o (= output channel) does the 27 FMAs against the weights (forward)
+// or accumulators (weight gradient) it keeps in registers.  P is never written to memory (the slot-packed path
+// wrote it in the forward pass and read it twice).  idx may be a row-restricted table (R kept rows).
+template <int S, int CI>
+struct NarrowInCfg {
+    static constexpr int J = S * CI;
+    static constexpr int PART = J * 32 + 32;
+    static size_t main_floats(int Vin) {
+        const size_t a = 8 + (size_t)Vin * CI, b = (size_t)kNarrowWarps * PART;
+        return ((a > b ? a : b) + 3) & ~(size_t)3;
+    }
+    static size_t smem_bytes(int Vin) { return (main_floats(Vin) + (size_t)kNarrowWarps * kNarrowRows * 32) * 4; }
+};
+
+// stage mesh `src` ([n] floats at any 4-byte phase) behind xs_raw, keeping the source's 16-byte phase; returns xs
+__device__ __forceinline__ float* narrow_stage_mesh(float* xs_raw, const float* src, int n) {
+    const int phase = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3);
+    float* xs = xs_raw + phase;
+    const int head = (4 - phase) & 3;
+    const int n4 = (n - head) >> 2, tail0 = head + 4 * n4;
+    __syncthreads();                                                 // previous item's reads are done
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) cp_async16(xs + head + 4 * i, src + head + 4 * i);
+    if ((int)threadIdx.x < head) cp_async4(xs + threadIdx.x, src + threadIdx.x);
+    if (tail0 + (int)threadIdx.x < n) cp_async4(xs + tail0 + threadIdx.x, src + tail0 + threadIdx.x);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    return xs;
+}
+
+// MODE 0: forward (out = y, aux = bias, act);  MODE 1: weight gradient (aux = dpre, out = per-CTA partials)
+template <int S, int CI, int MODE>
+__global__ void __launch_bounds__(kNarrowThreads, 1)
+narrow_in_kernel(const float* __restrict__ x, const int* __restrict__ idx, const float* __restrict__ W,
+                 const float* __restrict__ aux, float* __restrict__ out, int B, int parts, int R, int Vin,
+                 int act, int main_floats) {
+    using Cfg = NarrowInCfg<S, CI>;
+    constexpr int J = Cfg::J, JQ = (J + 3) / 4;
+    extern __shared__ float nb_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* gsw = nb_smem + main_floats + warp * kNarrowRows * 32;
+    const bool live = lane < J;
+    const int s = live ? lane / CI : 0, c = live ? lane - s * CI : 0;
+    float w[J];                                                      // MODE 0: W[lane, j];  MODE 1: dW accumulators
+#pragma unroll
+    for (int j = 0; j < J; ++j) w[j] = MODE == 0 ? __ldg(W + (size_t)lane * J + j) : 0.f;
+    float bsum = MODE == 0 ? (aux ? __ldg(aux + lane) : 0.f) : 0.f;  // MODE 0: bias[lane];  MODE 1: db accumulator
+    const int n = Vin * CI;
+    const int rows_per_part = (R + parts - 1) / parts;
+    const int step = kNarrowWarps * kNarrowRows;
+    for (int item = blockIdx.x; item < B * parts; item += gridDim.x) {
+        const int b = item / parts, pi = item - b * parts;
+        const float* xs = narrow_stage_mesh(nb_smem, x + (size_t)b * n, n) + c;
+        const int r_begin = pi * rows_per_part;
+        const int r_end = min(R, r_begin + rows_per_part);
+        const float* ab = MODE == 1 ? aux + (size_t)b * R * 32 + lane : nullptr;
+        float* ob = MODE == 0 ? out + (size_t)b * R * 32 + lane : nullptr;
+        auto load_idx = [&](int r0, int (&v)[kNarrowRows]) {
+#pragma unroll
+            for (int i = 0; i < kNarrowRows; ++i) v[i] = __ldg(idx + (size_t)min(r0 + i, R - 1) * S + s);
+        };
+        int nxt[kNarrowRows], nxt2[kNarrowRows];                     // two iterations ahead (see narrow_out_bwd_kernel)
+        const int r_first = r_begin + warp * kNarrowRows;
+        load_idx(r_first, nxt);
+        load_idx(r_first + step, nxt2);
+        for (int r0 = r_first; r0 < r_end; r0 += step) {
+            int v[kNarrowRows];
+#pragma unroll
+            for (int i = 0; i < kNarrowRows; ++i) { v[i] = nxt[i]; nxt[i] = nxt2[i]; }
+            load_idx(r0 + 2 * step, nxt2);
+            float dv[kNarrowRows];
+            if (MODE == 1) {
+#pragma unroll
+                for (int i = 0; i < kNarrowRows; ++i)
+                    dv[i] = r0 + i < r_end ? __ldg(ab + (size_t)min(r0 + i, R - 1) * 32) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < kNarrowRows; ++i) gsw[i * 32 + lane] = live ? xs[v[i] * CI] : 0.f;
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < kNarrowRows; ++i) {
+                float g[4 * JQ];
+#pragma unroll
+                for (int k = 0; k < JQ; ++k) {
+                    const float4 t = reinterpret_cast<const float4*>(gsw + i * 32)[k];
+                    g[4 * k] = t.x; g[4 * k + 1] = t.y; g[4 * k + 2] = t.z; g[4 * k + 3] = t.w;
+                }
+                if (MODE == 0) {
+                    float d0 = 0.f, d1 = 0.f, d2 = 0.f;              // three interleaved chains, fixed order
+#pragma unroll
+                    for (int j = 0; j < J; ++j) {
+                        if (j % 3 == 0) d0 = fmaf(g[j], w[j], d0);
+                        else if (j % 3 == 1) d1 = fmaf(g[j], w[j], d1);
+                        else d2 = fmaf(g[j], w[j], d2);
+                    }
+                    float d = ((d0 + d1) + d2) + bsum;
+                    if (act == 1) d = elu_fast(d);                    // SDVAE_ACT_ELU
+                    if (r0 + i < r_end) ob[(size_t)(r0 + i) * 32] = d;
+                } else {
+                    bsum += dv[i];                                   // dv = 0 for rows past the range
+#pragma unroll
+                    for (int j = 0; j < J; ++j) w[j] = fmaf(g[j], dv[i], w[j]);
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (MODE == 1) {
+        __syncthreads();
+        float* red = nb_smem;                                        // [kNarrowWarps][J*32] | [kNarrowWarps][32]
+#pragma unroll
+        for (int j = 0; j < J; ++j) red[(warp * J + j) * 32 + lane] = w[j];
+        red[kNarrowWarps * J * 32 + warp * 32 + lane] = bsum;
+        __syncthreads();
+        float* po = out + (size_t)blockIdx.x * Cfg::PART;
+        for (int i = threadIdx.x; i < Cfg::PART; i += blockDim.x) {
+            float t = 0.f;
+            if (i < J * 32) {
+                for (int wq = 0; wq < kNarrowWarps; ++wq) t += red[wq * J * 32 + i];
+            } else {
+                for (int wq = 0; wq < kNarrowWarps; ++wq) t += red[kNarrowWarps * J * 32 + wq * 32 + (i - J * 32)];
+            }
+            po[i] = t;
+        }
+    }
+}
+
+// dW[o, j] = sum_p part[p][j*32 + o];  db[o] = sum_p part[p][J*32 + o]      (partials in CTA order)
+__global__ void narrow_in_reduce_kernel(const float* __restrict__ part, int nparts, float* __restrict__ dW,
+                                        float* __restrict__ db, int J) {
+    const int total = J * 32 + 32;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float t = 0.f;
+    for (int p = 0; p < nparts; ++p) t += part[(size_t)p * total + i];
+    if (i < J * 32) { if (dW) dW[(size_t)(i & 31) * J + (i >> 5)] = t; }
+    else if (db) db[i - J * 32] = t;
+}
+
 }  // namespace sdvae

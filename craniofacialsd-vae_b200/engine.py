@@ -225,6 +225,7 @@ class TrainEngine:
         self.slot_en0 = self.slot_out = None
         self.narrow_out_ws = None
         self.narrow_out_plan = None
+        self.narrow_in_ws = None
         if not self.use_tc:
             return
         m, L, C, S = self.model, self.L, self.C, self.S
@@ -265,9 +266,10 @@ class TrainEngine:
         B, V = self.B, self.V
         if S[0] * C[0] <= 32 and C[1] == 32 and V[0] < 65536 and cabi.tc_supported(1, 32, 32, 128):
             R0 = self.sub[0].n_rows
-            self.slot_en0 = dict(plan=identity_plan(R0, self.dev), P=f(B * R0 * 32).view(B, R0, 32),
-                                 Wd=f(1024), wimg=f(cabi.tc_wimg_floats(1, 32, 32)),
-                                 dWd=f(1024), dbd=f(32))
+            if not cabi.narrow_in_supported(V[0], S[0], C[0], C[1]):
+                self.slot_en0 = dict(plan=identity_plan(R0, self.dev), P=f(B * R0 * 32).view(B, R0, 32),
+                                     Wd=f(1024), wimg=f(cabi.tc_wimg_floats(1, 32, 32)),
+                                     dWd=f(1024), dbd=f(32))
             # Output layer backward (32 -> 3) fused on the FMA units (csrc/narrow_conv.cuh): G stays on the SM
             # and is never materialised
             narrow = cabi.narrow_out_bwd_supported(V[0], S[0], C[1], C[0])
@@ -277,6 +279,10 @@ class TrainEngine:
                                  dWd=f(1024), dbd=f(32))
             if narrow:
                 self.narrow_out_ws = f(cabi.narrow_out_bwd_workspace(S[0], C[0]) // 4)
+        # First encoder block (3 -> 32) on the FMA units with the mesh's input resident in shared memory
+        # (csrc/narrow_conv.cuh): no slot-packed P buffer
+        if cabi.narrow_in_supported(V[0], S[0], C[0], C[1]):
+            self.narrow_in_ws = f(cabi.narrow_in_bwd_w_workspace(S[0], C[0]) // 4)
         sp = self.full[0].stage_plan()
         if self.full[0].n_rows == V[0] and cabi.narrow_out_fwd_supported(S[0], C[1], C[0], sp.ucap):
             self.narrow_out_plan = sp
@@ -286,8 +292,8 @@ class TrainEngine:
         m, L, C, S = self.model, self.L, self.C, self.S
         if self.slot_en0 is not None:
             cabi.slot_weight(m.en_layers[0].conv.layer.weight.data, self.slot_en0['Wd'], 0, C[1], S[0], C[0])
-            if self.narrow_out_ws is None:
-                cabi.slot_weight(m.de_layers[L + 1].layer.weight.data, self.slot_out['Wd'], 1, C[0], S[0], C[0])
+        if self.slot_out is not None and self.narrow_out_ws is None:
+            cabi.slot_weight(m.de_layers[L + 1].layer.weight.data, self.slot_out['Wd'], 1, C[0], S[0], C[0])
         if self._pack_table is None:
             # one launch for every image: the weights live in the flat arena and the images are persistent,
             # so a device table of raw pointers stays valid for the life of the engine
@@ -295,9 +301,9 @@ class TrainEngine:
             for (kind, _), e in self.tc.items():
                 for n0, nc, wimg in e['parts']:
                     ents.append((e['layer'].weight.data, wimg, e['seq'], e['cin'], e['cout'], kind == 'b', n0, nc))
-            if self.slot_en0 is not None:
-                for e in (self.slot_en0,) + ((self.slot_out,) if self.narrow_out_ws is None else ()):
-                    ents.append((e['Wd'], e['wimg'], 1, 32, 32, False, 0, 32))
+            for e in ((self.slot_en0,) if self.slot_en0 is not None else ()) + \
+                     ((self.slot_out,) if self.slot_out is not None and self.narrow_out_ws is None else ()):
+                ents.append((e['Wd'], e['wimg'], 1, 32, 32, False, 0, 32))
             self._pack_table = (cabi.tc_pack_table(ents, self.dev), len(ents))
         cabi.tc_pack_weights_batch(*self._pack_table)
 
@@ -321,7 +327,11 @@ class TrainEngine:
         self._pack_tc()
         x = self.x0
         for l in range(L):
-            if l == 0 and self.slot_en0 is not None:
+            if l == 0 and self.narrow_in_ws is not None:
+                lay, sub = m.en_layers[0].conv.layer, self.sub[0]
+                cabi.narrow_in_fwd(x, sub.idx, lay.weight.data, lay.bias.data, self.a[0], B, V[0], sub.n_rows,
+                                   S[0], C[0], C[1], cabi.ACT_ELU)
+            elif l == 0 and self.slot_en0 is not None:
                 e, sub = self.slot_en0, self.sub[0]
                 P = e['P'][:B]
                 cabi.slot_pack(x, None, sub.idx, P, B, V[0], sub.n_rows, S[0], C[0])
@@ -503,7 +513,11 @@ class TrainEngine:
         for l in range(L - 1, -1, -1):
             layer = m.en_layers[l].conv.layer
             x_in = self.a[l - 1] if l > 0 else self.x0
-            if l == 0 and self.slot_en0 is not None:
+            if l == 0 and self.narrow_in_ws is not None:
+                sub = self.sub[0]
+                cabi.narrow_in_bwd_w(self.x0, sub.idx, self.da[0], self.g(layer.weight), self.g(layer.bias),
+                                     self.narrow_in_ws, B, V[0], sub.n_rows, S[0], C[0], C[1])
+            elif l == 0 and self.slot_en0 is not None:
                 # dW = da0^T P with the slot-packed input of the forward pass: no gather at all
                 e = self.slot_en0
                 R0 = self.sub[0].n_rows

@@ -82,6 +82,10 @@ class SpiralConvFn(torch.autograd.Function):
             # 3-channel OUTPUT layer: fp32 FMA over shared-memory-staged source rows (csrc/narrow_conv.cuh)
             cabi.narrow_out_fwd(x, table.stage_plan(), weight, bias, y, B, Vin, R, S, Cin, Cout)
             done = True
+        elif _USE_TC and B > 0 and cabi.narrow_in_supported(Vin, S, Cin, Cout):
+            # 3-channel INPUT layer: fp32 FMA with the mesh's input resident in shared memory (csrc/narrow_conv.cuh)
+            cabi.narrow_in_fwd(x, table.idx, weight, bias, y, B, Vin, R, S, Cin, Cout, act)
+            done = True
         elif _USE_TC and B > 0 and _aligned(x, weight, bias):
             plan = table.plan_fwd()
             parts = _tc_parts(S, Cin, Cout, plan.rcap)
@@ -159,7 +163,10 @@ class SpiralConvFn(torch.autograd.Function):
                 cabi.dense_tc(G, ident, wimg, None, None, dx, B, Vin, cabi.ACT_NONE)
                 want_x = False
         if want_w:
-            if tc and packed is not None:
+            if _USE_TC and B > 0 and cabi.narrow_in_supported(Vin, S, Cin, Cout):
+                nws = _f32(cabi.narrow_in_bwd_w_workspace(S, Cin) // 4, like=x)
+                cabi.narrow_in_bwd_w(x, table.idx, dpre, dw, db, nws, B, Vin, R, S, Cin, Cout)
+            elif tc and packed is not None:
                 # 3-channel INPUT layer: dW = dpre^T P with the slot-packed input of the forward pass
                 dwd, dbd = _f32(32, 32, like=x), _f32(32, like=x)
                 cabi.spiralconv_bwd_w_tc(packed, identity_plan(R, x.device), dpre, dwd, dbd, ws, B, R, R, 1, 32, 32)

@@ -197,6 +197,20 @@ int sdvae_narrow_out_fwd(const float* x, const int32_t* tile_ptr, const int32_t*
                          const float* W, const float* bias, float* out, int B, int Vin, int Vout, int S, int Cin,
                          int Cout, int T, int ucap, sdvae_stream_t stream);
 
+/* ---- narrow-input layer (3 -> 32, model.py:104-110): forward and weight gradient -------------------
+ * y[b,r,o] = act(bias[o] + sum_{s,c} W[o, s*Cin+c] * x[b, idx[r,s], c]);   idx [R,S] (may be a row-restricted
+ * table), x [B,Vin,3], y [B,R,32].  dW[o, s*Cin+c] = sum_{b,r} dpre[b,r,o] * x[b, idx[r,s], c], db[o] = sum dpre.
+ * One mesh of x resident in shared memory, fp32 FMA, deterministic; supported (sdvae_narrow_in_supported) for
+ * S = 9, Cin = 3, Cout = 32 while a mesh fits.  dW / db may be NULL.  workspace: sdvae_narrow_in_bwd_w_workspace.
+ * Replaces: model.py:27-41 + F.elu for en_layers[0], and autograd's grad_weight GEMM over its gather. */
+int sdvae_narrow_in_supported(int Vin, int S, int Cin, int Cout);
+size_t sdvae_narrow_in_bwd_w_workspace(int S, int Cin);
+int sdvae_narrow_in_fwd(const float* x, const int32_t* idx, const float* W, const float* bias, float* y, int B,
+                        int Vin, int R, int S, int Cin, int Cout, int act, sdvae_stream_t stream);
+int sdvae_narrow_in_bwd_w(const float* x, const int32_t* idx, const float* dpre, float* dW, float* db,
+                          void* workspace, int B, int Vin, int R, int S, int Cin, int Cout,
+                          sdvae_stream_t stream);
+
 /* ---- Pool --------------------------------------------------------------------------------- */
 
 /* out[b,r,:] = sum_{j<Wd, col[r,j]>=0} val[r,j] * x[b, col[r,j], :]   (entries in storage order,

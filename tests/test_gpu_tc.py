@@ -371,6 +371,48 @@ def test_staged_narrow_output_forward_vs_fp64_oracle(cranio, orc, lvl, B, with_b
     assert not cabi.narrow_out_fwd_supported(S, 32, 3, 100000)
 
 
+@pytest.mark.parametrize('lvl,B,restricted', [(2, 3, False), (0, 2, True), (0, 21, True), (1, 37, False), (0, 5, False)])
+@pytest.mark.parametrize('act', [0, 1])
+def test_narrow_input_forward_and_weight_gradient_vs_fp64(cranio, orc, lvl, B, restricted, act):
+    """3 -> 32 first encoder block on the FMA units with the mesh's input resident in shared memory
+    (csrc/narrow_conv.cuh): forward (+ ELU) and weight / bias gradients against the oracle in fp64, on the full
+    table and on the table restricted to the rows the down-transform keeps; deterministic."""
+    from sdvae_b200 import cabi
+    from sdvae_b200.tables import pool_table, restricted_spiral_table, spiral_table
+    idx = cranio.spiral_tensors()[lvl]
+    V, S = idx.shape
+    tab = spiral_table(idx.to(DEV))
+    if restricted:
+        tab = restricted_spiral_table(idx.to(DEV), pool_table(cranio.down_tensors()[lvl].to(DEV)))
+    R = tab.n_rows
+    rows = tab.idx.cpu().long()
+    assert cabi.narrow_in_supported(V, S, 3, 32)
+    x = rand((B, V, 3), 41)
+    w = rand((32, S * 3), 42, 0.3).double().requires_grad_(True)
+    b = rand((32,), 43, 0.1).double().requires_grad_(True)
+    gy = rand((B, R, 32), 44)
+    pre = orc.spiral_conv(x.double(), rows, w, b)
+    y64 = orc.elu(pre) if act else pre
+    pre.backward(gy.double())
+    wf, bf = w.detach().float().to(DEV), b.detach().float().to(DEV)
+    ys = []
+    for _ in range(2):
+        y = torch.full((B, R, 32), float('nan'), device=DEV)
+        cabi.narrow_in_fwd(x.to(DEV), tab.idx, wf, bf, y, B, V, R, S, 3, 32, act)
+        ys.append(y)
+    assert nerr(ys[0], y64) < TC_TOL and torch.equal(ys[0], ys[1])
+    ws = torch.empty(cabi.narrow_in_bwd_w_workspace(S, 3) // 4, device=DEV)
+    gs = []
+    for _ in range(2):
+        dW = torch.full((32, S * 3), float('nan'), device=DEV)
+        db = torch.full((32,), float('nan'), device=DEV)
+        cabi.narrow_in_bwd_w(x.to(DEV), tab.idx, gy.to(DEV), dW, db, ws, B, V, R, S, 3, 32)
+        gs.append((dW, db))
+    assert nerr(gs[0][0], w.grad) < TC_TOL and nerr(gs[0][1], b.grad) < TC_TOL
+    assert torch.equal(gs[0][0], gs[1][0]) and torch.equal(gs[0][1], gs[1][1])
+    assert not cabi.narrow_in_supported(V, S, 4, 32) and not cabi.narrow_in_supported(30000, S, 3, 32)
+
+
 def test_tc_rejects_unsupported_shapes(cranio):
     from sdvae_b200 import cabi
     assert not cabi.tc_supported(9, 3, 32, 128)        # K = 27: stays on the FMA kernel

@@ -105,6 +105,9 @@ def main():
                 cabi.tc_pack_weights(w, wimg, S, cin, cout, False)
                 ms = timeit(lambda k: cabi.spiralconv_fwd_tc(xs[k], plan, wimg, b, ys[k], B, Vin, R, S, cin, cout, act), ns, args.iters)
                 row('conv fwd', name, B, 'tcgen05 3xTF32', ms, alg, flops)
+            elif cabi.narrow_in_supported(Vin, S, cin, cout):
+                ms = timeit(lambda k: cabi.narrow_in_fwd(xs[k], tab.idx, w, b, ys[k], B, Vin, R, S, cin, cout, act), ns, args.iters)
+                row('conv fwd', name, B, 'fp32 FMA, mesh input resident in smem', ms, alg, flops)
             elif S * cin <= 32 and cout == 32:
                 P = torch.empty(B, R, 32, device=DEV)
                 Wd = torch.empty(1024, device=DEV)
@@ -125,7 +128,11 @@ def main():
             ws = torch.empty(cabi.spiralconv_bwd_w_workspace(B * R, S, cin, cout) // 4 + 4, device=DEV)
             dW, db = torch.empty(cout, S * cin, device=DEV), torch.empty(cout, device=DEV)
             dWd, dbd = torch.empty(32, 32, device=DEV), torch.empty(32, device=DEV)
-            if S * cin <= 32 and cout == 32:
+            if cabi.narrow_in_supported(Vin, S, cin, cout):
+                nws_in = torch.empty(cabi.narrow_in_bwd_w_workspace(S, cin) // 4, device=DEV)
+                ms = timeit(lambda k: cabi.narrow_in_bwd_w(xs[k], tab.idx, ys[k], dW, db, nws_in, B, Vin, R, S, cin, cout), ns, args.iters)
+                row('conv dW', name, B, 'fp32 FMA, mesh input resident in smem', ms, alg, flops)
+            elif S * cin <= 32 and cout == 32:
                 # the engine's path: dW = dy^T P with the slot-packed input P of the forward pass
                 ipR = identity_plan(R, DEV)
                 Pk = torch.randn(B, R, 32, device=DEV)
