@@ -190,6 +190,28 @@ def time_dominant_kernel(eng, reps=10):
     return sec, alg_bytes, flops
 
 
+def time_pool_kernel(eng, reps=10):
+    """The finest up-sampling Pool forward ([B, 4260, 32] -> [B, 17039, 32], the largest memory-bound Pool of
+    the step), timed alone with CUDA events on the launching stream; inputs / outputs exceed L2 at the bench batch."""
+    from sdvae_b200 import cabi
+    V, B, C = eng.V, eng.B, eng.cin_de[0]
+    up = eng.up[0]
+    src = eng.d[1] if eng.L > 1 else eng.h
+    run = lambda: cabi.pool_fwd(src, up, eng.u[0], B, V[1], C)
+    for _ in range(3):
+        run()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(reps):
+        run()
+    e.record()
+    torch.cuda.synchronize()
+    sec = s.elapsed_time(e) / 1e3 / reps
+    alg_bytes = 4.0 * B * C * (V[1] + V[0]) + 8.0 * up.width * V[0]
+    return sec, alg_bytes
+
+
 def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -293,6 +315,15 @@ def run_ours(args):
                          "MMA-issuing thread, not by HBM"
                          if on_tc else "fp32-FMA contraction: compute-bound on the FMA pipe "
                          "(peak %.1f TFLOP/s)" % (148 * 128 * 2 * 1.965e9 / 1e12))}
+    psec, palg = time_pool_kernel(eng)
+    pool_roofline = {"bound": "hbm", "kernel": "pool_ell_fwd_staged_kernel: Pool up-sampling fwd [%d x %d -> %d x 32]"
+                                               % (eng.B, eng.V[1], eng.V[0]),
+                     "achieved": palg / psec / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": palg / psec / 1e9 / hbm_peak, "algorithmic_bytes": palg, "kernel_ms": psec * 1e3,
+                     # ncu --set full of this launch at 1024 meshes (profiles/r01_pool_staged_full_metrics.txt)
+                     "traffic": (0.587709e9 + 2.174347e9) * eng.B / 1024.0, "peak_source": peak_src,
+                     "note": "distinct source rows of each 128-row tile staged in shared memory (cp.async ring); "
+                             "bit-identical to the reference's storage-order arithmetic"}
     cpu = None
     if not args.no_cpu_baseline and world == 1:      # reported baseline: rank 0 at N = 1 only
         rate, sec = cpu_step_rate(tabs, args.ref_bs, 5, 2, args.seed)
@@ -310,12 +341,13 @@ def run_ours(args):
                    "parallelism": "dp%d (swap-grid rows)" % world,
                    "l2": "per-step working set (%.1f GB/GPU) exceeds the 126 MB L2" % (eng.B * 12.0e6 / 1e9),
                    "cuda_graph": bool(eng.use_graph),
-                   "contractions": ("tcgen05 3xTF32 for every SpiralConv pass (3-channel layers slot-packed "
-                                    "into dense 32x32 contractions)") if eng.tc else "fp32 FMA"},
+                   "contractions": ("tcgen05 3xTF32 for every 32/64-channel SpiralConv pass; the two 3-channel layers "
+                                    "on the fp32 FMA units from shared-memory-resident meshes / staged rows")
+                                   if eng.tc else "fp32 FMA"},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": int(x_pin.numel() * 4), "d2h_bytes_per_step": 32},
-        "roofline": roofline, "cpu_baseline": cpu,
+        "roofline": roofline, "pool_roofline": pool_roofline, "cpu_baseline": cpu,
         "losses_last_step": last, "params": eng.n_params,
     }
     print(json.dumps(line), flush=True)

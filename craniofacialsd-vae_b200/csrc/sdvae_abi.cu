@@ -643,7 +643,7 @@ int sdvae_narrow_out_bwd(const float* dy, const float* x, const int32_t* cell_pt
         if (rc) return rc;
     }
     if (dW || db) {
-        narrow_out_reduce_kernel<<<blocks_for(Cfg::PART, 256), 256, 0, st>>>(part, grid, dW, db, S, Cout);
+        narrow_out_reduce_kernel<<<blocks_for(32LL * Cfg::PART, 256), 256, 0, st>>>(part, grid, dW, db, S, Cout);
         return check_launch("narrow_out_reduce_kernel");
     }
     return SDVAE_OK;
@@ -707,7 +707,7 @@ int sdvae_narrow_in_bwd_w(const float* x, const int32_t* idx, const float* dpre,
         const int rc = check_launch("narrow_in_kernel<bwd_w>");
         if (rc) return rc;
     }
-    narrow_in_reduce_kernel<<<blocks_for(Cfg::PART, 256), 256, 0, st>>>(part, grid, dW, db, Cfg::J);
+    narrow_in_reduce_kernel<<<blocks_for(32LL * Cfg::PART, 256), 256, 0, st>>>(part, grid, dW, db, Cfg::J);
     return check_launch("narrow_in_reduce_kernel");
 }
 
