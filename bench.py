@@ -321,7 +321,7 @@ def run_ours(args):
                      "achieved": palg / psec / 1e9, "peak": hbm_peak, "unit": "GB/s",
                      "frac": palg / psec / 1e9 / hbm_peak, "algorithmic_bytes": palg, "kernel_ms": psec * 1e3,
                      # ncu --set full of this launch at 1024 meshes (profiles/r01_pool_staged_full_metrics.txt)
-                     "traffic": (0.587709e9 + 2.174347e9) * eng.B / 1024.0, "peak_source": peak_src,
+                     "traffic": (0.583874e9 + 2.175260e9) * eng.B / 1024.0, "peak_source": peak_src,
                      "note": "distinct source rows of each 128-row tile staged in shared memory (cp.async ring); "
                              "bit-identical to the reference's storage-order arithmetic"}
     cpu = None

@@ -55,7 +55,7 @@ def main():
             t0 = time.perf_counter()
             for _ in range(n):
                 tot = step()
-            float(tot)
+            float(tot.detach())
             torch.cuda.synchronize()
             dt = (time.perf_counter() - t0) / n
             print('| %d | %s | %.2f | %.0f |' % (bs * bs, 'tcgen05 3xTF32' if use_tc else 'fp32 FMA', dt * 1e3,
