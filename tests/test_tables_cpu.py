@@ -164,3 +164,22 @@ def test_pack_cells16_first_rows_and_overflow_marker():
         assert np.array_equal(f[has, k], 3 * src[ptr[:-1][has] + k])
     with pytest.raises(IndexError):
         tb.pack_cells16(np.array([0, 1]), np.array([0]), 30000, 3)
+
+
+def test_patch_order_halves_the_distinct_rows_of_a_tile():
+    """Groundwork for tile-local staging in the tensor-core gather kernels: in patch order a 128-row
+    tile of the level-0 spiral table reads about half the distinct rows it reads in the template's strip order."""
+    from sdvae_b200 import fixtures as fx, tables as tb
+    idx = fx.craniofacial_tables().spiral_tensors()[0].numpy()
+    V = idx.shape[0]
+    order = tb.patch_order(idx, 128)
+    assert order.shape == (V,) and np.array_equal(np.sort(order), np.arange(V))
+    new = tb.renumber_table(idx, order, order)
+    # same graph: row p of the new table is row order[p] of the old one, renamed
+    assert np.array_equal(order[new], idx[order])
+    old_d, new_d = tb.distinct_rows_per_row(idx, 128), tb.distinct_rows_per_row(new, 128)
+    assert old_d > 3.0 and new_d < 1.8, (old_d, new_d)
+    small = np.array([[0, 1, 2], [1, 0, 2], [2, 1, 3], [3, 2, -1]])
+    assert tb.distinct_rows_per_row(small, 2) == 1.5
+    assert np.array_equal(tb.renumber_table(small, [3, 2, 1, 0], [3, 2, 1, 0]),
+                          np.array([[0, 1, -1], [1, 2, 0], [2, 3, 1], [3, 2, 1]]))
