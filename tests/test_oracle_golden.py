@@ -133,3 +133,33 @@ def test_latent_consistency_matches_reference(golden, tag):
     assert float(loss) == pytest.approx(float(golden[tag + '_loss']), rel=2e-6)
     loss.backward()
     assert nerr(z.grad, golden[tag + '_grad']) < TOL
+
+
+def test_renumbered_tables_give_the_same_network(cranio):
+    """``MeshTables.renumbered`` (patch-wise vertex order, groundwork for tile-local staging): the oracle on the
+    renumbered tables maps the permuted input to the permuted reconstruction with identical latent codes, and
+    the four losses agree."""
+    from oracle import sdvae_oracle as orc
+    new, orders = cranio.renumbered(128)
+    o0 = torch.from_numpy(orders[0])
+    assert new.num_vertices == cranio.num_vertices
+    assert np.array_equal(orders[-1], np.arange(cranio.num_vertices[-1]))
+    for k, (name, idx) in enumerate(cranio.regions):               # same feature vertices, renamed
+        assert np.array_equal(np.sort(orders[0][new.regions[k][1]]), np.sort(idx))
+    net_a = orc.Net(3, [32, 32, 32, 64], 75, cranio.spiral_tensors(), cranio.down_tensors(), cranio.up_tensors(),
+                    False, True)
+    net_b = orc.Net(3, [32, 32, 32, 64], 75, new.spiral_tensors(), new.down_tensors(), new.up_tensors(),
+                    False, True)
+    params = orc.xavier_params(net_a.param_shapes(), seed=3, bias_scale=0.05)
+    x = torch.randn(2, cranio.num_vertices[0], 3, generator=torch.Generator().manual_seed(5))
+    eps = torch.randn(2, 75, generator=torch.Generator().manual_seed(6))
+    with torch.no_grad():
+        ra, za, mua, lva = net_a.forward(params, x, eps=eps, training=True)
+        rb, zb, mub, lvb = net_b.forward(params, x[:, o0], eps=eps, training=True)
+    assert torch.equal(mua, mub) and torch.equal(lva, lvb) and torch.equal(za, zb)
+    assert torch.equal(ra[:, o0], rb)
+    lap_a = tuple(torch.from_numpy(a) for a in cranio.lap)
+    lap_b = tuple(torch.from_numpy(a) for a in new.lap)
+    la = orc.laplacian_loss(ra, *lap_a)
+    lb = orc.laplacian_loss(rb, *lap_b)
+    assert abs(float(la) - float(lb)) <= 1e-6 * abs(float(la))

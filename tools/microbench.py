@@ -53,12 +53,15 @@ def main():
     ap.add_argument('--batches', default='1,16,256,1024')
     ap.add_argument('--iters', type=int, default=10)
     ap.add_argument('--layer', default='', help='substring of the conv layer names to run')
+    ap.add_argument('--renumber', action='store_true', help='experiment: template vertices renumbered patch-wise')
     ap.add_argument('--only', default='', help="'pool' or 'conv': run only that half of the sweep")
     args = ap.parse_args()
     from sdvae_b200 import cabi, fixtures as fx
     from sdvae_b200.tables import identity_plan, pool_table, restricted_spiral_table, spiral_table
     cabi.load()
     tabs = fx.craniofacial_tables()
+    if args.renumber:
+        tabs = tabs.renumbered(128)[0]
     sp = [s.to(DEV) for s in tabs.spiral_tensors()]
     dn = [d.to(DEV) for d in tabs.down_tensors()]
     up = [u.to(DEV) for u in tabs.up_tensors()]
