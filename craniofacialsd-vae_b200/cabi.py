@@ -446,7 +446,8 @@ POOL_STAGE_MIN_MESHES = 8       # below this the ring of staged meshes never fil
 
 def pool_fwd(x, table, out, B, Vin, Cc):
     """Pool forward through the staged kernel when the table has a usable stage plan, else the ELL gather."""
-    plan = table.stage_plan() if B >= POOL_STAGE_MIN_MESHES else None
+    aligned = x.data_ptr() % 16 == 0 and out.data_ptr() % 16 == 0
+    plan = table.stage_plan() if (B >= POOL_STAGE_MIN_MESHES and aligned) else None
     if plan is not None and pool_stage_supported(Cc, table.width, plan.ucap):
         pool_ell_fwd_staged(x, plan, out, B, Vin, table.n_rows, table.width, Cc)
     else:
