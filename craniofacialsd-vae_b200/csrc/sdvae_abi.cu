@@ -7,6 +7,7 @@
 #include "spiral_conv.cuh"
 #include "spiral_conv_umma.cuh"
 #include "spiral_conv_umma_bw.cuh"
+#include "spiral_conv_umma_staged.cuh"
 #include "slot_pack.cuh"
 #include "pool_misc.cuh"
 #include "narrow_conv.cuh"
@@ -135,6 +136,23 @@ static int dispatch_umma(umma::UmmaArgs& ua, int KS, cudaStream_t st) {
     if (KS == 64 && NT == 32) return launch_umma<64, 32, UNIFORM>(ua, st);
     if (KS == 64 && NT == 64) return launch_umma<64, 64, UNIFORM>(ua, st);
     return set_error(SDVAE_ERR_UNSUPPORTED, "tcgen05 path: unsupported layer shape");
+}
+
+template <int NT>
+static int launch_umma_staged(umma::StagedArgs& sa, cudaStream_t st) {
+    using Cfg = umma::StagedCfg<NT>;
+    auto kern = umma::gc_umma_staged_kernel<NT>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_done = true;
+    }
+    sa.nts = Cfg::tile_stages(sa.S, sa.rcap);
+    sa.ostage = Cfg::out_stage() ? 1 : 0;
+    const long long ntiles = (long long)sa.B * sa.L;
+    const int grid = ntiles < kNumSMs ? (int)ntiles : kNumSMs;
+    kern<<<grid, umma::kThreads, Cfg::smem_bytes(sa.S, sa.rcap, sa.nts), st>>>(sa);
+    return check_launch("gc_umma_staged_kernel");
 }
 
 // Meshes per CTA (MG) of the staged kernels: runs long enough to amortise the ring's fill, and a CTA count that
@@ -366,6 +384,48 @@ int sdvae_spiralconv_fwd_tc(const float* x, const int32_t* plan_cnt, const int32
     const int epi = act == SDVAE_ACT_ELU ? EPI_BIAS_ELU : EPI_BIAS;
     return tc_conv(x, plan_cnt, plan_src, plan_cell, rcap, wimg, bias, nullptr, y, B, Vin, Vout, S, Cin,
                    Cout, ldy, epi, true, (cudaStream_t)stream, "spiralconv_fwd_tc: unsupported layer shape");
+}
+
+/* ---- EXPERIMENTAL: tcgen05 forward with tile-local staging (spiral_conv_umma_staged.cuh) ------------
+ * Compiled but never run on a GPU in round 1; not dispatched by the engine / autograd functions / bench. */
+int sdvae_tc_staged_supported(int S, int Cin, int Cout, int rcap) {
+    if (Cin != 32 || S < 1 || Cout < 1 || tc_tile_n(Cout) == 0) return 0;
+    if (rcap < 32 || rcap > umma::kStagedMaxRcap || rcap % 32 != 0) return 0;
+    const int NT = tc_tile_n(Cout);
+    const int nts = NT == 16 ? umma::StagedCfg<16>::tile_stages(S, rcap)
+                  : NT == 32 ? umma::StagedCfg<32>::tile_stages(S, rcap) : umma::StagedCfg<64>::tile_stages(S, rcap);
+    return nts >= 2 ? 1 : 0;
+}
+
+int sdvae_spiralconv_fwd_tc_staged(const float* x, const int32_t* plan_cnt, const int32_t* plan_src,
+                                   const int32_t* plan_loc, int rcap, const float* wimg, const float* bias,
+                                   float* y, int B, int Vin, int Vout, int S, int Cin, int Cout, int act,
+                                   sdvae_stream_t stream) {
+    SDVAE_REQUIRE(x && plan_cnt && plan_src && plan_loc && wimg && y, "spiralconv_fwd_tc_staged: null pointer");
+    SDVAE_REQUIRE(B >= 0 && Vin > 0 && Vout > 0, "spiralconv_fwd_tc_staged: bad shape");
+    SDVAE_REQUIRE((long long)B * Vin < 2147483647LL, "spiralconv_fwd_tc_staged: B*rows exceeds int32");
+    SDVAE_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wimg) |
+                    reinterpret_cast<uintptr_t>(plan_src)) & 15) == 0,
+                  "spiralconv_fwd_tc_staged: x, wimg and plan_src must be 16-byte aligned");
+    if (!sdvae_tc_staged_supported(S, Cin, Cout, rcap))
+        return set_error(SDVAE_ERR_UNSUPPORTED, "spiralconv_fwd_tc_staged: unsupported layer shape");
+    const int NT = tc_tile_n(Cout);
+    if (NT >= 32) {
+        const uintptr_t al = reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(bias);
+        if (Cout != NT || (al & 15) != 0)
+            return set_error(SDVAE_ERR_UNSUPPORTED, "spiralconv_fwd_tc_staged: unsupported layer shape");
+    }
+    if (B == 0) return SDVAE_OK;
+    umma::StagedArgs sa{};
+    sa.in = x; sa.plan_cnt = plan_cnt; sa.plan_src = plan_src; sa.plan_loc = plan_loc;
+    sa.wimg = wimg; sa.bias = bias; sa.out = y;
+    sa.B = B; sa.in_rows = Vin; sa.out_rows = Vout; sa.L = sdvae_tc_plan_tiles(Vout);
+    sa.S = S; sa.rcap = rcap; sa.n_real = Cout; sa.ldo = Cout;
+    sa.epi = act == SDVAE_ACT_ELU ? EPI_BIAS_ELU : EPI_BIAS;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (NT == 16) return launch_umma_staged<16>(sa, st);
+    if (NT == 32) return launch_umma_staged<32>(sa, st);
+    return launch_umma_staged<64>(sa, st);
 }
 
 int sdvae_spiralconv_bwd_x_tc(const float* dpre, const int32_t* plan_cnt, const int32_t* plan_src,

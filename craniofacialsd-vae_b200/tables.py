@@ -257,6 +257,43 @@ def renumber_table(cols: np.ndarray, row_order: np.ndarray, src_order: np.ndarra
     return np.where(out >= 0, rank[np.clip(out, 0, None)], -1)
 
 
+def pack_rows_loader_order(rows: np.ndarray) -> np.ndarray:
+    """``rows [L, rcap]`` (rcap a multiple of 32, values < 65536) -> ``[L, rcap/2] int32``: 16-bit pairs in the
+    order the tcgen05 loader lanes consume them (``umma::plan_fetch`` / ``sdvae_tc_plan_build``): staged row
+    ``e = 32*j + 4*t + rsub`` sits in word ``16*j + 4*rsub + (t >> 1)``, low half for even ``t``."""
+    rows = np.asarray(rows, np.int64)
+    L, rcap = rows.shape
+    if rcap % 32 or (rows.size and (rows.min() < 0 or rows.max() >= 65536)):
+        raise ValueError('pack_rows_loader_order: rcap must be a multiple of 32 and rows must fit 16 bits')
+    r = rows.reshape(L, rcap // 32, 8, 4).astype(np.uint32)          # [L, j, t, rsub]
+    lo, hi = r[:, :, 0::2, :], r[:, :, 1::2, :]                      # [L, j, t>>1, rsub]
+    w = (lo | (hi << 16)).transpose(0, 1, 3, 2)                      # [L, j, rsub, t>>1]
+    return np.ascontiguousarray(w.reshape(L, rcap // 2)).view(np.int32)
+
+
+def staged_tile_plan(idx: np.ndarray, max_rcap: int = 288):
+    """Plan of the EXPERIMENTAL tcgen05 forward with tile-local staging (``sdvae_spiralconv_fwd_tc_staged``):
+    ``(cnt [L], src [L, rcap/2], loc [L, S, 128], rcap)`` for tiles of 128 output rows of the spiral table
+    ``idx [R, S]``.  Raises ``RuntimeError`` when a tile reads more than ``max_rcap`` distinct rows (the template's
+    strip order needs 547 at level 0; ``patch_order`` brings it to ~240, 262 at level 1)."""
+    idx = np.asarray(idx, np.int64)
+    R, S = idx.shape
+    tile_ptr, stage_src, loc, ucap = gather_stage_plan(idx, 128)
+    rcap = max(32, (ucap + 31) // 32 * 32)
+    if rcap > max_rcap:
+        raise RuntimeError('staged_tile_plan: a tile reads %d distinct rows (limit %d)' % (ucap, max_rcap))
+    L = tile_ptr.size - 1
+    cnt = np.diff(tile_ptr).astype(np.int32)
+    rows = np.zeros((L, rcap), np.int64)
+    for t in range(L):
+        rows[t, :cnt[t]] = stage_src[tile_ptr[t]:tile_ptr[t + 1]]
+    loc3 = np.zeros((L, S, 128), np.int32)
+    for t in range(L):
+        blk = loc[t * 128:(t + 1) * 128]                             # [<=128, S]
+        loc3[t, :, :blk.shape[0]] = blk.T
+    return cnt, pack_rows_loader_order(rows), loc3, rcap
+
+
 def pool_stage_plan(ell_col: np.ndarray, ell_val: np.ndarray, tile: int = POOL_STAGE_TILE):
     """Stage plan of the shared-memory Pool forward (include/sdvae_b200.h, ``sdvae_pool_ell_fwd_staged``):
     ``gather_stage_plan`` of the ELL columns, with each entry's position and value interleaved:
@@ -398,6 +435,20 @@ class SpiralTable:
         """Table of the rows in ``kept`` only (fused conv + selection pooling)."""
         return SpiralTable.build(self._np_idx[np.asarray(kept, np.int64)], self.n_src,
                                  self.idx.device)
+
+
+@dataclass
+class StagedTilePlan:
+    """Device copy of ``staged_tile_plan`` (EXPERIMENTAL kernel, see there)."""
+    cnt: torch.Tensor            # int32 [L]
+    src: torch.Tensor            # int32 [L, rcap/2]
+    loc: torch.Tensor            # int32 [L, S, 128]
+    rcap: int
+
+    @staticmethod
+    def build(idx_np: np.ndarray, device) -> "StagedTilePlan":
+        cnt, src, loc, rcap = staged_tile_plan(idx_np)
+        return StagedTilePlan(_dev(cnt, device), _dev(src, device), _dev(loc, device), int(rcap))
 
 
 @dataclass

@@ -413,6 +413,35 @@ def test_narrow_input_forward_and_weight_gradient_vs_fp64(cranio, orc, lvl, B, r
     assert not cabi.narrow_in_supported(V, S, 4, 32) and not cabi.narrow_in_supported(30000, S, 3, 32)
 
 
+@pytest.mark.skipif(__import__('os').environ.get('SDVAE_EXPERIMENTAL') != '1',
+                    reason='experimental kernel (compiled, never run on a GPU in round 1): set SDVAE_EXPERIMENTAL=1')
+@pytest.mark.parametrize('lvl,B,cout,act', [(3, 2, 32, 1), (0, 3, 32, 1), (1, 5, 32, 0), (3, 4, 64, 1)])
+def test_experimental_staged_tc_forward_equals_tc_forward(cranio, lvl, B, cout, act):
+    """tcgen05 forward with tile-local staging (csrc/spiral_conv_umma_staged.cuh) on the patch-ordered template
+    against the per-slot-gather tcgen05 forward: same operands, same MMA order -> identical bits."""
+    from sdvae_b200 import cabi
+    from sdvae_b200 import tables as tb
+    idx = cranio.spiral_tensors()[lvl].numpy()
+    o = tb.patch_order(idx, 128)
+    idx = tb.renumber_table(idx, o, o)
+    V, S = idx.shape
+    tab = tb.spiral_table(torch.from_numpy(idx).to(DEV))
+    plan = tab.plan_fwd()
+    sp = tb.StagedTilePlan.build(idx, DEV)
+    assert cabi.tc_staged_supported(S, 32, cout, sp.rcap)
+    x = rand((B, V, 32), 51).to(DEV)
+    w = rand((cout, S * 32), 52, 0.1).to(DEV)
+    b = rand((cout,), 53, 0.2).to(DEV)
+    wimg = torch.empty(cabi.tc_wimg_floats(S, 32, cout), device=DEV)
+    cabi.tc_pack_weights(w, wimg, S, 32, cout, False)
+    ya = torch.full((B, V, cout), float('nan'), device=DEV)
+    yb = torch.full((B, V, cout), float('nan'), device=DEV)
+    cabi.spiralconv_fwd_tc(x, plan, wimg, b, ya, B, V, V, S, 32, cout, act)
+    cabi.spiralconv_fwd_tc_staged(x, sp, wimg, b, yb, B, V, V, S, 32, cout, act)
+    torch.cuda.synchronize()
+    assert torch.equal(ya, yb)
+
+
 def test_tc_rejects_unsupported_shapes(cranio):
     from sdvae_b200 import cabi
     assert not cabi.tc_supported(9, 3, 32, 128)        # K = 27: stays on the FMA kernel

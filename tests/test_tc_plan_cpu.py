@@ -1,5 +1,6 @@
 """Host-side tile plans of the tcgen05 path (sdvae_tc_plan_build): bit-exact index work, no GPU."""
 import numpy as np
+import pytest
 
 from sdvae_b200 import cabi
 from sdvae_b200.tables import inverse_cells
@@ -93,3 +94,46 @@ def test_plan_rejects_rows_that_do_not_fit_16_bits():
     src = np.array([0, 1, 70000, 3], dtype=np.int32)      # packed plans carry 16-bit source rows
     with pytest.raises(RuntimeError):
         cabi.tc_plan_build(ptr, src, 4, 1)
+
+
+def test_staged_tile_plan_matches_the_c_packer_and_the_table():
+    """Plan of the EXPERIMENTAL staged tcgen05 forward: the numpy packer reproduces sdvae_tc_plan_build's
+    loader-lane order bit for bit, and (cnt, src, loc) re-address every gather of the table."""
+    from sdvae_b200 import cabi, fixtures as fx, tables as tb
+    tabs = fx.craniofacial_tables()
+    idx = tabs.spiral_tensors()[3].numpy()                        # 267 rows
+    o3 = tb.patch_order(idx, 128)
+    idx = tb.renumber_table(idx, o3, o3)                          # in patch order a tile reads <= 192 distinct rows
+    R, S = idx.shape
+    cnt, src, loc, rcap = tb.staged_tile_plan(idx)
+    L = (R + 127) // 128
+    assert cnt.shape == (L,) and src.shape == (L, rcap // 2) and loc.shape == (L, S, 128) and rcap % 32 == 0
+    # unpack the loader order again
+    w = src.view(np.uint32).reshape(L, rcap // 32, 4, 4)          # [L, j, rsub, t>>1]
+    rows = np.zeros((L, rcap // 32, 8, 4), np.int64)              # [L, j, t, rsub]
+    rows[:, :, 0::2, :] = (w & 0xFFFF).transpose(0, 1, 3, 2)
+    rows[:, :, 1::2, :] = (w >> 16).transpose(0, 1, 3, 2)
+    rows = rows.reshape(L, rcap)
+    for t in range(L):
+        lst = rows[t, :cnt[t]]
+        assert np.all(np.diff(lst) > 0) and not rows[t, cnt[t]:].any()
+        blk = idx[t * 128:(t + 1) * 128]
+        assert np.array_equal(lst[loc[t, :, :blk.shape[0]].T], blk)
+        assert not loc[t, :, blk.shape[0]:].any()
+    # the same lists through the C builder: one pseudo-row per tile whose only cell holds the tile's rows
+    assert rcap <= 192
+    if True:
+        ptr = np.zeros(L * 128 + 1, np.int32)
+        starts = np.concatenate([[0], np.cumsum(cnt)])
+        for t in range(L):
+            ptr[t * 128 + 1:(t + 1) * 128 + 1] = starts[t + 1]     # row 0 of tile t owns all its rows
+        flat = np.concatenate([rows[t, :cnt[t]] for t in range(L)]).astype(np.int32)
+        c_cnt, c_src, _, c_rcap = cabi.tc_plan_build(ptr, flat, L * 128, 1)
+        assert c_rcap == rcap
+        assert np.array_equal(c_cnt.ravel(), cnt) and np.array_equal(c_src.reshape(L, -1), src)
+    # the template's strip order does not fit at level 0; patch order does
+    idx0 = tabs.spiral_tensors()[0].numpy()
+    with pytest.raises(RuntimeError):
+        tb.staged_tile_plan(idx0)
+    order = tb.patch_order(idx0, 128)
+    assert tb.staged_tile_plan(tb.renumber_table(idx0, order, order))[3] <= 288
