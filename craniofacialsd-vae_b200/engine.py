@@ -249,6 +249,17 @@ class TrainEngine:
             self.tc[(kind, name)] = dict(layer=layer, plan=plan, cin=cin, cout=cout, seq=table.seq,
                                          parts=[(n0, nc, f(cabi.tc_wimg_floats(table.seq, ks, nc)))
                                                 for n0, nc in parts])
+            # EXPERIMENTAL switch (off unless SDVAE_STAGED_FWD=1; the kernel has never run on a GPU):
+            # forward passes with 32 input channels through the tile-local-staging kernel when a tile's distinct
+            # rows fit its stage (they do on a patch-ordered template: bench.py --renumber)
+            if kind == 'f' and ks == 32 and len(parts) == 1 and os.environ.get('SDVAE_STAGED_FWD') == '1':
+                from .tables import StagedTilePlan
+                try:
+                    sp = StagedTilePlan.build(table._np_idx, self.dev)
+                except RuntimeError:
+                    sp = None
+                if sp is not None and cabi.tc_staged_supported(table.seq, ks, n, sp.rcap):
+                    self.tc[(kind, name)]['staged'] = sp
 
         for l in range(L):
             enc = m.en_layers[l].conv.layer
@@ -310,6 +321,10 @@ class TrainEngine:
     # ------------------------------------------------------------------ pieces
     def _conv(self, x, table, layer, out, act, B, Vin, Cin, Cout, name=None):
         e = self.tc.get(('f', name))
+        if e is not None and e.get('staged') is not None:
+            cabi.spiralconv_fwd_tc_staged(x, e['staged'], e['parts'][0][2], layer.bias.data, out, B, Vin,
+                                          table.n_rows, table.seq, Cin, Cout, act)
+            return
         if e is not None:
             for n0, nc, wimg in e['parts']:
                 full = nc == Cout
