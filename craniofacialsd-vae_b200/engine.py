@@ -19,9 +19,11 @@ preallocated buffers, without autograd:
   seven ``.item()`` syncs, model_manager.py:320-326);
 * the whole step -- data-parallel collectives included -- is replayed from a CUDA graph
   (one per swapped region, since the region's latent slice is a kernel argument);
-* every SpiralConv pass runs on the tcgen05 tensor-core kernels (``use_tc``): wide layers
-  through tile plans of the spiral / inverse tables, the two 3-channel layers slot-packed
-  into dense 32 x 32 contractions (csrc/slot_pack.cuh), 64 -> 64 layers in two passes.
+* the 32/64-channel SpiralConv passes run on the tcgen05 tensor-core kernels (``use_tc``)
+  through tile plans of the spiral / inverse tables (64 -> 64 layers in two passes); the two
+  3-channel layers run on the fp32 FMA units with one mesh resident in shared memory
+  (csrc/narrow_conv.cuh; slot packing into dense 32 x 32 contractions, csrc/slot_pack.cuh,
+  is their fallback); Pool forward stages each tile's distinct source rows in shared memory.
 
 Data parallelism: rank r owns rows ``[r*bs/N, (r+1)*bs/N)`` of the
 ``bs x bs`` swap grid.  Mean losses are normalised by the GLOBAL counts, the
