@@ -124,6 +124,21 @@ def main():
                     cabi.dense_tc(P, ip, wimg, b, None, ys[k], B, R, act)
                 ms = timeit(fwd_slot, ns, args.iters)
                 row('conv fwd', name, B, 'slot-pack + dense tcgen05', ms, alg, flops)
+            elif cin in (32, 64) and cout == 64 and cabi.tc_supported(S, cin, 32, plan.rcap):
+                # the engine's path for 64 output channels whose weight image does not fit beside the rings:
+                # two passes of 32 output channels, each writing its columns of y (functional._tc_parts)
+                wimgs = []
+                for n0 in (0, 32):
+                    wi = torch.empty(cabi.tc_wimg_floats(S, cin, 32), device=DEV)
+                    cabi.tc_pack_weights(w, wi, S, cin, cout, False, n0, 32)
+                    wimgs.append(wi)
+
+                def fwd_two(k):
+                    for i, n0 in enumerate((0, 32)):
+                        cabi.spiralconv_fwd_tc(xs[k], plan, wimgs[i], b[n0:], ys[k].view(-1)[n0:], B, Vin, R, S, cin,
+                                               32, act, cout)
+                ms = timeit(fwd_two, ns, args.iters)
+                row('conv fwd', name, B, 'tcgen05 3xTF32, two 32-channel passes', ms, alg, flops)
             else:
                 ms = timeit(lambda k: cabi.spiralconv_fwd(xs[k], tab.idx, w, b, ys[k], B, Vin, R, S, cin, cout, act), ns, args.iters)
                 row('conv fwd', name, B, 'fp32 FMA', ms, alg, flops)
@@ -155,7 +170,7 @@ def main():
                     cabi.slot_grad(dWd, dbd, dW, db, 1, cout, S, cout)
                 ms = timeit(dw_slot_out, ns, args.iters)
                 row('conv dW', name, B, 'dense tcgen05 on slot-packed G (G from the dx pass)', ms, alg, flops)
-            elif cin == 32 and cabi.tc_bwd_w_supported(S, cin, cout, plan.rcap):
+            elif cin in (32, 64) and cabi.tc_bwd_w_supported(S, cin, cout, plan.rcap):   # 64: 32-channel passes inside
                 ms = timeit(lambda k: cabi.spiralconv_bwd_w_tc(xs[k], plan, ys[k], dW, db, ws, B, Vin, R, S, cin, cout), ns, args.iters)
                 row('conv dW', name, B, 'tcgen05 3xTF32', ms, alg, flops)
             else:
@@ -170,6 +185,19 @@ def main():
                 cabi.tc_pack_weights(w, wimg_t, S, cin, cout, True)
                 ms = timeit(lambda k: cabi.spiralconv_bwd_x_tc(ys[k], pb, wimg_t, None, xs[k], B, R, Vin, S, cout, cin), ns, args.iters)
                 row('conv dx', name, B, 'tcgen05 3xTF32', ms, alg, flops)
+            elif cout in (32, 64) and cin == 64 and cabi.tc_supported(S, cout, 32, pb.rcap):
+                # 64 input channels: two passes of 32, each writing its columns of dx (functional._tc_parts)
+                wts = []
+                for n0 in (0, 32):
+                    wi = torch.empty(cabi.tc_wimg_floats(S, cout, 32), device=DEV)
+                    cabi.tc_pack_weights(w, wi, S, cin, cout, True, n0, 32)
+                    wts.append(wi)
+
+                def dx_two(k):
+                    for i, n0 in enumerate((0, 32)):
+                        cabi.spiralconv_bwd_x_tc(ys[k], pb, wts[i], None, xs[k].view(-1)[n0:], B, R, Vin, S, cout, 32, cin)
+                ms = timeit(dx_two, ns, args.iters)
+                row('conv dx', name, B, 'tcgen05 3xTF32, two 32-channel passes', ms, alg, flops)
             elif S * cout <= 32 and cin == 32:
                 G = torch.empty(B, Vin, 32, device=DEV)
                 Wd = torch.empty(1024, device=DEV)
