@@ -68,11 +68,16 @@ class StepConfig:
 class TrainEngine:
     def __init__(self, model, laplacian: Optional[LaplacianTable], region_features: Sequence[np.ndarray],
                  latent_regions: Sequence[Sequence[int]], cfg: StepConfig, process_group=None,
-                 use_graph: bool = True, use_tc: bool = True):
+                 use_graph: bool = True, use_tc: bool = True, renumber: Optional[bool] = None):
         """``model``: a ``sdvae_b200.model.Model`` on the CUDA device.
         ``region_features[k]``: vertex ids swapped for region k; ``latent_regions[k]`` = [r0, r1].
         ``use_tc``: run the wide SpiralConv contractions (C_in in {32, 64}) on the tcgen05 tensor-core
-        kernels (error-compensated 3xTF32); False keeps every contraction on the fp32-FMA kernels."""
+        kernels (error-compensated 3xTF32); False keeps every contraction on the fp32-FMA kernels.
+        ``renumber`` (default: env ``SDVAE_RENUMBER`` == '1', else off): EXPERIMENTAL, host side checked on CPU
+        only -- run the network on a patch-wise renumbering of the internal vertex levels
+        (``tables.renumbered_model_tables``; the batch is permuted on load, ``recon_template_order()`` undoes it):
+        what the tile-local-staging kernels need.  Losses and parameter gradients do not depend
+        on the vertex order."""
         self.model = model
         self.cfg = cfg
         self.dev = next(model.parameters()).device
@@ -101,6 +106,7 @@ class TrainEngine:
         # SDVAE_DP_GRAPH=0 keeps multi-GPU steps eager.
         self.use_graph = use_graph and (self.world == 1 or os.environ.get('SDVAE_DP_GRAPH', '1') != '0')
         self.use_tc = bool(use_tc)
+        self.renumber = (os.environ.get('SDVAE_RENUMBER') == '1') if renumber is None else bool(renumber)
         self._graphs: Dict[int, torch.cuda.CUDAGraph] = {}
         self.fixed_eps: Optional[torch.Tensor] = None
         self.launches_per_step = 0
@@ -110,6 +116,10 @@ class TrainEngine:
         masks = np.zeros((len(region_features), V0), np.uint8)
         for k, idx in enumerate(region_features):
             masks[k, np.asarray(idx, np.int64)] = 1
+        if self.order0 is not None:                       # engine-internal vertex order (renumber)
+            masks = np.ascontiguousarray(masks[:, self.order0])
+            if self.lap is not None:
+                self.lap = self.lap.renumbered(self.order0)
         self.masks = torch.from_numpy(masks).to(self.dev)
         self._build_arenas()
         self._alloc_buffers()
@@ -118,14 +128,22 @@ class TrainEngine:
     # ------------------------------------------------------------------ tables
     def _build_tables(self):
         m = self.model
-        self.V = [int(s.shape[0]) for s in m.spiral_indices] + [int(m.num_vert)]
+        spirals, downs, ups = list(m.spiral_indices), list(m.down_transform), list(m.up_transform)
+        self.order0 = self.order0_dev = None
+        if self.renumber:
+            from .tables import renumbered_model_tables
+            spirals, downs, ups, orders = renumbered_model_tables(spirals, downs, ups)
+            self._renumbered_tables = (spirals, downs, ups)   # derived tables are cached on these tensors: keep them
+            self.order0 = orders[0]
+            self.order0_dev = torch.from_numpy(orders[0]).to(self.dev)
+        self.V = [int(s.shape[0]) for s in spirals] + [int(m.num_vert)]
         self.C = [int(m.in_channels)] + [int(c) for c in m.out_channels]
-        self.S = [int(s.shape[1]) for s in m.spiral_indices]
-        self.full: List[SpiralTable] = [spiral_table(s) for s in m.spiral_indices]
+        self.S = [int(s.shape[1]) for s in spirals]
+        self.full: List[SpiralTable] = [spiral_table(s) for s in spirals]
         self.sub: List[SpiralTable] = []
-        self.up: List[PoolTable] = [pool_table(u) for u in m.up_transform]
+        self.up: List[PoolTable] = [pool_table(u) for u in ups]
         for lvl in range(self.L):
-            sub = restricted_spiral_table(m.spiral_indices[lvl], pool_table(m.down_transform[lvl]))
+            sub = restricted_spiral_table(spirals[lvl], pool_table(downs[lvl]))
             if sub is None:
                 raise RuntimeError(
                     'TrainEngine: down_transform[%d] is not a pure vertex selection; use the '
@@ -597,7 +615,13 @@ class TrainEngine:
     def load_batch(self, x_host_or_dev: torch.Tensor):
         """Copy the un-swapped batch ``[bs, V, 3]`` (pinned host or device) into the
         engine's input buffer, asynchronously on the current stream."""
-        self.x_in.copy_(x_host_or_dev, non_blocking=True)
+        if self.order0_dev is None:
+            self.x_in.copy_(x_host_or_dev, non_blocking=True)
+        else:                                             # template order -> the engine's internal order
+            if getattr(self, 'x_raw', None) is None:
+                self.x_raw = torch.empty_like(self.x_in)
+            self.x_raw.copy_(x_host_or_dev, non_blocking=True)
+            torch.index_select(self.x_raw, 1, self.order0_dev, out=self.x_in)
 
     def set_fixed_eps(self, eps: Optional[torch.Tensor]):
         """Parity tests: use this re-parameterisation noise instead of drawing it."""
@@ -620,7 +644,21 @@ class TrainEngine:
         """Copy this rank's ``B`` already-assembled meshes straight into the network input
         (use with ``step(region=None)``: no device-side swap, no latent-consistency term
         unless ``lc_region`` is given)."""
-        self.x0.copy_(x_local, non_blocking=True)
+        if self.order0_dev is None:
+            self.x0.copy_(x_local, non_blocking=True)
+        else:
+            if getattr(self, 'x0_raw', None) is None:
+                self.x0_raw = torch.empty_like(self.x0)
+            self.x0_raw.copy_(x_local, non_blocking=True)
+            torch.index_select(self.x0_raw, 1, self.order0_dev, out=self.x0)
+
+    def recon_template_order(self) -> torch.Tensor:
+        """The reconstruction of the last forward pass ``[B, V, 3]`` in the template's vertex order."""
+        if self.order0_dev is None:
+            return self.recon
+        out = torch.empty_like(self.recon)
+        out.index_copy_(1, self.order0_dev, self.recon)
+        return out
 
     def step(self, region: Optional[int], sync_losses: bool = False):
         """One training iteration on the batch previously given to ``load_batch``.

@@ -276,22 +276,12 @@ class MeshTables:
         A network on the new tables maps ``x[:, orders[0]]`` to ``recon[:, orders[0]]`` with the same latent
         codes: every per-vertex sum keeps its terms and their order (spiral slots, storage order of the
         transform entries).  Groundwork for tile-local staging; nothing applies it by default."""
-        from .tables import patch_order
-        nlev = len(self.spirals)
-        nv = self.num_vertices
-        orders = [patch_order(s, tile) for s in self.spirals] + [np.arange(nv[-1], dtype=np.int64)]
-        ranks = []
-        for o in orders:
-            r = np.empty(o.size, np.int64)
-            r[o] = np.arange(o.size)
-            ranks.append(r)
-        spirals = [ranks[l][np.asarray(self.spirals[l], np.int64)[orders[l]]] for l in range(nlev)]
-        down = [(ranks[l + 1][np.asarray(r, np.int64)], ranks[l][np.asarray(c, np.int64)], v, shape)
-                for l, (r, c, v, shape) in enumerate(self.down)]
-        up = [(ranks[l][np.asarray(r, np.int64)], ranks[l + 1][np.asarray(c, np.int64)], v, shape)
-              for l, (r, c, v, shape) in enumerate(self.up)]
-        lap = (ranks[0][np.asarray(self.lap[0], np.int64)], ranks[0][np.asarray(self.lap[1], np.int64)], self.lap[2])
-        regions = [(k, np.sort(ranks[0][np.asarray(idx, np.int64)])) for k, idx in self.regions]
+        from .tables import renumber_levels
+        spirals, down, up, orders = renumber_levels(self.spirals, self.down, self.up, tile)
+        rank0 = np.empty(orders[0].size, np.int64)
+        rank0[orders[0]] = np.arange(orders[0].size)
+        lap = (rank0[np.asarray(self.lap[0], np.int64)], rank0[np.asarray(self.lap[1], np.int64)], self.lap[2])
+        regions = [(k, np.sort(rank0[np.asarray(idx, np.int64)])) for k, idx in self.regions]
         return MeshTables(spirals, down, up, lap, regions, self.name + '-patch%d' % tile), orders
 
     # ---- compact on-disk bundle (tests/golden/*.npz) -----------------------

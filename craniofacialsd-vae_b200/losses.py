@@ -38,6 +38,7 @@ class LaplacianTable:
     t_ptr: torch.Tensor
     t_row: torch.Tensor
     t_val: torch.Tensor
+    coo: Optional[tuple] = None      # the (row, col, val) it was built from, in storage order (host, for renumbered)
 
     @staticmethod
     def build(row, col, val, n_vert: int, device) -> "LaplacianTable":
@@ -46,7 +47,16 @@ class LaplacianTable:
         ec, ev = ell_from_coo(row, col, val, n_vert, n_vert)
         tp, tr, tv = transposed_csr(row, col, val, n_vert)
         d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
-        return LaplacianTable(int(n_vert), int(ec.shape[1]), d(ec), d(ev), d(tp), d(tr), d(tv))
+        return LaplacianTable(int(n_vert), int(ec.shape[1]), d(ec), d(ev), d(tp), d(tr), d(tv), (row, col, val))
+
+    def renumbered(self, order: np.ndarray) -> "LaplacianTable":
+        """The same operator with its vertices listed in ``order`` (new position -> old vertex); the entries keep
+        their storage order (rows of the operator and columns of its transpose sum in the same order as before)."""
+        order = np.asarray(order, np.int64)
+        rank = np.empty(order.size, np.int64)
+        rank[order] = np.arange(order.size)
+        row, col, val = self.coo
+        return LaplacianTable.build(rank[row], rank[col], val, self.n_vert, self.ell_col.device)
 
     @staticmethod
     def from_sparse(lap: torch.Tensor) -> "LaplacianTable":

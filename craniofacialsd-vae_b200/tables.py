@@ -294,6 +294,54 @@ def staged_tile_plan(idx: np.ndarray, max_rcap: int = 288):
     return cnt, pack_rows_loader_order(rows), loc3, rcap
 
 
+def renumber_levels(spirals, downs, ups, tile: int = 128):
+    """Patch-wise renumbering of every level but the coarsest (``patch_order``), applied consistently to the spiral
+    tables ``spirals[l] [V_l, S]`` and to the transforms ``downs[l]`` (``[V_{l+1}, V_l]``) / ``ups[l]``
+    (``[V_l, V_{l+1}]``) given as ``(row, col, val, shape)`` in storage order.  Entries keep their storage order
+    (so every per-vertex sum keeps its terms and their order); the coarsest level keeps its numbering (the latent
+    ``Linear`` layers flatten it, model.py:151,166).  Returns ``(spirals', downs', ups', orders)`` with
+    ``orders[l]`` = new position -> old vertex."""
+    nlev = len(spirals)
+    n_last = int(downs[-1][3][0])
+    orders = [patch_order(np.asarray(s, np.int64), tile) for s in spirals] + [np.arange(n_last, dtype=np.int64)]
+    ranks = []
+    for o in orders:
+        r = np.empty(o.size, np.int64)
+        r[o] = np.arange(o.size)
+        ranks.append(r)
+    sp = [ranks[l][np.asarray(spirals[l], np.int64)[orders[l]]] for l in range(nlev)]
+    dn = [(ranks[l + 1][np.asarray(r, np.int64)], ranks[l][np.asarray(c, np.int64)], v, shape)
+          for l, (r, c, v, shape) in enumerate(downs)]
+    up = [(ranks[l][np.asarray(r, np.int64)], ranks[l + 1][np.asarray(c, np.int64)], v, shape)
+          for l, (r, c, v, shape) in enumerate(ups)]
+    return sp, dn, up, orders
+
+
+def renumbered_model_tables(spiral_indices, down_transform, up_transform, tile: int = 128):
+    """``renumber_levels`` on a model's own tensors (``LongTensor[V,S]`` spirals, sparse COO transforms on any
+    device): returns new tensors of the same kinds on the same device, and ``orders`` (NumPy)."""
+    dev = spiral_indices[0].device
+
+    def coo(t):
+        ind = t._indices().detach().cpu().numpy()
+        return ind[0], ind[1], t._values().detach().cpu().numpy().astype(np.float32), tuple(int(x) for x in t.shape)
+
+    sp, dn, up, orders = renumber_levels([s.detach().cpu().numpy() for s in spiral_indices],
+                                         [coo(t) for t in down_transform], [coo(t) for t in up_transform], tile)
+
+    def sparse(e):
+        r, c, v, shape = e
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            t = torch.sparse_coo_tensor(torch.from_numpy(np.stack([r, c]).astype(np.int64)),
+                                        torch.from_numpy(np.asarray(v, np.float32)), torch.Size(shape))
+        return t.to(dev)
+
+    return ([torch.from_numpy(np.ascontiguousarray(s)).long().to(dev) for s in sp],
+            [sparse(e) for e in dn], [sparse(e) for e in up], orders)
+
+
 def pool_stage_plan(ell_col: np.ndarray, ell_val: np.ndarray, tile: int = POOL_STAGE_TILE):
     """Stage plan of the shared-memory Pool forward (include/sdvae_b200.h, ``sdvae_pool_ell_fwd_staged``):
     ``gather_stage_plan`` of the ELL columns, with each entry's position and value interleaved:

@@ -120,14 +120,14 @@ TC_GRAD_TOL = 1e-4
 TC_LOSS_RTOL = 1e-4
 
 
-def _engine(model, tabs, bs, use_graph, use_tc=False, **kw):
+def _engine(model, tabs, bs, use_graph, use_tc=False, renumber=False, **kw):
     from sdvae_b200 import losses
     from sdvae_b200.engine import StepConfig, TrainEngine
     cfg = StepConfig(batch_size=bs, **kw)
     lt = losses.LaplacianTable.build(*tabs.lap, tabs.num_vertices[0], DEV)
     lat = tabs.latent_regions(model.latent_size)
     return TrainEngine(model, lt, [r[1] for r in tabs.regions], [lat[k] for k in tabs.region_keys()],
-                       cfg, use_graph=use_graph, use_tc=use_tc)
+                       cfg, use_graph=use_graph, use_tc=use_tc, renumber=renumber)
 
 
 def _check_grads(eng, model, trainer, tol):
@@ -169,6 +169,35 @@ def test_engine_steps_vs_oracle_trainer(golden, cranio, use_graph, use_tc):
     for k, v in trainer.params.items():          # every element moved by at most ~lr per step
         assert float((sd[k].cpu() - v.detach()).abs().max()) < 3 * 2.1e-3, k
         assert float((sd[k].cpu() - params[k]).abs().max()) > 0.0, k
+
+
+@pytest.mark.skipif(__import__('os').environ.get('SDVAE_EXPERIMENTAL') != '1',
+                    reason='engine-internal renumbering: host side checked on CPU, never run on a GPU in round 1')
+@pytest.mark.parametrize('use_tc', [False, True])
+def test_experimental_engine_on_renumbered_levels_vs_oracle(golden, cranio, use_tc):
+    """TrainEngine(renumber=True): the network runs on patch-wise renumbered internal levels; losses and all 24
+    parameter gradients still match the oracle on the template's own numbering, and the reconstruction comes
+    back in template order."""
+    from oracle import sdvae_oracle as orc
+    net, params, model = build_pair(cranio, 3, [32, 32, 32, 64], 75, False, True, 77, DEV)
+    eng = _engine(model, cranio, 2, False, use_tc=use_tc, renumber=True, lr=1e-3)
+    lap = tuple(torch.from_numpy(a) for a in cranio.lap)
+    trainer = orc.Trainer(net, params, lap, W, lr=1e-3)
+    x2 = torch.from_numpy(golden['A_x_unswapped'])
+    keys = cranio.region_keys()
+    eps = rand((4, 75), 100)
+    feat = torch.from_numpy(cranio.regions[3][1])
+    xa = orc.swap_features(x2, feat)
+    want = trainer.step(xa, 2, cranio.latent_regions(75)[keys[3]], eps=eps)
+    eng.set_fixed_eps(eps.to(DEV))
+    eng.load_batch(x2.to(DEV))
+    got = eng.step(3, sync_losses=True)
+    for k in ('reconstruction', 'kl', 'latent_consistency', 'laplacian', 'tot'):
+        assert got[k] == pytest.approx(want[k], rel=TC_LOSS_RTOL if use_tc else 5e-5), k
+    _check_grads(eng, model, trainer, TC_GRAD_TOL if use_tc else 5 * TOL)
+    with torch.no_grad():
+        recon_ref = net.forward(params, xa, eps=eps, training=True)[0]
+    assert nerr(eng.recon_template_order(), recon_ref) < (TC_GRAD_TOL if use_tc else 5 * TOL)
 
 
 @pytest.mark.parametrize('use_tc', [False, True])

@@ -183,3 +183,25 @@ def test_patch_order_halves_the_distinct_rows_of_a_tile():
     assert tb.distinct_rows_per_row(small, 2) == 1.5
     assert np.array_equal(tb.renumber_table(small, [3, 2, 1, 0], [3, 2, 1, 0]),
                           np.array([[0, 1, -1], [1, 2, 0], [2, 3, 1], [3, 2, 1]]))
+
+
+def test_renumbered_model_tables_and_laplacian_are_consistent():
+    """Host side of TrainEngine(renumber=True): ``renumbered_model_tables`` on the model's own tensors equals
+    ``MeshTables.renumbered``; ``LaplacianTable.renumbered`` is the same operator on the new numbering."""
+    from sdvae_b200 import fixtures as fx, tables as tb
+    from sdvae_b200.losses import LaplacianTable
+    tabs = fx.craniofacial_tables()
+    new, orders = tabs.renumbered(128)
+    sp, dn, up, orders2 = tb.renumbered_model_tables(tabs.spiral_tensors(), tabs.down_tensors(), tabs.up_tensors())
+    assert all(np.array_equal(a, b) for a, b in zip(orders, orders2))
+    for a, b in zip(sp, new.spiral_tensors()):
+        assert torch.equal(a, b)
+    for got, want in zip(dn + up, new.down_tensors() + new.up_tensors()):
+        assert got.shape == want.shape and torch.equal(got._indices(), want._indices())
+        assert torch.equal(got._values(), want._values())
+    V = tabs.num_vertices[0]
+    lt = LaplacianTable.build(*tabs.lap, V, 'cpu')
+    ln = lt.renumbered(orders[0])
+    want = LaplacianTable.build(*new.lap, V, 'cpu')
+    for f in ('ell_col', 'ell_val', 't_ptr', 't_row', 't_val'):
+        assert torch.equal(getattr(ln, f), getattr(want, f)), f
