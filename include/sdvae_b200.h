@@ -178,6 +178,15 @@ int sdvae_spiralconv_fwd_tc_staged(const float* x, const int32_t* plan_cnt, cons
                                    float* y, int B, int Vin, int Vout, int S, int Cin, int Cout, int act,
                                    sdvae_stream_t stream);
 
+/* EXPERIMENTAL, as above: sdvae_spiralconv_bwd_w_tc with tile-local staging (same plan as the staged forward;
+ * workspace as for sdvae_spiralconv_bwd_w_tc; results are meant to be bit-identical to it).
+ * Replaces: autograd of model.py:40 (grad_weight / grad_bias), as sdvae_spiralconv_bwd_w_tc. */
+int sdvae_tc_bwd_w_staged_supported(int S, int Cin, int Cout, int rcap);
+int sdvae_spiralconv_bwd_w_tc_staged(const float* x, const int32_t* plan_cnt, const int32_t* plan_src,
+                                     const int32_t* plan_loc, int rcap, const float* dpre, float* dW, float* db,
+                                     void* workspace, int B, int Vin, int Vout, int S, int Cin, int Cout,
+                                     sdvae_stream_t stream);
+
 /* ---- narrow-output layer (32 -> 3, model.py:135-136): the whole backward in one pass --------------
  * G[u, s*Cout + n] = sum_{v in cell(u,s)} dy[b, v, n]   (cell_ptr [Vin*S+1], cell_src: the inverse spiral table
  *                                                         in cell-CSR form, rows ascending inside a cell)

@@ -442,6 +442,35 @@ def test_experimental_staged_tc_forward_equals_tc_forward(cranio, lvl, B, cout, 
     assert torch.equal(ya, yb)
 
 
+@pytest.mark.skipif(__import__('os').environ.get('SDVAE_EXPERIMENTAL') != '1',
+                    reason='experimental kernel (compiled, never run on a GPU in round 1): set SDVAE_EXPERIMENTAL=1')
+@pytest.mark.parametrize('lvl,B,cin,cout', [(3, 2, 32, 32), (0, 3, 32, 32), (1, 5, 32, 64), (3, 4, 64, 64)])
+def test_experimental_staged_tc_weight_gradient_equals_tc_weight_gradient(cranio, lvl, B, cin, cout):
+    """tcgen05 weight gradient with tile-local staging (csrc/spiral_conv_umma_bw_staged.cuh) on the patch-ordered
+    template against bw_umma_kernel: same operands, same MMA and drain order -> identical bits."""
+    from sdvae_b200 import cabi
+    from sdvae_b200 import tables as tb
+    idx = cranio.spiral_tensors()[lvl].numpy()
+    o = tb.patch_order(idx, 128)
+    idx = tb.renumber_table(idx, o, o)
+    V, S = idx.shape
+    tab = tb.spiral_table(torch.from_numpy(idx).to(DEV))
+    plan = tab.plan_fwd()
+    sp = tb.StagedTilePlan.build(idx, DEV)
+    assert cabi.tc_bwd_w_supported(S, cin, cout, plan.rcap) and cabi.tc_bwd_w_staged_supported(S, cin, cout, sp.rcap)
+    x = rand((B, V, cin), 61).to(DEV)
+    g = rand((B, V, cout), 62).to(DEV)
+    ws = torch.empty(cabi.spiralconv_bwd_w_workspace(B * V, S, cin, cout) // 4 + 4, device=DEV)
+    outs = []
+    for fn, p in ((cabi.spiralconv_bwd_w_tc, plan), (cabi.spiralconv_bwd_w_tc_staged, sp)):
+        dW = torch.full((cout, S * cin), float('nan'), device=DEV)
+        db = torch.full((cout,), float('nan'), device=DEV)
+        fn(x, p, g, dW, db, ws, B, V, V, S, cin, cout)
+        torch.cuda.synchronize()
+        outs.append((dW, db))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 def test_tc_rejects_unsupported_shapes(cranio):
     from sdvae_b200 import cabi
     assert not cabi.tc_supported(9, 3, 32, 128)        # K = 27: stays on the FMA kernel
