@@ -53,6 +53,9 @@ _SIGNATURES = {
     "sdvae_narrow_out_bwd_supported": (C.c_int, [C.c_int] * 4),
     "sdvae_narrow_out_bwd_workspace": (C.c_size_t, [C.c_int, C.c_int]),
     "sdvae_narrow_out_bwd": (C.c_int, [_c_fp] * 10 + [C.c_int] * 7 + [_c_fp]),
+    "sdvae_tile_supported": (C.c_int, [C.c_int] * 5),
+    "sdvae_spiralconv_fwd_tile": (C.c_int, [_c_fp] * 4 + [C.c_int] + [_c_fp] * 3 + [C.c_int] * 7 + [_c_fp]),
+    "sdvae_spiralconv_bwd_x_tile": (C.c_int, [_c_fp] * 5 + [C.c_int] * 2 + [_c_fp] * 3 + [C.c_int] * 6 + [_c_fp]),
     "sdvae_tc_staged_supported": (C.c_int, [C.c_int] * 4),
     "sdvae_spiralconv_fwd_tc_staged": (C.c_int, [_c_fp] * 3 + [_c_fp, C.c_int] + [_c_fp] * 3 + [C.c_int] * 7 + [_c_fp]),
     "sdvae_tc_bwd_w_staged_supported": (C.c_int, [C.c_int] * 4),
@@ -114,7 +117,7 @@ _KERNELS_PER_CALL = {
     "spiralconv_fwd": 1, "weight_transpose": 1, "spiralconv_bwd_x": 1, "spiralconv_bwd_w": 2,
     "tc_pack_weights": 1, "spiralconv_fwd_tc": 1, "spiralconv_bwd_x_tc": 1,
     "spiralconv_bwd_w_tc": 2, "dense_tc": 1, "slot_pack": 1, "slot_weight": 1, "slot_grad": 1,
-    "dense_fwd": 1, "transpose2d": 1, "spiralconv_fwd_tc_staged": 1, "spiralconv_bwd_w_tc_staged": 2, "narrow_out_bwd": 2, "narrow_out_fwd": 1, "narrow_in_fwd": 1, "narrow_in_bwd_w": 2, "pool_ell_fwd": 1, "pool_ell_fwd_staged": 1, "csr_rowsum": 1, "elu_fwd": 1,
+    "dense_fwd": 1, "transpose2d": 1, "spiralconv_fwd_tc_staged": 1, "spiralconv_fwd_tile": 1, "spiralconv_bwd_x_tile": 1, "spiralconv_bwd_w_tc_staged": 2, "narrow_out_bwd": 2, "narrow_out_fwd": 1, "narrow_in_fwd": 1, "narrow_in_bwd_w": 2, "pool_ell_fwd": 1, "pool_ell_fwd_staged": 1, "csr_rowsum": 1, "elu_fwd": 1,
     "elu_bwd": 1, "reparam_fwd": 1, "reparam_bwd": 1, "axpy3": 1, "swap": 1, "mse_lap_fwd": 3,
     "mse_lap_bwd": 1, "kl_fwd_bwd": 2, "lc_fwd_bwd": 3, "total_loss": 1, "adam_tick": 1,
     "adam_step": 1,
@@ -202,12 +205,13 @@ def tc_wimg_floats(S, KS, N) -> int:
     return int(load().sdvae_tc_wimg_floats(S, KS, N))
 
 
-def tc_pack_weights(weight, wimg, S, Cin, Cout, transposed, n0=0, n_cnt=None):
-    """Packed weight image of output channels [n0, n0 + n_cnt) (input channels if ``transposed``)."""
+def tc_pack_weights(weight, wimg, S, Cin, Cout, transposed, n0=0, n_cnt=None, kperm=False):
+    """Packed weight image of output channels [n0, n0 + n_cnt) (input channels if ``transposed``);
+    ``kperm``: the K order of the tile-staged kernels (csrc/spiral_conv_tile.cuh)."""
     if n_cnt is None:
         n_cnt = (Cin if transposed else Cout) - n0
     rc = load().sdvae_tc_pack_weights_part(_f(weight, "weight"), _f(wimg, "wimg"), S, Cin, Cout,
-                                           1 if transposed else 0, n0, n_cnt, _stream())
+                                           (1 if transposed else 0) | (2 if kperm else 0), n0, n_cnt, _stream())
     if rc:
         _err(rc, "tc_pack_weights")
     add_launches(_KERNELS_PER_CALL["tc_pack_weights"])
@@ -224,7 +228,8 @@ def tc_pack_table(entries, device) -> torch.Tensor:
     n_cnt)`` tuples.  The tensors must outlive the table (it holds raw pointers)."""
     arr = (PackEntry * len(entries))()
     for i, (w, img, S, Cin, Cout, tr, n0, nc) in enumerate(entries):
-        arr[i] = PackEntry(_f(w, "weight"), _f(img, "wimg"), S, Cin, Cout, 1 if tr else 0, n0, nc)
+        # tr: bool (transposed) or the flag word of sdvae_pack_entry (bit 0 transposed, bit 1 kperm image)
+        arr[i] = PackEntry(_f(w, "weight"), _f(img, "wimg"), S, Cin, Cout, int(tr), n0, nc)
     host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8) if len(entries) else torch.zeros(0, dtype=torch.uint8)
     return host.to(device)
 
@@ -367,6 +372,37 @@ def pool_ell_fwd(x, col, val, out, B, Vin, Vout, Wd, Cc):
     if rc:
         _err(rc, "pool_ell_fwd")
     add_launches(_KERNELS_PER_CALL["pool_ell_fwd"])
+
+
+def tile_supported(S: int, Cin: int, Cout: int, rcap: int, ecap: int = 0) -> bool:
+    return bool(load().sdvae_tile_supported(int(S), int(Cin), int(Cout), int(rcap), int(ecap)))
+
+
+def _i16(t, name):
+    return _chk(t, torch.int16, name)
+
+
+def spiralconv_fwd_tile(x, plan, wimg, bias, y, B, Vin, Vout, S, Cin, Cout, act):
+    """SpiralConv (+ELU) forward on tcgen05 with tile-local staging; ``plan`` = ``tables.TileStagePlan`` of the
+    forward gather, ``wimg`` packed with ``tc_pack_weights(..., kperm=True)``."""
+    rc = load().sdvae_spiralconv_fwd_tile(_f(x, "x"), _i(plan.cnt, "plan_cnt"), _i(plan.src, "plan_src"),
+                                          _i(plan.cell, "plan_cell"), plan.rcap, _f(wimg, "wimg"), _fo(bias, "bias"),
+                                          _f(y, "y"), B, Vin, Vout, S, Cin, Cout, act, _stream())
+    if rc:
+        _err(rc, "spiralconv_fwd_tile")
+    add_launches(_KERNELS_PER_CALL["spiralconv_fwd_tile"])
+
+
+def spiralconv_bwd_x_tile(dpre, plan, wimg_t, gate, dx, B, Vrows, Vdst, S, Cout, Cin):
+    """Backward-to-input of SpiralConv on tcgen05 with tile-local staging; ``plan`` = ``TileStagePlan`` of the
+    inverse table, ``wimg_t`` packed with ``tc_pack_weights(..., transposed=True, kperm=True)``."""
+    rc = load().sdvae_spiralconv_bwd_x_tile(_f(dpre, "dpre"), _i(plan.cnt, "plan_cnt"), _i(plan.src, "plan_src"),
+                                            _i(plan.cell, "plan_cell"), _i16(plan.ext, "plan_ext"), plan.rcap,
+                                            plan.ecap, _f(wimg_t, "wimg_t"), _fo(gate, "gate"), _f(dx, "dx"),
+                                            B, Vrows, Vdst, S, Cout, Cin, _stream())
+    if rc:
+        _err(rc, "spiralconv_bwd_x_tile")
+    add_launches(_KERNELS_PER_CALL["spiralconv_bwd_x_tile"])
 
 
 def tc_staged_supported(S: int, Cin: int, Cout: int, rcap: int) -> bool:

@@ -9,6 +9,7 @@
 #include "spiral_conv_umma_bw.cuh"
 #include "spiral_conv_umma_staged.cuh"
 #include "spiral_conv_umma_bw_staged.cuh"
+#include "spiral_conv_tile.cuh"
 #include "slot_pack.cuh"
 #include "pool_misc.cuh"
 #include "narrow_conv.cuh"
@@ -156,6 +157,18 @@ static int launch_umma_staged(umma::StagedArgs& sa, cudaStream_t st) {
     return check_launch("gc_umma_staged_kernel");
 }
 
+template <bool RAGGED>
+static int launch_tile(tile::TileArgs& ta, cudaStream_t st) {
+    auto kern = tile::gt_kernel<RAGGED>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   // per device, cheap
+    ta.nts = tile::TileCfg::stages(ta.S, ta.rcap, ta.ecap);
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SDVAE_DBG"); dbg = e ? atoi(e) : 0; } ta.dbg = dbg; }
+    const long long ntiles = (long long)ta.B * ta.L;
+    const int grid = ntiles < kNumSMs ? (int)ntiles : kNumSMs;
+    kern<<<grid, tile::kTThreads, tile::TileCfg::smem_bytes(ta.S, ta.rcap, ta.ecap, ta.nts), st>>>(ta);
+    return check_launch("gt_kernel");
+}
+
 // Meshes per CTA (MG) of the staged kernels: runs long enough to amortise the ring's fill, and a CTA count that
 // fills whole waves of the resident CTAs (a wave lasts ~MG mesh-tiles: minimise waves x (MG + fill)).
 static int pick_mesh_group(int B, int L, long long slots, int nst) {
@@ -266,22 +279,23 @@ size_t sdvae_tc_wimg_floats(int S, int KS, int N) {
 
 int sdvae_tc_pack_weights(const float* W, float* wimg, int S, int Cin, int Cout, int transposed,
                           sdvae_stream_t stream) {
-    return sdvae_tc_pack_weights_part(W, wimg, S, Cin, Cout, transposed, 0, transposed ? Cin : Cout, stream);
+    return sdvae_tc_pack_weights_part(W, wimg, S, Cin, Cout, transposed, 0, (transposed & 1) ? Cin : Cout, stream);
 }
 
 int sdvae_tc_pack_weights_part(const float* W, float* wimg, int S, int Cin, int Cout, int transposed,
                                int n0, int n_cnt, sdvae_stream_t stream) {
     SDVAE_REQUIRE(W && wimg && S > 0 && Cin > 0 && Cout > 0, "tc_pack_weights: bad argument");
-    const int KS = transposed ? Cout : Cin, Nfull = transposed ? Cin : Cout, N = n_cnt;
+    const int tr = transposed & 1;       // bit 1 of the flag word: kperm image (tile-staged kernels)
+    const int KS = tr ? Cout : Cin, Nfull = tr ? Cin : Cout, N = n_cnt;
     SDVAE_REQUIRE(n0 >= 0 && n_cnt > 0 && n0 + n_cnt <= Nfull, "tc_pack_weights: bad output-channel range");
     if (!tc_shape_ok(S, KS, N, 128)) return set_error(SDVAE_ERR_UNSUPPORTED, "tc_pack_weights: unsupported layer shape");
     SDVAE_REQUIRE((reinterpret_cast<uintptr_t>(wimg) & 15) == 0, "tc_pack_weights: wimg must be 16-byte aligned");
     umma::PackArgs a;
     // rows n0 .. n0+n_cnt of the (transposed) weight: forward W[n, k] -> offset n0 rows; transposed
     // Wt[c, s*Cout + o] = W[o, s*Cin + c] -> offset n0 columns
-    a.W = transposed ? W + n0 : W + (size_t)n0 * S * Cin;
+    a.W = tr ? W + n0 : W + (size_t)n0 * S * Cin;
     a.img = wimg; a.NT = tc_tile_n(N); a.KS = KS; a.S = S; a.n_real = N; a.ldw = S * Cin;
-    a.transposed = transposed ? 1 : 0; a.cin = Cin;
+    a.transposed = transposed & 3; a.cin = Cin;
     const long long total = (long long)S * (KS / 32) * 2 * a.NT * 32;
     umma::umma_pack_weights_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a);
     return check_launch("umma_pack_weights_kernel");
@@ -436,6 +450,57 @@ int sdvae_spiralconv_bwd_x_tc(const float* dpre, const int32_t* plan_cnt, const 
     return tc_conv(dpre, plan_cnt, plan_src, plan_cell, rcap, wimg_t, nullptr, gate, dx, B, Vrows, Vdst, S,
                    Cout, Cin, lddx, gate ? EPI_GATE : EPI_NONE, false, (cudaStream_t)stream,
                    "spiralconv_bwd_x_tc: unsupported layer shape");
+}
+
+/* ---- tcgen05 SpiralConv with tile-local staging and stage-granular hand-offs (spiral_conv_tile.cuh) -------- */
+int sdvae_tile_supported(int S, int Cin, int Cout, int rcap, int ecap) {
+    if (Cin != 32 || Cout != 32 || S < 3 || S % tile::kTChunksPerStage != 0) return 0;
+    if (rcap < 32 || rcap > tile::kTMaxRcap || rcap % 32 != 0) return 0;
+    if (ecap < 0 || ecap % 8 != 0 || ecap > 16384) return 0;
+    return tile::TileCfg::stages(S, rcap, ecap) >= 2 ? 1 : 0;
+}
+
+static int tile_conv(const float* in, const int32_t* plan_cnt, const int32_t* plan_src, const uint32_t* plan_cell,
+                     const uint16_t* plan_ext, int rcap, int ecap, const float* wimg, const float* bias,
+                     const float* gate, float* out, int B, int in_rows, int out_rows, int S, int epi, bool ragged,
+                     cudaStream_t st, const char* who) {
+    SDVAE_REQUIRE(in && plan_cnt && plan_src && plan_cell && wimg && out && (!ragged || plan_ext || ecap == 0),
+                  "spiralconv tile: null pointer");
+    SDVAE_REQUIRE(B >= 0 && in_rows > 0 && out_rows > 0, "spiralconv tile: bad shape");
+    SDVAE_REQUIRE((long long)B * in_rows < 2147483647LL && (long long)B * out_rows < 2147483647LL,
+                  "spiralconv tile: B*rows exceeds int32");
+    const uintptr_t al = reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(wimg) |
+                         reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias) |
+                         reinterpret_cast<uintptr_t>(gate) | reinterpret_cast<uintptr_t>(plan_src) |
+                         reinterpret_cast<uintptr_t>(plan_cell) | reinterpret_cast<uintptr_t>(plan_ext);
+    SDVAE_REQUIRE((al & 15) == 0, "spiralconv tile: tensors and plan tables must be 16-byte aligned");
+    if (!sdvae_tile_supported(S, 32, 32, rcap, ecap)) return set_error(SDVAE_ERR_UNSUPPORTED, who);
+    if (B == 0) return SDVAE_OK;
+    tile::TileArgs ta{};
+    ta.in = in; ta.plan_cnt = plan_cnt; ta.plan_src = plan_src; ta.plan_cell = plan_cell; ta.plan_ext = plan_ext;
+    ta.wimg = wimg; ta.bias = bias; ta.gate = gate; ta.out = out;
+    ta.B = B; ta.in_rows = in_rows; ta.out_rows = out_rows; ta.L = sdvae_tc_plan_tiles(out_rows);
+    ta.S = S; ta.rcap = rcap; ta.ecap = ecap; ta.ldo = 32; ta.epi = epi;
+    return ragged ? launch_tile<true>(ta, st) : launch_tile<false>(ta, st);
+}
+
+int sdvae_spiralconv_fwd_tile(const float* x, const int32_t* plan_cnt, const int32_t* plan_src,
+                              const uint32_t* plan_cell, int rcap, const float* wimg, const float* bias, float* y,
+                              int B, int Vin, int Vout, int S, int Cin, int Cout, int act, sdvae_stream_t stream) {
+    if (Cin != 32 || Cout != 32) return set_error(SDVAE_ERR_UNSUPPORTED, "spiralconv_fwd_tile: unsupported layer shape");
+    const int epi = act == SDVAE_ACT_ELU ? EPI_BIAS_ELU : EPI_BIAS;
+    return tile_conv(x, plan_cnt, plan_src, plan_cell, nullptr, rcap, 0, wimg, bias, nullptr, y, B, Vin, Vout, S, epi,
+                     false, (cudaStream_t)stream, "spiralconv_fwd_tile: unsupported layer shape");
+}
+
+int sdvae_spiralconv_bwd_x_tile(const float* dpre, const int32_t* plan_cnt, const int32_t* plan_src,
+                                const uint32_t* plan_cell, const uint16_t* plan_ext, int rcap, int ecap,
+                                const float* wimg_t, const float* gate, float* dx, int B, int Vrows, int Vdst, int S,
+                                int Cout, int Cin, sdvae_stream_t stream) {
+    if (Cin != 32 || Cout != 32) return set_error(SDVAE_ERR_UNSUPPORTED, "spiralconv_bwd_x_tile: unsupported layer shape");
+    return tile_conv(dpre, plan_cnt, plan_src, plan_cell, plan_ext, rcap, ecap, wimg_t, nullptr, gate, dx, B, Vrows, Vdst,
+                     S, gate ? EPI_GATE : EPI_NONE, true, (cudaStream_t)stream,
+                     "spiralconv_bwd_x_tile: unsupported layer shape");
 }
 
 int sdvae_dense_tc(const float* x, const int32_t* plan_cnt, const int32_t* plan_src, int rcap,

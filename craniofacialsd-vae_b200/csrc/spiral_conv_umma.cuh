@@ -282,12 +282,21 @@ __device__ __forceinline__ void plan_issue(const PlanRegs<PV>& p, uint32_t dst0,
     }
 }
 
+// K permutation of the tile-staged kernels (spiral_conv_tile.cuh): channel held by A column kk of a 32-wide K
+// chunk.  Thread q = (kk >> 1) & 3 of a row reads the 16-byte pieces q (channels 4q..4q+3 -> column groups
+// n = kk >> 3 = 0, 1) and q + 4 (channels 16+4q.. -> n = 2, 3) of the staged row.
+__host__ __device__ constexpr int kperm(int kk) {
+    return ((kk >> 4) << 4) + (((kk >> 1) & 3) << 2) + (((kk >> 3) & 1) << 1) + (kk & 1);
+}
+
 // ---- weight image ----------------------------------------------------------------------------
 // img[chunk][j][32]:  j < NT -> hi part of W row j,  j >= NT -> lo part of row j-NT; rows >= n_real
 // are zero.  `transposed` selects the backward-to-input weight  Wt[c, s*Cout + o] = W[o, s*Cin + c]
 // read straight from the forward weight (so no separate transpose pass is needed):
 //   forward   : n = output channel, k = s*KS + c      -> W[n*ldw + k]            (KS = Cin)
 //   transposed: n = input channel c, k = s*KS + o     -> W[o*ldw + s*cin + n]    (KS = Cout)
+// `transposed` is a flag word: bit 0 = transposed, bit 1 = K position kk of every 32-wide chunk holds channel
+// kperm(kk) (the images of the tile-staged kernels).
 struct PackArgs {
     const float* W;
     float* img;
@@ -302,10 +311,10 @@ __global__ void umma_pack_weights_kernel(const PackArgs a) {
         const int j = (t >> 5) % (2 * a.NT);
         const int ch = (t >> 5) / (2 * a.NT);
         const int n = j % a.NT, part = j / a.NT;
-        const int k = ch * 32 + kk;
+        const int k = ch * 32 + ((a.transposed & 2) ? kperm(kk) : kk);
         float w = 0.f;
         if (n < a.n_real) {
-            if (!a.transposed) {
+            if (!(a.transposed & 1)) {
                 w = a.W[(size_t)n * a.ldw + k];
             } else {
                 const int s = k / a.KS, o = k - s * a.KS;
@@ -327,8 +336,8 @@ __device__ __forceinline__ int pack_tile_n(int N) { return N <= 16 ? 16 : (N <= 
 __global__ void umma_pack_weights_batch_kernel(const PackEntry* __restrict__ entries) {
     const PackEntry e = entries[blockIdx.y];
     PackArgs a;
-    a.KS = e.transposed ? e.Cout : e.Cin;
-    a.W = e.transposed ? e.W + e.n0 : e.W + (size_t)e.n0 * e.S * e.Cin;
+    a.KS = (e.transposed & 1) ? e.Cout : e.Cin;
+    a.W = (e.transposed & 1) ? e.W + e.n0 : e.W + (size_t)e.n0 * e.S * e.Cin;
     a.img = e.img; a.NT = pack_tile_n(e.n_cnt); a.S = e.S; a.n_real = e.n_cnt; a.ldw = e.S * e.Cin;
     a.transposed = e.transposed; a.cin = e.Cin;
     const int K = a.S * a.KS;
@@ -338,10 +347,10 @@ __global__ void umma_pack_weights_batch_kernel(const PackEntry* __restrict__ ent
         const int j = (t >> 5) % (2 * a.NT);
         const int ch = (t >> 5) / (2 * a.NT);
         const int n = j % a.NT, part = j / a.NT;
-        const int k = ch * 32 + kk;
+        const int k = ch * 32 + ((a.transposed & 2) ? kperm(kk) : kk);
         float w = 0.f;
         if (n < a.n_real) {
-            if (!a.transposed) {
+            if (!(a.transposed & 1)) {
                 w = a.W[(size_t)n * a.ldw + k];
             } else {
                 const int s = k / a.KS, o = k - s * a.KS;

@@ -294,6 +294,72 @@ def staged_tile_plan(idx: np.ndarray, max_rcap: int = 288):
     return cnt, pack_rows_loader_order(rows), loc3, rcap
 
 
+TILE_MAX_RCAP = 288            # distinct rows per tile the tile-staged tcgen05 kernels take (csrc/spiral_conv_tile.cuh)
+
+
+def tile_plan(cell_ptr: np.ndarray, cell_src: np.ndarray, out_rows: int, seq: int, max_rcap: int = TILE_MAX_RCAP):
+    """Tile plan of a cell-form table for the tile-staged tcgen05 kernels (``sdvae_spiralconv_fwd_tile`` /
+    ``sdvae_spiralconv_bwd_x_tile``, layout in include/sdvae_b200.h): cell ``(r, s)`` = rows
+    ``cell_src[cell_ptr[r*seq+s] : cell_ptr[r*seq+s+1]]`` (in that order -- the kernel sums them in order).
+    Returns ``(cnt [L], src [L, rcap/2], cell [L, seq*128] uint32, ext [L, ecap] uint16, rcap, ecap)``;
+    ``ecap == 0`` for forward tables (one row per cell).  Raises ``RuntimeError`` when a tile reads more than
+    ``max_rcap`` distinct rows (number the level patch-wise first: ``patch_order``)."""
+    cell_ptr = np.asarray(cell_ptr, np.int64)
+    cell_src = np.asarray(cell_src, np.int64)
+    R, S = int(out_rows), int(seq)
+    if cell_ptr.size != R * S + 1:
+        raise ValueError('tile_plan: cell_ptr must have out_rows*seq + 1 entries')
+    L = (R + 127) // 128
+    counts = np.diff(cell_ptr)                                   # [R*S]
+    if counts.size and counts.max() > 31:
+        raise RuntimeError('tile_plan: a cell holds more than 31 rows')
+    cnts, rows_l, locs_l = [], [], []
+    for t in range(L):
+        e0, e1 = cell_ptr[t * 128 * S], cell_ptr[min(R, (t + 1) * 128) * S]
+        uniq, inv = np.unique(cell_src[e0:e1], return_inverse=True)
+        cnts.append(uniq.size)
+        rows_l.append(uniq)
+        locs_l.append(inv.astype(np.int64))
+    ucap = max(cnts) if cnts else 0
+    rcap = max(32, (ucap + 31) // 32 * 32)
+    if rcap > max_rcap:
+        raise RuntimeError('tile_plan: a tile reads %d distinct rows (limit %d)' % (ucap, max_rcap))
+    rows = np.zeros((L, rcap), np.int64)
+    cell = np.zeros((L, S, 128), np.uint32)
+    cell[:, :, :] = np.uint32(1 << 9)                            # rows past the table: one (valid) row, never stored
+    ext_l = []
+    r_loc = np.arange(128)
+    word_pos = (r_loc >> 5) * 32 + (r_loc & 7) * 4 + ((r_loc >> 3) & 3)      # position of tile row r inside a slot
+    for t in range(L):
+        rows[t, :cnts[t]] = rows_l[t]
+        r0, r1 = t * 128, min(R, (t + 1) * 128)
+        n = r1 - r0
+        c = counts[r0 * S:r1 * S]                                # [n*S], cell (r, s) at r*S + s
+        start = cell_ptr[r0 * S:r1 * S] - cell_ptr[r0 * S]
+        loc = locs_l[t]
+        first = np.where(c > 0, loc[np.minimum(start, max(loc.size - 1, 0))] if loc.size else 0, 0)
+        extra = np.maximum(c - 1, 0)
+        eoff = np.concatenate([[0], np.cumsum(extra)[:-1]]) if c.size else np.zeros(0, np.int64)
+        # ext entries: for every cell its rows 2.. in order
+        if extra.sum():
+            sel = np.ones(loc.size, bool)
+            sel[start[c > 0]] = False                            # drop the first row of every non-empty cell
+            ext_l.append(loc[sel].astype(np.uint16))
+        else:
+            ext_l.append(np.zeros(0, np.uint16))
+        w = (first.astype(np.uint64) | (c.astype(np.uint64) << 9) | (eoff.astype(np.uint64) << 14))
+        if w.size and w.max() >= (1 << 32):
+            raise RuntimeError('tile_plan: cell word overflow')
+        w = w.astype(np.uint32).reshape(n, S)
+        cell[t][:, word_pos[:n]] = w.T
+    ecap = max((e.size for e in ext_l), default=0)
+    ecap = (ecap + 7) // 8 * 8
+    ext = np.zeros((L, max(ecap, 8)), np.uint16)
+    for t, e in enumerate(ext_l):
+        ext[t, :e.size] = e
+    return (np.asarray(cnts, np.int32), pack_rows_loader_order(rows), cell.reshape(L, S * 128), ext, rcap, ecap)
+
+
 def renumber_levels(spirals, downs, ups, tile: int = 128):
     """Patch-wise renumbering of every level but the coarsest (``patch_order``), applied consistently to the spiral
     tables ``spirals[l] [V_l, S]`` and to the transforms ``downs[l]`` (``[V_{l+1}, V_l]``) / ``ups[l]``
@@ -421,6 +487,8 @@ class SpiralTable:
     _stage: Optional[dict] = None
     _plan_fwd: Optional["TilePlan"] = None
     _plan_bwd: Optional["TilePlan"] = None
+    _tile_fwd: Optional[tuple] = None
+    _tile_bwd: Optional[tuple] = None
 
     @staticmethod
     def build(idx_np: np.ndarray, n_src: int, device) -> "SpiralTable":
@@ -479,10 +547,53 @@ class SpiralTable:
             self._plan_bwd = TilePlan.try_build(ptr, src, self.n_src, self.seq, self.idx.device)
         return self._plan_bwd
 
+    def tile_fwd(self) -> Optional["TileStagePlan"]:
+        """Tile-staged plan of the forward gather, or ``None`` when a 128-row tile reads too many distinct rows
+        (template strip order: renumber the level patch-wise, ``patch_order``)."""
+        if self._tile_fwd is None:
+            n = self.n_rows * self.seq
+            self._tile_fwd = (TileStagePlan.try_build(np.arange(n + 1, dtype=np.int64), self._np_idx.ravel(),
+                                                      self.n_rows, self.seq, self.idx.device),)
+        return self._tile_fwd[0]
+
+    def tile_bwd(self) -> Optional["TileStagePlan"]:
+        """Tile-staged plan of the backward-to-input gather (inverse table), or ``None``."""
+        if self._tile_bwd is None:
+            ptr, src = inverse_cells(self._np_idx, self.n_src)
+            self._tile_bwd = (TileStagePlan.try_build(ptr, src, self.n_src, self.seq, self.idx.device),)
+        return self._tile_bwd[0]
+
     def restrict(self, kept: np.ndarray) -> "SpiralTable":
         """Table of the rows in ``kept`` only (fused conv + selection pooling)."""
         return SpiralTable.build(self._np_idx[np.asarray(kept, np.int64)], self.n_src,
                                  self.idx.device)
+
+
+@dataclass
+class TileStagePlan:
+    """Device copy of ``tile_plan`` (tile-staged tcgen05 kernels, csrc/spiral_conv_tile.cuh)."""
+    cnt: torch.Tensor            # int32 [L]
+    src: torch.Tensor            # int32 [L, rcap/2]
+    cell: torch.Tensor           # int32 view of uint32 [L, S*128]
+    ext: torch.Tensor            # int16 view of uint16 [L, max(ecap, 8)]
+    rcap: int
+    ecap: int
+    out_rows: int
+    seq: int
+
+    @staticmethod
+    def build(cell_ptr, cell_src, out_rows: int, seq: int, device) -> "TileStagePlan":
+        cnt, src, cell, ext, rcap, ecap = tile_plan(cell_ptr, cell_src, out_rows, seq)
+        return TileStagePlan(_dev(cnt, device), _dev(src, device), _dev(cell.view(np.int32), device),
+                             _dev(ext.view(np.int16), device), int(rcap), int(ecap), int(out_rows), int(seq))
+
+    @staticmethod
+    def try_build(cell_ptr, cell_src, out_rows: int, seq: int, device) -> Optional["TileStagePlan"]:
+        """``build``, or ``None`` when a tile reads more distinct rows than a tile stage holds."""
+        try:
+            return TileStagePlan.build(cell_ptr, cell_src, out_rows, seq, device)
+        except RuntimeError:
+            return None
 
 
 @dataclass

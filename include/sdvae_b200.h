@@ -90,7 +90,7 @@ int sdvae_tc_pack_weights(const float* W, float* wimg, int S, int Cin, int Cout,
 typedef struct {
     const float* W;     /* layer weight [Cout, S*Cin] */
     float* wimg;        /* destination image, sdvae_tc_wimg_floats(S, KS, n_cnt) floats */
-    int S, Cin, Cout, transposed, n0, n_cnt;
+    int S, Cin, Cout, transposed /* flag word: bit 0 transposed, bit 1 kperm image */, n0, n_cnt;
 } sdvae_pack_entry;
 int sdvae_tc_pack_weights_batch(const sdvae_pack_entry* entries, int n, sdvae_stream_t stream);
 /* The same for output channels [n0, n0 + n_cnt) only (input channels for the transposed weight): a layer
@@ -115,6 +115,29 @@ int sdvae_spiralconv_bwd_x_tc(const float* dpre, const int32_t* plan_cnt, const 
                               const int32_t* plan_cell, int rcap, const float* wimg_t, const float* gate,
                               float* dx, int B, int Vrows, int Vdst, int S, int Cout, int Cin, int lddx,
                               sdvae_stream_t stream);
+
+/* The same two passes with TILE-LOCAL STAGING (csrc/spiral_conv_tile.cuh), for 32 -> 32 channel layers whose
+ * level is numbered so that a tile of 128 consecutive output rows reads at most 288 distinct source rows
+ * (tables.patch_order): the tile's distinct rows are copied once into shared memory and gathered there, the
+ * A operand reaches the MMA thread in stages of three K chunks.  Replaces model.py:27-41 + F.elu
+ * (model.py:68,84) / autograd of model.py:34,40 w.r.t. the input, exactly as the two entries above.
+ * Tile plan (tables.tile_plan), per tile of 128 output rows:
+ *   plan_cnt  [L]           distinct source rows of the tile
+ *   plan_src  [L, rcap/2]   those rows, 16-bit pairs in loader-lane order (as sdvae_tc_plan_build's src with S = 1)
+ *   plan_cell [L, S*128]    word of (slot s, tile row r) at s*128 + (r>>5)*32 + (r&7)*4 + ((r>>3)&3):
+ *                           bits 0..8 position of the cell's first row in the tile's list, bits 9..13 rows in the
+ *                           cell, bits 14.. offset of the cell's further rows in plan_ext
+ *   plan_ext  [L, ecap]     (backward plans) 16-bit positions of the 2nd, 3rd ... rows of the cells
+ * wimg: sdvae_tc_pack_weights with flag bit 1 set (`transposed | 2`: K positions of every 32-wide chunk permuted
+ * the way the kernel's conflict-free shared-memory gather delivers them). */
+int sdvae_tile_supported(int S, int Cin, int Cout, int rcap, int ecap);
+int sdvae_spiralconv_fwd_tile(const float* x, const int32_t* plan_cnt, const int32_t* plan_src,
+                              const uint32_t* plan_cell, int rcap, const float* wimg, const float* bias, float* y,
+                              int B, int Vin, int Vout, int S, int Cin, int Cout, int act, sdvae_stream_t stream);
+int sdvae_spiralconv_bwd_x_tile(const float* dpre, const int32_t* plan_cnt, const int32_t* plan_src,
+                                const uint32_t* plan_cell, const uint16_t* plan_ext, int rcap, int ecap,
+                                const float* wimg_t, const float* gate, float* dx, int B, int Vrows, int Vdst, int S,
+                                int Cout, int Cin, sdvae_stream_t stream);
 
 /* Weight gradient on the tensor cores, as sdvae_spiralconv_bwd_w (same workspace size), for
  * C_in in {32, 64}, C_out <= 64 (passes of 32 x <= 32 channels).  (plan_cnt, plan_src, rcap) is the FORWARD tile plan of the layer's table

@@ -1,0 +1,115 @@
+#!/usr/bin/env python
+"""Development check + timing of the tile-staged tcgen05 SpiralConv kernels (csrc/spiral_conv_tile.cuh) against a
+float64 evaluation on the GPU and against the per-slot-gather tcgen05 kernels, on the patch-ordered craniofacial
+template.   python tools/tile_check.py [--levels 0,1] [--B 1024] [--iters 5] [--skip-check]"""
+import argparse, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from sdvae_b200 import cabi, fixtures as fx, tables as tb
+
+DEV = 'cuda:0'
+
+
+def nerr(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+def ev_time(fn, iters, nbuf):
+    fn(0); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i % nbuf)
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--levels', default='0,1')
+    ap.add_argument('--B', type=int, default=1024)
+    ap.add_argument('--iters', type=int, default=6)
+    ap.add_argument('--skip-check', action='store_true')
+    ap.add_argument('--skip-old', action='store_true')
+    ap.add_argument('--only', default='fwd,dx')
+    a = ap.parse_args()
+    tabs = fx.craniofacial_tables().renumbered(128)[0]
+    S = 9
+    for lvl in [int(t) for t in a.levels.split(',')]:
+        idx = tabs.spiral_tensors()[lvl]
+        V = idx.shape[0]
+        tab = tb.spiral_table(idx.to(DEV))
+        t0 = time.time()
+        pf, pb = tab.tile_fwd(), tab.tile_bwd()
+        print('level %d V=%d: tile plans rcap fwd %d bwd %d ecap %d (%.2fs)' % (lvl, V, pf.rcap, pb.rcap, pb.ecap, time.time() - t0), flush=True)
+        assert cabi.tile_supported(S, 32, 32, pf.rcap, 0) and cabi.tile_supported(S, 32, 32, pb.rcap, pb.ecap)
+        g = torch.Generator(device='cpu').manual_seed(lvl)
+        W = (torch.randn(32, S * 32, generator=g) * 0.1).to(DEV)
+        bias = (torch.randn(32, generator=g) * 0.2).to(DEV)
+        wimg = torch.empty(cabi.tc_wimg_floats(S, 32, 32), device=DEV)
+        wimg_o = torch.empty_like(wimg)
+        wimg_t = torch.empty_like(wimg)
+        wimg_to = torch.empty_like(wimg)
+        cabi.tc_pack_weights(W, wimg, S, 32, 32, False, kperm=True)
+        cabi.tc_pack_weights(W, wimg_o, S, 32, 32, False)
+        cabi.tc_pack_weights(W, wimg_t, S, 32, 32, True, kperm=True)
+        cabi.tc_pack_weights(W, wimg_to, S, 32, 32, True)
+        idx_d = idx.to(DEV)
+        if not a.skip_check:
+            for B in (3, 41):
+                x = torch.randn(B, V, 32, generator=g).to(DEV)
+                if 'fwd' in a.only:
+                    for act in (1, 0):
+                        y = torch.full((B, V, 32), float('nan'), device=DEV)
+                        cabi.spiralconv_fwd_tile(x, pf, wimg, bias, y, B, V, V, S, 32, 32, act)
+                        torch.cuda.synchronize()
+                        ref = (x.double()[:, idx_d.view(-1)].view(B, V, S * 32) @ W.double().t()) + bias.double()
+                        if act:
+                            ref = torch.where(ref > 0, ref, torch.expm1(ref))
+                        y2 = torch.full((B, V, 32), float('nan'), device=DEV)
+                        cabi.spiralconv_fwd_tile(x, pf, wimg, bias, y2, B, V, V, S, 32, 32, act)
+                        torch.cuda.synchronize()
+                        print('  fwd  B=%d act=%d: normwise err vs fp64 %.3e   deterministic %s' % (B, act, nerr(y, ref), torch.equal(y, y2)), flush=True)
+                        del ref
+                if 'dx' in a.only:
+                    dpre = torch.randn(B, V, 32, generator=g).to(DEV)
+                    gate = torch.randn(B, V, 32, generator=g).to(DEV)
+                    for use_gate in (False, True):
+                        dx = torch.full((B, V, 32), float('nan'), device=DEV)
+                        cabi.spiralconv_bwd_x_tile(dpre, pb, wimg_t, gate if use_gate else None, dx, B, V, V, S, 32, 32)
+                        torch.cuda.synchronize()
+                        dG = (dpre.double() @ W.double()).view(B, V * S, 32)
+                        ref = torch.zeros(B, V, 32, dtype=torch.float64, device=DEV)
+                        ref.index_add_(1, idx_d.view(-1), dG)
+                        if use_gate:
+                            ref = ref * torch.where(gate > 0, torch.ones_like(gate), gate + 1).double()
+                        dx2 = torch.full((B, V, 32), float('nan'), device=DEV)
+                        cabi.spiralconv_bwd_x_tile(dpre, pb, wimg_t, gate if use_gate else None, dx2, B, V, V, S, 32, 32)
+                        torch.cuda.synchronize()
+                        print('  dx   B=%d gate=%d: normwise err vs fp64 %.3e   deterministic %s' % (B, use_gate, nerr(dx, ref), torch.equal(dx, dx2)), flush=True)
+                        del ref, dG
+        # ---- timing ----
+        B = a.B
+        nbuf = max(2, int(np.ceil(300e6 / (B * V * 128))) + 1)          # rotate buffers larger than L2
+        xs = [torch.randn(B, V, 32, device=DEV) for _ in range(nbuf)]
+        ys = [torch.empty(B, V, 32, device=DEV) for _ in range(nbuf)]
+        alg = 2 * B * V * 128
+        flops = 2.0 * B * V * 288 * 32
+        def rep(name, ms):
+            print('  %-34s B=%d  %.4f ms  %.0f GB/s alg (%.3f of 6556)  %.1f TFLOP/s' % (name, B, ms, alg / ms / 1e6, alg / ms / 1e6 / 6556.2, flops / ms / 1e9), flush=True)
+        if 'fwd' in a.only:
+            rep('fwd tile-staged', ev_time(lambda i: cabi.spiralconv_fwd_tile(xs[i], pf, wimg, bias, ys[i], B, V, V, S, 32, 32, 1), a.iters, nbuf))
+            if not a.skip_old:
+                po = tab.plan_fwd()
+                rep('fwd per-slot gather (gc_umma)', ev_time(lambda i: cabi.spiralconv_fwd_tc(xs[i], po, wimg_o, bias, ys[i], B, V, V, S, 32, 32, 1), a.iters, nbuf))
+        if 'dx' in a.only:
+            rep('dx  tile-staged', ev_time(lambda i: cabi.spiralconv_bwd_x_tile(xs[i], pb, wimg_t, None, ys[i], B, V, V, S, 32, 32), a.iters, nbuf))
+            if not a.skip_old:
+                po = tab.plan_bwd()
+                rep('dx  per-slot gather (gc_umma)', ev_time(lambda i: cabi.spiralconv_bwd_x_tc(xs[i], po, wimg_to, None, ys[i], B, V, V, S, 32, 32), a.iters, nbuf))
+        del xs, ys
+
+
+if __name__ == '__main__':
+    main()
