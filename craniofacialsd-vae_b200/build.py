@@ -8,7 +8,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libsdvae_b200.so")
 SOURCES = ["sdvae_abi.cu"]
-HEADERS = ["common.cuh", "spiral_conv.cuh", "spiral_conv_umma.cuh", "spiral_conv_umma_bw.cuh", "spiral_conv_umma_staged.cuh", "spiral_conv_umma_bw_staged.cuh", "slot_pack.cuh", "pool_misc.cuh", "narrow_conv.cuh", "loss.cuh"]
+HEADERS = ["common.cuh", "spiral_conv.cuh", "spiral_conv_umma.cuh", "spiral_conv_umma_bw.cuh", "spiral_conv_umma_staged.cuh", "spiral_conv_umma_bw_staged.cuh", "spiral_conv_tile.cuh", "slot_pack.cuh", "pool_misc.cuh", "narrow_conv.cuh", "loss.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -31,7 +31,8 @@ def build_library(force=False, verbose=False):
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found; cannot build " + LIB_PATH)
     tmp = LIB_PATH + ".tmp%d" % os.getpid()
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = ["-DSDVAE_TUNING"] if os.environ.get("SDVAE_TUNING") == "1" else []   # per-role cycle counters / ablations
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:

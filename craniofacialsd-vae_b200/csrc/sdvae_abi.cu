@@ -454,9 +454,9 @@ int sdvae_spiralconv_bwd_x_tc(const float* dpre, const int32_t* plan_cnt, const 
 
 /* ---- tcgen05 SpiralConv with tile-local staging and stage-granular hand-offs (spiral_conv_tile.cuh) -------- */
 int sdvae_tile_supported(int S, int Cin, int Cout, int rcap, int ecap) {
-    if (Cin != 32 || Cout != 32 || S < 3 || S % tile::kTChunksPerStage != 0) return 0;
+    if (Cin != 32 || Cout != 32 || S < 6 || S > 42 || S % tile::kTChunksPerStage != 0) return 0;   // every splitter set needs a slot in every tile
     if (rcap < 32 || rcap > tile::kTMaxRcap || rcap % 32 != 0) return 0;
-    if (ecap < 0 || ecap % 8 != 0 || ecap > 16384) return 0;
+    if (ecap < 0 || ecap % 64 != 0 || ecap > 1984) return 0;     // 128-byte aligned tile stages; 11-bit offsets into plan_ext
     return tile::TileCfg::stages(S, rcap, ecap) >= 2 ? 1 : 0;
 }
 

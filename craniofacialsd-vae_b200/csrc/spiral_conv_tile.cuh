@@ -24,8 +24,8 @@
 //   plan_src [L, rcap/2]     those rows, 16-bit pairs in loader-lane order (umma::plan_fetch, S = 1)
 //   plan_cell[L, S*128]      one word per (slot s, tile row r), stored at  s*128 + (r>>5)*32 + (r&7)*4 + ((r>>3)&3)
 //                            (the four words of a splitter thread are one 16-byte load):
-//                              bits 0..8 position of the cell's first row in the tile's list, bits 9..13 rows in the
-//                              cell, bits 14.. offset of its 2nd, 3rd, ... rows in plan_ext
+//                              bits 0..15 byte offset (position * 128) of the cell's first row in the tile's list,
+//                              bits 16..20 rows in the cell, bits 21.. offset of its 2nd, 3rd, ... rows in plan_ext
 //   plan_ext [L, ecap]       16-bit positions of the 2nd, 3rd ... rows of the cells (RAGGED plans only)
 #pragma once
 #include "spiral_conv_umma.cuh"
@@ -95,6 +95,93 @@ __device__ __forceinline__ void tmem_st_16x256b_x8(uint32_t taddr, const float (
         : "memory");
 }
 
+// ---- shared-memory access by 32-bit shared address (no generic-address arithmetic in the per-unit loops) ----
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16u(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void warp_arrive_a(uint32_t bar, int lane) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive_a(bar);
+}
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(kSuspendHintNs) : "memory");
+    return ok != 0;
+}
+// bounded wait with a short back-off between polls (a failed try_wait returns after ~40 clk whatever the hint says;
+// 16 splitter warps polling back to back took a third of the SM's issue slots, profiles/r02_gt_v2_stalls.txt)
+template <unsigned NS>
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait_a(bar, parity)) return;
+    int spins = 0;
+    do {
+        __nanosleep(NS);
+        if (++spins > kSpinLimit) __trap();
+    } while (!mbar_try_wait_a(bar, parity));
+}
+
+// ---- packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2): the kernel is bound by instruction issue ----
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; sub.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+// elu_fast (common.cuh) on a pair: same polynomial / ex2 branches, the polynomial in FFMA2
+__device__ __forceinline__ float2 elu_fast2(float2 v) {
+    const float2 vv = v;
+    float2 p = make_float2(2.7557319e-6f, 2.7557319e-6f);
+    p = fma2(p, vv, make_float2(2.4801587e-5f, 2.4801587e-5f));
+    p = fma2(p, vv, make_float2(1.9841270e-4f, 1.9841270e-4f));
+    p = fma2(p, vv, make_float2(1.3888889e-3f, 1.3888889e-3f));
+    p = fma2(p, vv, make_float2(8.3333333e-3f, 8.3333333e-3f));
+    p = fma2(p, vv, make_float2(4.1666667e-2f, 4.1666667e-2f));
+    p = fma2(p, vv, make_float2(1.6666667e-1f, 1.6666667e-1f));
+    p = fma2(p, vv, make_float2(0.5f, 0.5f));
+    p = fma2(p, vv, make_float2(1.0f, 1.0f));
+    p = mul2(p, vv);
+    const float2 e = add2(make_float2(__expf(v.x), __expf(v.y)), make_float2(-1.0f, -1.0f));
+    const float nx = v.x > -0.5f ? p.x : e.x, ny = v.y > -0.5f ? p.y : e.y;
+    return make_float2(v.x > 0.f ? v.x : nx, v.y > 0.f ? v.y : ny);
+}
+
 template <bool RAGGED>
 __global__ void __launch_bounds__(kTThreads, 1)
 gt_kernel(const TileArgs a) {
@@ -123,7 +210,7 @@ gt_kernel(const TileArgs a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int i = 0; i < kTMaxStages; ++i) { mbar_init(tile_full + i, 1); mbar_init(tile_empty + i, 4 * NCH); }
+        for (int i = 0; i < kTMaxStages; ++i) { mbar_init(tile_full + i, 1); mbar_init(tile_empty + i, kTSplitWarps); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(a_full + i, 4 * kTChunksPerStage); mbar_init(a_empty + i, 1);
             mbar_init(t_full + i, 1); mbar_init(t_empty + i, kTEpilogueWarps);
@@ -163,15 +250,19 @@ gt_kernel(const TileArgs a) {
                 const uint64_t desc0 = smem_desc_sw128(smem_u32(B_s));
                 const uint32_t desc_hi = (uint32_t)(desc0 >> 32), desc_lo0 = (uint32_t)desc0;
                 int st = 0; uint32_t sph = 0;
+                const bool prof = SDVAE_DBG_ON(a, 32) && blockIdx.x == 0;
+                WaitClock w_afull(prof), w_tempty(prof);
+                const long long t_begin = prof ? clock64() : 0;
 #pragma unroll 1
                 for (int it = 0; it < my_tiles; ++it) {
                     const int acc = it & 1;
-                    mbar_wait(t_empty + acc, ((it >> 1) & 1) ^ 1);
+                    w_tempty.timed([&] { mbar_wait(t_empty + acc, ((it >> 1) & 1) ^ 1); });
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * kTNT);
 #pragma unroll 1
                     for (int c0 = 0; c0 < NCH; c0 += kTChunksPerStage) {
-                        mbar_wait(a_full + st, sph);
+                        w_afull.timed([&] { mbar_wait(a_full + st, sph); });
                         tc_fence_after();
+                        if (!SDVAE_DBG_ON(a, 4))
 #pragma unroll
                         for (int c = 0; c < kTChunksPerStage; ++c) {
                             const uint32_t a_hi = tmem_base + (uint32_t)(kTAccCols + st * kTStageCols + c * 64), a_lo = a_hi + 32;
@@ -188,6 +279,7 @@ gt_kernel(const TileArgs a) {
                         if (++st == 2) { st = 0; sph ^= 1; }
                     }
                 }
+                if (prof) { g_prof[0] = clock64() - t_begin; g_prof[1] = w_afull.acc; g_prof[2] = w_tempty.acc; g_prof[3] = G; }
             }
             __syncwarp();
         } else {
@@ -203,6 +295,9 @@ gt_kernel(const TileArgs a) {
                 long long t0 = (long long)blockIdx.x + (long long)lw * gridDim.x;
                 int b = (int)(t0 / a.L), jt = (int)(t0 - (long long)b * a.L);
                 uint32_t tph = 0;
+                const bool prof = SDVAE_DBG_ON(a, 32) && blockIdx.x == 0 && lw == 0;
+                WaitClock w_tempty(prof), w_copy(prof);
+                const long long t_begin = prof ? clock64() : 0;
 #pragma unroll 1
                 for (int it = lw; it < my_tiles; it += NTS) {
                     PlanRegs<PV> now;
@@ -210,7 +305,8 @@ gt_kernel(const TileArgs a) {
                     const float* base = a.in + (size_t)b * a.in_rows * 32 + 4 * q;
                     const char* cell_g = reinterpret_cast<const char*>(a.plan_cell + (size_t)jt * S * 128);
                     const char* ext_g = RAGGED ? reinterpret_cast<const char*>(a.plan_ext + (size_t)jt * a.ecap) : nullptr;
-                    mbar_wait_relaxed(tile_empty + lw, tph ^ 1);
+                    w_tempty.timed([&] { mbar_wait_relaxed(tile_empty + lw, tph ^ 1); });
+                    if (!SDVAE_DBG_ON(a, 1))
                     {   // rows: staged row e = 32*j + 4*t + rsub, piece q (no swizzle: the splitter reads are conflict-free by construction)
                         const char* gb = reinterpret_cast<const char*>(base);
 #pragma unroll
@@ -233,7 +329,7 @@ gt_kernel(const TileArgs a) {
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst_cell + (uint32_t)off), "l"(src));
                     }
                     cp_async_commit();
-                    cp_async_wait<0>();
+                    w_copy.timed([&] { cp_async_wait<0>(); });
                     warp_arrive(tile_full + lw, lane);
                     tph ^= 1;
                     for (int k = 0; k < NTS; ++k) {
@@ -241,6 +337,7 @@ gt_kernel(const TileArgs a) {
                         if (jt >= a.L) { jt -= a.L; ++b; }
                     }
                 }
+                if (prof && lane == 0) { g_prof[8] = clock64() - t_begin; g_prof[9] = w_tempty.acc; g_prof[10] = w_copy.acc; }
             }
         }
     } else if (warp < kTFirstSplitWarp) {
@@ -251,10 +348,13 @@ gt_kernel(const TileArgs a) {
         const int ldo = a.ldo;
         const bool has_bias = (EPI == EPI_BIAS || EPI == EPI_BIAS_ELU) && a.bias != nullptr;
         int b = (int)blockIdx.x / a.L, jt = (int)blockIdx.x - b * a.L;
+        const bool prof = SDVAE_DBG_ON(a, 32) && blockIdx.x == 0 && warp == 0;
+        WaitClock w_tfull(prof);
+        const long long t_begin = prof ? clock64() : 0;
 #pragma unroll 1
         for (int it = 0; it < my_tiles; ++it) {
             const int acc = it & 1;
-            mbar_wait_relaxed(t_full + acc, (it >> 1) & 1);
+            w_tfull.timed([&] { mbar_wait_relaxed(t_full + acc, (it >> 1) & 1); });
             tc_fence_after();
             const int r = jt * kBM + q4 * 32 + lane;
             const size_t m = (size_t)b * a.out_rows + (r < a.out_rows ? r : 0);
@@ -270,17 +370,25 @@ gt_kernel(const TileArgs a) {
                     warp_arrive(t_empty + acc, lane);
                 }
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] += d2[j];
+                for (int j = 0; j < 16; j += 2) {
+                    const float2 t = add2(make_float2(v[j], v[j + 1]), make_float2(d2[j], d2[j + 1]));
+                    v[j] = t.x; v[j + 1] = t.y;
+                }
                 if (has_bias) {
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
                         const float4 bv = ldg4(a.bias + c0 + j);
-                        v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+                        const float2 t0 = add2(make_float2(v[j], v[j + 1]), make_float2(bv.x, bv.y));
+                        const float2 t1 = add2(make_float2(v[j + 2], v[j + 3]), make_float2(bv.z, bv.w));
+                        v[j] = t0.x; v[j + 1] = t0.y; v[j + 2] = t1.x; v[j + 3] = t1.y;
                     }
                 }
                 if (EPI == EPI_BIAS_ELU) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = elu_fast(v[j]);
+                    for (int j = 0; j < 16; j += 2) {
+                        const float2 t = elu_fast2(make_float2(v[j], v[j + 1]));
+                        v[j] = t.x; v[j + 1] = t.y;
+                    }
                 }
                 if (EPI == EPI_GATE) {
                     const float* grow = a.gate + m * ldo + c0;
@@ -309,6 +417,7 @@ gt_kernel(const TileArgs a) {
             b += db; jt += djt;
             if (jt >= a.L) { jt -= a.L; ++b; }
         }
+        if (prof && lane == 0) { g_prof[16] = clock64() - t_begin; g_prof[17] = w_tfull.acc; }
     } else {
         reg_inc<kTRegsSplit>();
         // ================= splitters =================
@@ -317,75 +426,102 @@ gt_kernel(const TileArgs a) {
         // 32*q4 + 16*g + 8*h + l4 (g, h in {0, 1}): for each it reads the two 16-byte pieces qq and qq + 4 of the
         // staged row(s) of the cell -- rows with even l4 the low 64-byte half first, rows with odd l4 the high half
         // first, so the eight lanes of an LDS.128 phase (two rows) always cover all 32 banks.
+        // The kernel is bound by instruction issue (profiles/r02_gt_*): everything per unit that is not a row read,
+        // a select, a split or a TMEM store is kept out of this loop.
         const int set = (warp - kTFirstSplitWarp) >> 2;
         const int q4 = warp & 3;
         const int l4 = lane >> 2, qq = lane & 3;
         const bool odd = (l4 & 1) != 0;
-        const uint32_t offX = (uint32_t)qq * 16u + (odd ? 64u : 0u), offY = (uint32_t)qq * 16u + (odd ? 0u : 64u);
+        const uint32_t offX = (uint32_t)qq * 16u + (odd ? 64u : 0u);       // second read: offX ^ 64
+        const uint32_t T_a = smem_u32(T_s);
         const uint32_t cell_off = (uint32_t)ROWS_BYTES + (uint32_t)(q4 * 32 + l4 * 4) * 4u;
+        const uint32_t ext_off = (uint32_t)(ROWS_BYTES + CELL_BYTES);
         const uint32_t t_lane = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)kTAccCols;
-        int g = set, ch = set, it = 0;
-        while (ch >= NCH) { ch -= NCH; ++it; }
+        const uint32_t bar_tile_full = smem_u32(tile_full), bar_tile_empty = smem_u32(tile_empty);
+        const uint32_t bar_a_full = smem_u32(a_full), bar_a_empty = smem_u32(a_empty);
+        int ts = 0; uint32_t tph = 0;
+        uint32_t stage_a = T_a;
+        const bool prof = SDVAE_DBG_ON(a, 32) && blockIdx.x == 0 && warp == kTFirstSplitWarp;
+        long long seg[6] = {0, 0, 0, 0, 0, 0};
+        const long long t_begin = prof ? clock64() : 0;
+        long long t_prev = t_begin;
+#define SDVAE_SEG(i) do { if (prof) { const long long t_now_ = clock64(); seg[i] += t_now_ - t_prev; t_prev = t_now_; } } while (0)
 #pragma unroll 1
-        while (g < G) {
-            const int ts = it % NTS;
-            const uint32_t tph = (uint32_t)((it / NTS) & 1);
-            const int sg = g / kTChunksPerStage;                 // stage round of this chunk
-            const int st = sg & 1;
-            const uint32_t sph = (uint32_t)((sg >> 1) & 1);
-            const int sub = g - sg * kTChunksPerStage;
-            mbar_wait_relaxed(a_empty + st, sph ^ 1);            // order: the TMEM stage first, then the tile stage
-            mbar_wait_relaxed(tile_full + ts, tph);
-            const uint8_t* stage = T_s + (size_t)ts * STAGE_BYTES;
-            const uint4 cw = *reinterpret_cast<const uint4*>(stage + cell_off + (uint32_t)ch * 512u);
-            const uint32_t words[4] = {cw.x, cw.y, cw.z, cw.w};
-            const uint32_t t_a = t_lane + (uint32_t)(st * kTStageCols + sub * 64);
-            tc_fence_after();
+        for (int it = 0; it < my_tiles; ++it) {
+            // chunk g = it*NCH + ch belongs to set g & 3; NCH = 1 (mod 4) is not assumed: first slot of this set in the tile
+            int ch = (set - it * NCH) & 3;
+            mbar_wait_a<64>(bar_tile_full + (uint32_t)ts * 8u, tph);
+            SDVAE_SEG(0);
+            const uint32_t baseX = stage_a + offX;
+#pragma unroll 1
+            for (; ch < NCH; ch += kTSplitSets) {
+                const int sg = it * (NCH / kTChunksPerStage) + ((ch * 43) >> 7);     // stage round of the chunk (ch / 3)
+                const int sub = ch - 3 * ((ch * 43) >> 7);
+                const int st = sg & 1;
+                const uint32_t sph = (uint32_t)((sg >> 1) & 1);
+                const uint4 cw = lds128u(stage_a + cell_off + (uint32_t)ch * 512u);
+                const uint32_t words[4] = {cw.x, cw.y, cw.z, cw.w};
+                float4 X[4], Y[4];
 #pragma unroll
-            for (int gg = 0; gg < 2; ++gg) {
-                float r[32];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t w = words[gg * 2 + h];
-                    const uint8_t* row = stage + (w & 0x1ffu) * 128u;
-                    float4 X = *reinterpret_cast<const float4*>(row + offX);
-                    float4 Y = *reinterpret_cast<const float4*>(row + offY);
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t w = words[k];
+                    const uint32_t ax = baseX + (w & 0xffffu);
+                    X[k] = lds128(ax);
+                    Y[k] = lds128(ax ^ 64u);
                     if (RAGGED) {
-                        const int cnt = (int)((w >> 9) & 0x1fu);
-                        if (cnt == 0) { X = make_float4(0.f, 0.f, 0.f, 0.f); Y = X; }
-                        const uint16_t* ext = reinterpret_cast<const uint16_t*>(stage + ROWS_BYTES + CELL_BYTES) + (w >> 14);
+                        const int cnt = (int)((w >> 16) & 0x1fu);
+                        if (cnt == 0) { X[k] = make_float4(0.f, 0.f, 0.f, 0.f); Y[k] = X[k]; }
+                        uint32_t ea = stage_a + ext_off + ((w >> 21) << 1);
 #pragma unroll 1
-                        for (int e = 1; e < cnt; ++e) {           // in-order sum: deterministic scatter-add
-                            const uint8_t* row2 = stage + (uint32_t)ext[e - 1] * 128u;
-                            const float4 X2 = *reinterpret_cast<const float4*>(row2 + offX);
-                            const float4 Y2 = *reinterpret_cast<const float4*>(row2 + offY);
-                            X.x += X2.x; X.y += X2.y; X.z += X2.z; X.w += X2.w;
-                            Y.x += Y2.x; Y.y += Y2.y; Y.z += Y2.z; Y.w += Y2.w;
-                        }
-                    }
-                    const float4 P = odd ? Y : X;                // piece qq     : channels 4qq .. 4qq+3   -> n = 0, 1
-                    const float4 Q = odd ? X : Y;                // piece qq + 4 : channels 16+4qq ..      -> n = 2, 3
-                    const float v8[8] = {P.x, P.y, P.z, P.w, Q.x, Q.y, Q.z, Q.w};
-#pragma unroll
-                    for (int n = 0; n < 4; ++n) {
-#pragma unroll
-                        for (int bb = 0; bb < 2; ++bb) {
-                            float hi, lo;
-                            split_tf32f(v8[2 * n + bb], hi, lo);
-                            r[4 * n + 2 * h + bb] = hi;
-                            r[16 + 4 * n + 2 * h + bb] = lo;
+                        for (int e = 1; e < cnt; ++e, ea += 2) {   // in-order sum: deterministic scatter-add
+                            const uint32_t ax2 = baseX + (lds16u(ea) << 7);
+                            const float4 X2 = lds128(ax2);
+                            const float4 Y2 = lds128(ax2 ^ 64u);
+                            X[k].x += X2.x; X[k].y += X2.y; X[k].z += X2.z; X[k].w += X2.w;
+                            Y[k].x += Y2.x; Y[k].y += Y2.y; Y[k].z += Y2.z; Y[k].w += Y2.w;
                         }
                     }
                 }
-                tmem_st_16x256b_x8(t_a + ((uint32_t)(16 * gg) << 16), r);
+                SDVAE_SEG(1);
+                mbar_wait_a<32>(bar_a_empty + (uint32_t)st * 8u, sph ^ 1);   // the MMAs of the stage's previous round are done
+                __syncwarp();                                    // the cell loops and the wait diverge; tcgen05.st is warp-collective
+                tc_fence_after();
+                SDVAE_SEG(3);
+                const uint32_t t_a = t_lane + (uint32_t)(st * kTStageCols + sub * 64);
+#pragma unroll
+                for (int gg = 0; gg < 2; ++gg) {
+                    float r[32];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float4 x = X[gg * 2 + h], y = Y[gg * 2 + h];
+                        const float4 P = odd ? y : x;            // piece qq     : channels 4qq .. 4qq+3   -> n = 0, 1
+                        const float4 Q = odd ? x : y;            // piece qq + 4 : channels 16+4qq ..      -> n = 2, 3
+                        const float v8[8] = {P.x, P.y, P.z, P.w, Q.x, Q.y, Q.z, Q.w};
+#pragma unroll
+                        for (int n = 0; n < 4; ++n) {
+                            const float2 v2 = make_float2(v8[2 * n], v8[2 * n + 1]);
+                            const float2 hi = make_float2(__uint_as_float(__float_as_uint(v2.x) & 0xffffe000u),
+                                                          __uint_as_float(__float_as_uint(v2.y) & 0xffffe000u));
+                            const float2 lo = sub2(v2, hi);
+                            r[4 * n + 2 * h] = hi.x; r[4 * n + 2 * h + 1] = hi.y;
+                            r[16 + 4 * n + 2 * h] = lo.x; r[16 + 4 * n + 2 * h + 1] = lo.y;
+                        }
+                    }
+                    if (!SDVAE_DBG_ON(a, 16)) tmem_st_16x256b_x8(t_a + ((uint32_t)(16 * gg) << 16), r);
+                }
+                tmem_st_wait();
+                SDVAE_SEG(4);
+                tc_fence_before();
+                if (lane == 0) mbar_arrive_a(bar_a_full + (uint32_t)st * 8u);     // (wait::st is warp-collective: every lane is done)
+                SDVAE_SEG(5);
             }
-            warp_arrive(tile_empty + ts, lane);      // this warp's reads of the tile stage for this chunk are done
-            tmem_st_wait();
-            tc_fence_before();
-            warp_arrive(a_full + st, lane);
-            g += kTSplitSets; ch += kTSplitSets;
-            while (ch >= NCH) { ch -= NCH; ++it; }
+            if (lane == 0) mbar_arrive_a(bar_tile_empty + (uint32_t)ts * 8u);     // this warp is done with the tile stage
+            stage_a += (uint32_t)STAGE_BYTES;
+            if (++ts == NTS) { ts = 0; tph ^= 1; stage_a = T_a; }
+            SDVAE_SEG(2);
         }
+#undef SDVAE_SEG
+        if (prof && lane == 0) { g_prof[24] = clock64() - t_begin; for (int i = 0; i < 6; ++i) g_prof[25 + i] = seg[i]; }
     }
 
     tc_fence_before();

@@ -326,7 +326,7 @@ def tile_plan(cell_ptr: np.ndarray, cell_src: np.ndarray, out_rows: int, seq: in
         raise RuntimeError('tile_plan: a tile reads %d distinct rows (limit %d)' % (ucap, max_rcap))
     rows = np.zeros((L, rcap), np.int64)
     cell = np.zeros((L, S, 128), np.uint32)
-    cell[:, :, :] = np.uint32(1 << 9)                            # rows past the table: one (valid) row, never stored
+    cell[:, :, :] = np.uint32(1 << 16)                           # rows past the table: one (valid) row, never stored
     ext_l = []
     r_loc = np.arange(128)
     word_pos = (r_loc >> 5) * 32 + (r_loc & 7) * 4 + ((r_loc >> 3) & 3)      # position of tile row r inside a slot
@@ -347,13 +347,13 @@ def tile_plan(cell_ptr: np.ndarray, cell_src: np.ndarray, out_rows: int, seq: in
             ext_l.append(loc[sel].astype(np.uint16))
         else:
             ext_l.append(np.zeros(0, np.uint16))
-        w = (first.astype(np.uint64) | (c.astype(np.uint64) << 9) | (eoff.astype(np.uint64) << 14))
+        w = ((first.astype(np.uint64) << 7) | (c.astype(np.uint64) << 16) | (eoff.astype(np.uint64) << 21))
         if w.size and w.max() >= (1 << 32):
             raise RuntimeError('tile_plan: cell word overflow')
         w = w.astype(np.uint32).reshape(n, S)
         cell[t][:, word_pos[:n]] = w.T
     ecap = max((e.size for e in ext_l), default=0)
-    ecap = (ecap + 7) // 8 * 8
+    ecap = (ecap + 63) // 64 * 64                               # keeps every tile stage 128-byte aligned
     ext = np.zeros((L, max(ecap, 8)), np.uint16)
     for t, e in enumerate(ext_l):
         ext[t, :e.size] = e

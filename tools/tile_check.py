@@ -15,6 +15,23 @@ def nerr(a, b):
     return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
 
 
+def print_prof(tag):
+    if not (int(os.environ.get('SDVAE_DBG', '0')) & 32):
+        return
+    import ctypes
+    buf = (ctypes.c_longlong * 64)()
+    cabi.load().sdvae_debug_read_prof(buf)
+    p = list(buf)
+    ch = max(p[3], 1)
+    print('  prof %s (CTA 0, clk; per chunk in brackets) chunks %d' % (tag, p[3]))
+    print('    mma      total %d [%.0f]  wait a_full %d [%.0f]  wait t_empty %d' % (p[0], p[0] / ch, p[1], p[1] / ch, p[2]))
+    print('    loader0  total %d  wait tile_empty %d  wait copies %d' % (p[8], p[9], p[10]))
+    print('    epilogue total %d  wait t_full %d' % (p[16], p[17]))
+    u = max(ch / 4, 1)
+    print('    split0   total %d [%.0f per unit]: wait tile_full %.0f  gather+split %.0f  arrive tile_empty %.0f  wait a_empty %.0f  st %.0f  arrive a_full+advance %.0f'
+          % (p[24], p[24] / u, p[25] / u, p[26] / u, p[27] / u, p[28] / u, p[29] / u, p[30] / u), flush=True)
+
+
 def ev_time(fn, iters, nbuf):
     fn(0); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -100,11 +117,13 @@ def main():
             print('  %-34s B=%d  %.4f ms  %.0f GB/s alg (%.3f of 6556)  %.1f TFLOP/s' % (name, B, ms, alg / ms / 1e6, alg / ms / 1e6 / 6556.2, flops / ms / 1e9), flush=True)
         if 'fwd' in a.only:
             rep('fwd tile-staged', ev_time(lambda i: cabi.spiralconv_fwd_tile(xs[i], pf, wimg, bias, ys[i], B, V, V, S, 32, 32, 1), a.iters, nbuf))
+            print_prof('fwd')
             if not a.skip_old:
                 po = tab.plan_fwd()
                 rep('fwd per-slot gather (gc_umma)', ev_time(lambda i: cabi.spiralconv_fwd_tc(xs[i], po, wimg_o, bias, ys[i], B, V, V, S, 32, 32, 1), a.iters, nbuf))
         if 'dx' in a.only:
             rep('dx  tile-staged', ev_time(lambda i: cabi.spiralconv_bwd_x_tile(xs[i], pb, wimg_t, None, ys[i], B, V, V, S, 32, 32), a.iters, nbuf))
+            print_prof('dx')
             if not a.skip_old:
                 po = tab.plan_bwd()
                 rep('dx  per-slot gather (gc_umma)', ev_time(lambda i: cabi.spiralconv_bwd_x_tc(xs[i], po, wimg_to, None, ys[i], B, V, V, S, 32, 32), a.iters, nbuf))
