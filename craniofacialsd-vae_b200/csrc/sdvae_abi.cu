@@ -157,16 +157,26 @@ static int launch_umma_staged(umma::StagedArgs& sa, cudaStream_t st) {
     return check_launch("gc_umma_staged_kernel");
 }
 
-template <bool RAGGED>
-static int launch_tile(tile::TileArgs& ta, cudaStream_t st) {
-    auto kern = tile::gt_kernel<RAGGED>;
+template <bool RAGGED, int NSETS>
+static int launch_tile_n(tile::TileArgs& ta, cudaStream_t st) {
+    auto kern = tile::gt_kernel<RAGGED, NSETS>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   // per device, cheap
     ta.nts = tile::TileCfg::stages(ta.S, ta.rcap, ta.ecap);
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SDVAE_DBG"); dbg = e ? atoi(e) : 0; } ta.dbg = dbg; }
     const long long ntiles = (long long)ta.B * ta.L;
     const int grid = ntiles < kNumSMs ? (int)ntiles : kNumSMs;
-    kern<<<grid, tile::kTThreads, tile::TileCfg::smem_bytes(ta.S, ta.rcap, ta.ecap, ta.nts), st>>>(ta);
+    kern<<<grid, tile::TileWarps<NSETS>::kThreads, tile::TileCfg::smem_bytes(ta.S, ta.rcap, ta.ecap, ta.nts), st>>>(ta);
     return check_launch("gt_kernel");
+}
+
+template <bool RAGGED>
+static int launch_tile(tile::TileArgs& ta, cudaStream_t st) {
+    static int nsets = -1;      // tuning switch (SDVAE_TILE_SETS = 4 | 5 | 6)
+    if (nsets < 0) { const char* e = getenv("SDVAE_TILE_SETS"); nsets = e ? atoi(e) : 6; }
+    if (ta.S < nsets) return launch_tile_n<RAGGED, 4>(ta, st);      // every splitter set needs a slot in every tile
+    if (nsets == 4) return launch_tile_n<RAGGED, 4>(ta, st);
+    if (nsets == 5) return launch_tile_n<RAGGED, 5>(ta, st);
+    return launch_tile_n<RAGGED, 6>(ta, st);
 }
 
 // Meshes per CTA (MG) of the staged kernels: runs long enough to amortise the ring's fill, and a CTA count that

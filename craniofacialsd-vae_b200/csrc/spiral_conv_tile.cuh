@@ -12,10 +12,14 @@
 //     copied ONCE into a tile stage together with the tile's cell words (host-built TILE PLAN, tables.tile_plan);
 //   * the A operand is handed to the MMA thread per STAGE of three K chunks (a third of the barrier rounds,
 //     24 MMAs per wait + commit);
-//   * the splitters gather from shared memory WITHOUT bank conflicts for arbitrary rows: they write the TMEM
-//     A operand with tcgen05.st.16x256b (four threads per row), the four threads of a row read one 64-byte half
-//     of it with one LDS.128, and the two rows of an 8-lane phase read opposite halves.  The price is a fixed
-//     permutation of the 32 channels of a K chunk (kperm below), applied to the weight image by the packer.
+//   * the splitters gather from shared memory (almost) without bank conflicts for arbitrary rows: they write the
+//     TMEM A operand with tcgen05.st.16x256b (four threads per row), the four threads of a row read one 64-byte
+//     half of it with one LDS.128; staged rows at odd positions of the tile stage are stored high half first, and
+//     the plan builder places the rows (max-cut) so that the two rows of an 8-lane phase mostly sit at positions
+//     of different parity (~75 % of the phases conflict-free, the rest 2-way).  [Reading opposite halves by lane
+//     parity instead is always conflict-free but costs 32 selects per unit -- and the kernel is bound by the ALU
+//     pipe, profiles/r02_gt_v3_stalls.txt.]  The price is a fixed permutation of the 32 channels of a K chunk
+//     (kperm), applied to the weight image by the packer.
 // Precision, weight image, MMA form (TS: A from TMEM, B = resident weight image), epilogue: as gc_umma_kernel
 // (error-compensated 3xTF32, fp32 accumulation in TMEM).
 //
@@ -24,9 +28,10 @@
 //   plan_src [L, rcap/2]     those rows, 16-bit pairs in loader-lane order (umma::plan_fetch, S = 1)
 //   plan_cell[L, S*128]      one word per (slot s, tile row r), stored at  s*128 + (r>>5)*32 + (r&7)*4 + ((r>>3)&3)
 //                            (the four words of a splitter thread are one 16-byte load):
-//                              bits 0..15 byte offset (position * 128) of the cell's first row in the tile's list,
+//                              bits 0..15 byte offset of the LOW 64-byte half of the cell's first row in the tile stage
+//                              (position p: p*128 + 64*(p & 1) -- rows at odd positions are stored high half first),
 //                              bits 16..20 rows in the cell, bits 21.. offset of its 2nd, 3rd, ... rows in plan_ext
-//   plan_ext [L, ecap]       16-bit positions of the 2nd, 3rd ... rows of the cells (RAGGED plans only)
+//   plan_ext [L, ecap]       16-bit byte offsets (same form) of the 2nd, 3rd ... rows of the cells (RAGGED plans only)
 #pragma once
 #include "spiral_conv_umma.cuh"
 
@@ -36,15 +41,25 @@ namespace tile {
 using namespace umma;
 
 constexpr int kTEpilogueWarps = 4;
-constexpr int kTSplitSets = 4;
-constexpr int kTSplitWarps = 4 * kTSplitSets;
 constexpr int kTMaxStages = 3;                                  // tile-stage ring depth limit (one loader warp each)
 constexpr int kTFirstSplitWarp = kTEpilogueWarps;               // 4
-constexpr int kTFirstLoadWarp = kTFirstSplitWarp + kTSplitWarps;  // 20
-constexpr int kTMmaWarp = kTFirstLoadWarp + kTMaxStages;        // 23
-constexpr int kTThreads = (kTMmaWarp + 1) * 32;                 // 768 -> 80 registers per thread at launch
-// setmaxnreg budgets per warpgroup: 128*64 + 512*88 + 128*64 = 61440 = 768*80
-constexpr int kTRegsEpilogue = 64, kTRegsSplit = 88, kTRegsLoad = 64;
+// Warp layout for NSETS splitter sets (4 warps each, one per TMEM lane quarter):
+//   warps 0..3 epilogue | 4 .. 4+4*NSETS-1 splitters | then kTMaxStages loader warps | then the MMA warp.
+// The splitters are LATENCY-bound (a unit is a serial chain of two barrier waits, two dependent shared-memory
+// round trips, ~70 ALU instructions, two TMEM stores and their completion wait: ~1300 clk with the SM's other
+// warps competing), so throughput = sets in flight / unit latency: more sets, fewer registers each.
+template <int NSETS>
+struct TileWarps {
+    static constexpr int kSplitWarps = 4 * NSETS;
+    static constexpr int kFirstLoadWarp = kTFirstSplitWarp + kSplitWarps;
+    static constexpr int kMmaWarp = kFirstLoadWarp + kTMaxStages;
+    static constexpr int kThreads = (kMmaWarp + 1) * 32;        // 4 sets: 768, 5: 896, 6: 1024
+    // setmaxnreg budgets per warpgroup (sum = kThreads * registers at launch)
+    static constexpr int kRegsEpilogue = NSETS == 4 ? 64 : (NSETS == 5 ? 56 : 64);
+    static constexpr int kRegsSplit = NSETS == 4 ? 88 : (NSETS == 5 ? 80 : 64);
+    static constexpr int kRegsLoad = NSETS == 4 ? 64 : (NSETS == 5 ? 48 : 64);
+    static constexpr bool kRealloc = NSETS != 6;
+};
 constexpr int kTMaxRcap = 288;                                  // distinct rows per tile (multiple of 32)
 constexpr int kTChunksPerStage = 3;                             // K chunks per TMEM A stage
 constexpr int kTNT = 32;
@@ -182,9 +197,12 @@ __device__ __forceinline__ float2 elu_fast2(float2 v) {
     return make_float2(v.x > 0.f ? v.x : nx, v.y > 0.f ? v.y : ny);
 }
 
-template <bool RAGGED>
-__global__ void __launch_bounds__(kTThreads, 1)
+template <bool RAGGED, int NSETS>
+__global__ void __launch_bounds__(TileWarps<NSETS>::kThreads, 1)
 gt_kernel(const TileArgs a) {
+    using TW = TileWarps<NSETS>;
+    constexpr int kTSplitSets = NSETS, kTSplitWarps = TW::kSplitWarps, kTFirstLoadWarp = TW::kFirstLoadWarp;
+    constexpr int kTMmaWarp = TW::kMmaWarp, kTThreads = TW::kThreads;
     const int S = a.S;
     const int NCH = S;                                      // one 32-wide K chunk per slot
     const int NTS = a.nts;
@@ -241,7 +259,7 @@ gt_kernel(const TileArgs a) {
     const int db = (int)gridDim.x / a.L, djt = (int)gridDim.x - db * a.L;
 
     if (warp >= kTFirstLoadWarp) {
-        reg_dec<kTRegsLoad>();
+        if (TW::kRealloc) reg_dec<TW::kRegsLoad>();
         if (warp == kTMmaWarp) {
             // ================= MMA issuer: one wait + 24 MMAs + one commit per stage of three chunks =================
             if (elect_one()) {
@@ -288,7 +306,7 @@ gt_kernel(const TileArgs a) {
             if (lw < NTS) {
                 const int q = lane & 7, rsub = lane >> 3;
                 uint8_t* stage = T_s + (size_t)lw * STAGE_BYTES;
-                const uint32_t dst_rows = smem_u32(stage) + (uint32_t)rsub * 128u + (uint32_t)q * 16u;
+                const uint32_t dst_rows = smem_u32(stage) + (uint32_t)rsub * 128u + (((uint32_t)q * 16u) ^ ((uint32_t)(rsub & 1) << 6));   // odd positions: high half first
                 const uint32_t dst_cell = smem_u32(stage) + (uint32_t)ROWS_BYTES;
                 const int n_cell16 = (CELL_BYTES + a.ecap * 2) >> 4;       // cell words and ext are contiguous in the stage
                 constexpr int PV = kTMaxRcap / 32;
@@ -341,7 +359,7 @@ gt_kernel(const TileArgs a) {
             }
         }
     } else if (warp < kTFirstSplitWarp) {
-        reg_dec<kTRegsEpilogue>();
+        if (TW::kRealloc) reg_dec<TW::kRegsEpilogue>();
         // ================= epilogue (as gc_umma_kernel's forward epilogue, rows staged for coalesced stores) ======
         const int q4 = warp & 3;
         const int EPI = a.epi;
@@ -419,20 +437,18 @@ gt_kernel(const TileArgs a) {
         }
         if (prof && lane == 0) { g_prof[16] = clock64() - t_begin; g_prof[17] = w_tfull.acc; }
     } else {
-        reg_inc<kTRegsSplit>();
+        if (TW::kRealloc) reg_inc<TW::kRegsSplit>();
         // ================= splitters =================
         // set k takes the chunks g = k (mod 4) of the CTA's chunk sequence (tile iteration, slot); its four warps
         // own the four TMEM lane quarters.  Thread (l4 = lane >> 2, qq = lane & 3) serves the tile rows
         // 32*q4 + 16*g + 8*h + l4 (g, h in {0, 1}): for each it reads the two 16-byte pieces qq and qq + 4 of the
-        // staged row(s) of the cell -- rows with even l4 the low 64-byte half first, rows with odd l4 the high half
-        // first, so the eight lanes of an LDS.128 phase (two rows) always cover all 32 banks.
-        // The kernel is bound by instruction issue (profiles/r02_gt_*): everything per unit that is not a row read,
-        // a select, a split or a TMEM store is kept out of this loop.
+        // staged row(s) of the cell (the plan word holds the byte offset of the row's low half).
+        // The kernel is bound by the ALU pipe / instruction issue (profiles/r02_gt_*): everything per unit that is
+        // not a row read, a split or a TMEM store is kept out of this loop.
         const int set = (warp - kTFirstSplitWarp) >> 2;
         const int q4 = warp & 3;
         const int l4 = lane >> 2, qq = lane & 3;
-        const bool odd = (l4 & 1) != 0;
-        const uint32_t offX = (uint32_t)qq * 16u + (odd ? 64u : 0u);       // second read: offX ^ 64
+        const uint32_t offX = (uint32_t)qq * 16u;                          // low half (pieces 0..3); high half: ^ 64
         const uint32_t T_a = smem_u32(T_s);
         const uint32_t cell_off = (uint32_t)ROWS_BYTES + (uint32_t)(q4 * 32 + l4 * 4) * 4u;
         const uint32_t ext_off = (uint32_t)(ROWS_BYTES + CELL_BYTES);
@@ -446,56 +462,54 @@ gt_kernel(const TileArgs a) {
         const long long t_begin = prof ? clock64() : 0;
         long long t_prev = t_begin;
 #define SDVAE_SEG(i) do { if (prof) { const long long t_now_ = clock64(); seg[i] += t_now_ - t_prev; t_prev = t_now_; } } while (0)
+        int first = set;                                         // first slot of this set in the current tile: chunk g = it*NCH + ch belongs to set g % NSETS
 #pragma unroll 1
         for (int it = 0; it < my_tiles; ++it) {
-            // chunk g = it*NCH + ch belongs to set g & 3; NCH = 1 (mod 4) is not assumed: first slot of this set in the tile
-            int ch = (set - it * NCH) & 3;
             mbar_wait_a<64>(bar_tile_full + (uint32_t)ts * 8u, tph);
             SDVAE_SEG(0);
             const uint32_t baseX = stage_a + offX;
 #pragma unroll 1
-            for (; ch < NCH; ch += kTSplitSets) {
+            for (int ch = first; ch < NCH; ch += kTSplitSets) {
                 const int sg = it * (NCH / kTChunksPerStage) + ((ch * 43) >> 7);     // stage round of the chunk (ch / 3)
                 const int sub = ch - 3 * ((ch * 43) >> 7);
                 const int st = sg & 1;
                 const uint32_t sph = (uint32_t)((sg >> 1) & 1);
                 const uint4 cw = lds128u(stage_a + cell_off + (uint32_t)ch * 512u);
                 const uint32_t words[4] = {cw.x, cw.y, cw.z, cw.w};
-                float4 X[4], Y[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t w = words[k];
-                    const uint32_t ax = baseX + (w & 0xffffu);
-                    X[k] = lds128(ax);
-                    Y[k] = lds128(ax ^ 64u);
-                    if (RAGGED) {
-                        const int cnt = (int)((w >> 16) & 0x1fu);
-                        if (cnt == 0) { X[k] = make_float4(0.f, 0.f, 0.f, 0.f); Y[k] = X[k]; }
-                        uint32_t ea = stage_a + ext_off + ((w >> 21) << 1);
-#pragma unroll 1
-                        for (int e = 1; e < cnt; ++e, ea += 2) {   // in-order sum: deterministic scatter-add
-                            const uint32_t ax2 = baseX + (lds16u(ea) << 7);
-                            const float4 X2 = lds128(ax2);
-                            const float4 Y2 = lds128(ax2 ^ 64u);
-                            X[k].x += X2.x; X[k].y += X2.y; X[k].z += X2.z; X[k].w += X2.w;
-                            Y[k].x += Y2.x; Y[k].y += Y2.y; Y[k].z += Y2.z; Y[k].w += Y2.w;
-                        }
-                    }
-                }
-                SDVAE_SEG(1);
-                mbar_wait_a<32>(bar_a_empty + (uint32_t)st * 8u, sph ^ 1);   // the MMAs of the stage's previous round are done
-                __syncwarp();                                    // the cell loops and the wait diverge; tcgen05.st is warp-collective
-                tc_fence_after();
-                SDVAE_SEG(3);
                 const uint32_t t_a = t_lane + (uint32_t)(st * kTStageCols + sub * 64);
+                mbar_wait_a<32>(bar_a_empty + (uint32_t)st * 8u, sph ^ 1);   // the MMAs of the stage's previous round are done
+                __syncwarp();                                    // the wait (and the cell loops below) diverge; tcgen05.st is warp-collective
+                tc_fence_after();
+                SDVAE_SEG(1);
 #pragma unroll
                 for (int gg = 0; gg < 2; ++gg) {
+                    float4 X[2], Y[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t w = words[gg * 2 + h];
+                        const uint32_t ax = baseX + (w & 0xffffu);
+                        X[h] = lds128(ax);
+                        Y[h] = lds128(ax ^ 64u);
+                        if (RAGGED) {
+                            const int cnt = (int)((w >> 16) & 0x1fu);
+                            if (cnt == 0) { X[h] = make_float4(0.f, 0.f, 0.f, 0.f); Y[h] = X[h]; }
+                            uint32_t ea = stage_a + ext_off + ((w >> 21) << 1);
+#pragma unroll 1
+                            for (int e = 1; e < cnt; ++e, ea += 2) {   // in-order sum: deterministic scatter-add
+                                const uint32_t ax2 = baseX + lds16u(ea);
+                                const float4 X2 = lds128(ax2);
+                                const float4 Y2 = lds128(ax2 ^ 64u);
+                                X[h].x += X2.x; X[h].y += X2.y; X[h].z += X2.z; X[h].w += X2.w;
+                                Y[h].x += Y2.x; Y[h].y += Y2.y; Y[h].z += Y2.z; Y[h].w += Y2.w;
+                            }
+                        }
+                    }
+                    if (RAGGED) __syncwarp();
                     float r[32];
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const float4 x = X[gg * 2 + h], y = Y[gg * 2 + h];
-                        const float4 P = odd ? y : x;            // piece qq     : channels 4qq .. 4qq+3   -> n = 0, 1
-                        const float4 Q = odd ? x : y;            // piece qq + 4 : channels 16+4qq ..      -> n = 2, 3
+                        const float4 P = X[h];                   // piece qq     : channels 4qq .. 4qq+3   -> n = 0, 1
+                        const float4 Q = Y[h];                   // piece qq + 4 : channels 16+4qq ..      -> n = 2, 3
                         const float v8[8] = {P.x, P.y, P.z, P.w, Q.x, Q.y, Q.z, Q.w};
 #pragma unroll
                         for (int n = 0; n < 4; ++n) {
@@ -518,6 +532,8 @@ gt_kernel(const TileArgs a) {
             if (lane == 0) mbar_arrive_a(bar_tile_empty + (uint32_t)ts * 8u);     // this warp is done with the tile stage
             stage_a += (uint32_t)STAGE_BYTES;
             if (++ts == NTS) { ts = 0; tph ^= 1; stage_a = T_a; }
+            first -= NCH % kTSplitSets;
+            if (first < 0) first += kTSplitSets;
             SDVAE_SEG(2);
         }
 #undef SDVAE_SEG

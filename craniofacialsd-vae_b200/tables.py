@@ -297,13 +297,43 @@ def staged_tile_plan(idx: np.ndarray, max_rcap: int = 288):
 TILE_MAX_RCAP = 288            # distinct rows per tile the tile-staged tcgen05 kernels take (csrc/spiral_conv_tile.cuh)
 
 
+def _two_colour(n: int, a: np.ndarray, b: np.ndarray, sweeps: int = 12, seed: int = 0) -> np.ndarray:
+    """Local-search max-cut: colours in {0, 1} for ``n`` vertices so that as many pairs ``(a[i], b[i])`` as possible
+    get different colours (a triangulated surface is far from bipartite: ~75 % of the pairs end up cut)."""
+    colour = np.zeros(n, np.int64)
+    if n == 0 or a.size == 0:
+        return colour
+    keep = a != b
+    a, b = a[keep], b[keep]
+    order = np.argsort(np.concatenate([a, b]), kind='stable')
+    nbr = np.concatenate([b, a])[order]
+    ptr = np.concatenate([[0], np.cumsum(np.bincount(np.concatenate([a, b]), minlength=n))])
+    rng = np.random.RandomState(seed)
+    colour = rng.randint(0, 2, n).astype(np.int64)
+    for _ in range(sweeps):
+        changed = 0
+        for v in rng.permutation(n):
+            nb = nbr[ptr[v]:ptr[v + 1]]
+            if nb.size and 2 * int((colour[nb] == colour[v]).sum()) > nb.size:
+                colour[v] ^= 1
+                changed += 1
+        if not changed:
+            break
+    return colour
+
+
 def tile_plan(cell_ptr: np.ndarray, cell_src: np.ndarray, out_rows: int, seq: int, max_rcap: int = TILE_MAX_RCAP):
     """Tile plan of a cell-form table for the tile-staged tcgen05 kernels (``sdvae_spiralconv_fwd_tile`` /
     ``sdvae_spiralconv_bwd_x_tile``, layout in include/sdvae_b200.h): cell ``(r, s)`` = rows
     ``cell_src[cell_ptr[r*seq+s] : cell_ptr[r*seq+s+1]]`` (in that order -- the kernel sums them in order).
     Returns ``(cnt [L], src [L, rcap/2], cell [L, seq*128] uint32, ext [L, ecap] uint16, rcap, ecap)``;
     ``ecap == 0`` for forward tables (one row per cell).  Raises ``RuntimeError`` when a tile reads more than
-    ``max_rcap`` distinct rows (number the level patch-wise first: ``patch_order``)."""
+    ``max_rcap`` distinct rows (number the level patch-wise first: ``patch_order``).
+
+    Position parity: the kernel's two 64-byte halves of a staged row sit in the order (low, high) at even
+    positions and (high, low) at odd ones, and the 8 lanes of a shared-memory read phase serve two consecutive tile
+    rows: the read is conflict-free when their two staged rows sit at positions of different parity.  The
+    positions are therefore chosen by a max-cut over the pairs (first rows of the cells of tile rows 2i, 2i+1)."""
     cell_ptr = np.asarray(cell_ptr, np.int64)
     cell_src = np.asarray(cell_src, np.int64)
     R, S = int(out_rows), int(seq)
@@ -313,41 +343,60 @@ def tile_plan(cell_ptr: np.ndarray, cell_src: np.ndarray, out_rows: int, seq: in
     counts = np.diff(cell_ptr)                                   # [R*S]
     if counts.size and counts.max() > 31:
         raise RuntimeError('tile_plan: a cell holds more than 31 rows')
-    cnts, rows_l, locs_l = [], [], []
+    per_tile = []
+    ucap = 0
     for t in range(L):
         e0, e1 = cell_ptr[t * 128 * S], cell_ptr[min(R, (t + 1) * 128) * S]
         uniq, inv = np.unique(cell_src[e0:e1], return_inverse=True)
-        cnts.append(uniq.size)
-        rows_l.append(uniq)
-        locs_l.append(inv.astype(np.int64))
-    ucap = max(cnts) if cnts else 0
+        per_tile.append((uniq, inv.astype(np.int64)))
+        ucap = max(ucap, uniq.size)
     rcap = max(32, (ucap + 31) // 32 * 32)
     if rcap > max_rcap:
         raise RuntimeError('tile_plan: a tile reads %d distinct rows (limit %d)' % (ucap, max_rcap))
     rows = np.zeros((L, rcap), np.int64)
+    cnts = np.zeros(L, np.int32)
     cell = np.zeros((L, S, 128), np.uint32)
     cell[:, :, :] = np.uint32(1 << 16)                           # rows past the table: one (valid) row, never stored
     ext_l = []
     r_loc = np.arange(128)
     word_pos = (r_loc >> 5) * 32 + (r_loc & 7) * 4 + ((r_loc >> 3) & 3)      # position of tile row r inside a slot
+    half = rcap // 2
     for t in range(L):
-        rows[t, :cnts[t]] = rows_l[t]
+        uniq, loc = per_tile[t]
         r0, r1 = t * 128, min(R, (t + 1) * 128)
         n = r1 - r0
         c = counts[r0 * S:r1 * S]                                # [n*S], cell (r, s) at r*S + s
         start = cell_ptr[r0 * S:r1 * S] - cell_ptr[r0 * S]
-        loc = locs_l[t]
-        first = np.where(c > 0, loc[np.minimum(start, max(loc.size - 1, 0))] if loc.size else 0, 0)
+        first = np.where(c > 0, loc[np.minimum(start, max(loc.size - 1, 0))] if loc.size else 0, -1).reshape(n, S)
+        # pairs of staged rows read by one shared-memory phase: tile rows (2i, 2i+1), same slot
+        ne = n - (n & 1)
+        pa, pb = first[0:ne:2].ravel(), first[1:ne:2].ravel()
+        ok = (pa >= 0) & (pb >= 0)
+        colour = _two_colour(uniq.size, pa[ok], pb[ok], seed=t)
+        # positions: colour 0 -> even, colour 1 -> odd; the overflow of the larger class takes what is left
+        pos = np.full(uniq.size, -1, np.int64)
+        free = [list(range(0, rcap, 2)), list(range(1, rcap, 2))]
+        for col in (0, 1):
+            ids = np.flatnonzero(colour == col)
+            k = min(ids.size, half)
+            pos[ids[:k]] = free[col][:k]
+            free[col] = free[col][k:]
+        rest = np.flatnonzero(pos < 0)
+        spare = sorted(free[0] + free[1])
+        pos[rest] = spare[:rest.size]
+        rows[t, pos] = uniq
+        cnts[t] = int(pos.max()) + 1 if pos.size else 0
+        off = (pos << 7) | ((pos & 1) << 6)                      # byte offset of the LOW half of the staged row
+        floc = np.where(c > 0, off[np.maximum(first.ravel(), 0)] if off.size else 0, 0)
         extra = np.maximum(c - 1, 0)
         eoff = np.concatenate([[0], np.cumsum(extra)[:-1]]) if c.size else np.zeros(0, np.int64)
-        # ext entries: for every cell its rows 2.. in order
         if extra.sum():
             sel = np.ones(loc.size, bool)
             sel[start[c > 0]] = False                            # drop the first row of every non-empty cell
-            ext_l.append(loc[sel].astype(np.uint16))
+            ext_l.append(off[loc[sel]].astype(np.uint16))
         else:
             ext_l.append(np.zeros(0, np.uint16))
-        w = ((first.astype(np.uint64) << 7) | (c.astype(np.uint64) << 16) | (eoff.astype(np.uint64) << 21))
+        w = (floc.astype(np.uint64) | (c.astype(np.uint64) << 16) | (eoff.astype(np.uint64) << 21))
         if w.size and w.max() >= (1 << 32):
             raise RuntimeError('tile_plan: cell word overflow')
         w = w.astype(np.uint32).reshape(n, S)
@@ -357,7 +406,7 @@ def tile_plan(cell_ptr: np.ndarray, cell_src: np.ndarray, out_rows: int, seq: in
     ext = np.zeros((L, max(ecap, 8)), np.uint16)
     for t, e in enumerate(ext_l):
         ext[t, :e.size] = e
-    return (np.asarray(cnts, np.int32), pack_rows_loader_order(rows), cell.reshape(L, S * 128), ext, rcap, ecap)
+    return (cnts, pack_rows_loader_order(rows), cell.reshape(L, S * 128), ext, rcap, ecap)
 
 
 def renumber_levels(spirals, downs, ups, tile: int = 128):

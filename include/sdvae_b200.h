@@ -125,9 +125,10 @@ int sdvae_spiralconv_bwd_x_tc(const float* dpre, const int32_t* plan_cnt, const 
  *   plan_cnt  [L]           distinct source rows of the tile
  *   plan_src  [L, rcap/2]   those rows, 16-bit pairs in loader-lane order (as sdvae_tc_plan_build's src with S = 1)
  *   plan_cell [L, S*128]    word of (slot s, tile row r) at s*128 + (r>>5)*32 + (r&7)*4 + ((r>>3)&3):
- *                           bits 0..15 byte offset (position * 128) of the cell's first row in the tile's list,
+ *                           bits 0..15 byte offset of the low 64-byte half of the cell's first row in the tile stage
+ *                           (position p: p*128 + 64*(p&1): rows at odd positions are stored high half first),
  *                           bits 16..20 rows in the cell, bits 21.. offset of the cell's further rows in plan_ext
- *   plan_ext  [L, ecap]     (backward plans) 16-bit positions of the 2nd, 3rd ... rows of the cells
+ *   plan_ext  [L, ecap]     (backward plans) 16-bit byte offsets (same form) of the 2nd, 3rd ... rows of the cells
  * wimg: sdvae_tc_pack_weights with flag bit 1 set (`transposed | 2`: K positions of every 32-wide chunk permuted
  * the way the kernel's conflict-free shared-memory gather delivers them). */
 int sdvae_tile_supported(int S, int Cin, int Cout, int rcap, int ecap);
