@@ -32,6 +32,7 @@ def build_library(force=False, verbose=False):
         raise RuntimeError("nvcc not found; cannot build " + LIB_PATH)
     tmp = LIB_PATH + ".tmp%d" % os.getpid()
     extra = ["-DSDVAE_TUNING"] if os.environ.get("SDVAE_TUNING") == "1" else []   # per-role cycle counters / ablations
+    extra += os.environ.get("SDVAE_EXTRA_FLAGS", "").split()                      # e.g. compile-time ablations (-DSDVAE_ABL=..)
     cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

@@ -32,6 +32,23 @@ def print_prof(tag):
           % (p[24], p[24] / u, p[25] / u, p[26] / u, p[27] / u, p[28] / u, p[29] / u, p[30] / u), flush=True)
 
 
+def print_timeline(tag):
+    if not (int(os.environ.get('SDVAE_DBG', '0')) & 64):
+        return
+    import ctypes
+    buf = (ctypes.c_longlong * 256)()
+    cabi.load().sdvae_debug_read_timeline(buf)
+    t = list(buf)
+    t0 = min(x for x in t if x > 0)
+    print('  timeline %s (CTA 0, clk relative; chunks 400..415 = rounds 200..207)' % tag)
+    for r in range(8):
+        print('    round %d  mma-hi: a_full seen %6d, 8 MMAs issued %6d | mma-lo: %6d, %6d' % (200 + r, t[r * 4] - t0, t[r * 4 + 1] - t0, t[64 + r * 4] - t0, t[64 + r * 4 + 1] - t0))
+    for g in range(16):
+        x = t[128 + g * 4:128 + g * 4 + 4]
+        if x[0] > 0:
+            print('    chunk %d (set %d, q4 0): split done / wait a_empty %6d, a_empty seen %6d, STTM done %6d, a_full arrive %6d' % (400 + g, g % 4, x[0] - t0, x[1] - t0, x[2] - t0, x[3] - t0))
+
+
 def ev_time(fn, iters, nbuf):
     fn(0); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -117,7 +134,7 @@ def main():
             print('  %-34s B=%d  %.4f ms  %.0f GB/s alg (%.3f of 6556)  %.1f TFLOP/s' % (name, B, ms, alg / ms / 1e6, alg / ms / 1e6 / 6556.2, flops / ms / 1e9), flush=True)
         if 'fwd' in a.only:
             rep('fwd tile-staged', ev_time(lambda i: cabi.spiralconv_fwd_tile(xs[i], pf, wimg, bias, ys[i], B, V, V, S, 32, 32, 1), a.iters, nbuf))
-            print_prof('fwd')
+            print_prof('fwd'); print_timeline('fwd')
             if not a.skip_old:
                 po = tab.plan_fwd()
                 rep('fwd per-slot gather (gc_umma)', ev_time(lambda i: cabi.spiralconv_fwd_tc(xs[i], po, wimg_o, bias, ys[i], B, V, V, S, 32, 32, 1), a.iters, nbuf))
