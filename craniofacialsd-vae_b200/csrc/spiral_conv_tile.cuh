@@ -8,19 +8,23 @@
 //   * L2->SM fabric: it copies 9 x 128 gathered rows per 128-row tile.  Here a tile's DISTINCT source rows (~200
 //     once the level is numbered patch-wise) are copied ONCE into a tile stage together with the tile's cell
 //     words (host-built TILE PLAN, tables.tile_plan) and gathered from shared memory.
-//   * tcgen05.mma ISSUE RATE: one warp issues one kind::tf32 MMA per ~66 clk whatever its N (measured,
-//     tools/mma_issue_bench.cu: 531 clk per K chunk of 8 MMAs against 192 clk of tensor-pipe time; a second
-//     issuing warp doubles the rate).  Here TWO warps issue: one the A_hi x [W_hi; W_lo] chain (N = 64), one the
-//     A_lo x W_hi chain (N = 32) into its own accumulator columns -- each chain keeps a fixed order, so the result
-//     stays bit-reproducible; the epilogue adds the three column ranges.
-//   * barrier traffic: the A operand is handed over per STAGE of two K chunks (one wait + 8 MMAs + one commit per
-//     issuing warp and stage).
+//   * the TMEM A ring is the scarce resource: 384 columns = 6 K chunks of (32 hi + 32 lo) columns, and a chunk
+//     lives in it from the moment its stage is free until its MMAs have completed -- two TMEM stores (~155 clk
+//     each per warp, tools/sttm_bench.cu), tcgen05.wait::st (~300 clk), the hand-off to the MMA thread, the MMAs
+//     (192 clk of tensor pipe) and the commit back: ~1100 clk.  Six chunks in flight at that latency is just the
+//     tensor pipe's pace, so every stage is ONE chunk (the ring never waits for a neighbour), everything a
+//     splitter can do before its stage is free (gather, hi/lo split into registers) is done before, and the MMA
+//     thread polls the next chunk's barrier in the middle of the current chunk's MMAs (tools/mma_loop_bench.cu: the
+//     thread issues at the tensor pipe's pace only while nothing but MMAs sits in its instruction stream; a
+//     completed try_wait costs it 34 clk, any shared-memory load 135 clk).
 //   * shared-memory bank conflicts of a gather from arbitrary rows: the splitters write the TMEM A operand with
 //     tcgen05.st.16x256b (four threads per row); the four threads of a row read one 64-byte half of it with one
 //     LDS.128; staged rows at odd positions of the tile stage are stored high half first, and the plan builder
 //     places the rows (max-cut) so that the two rows of an 8-lane phase mostly sit at positions of different
 //     parity (~75 % of the phases conflict-free, the rest 2-way).  The price is a fixed permutation of the 32
 //     channels of a K chunk (kperm), applied to the weight image by the packer.
+//   (tools/mma_issue_bench.cu / sttm_bench.cu: one thread issues kind::tf32 MMAs at the tensor pipe's pace --
+//   32 clk for N = 64, 16 clk for N = 32 -- when nothing but the MMAs sits in its instruction stream.)
 // Precision and weight image as gc_umma_kernel (error-compensated 3xTF32, fp32 accumulation in TMEM).
 //
 // Tile plan (per tile t of 128 output rows; all tables static, built once on the host):
@@ -34,10 +38,9 @@
 //   plan_ext [L, ecap]       16-bit byte offsets (same form) of the 2nd, 3rd ... rows of the cells (RAGGED plans only)
 //
 // Warp roles (24 warps): 0..3 epilogue | 4..19 splitters, four sets of four (warp % 4 = TMEM lane quarter), set k
-// takes the chunks g = k (mod 4) | 20..21 loaders (one tile stage each) | 22 MMA issuer of the hi chain (+ TMEM
-// allocation) | 23 MMA issuer of the lo chain.
-// TMEM columns: [0, 192) two accumulator buffers of (64 hi-chain + 32 lo-chain) columns; [192, 448) A ring: two
-// stages of two chunks of (32 hi + 32 lo) columns.
+// takes the chunks g = k (mod 4) | 20..22 loaders (one tile stage each) | 23 TMEM allocation + MMA issue.
+// TMEM columns: [0, 128) two accumulators of 2*32 columns (A_hi x [W_hi; W_lo] lands in both halves, A_lo x W_hi in
+// the first; the epilogue adds the halves); [128, 512) A ring: six stages of one chunk.
 #pragma once
 #include "spiral_conv_umma.cuh"
 
@@ -49,19 +52,15 @@ using namespace umma;
 constexpr int kTEpilogueWarps = 4;
 constexpr int kTSplitSets = 4;
 constexpr int kTSplitWarps = 4 * kTSplitSets;
-constexpr int kTMaxStages = 3;                                  // tile-stage ring depth limit
-constexpr int kTLoadWarps = 2;                                  // loader warp w fills the stages of the tiles it = w (mod 2)
+constexpr int kTMaxStages = 3;                                  // tile-stage ring depth limit (one loader warp each)
 constexpr int kTFirstSplitWarp = kTEpilogueWarps;               // 4
 constexpr int kTFirstLoadWarp = kTFirstSplitWarp + kTSplitWarps;  // 20
-constexpr int kTMmaWarpHi = kTFirstLoadWarp + kTLoadWarps;      // 22
-constexpr int kTMmaWarpLo = kTMmaWarpHi + 1;                    // 23
-constexpr int kTThreads = (kTMmaWarpLo + 1) * 32;               // 768 -> 80 registers per thread
+constexpr int kTMmaWarp = kTFirstLoadWarp + kTMaxStages;        // 23
+constexpr int kTThreads = (kTMmaWarp + 1) * 32;                 // 768 -> 80 registers per thread
 constexpr int kTMaxRcap = 288;                                  // distinct rows per tile (multiple of 32)
-constexpr int kTChunksPerStage = 2;                             // K chunks per TMEM A stage
 constexpr int kTNT = 32;
-constexpr int kTAccCols = 3 * kTNT;                             // per accumulator buffer: 64 (hi chain) + 32 (lo chain)
-constexpr int kTARing = 2 * kTAccCols;                          // first column of the A ring (192)
-constexpr int kTStageCols = kTChunksPerStage * 64;              // 128: (32 hi + 32 lo) per chunk
+constexpr int kTAccCols = 4 * kTNT;                             // two accumulators of 2*NT columns
+constexpr int kTAStages = 6;                                    // TMEM A ring: stages of ONE K chunk (32 hi + 32 lo columns)
 constexpr int kTBChunk = 2 * kTNT * 128;                        // weight image bytes per K chunk
 
 struct TileArgs {
@@ -138,6 +137,14 @@ __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n}\n"
         : "=r"(ok) : "r"(bar), "r"(parity), "r"(kSuspendHintNs) : "memory");
     return ok != 0;
+}
+__device__ __forceinline__ void red_add_release_a(uint32_t addr, uint32_t v) {
+    asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_a(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
 }
 // bounded wait with a short back-off between polls (a failed try_wait returns after ~40 clk whatever the hint says;
 // 16 splitter warps polling back to back took a third of the SM's issue slots, profiles/r02_gt_v2_stalls.txt)
@@ -218,23 +225,21 @@ gt_kernel(const TileArgs a) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(O_s + kOutStageBytes);
     uint64_t* tile_full = bars;                             // [NTS]  loader    -> splitters
     uint64_t* tile_empty = bars + kTMaxStages;              // [NTS]  splitters -> loader
-    uint64_t* a_full = bars + 2 * kTMaxStages;              // [2]    splitters -> MMA warps (per A stage of 2 chunks)
-    uint64_t* a_empty = a_full + 2;                         // [2]    MMA warps (commit) -> splitters
-    uint64_t* t_full = a_empty + 2;                         // [2]    MMA warps (commit) -> epilogue
-    uint64_t* t_empty = t_full + 2;                         // [2]    epilogue -> MMA warps
+    uint64_t* a_empty = bars + 2 * kTMaxStages;             // [6]    MMA (commit) -> splitters, per A stage
+    uint64_t* a_full = a_empty + kTAStages;                 // [6]    splitters (one arrival per warp) -> MMA
+    uint64_t* t_full = a_full + kTAStages;                  // [2]    MMA (commit) -> epilogue
+    uint64_t* t_empty = t_full + 2;                         // [2]    epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
         for (int i = 0; i < kTMaxStages; ++i) { mbar_init(tile_full + i, 1); mbar_init(tile_empty + i, kTSplitWarps); }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(a_full + i, 4 * kTChunksPerStage); mbar_init(a_empty + i, 2);
-            mbar_init(t_full + i, 2); mbar_init(t_empty + i, kTEpilogueWarps);
-        }
+        for (int i = 0; i < kTAStages; ++i) { mbar_init(a_empty + i, 1); mbar_init(a_full + i, 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, kTEpilogueWarps); }
         fence_barrier_init();
     }
-    if (warp == kTMmaWarpHi) {
+    if (warp == kTMmaWarp) {
         __syncwarp();
         tmem_alloc(tmem_slot, kTmemCols);
         tmem_relinquish();
@@ -254,51 +259,56 @@ gt_kernel(const TileArgs a) {
 
     const int ntiles = a.B * a.L;
     const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int G = my_tiles * NCH;                           // chunks this CTA processes; chunk g: stage round g >> 1
+    const int G = my_tiles * NCH;                           // chunks this CTA processes; chunk g lives in A stage g % 6
     const int db = (int)gridDim.x / a.L, djt = (int)gridDim.x - db * a.L;
 
-    if (warp >= kTMmaWarpHi) {
-        // ================= MMA issuers =================
-        // warp 22: D_hi[:, 0:64] += A_hi x [W_hi; W_lo]^T ; warp 23: D_lo[:, 0:32] += A_lo x W_hi^T -- one wait + 8 MMAs +
-        // one commit per stage of two chunks.  Stage rounds run over the CTA's whole chunk sequence, across tiles.
+    if (warp == kTMmaWarp) {
+        // ================= MMA issuer =================
+        // per chunk: 4 x (A_hi x [W_hi; W_lo], N = 64; A_lo x W_hi, N = 32), commit -> a_empty[stage]; per tile: commit ->
+        // t_full.  tools/mma_loop_bench.cu: this thread issues at the tensor pipe's pace (192 clk per chunk) as long as
+        // nothing else sits between the MMAs; a completed mbarrier.try_wait costs 34 clk there, a shared-memory load
+        // (any flavour) 135 clk -- so the hand-off is an mbarrier, and the readiness of the NEXT chunk is polled in
+        // the middle of the current chunk's MMAs, where the tensor pipe still has queued work.
         if (elect_one()) {
-            const bool lo_chain = warp == kTMmaWarpLo;
-            const uint32_t IDESC = lo_chain ? idesc_tf32(kBM, kTNT) : idesc_tf32(kBM, 2 * kTNT);
+            constexpr uint32_t IDESC1 = idesc_tf32(kBM, 2 * kTNT);
+            constexpr uint32_t IDESC2 = idesc_tf32(kBM, kTNT);
             const uint64_t desc0 = smem_desc_sw128(smem_u32(B_s));
             const uint32_t desc_hi = (uint32_t)(desc0 >> 32), desc_lo0 = (uint32_t)desc0;
-            const uint32_t a_off = lo_chain ? 32u : 0u, d_off = lo_chain ? 2u * kTNT : 0u;
-            int st = 0; uint32_t sph = 0; int g = 0;
-            const bool prof = SDVAE_DBG_ON(a, 32) && blockIdx.x == 0 && !lo_chain;
+            const uint32_t bar_full = smem_u32(a_full);
+            int st = 0; uint32_t sph = 0;                        // stage / phase of the current chunk
+            const bool prof = SDVAE_DBG_ON(a, 32) && blockIdx.x == 0;
             WaitClock w_afull(prof), w_tempty(prof);
             const long long t_begin = prof ? clock64() : 0;
+            bool ready = my_tiles > 0 && mbar_try_wait_a(bar_full, 0u);
 #pragma unroll 1
             for (int it = 0; it < my_tiles; ++it) {
                 const int acc = it & 1;
                 w_tempty.timed([&] { mbar_wait(t_empty + acc, ((it >> 1) & 1) ^ 1); });
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kTAccCols) + d_off;
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * kTNT);
 #pragma unroll 1
-                for (int ch = 0; ch < NCH; ++ch, ++g) {
-                    const int sub = g & 1;
-                    if (sub == 0) {
-                        w_afull.timed([&] { mbar_wait(a_full + st, sph); });
-                        tc_fence_after();
-                        if (SDVAE_DBG_ON(a, 64) && blockIdx.x == 0 && g >= 400 && g < 416) g_tl[(lo_chain ? 64 : 0) + ((g - 400) >> 1) * 4 + 0] = clock64();
-                    }
-                    const uint32_t a_t = tmem_base + (uint32_t)(kTARing + st * kTStageCols + sub * 64) + a_off;
+                for (int ch = 0; ch < NCH; ++ch) {
+                    if (!ready) w_afull.timed([&] {
+                        int spins = 0;
+                        while (!mbar_try_wait_a(bar_full + (uint32_t)st * 8u, sph)) { if (++spins > kSpinLimit) __trap(); }
+                    });
+                    tc_fence_after();
+                    const uint32_t a_hi = tmem_base + (uint32_t)(kTAccCols + st * 64), a_lo = a_hi + 32;
                     const uint32_t dl = desc_lo0 + (uint32_t)(ch * (kTBChunk >> 4));
+                    uint64_t* const my_empty = a_empty + st;
+                    if (++st == kTAStages) { st = 0; sph ^= 1; }
+                    const bool more = ch + 1 < NCH || it + 1 < my_tiles;
                     if (!(SDVAE_ABL & 4) && !SDVAE_DBG_ON(a, 4)) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(dl + 2u * k);
-                            umma_tf32_ts(d_tmem, a_t + k * 8, bd, IDESC, (ch | k) != 0);
+                            umma_tf32_ts(d_tmem, a_hi + k * 8, bd, IDESC1, (ch | k) != 0);
+                            umma_tf32_ts(d_tmem, a_lo + k * 8, bd, IDESC2, 1u);
+                            if (k == 1) ready = more && mbar_try_wait_a(bar_full + (uint32_t)st * 8u, sph);
                         }
+                    } else {
+                        ready = more && mbar_try_wait_a(bar_full + (uint32_t)st * 8u, sph);
                     }
-                    if (sub == 1 || g == G - 1) {
-                        if (SDVAE_DBG_ON(a, 64) && blockIdx.x == 0 && g >= 400 && g < 416) g_tl[(lo_chain ? 64 : 0) + ((g - 400) >> 1) * 4 + 1] = clock64();
-                        umma_commit(a_empty + st);
-                        if (++st == 2) { st = 0; sph ^= 1; }
-                    }
+                    umma_commit(my_empty);
                 }
                 umma_commit(t_full + acc);
             }
@@ -316,12 +326,12 @@ gt_kernel(const TileArgs a) {
             constexpr int PV = kTMaxRcap / 32;
             long long t0 = (long long)blockIdx.x + (long long)lw * gridDim.x;
             int b = (int)(t0 / a.L), jt = (int)(t0 - (long long)b * a.L);
-            int ts = lw % NTS; uint32_t tph = 0;                       // stage / phase of tile `it`
+            int ts = lw % NTS; uint32_t tph = (uint32_t)((lw / NTS) & 1);                       // stage / phase of tile `it` (NTS may be 2: the third loader then alternates)
             const bool prof = SDVAE_DBG_ON(a, 32) && blockIdx.x == 0 && lw == 0;
             WaitClock w_tempty(prof), w_copy(prof);
             const long long t_begin = prof ? clock64() : 0;
 #pragma unroll 1
-            for (int it = lw; it < my_tiles; it += kTLoadWarps) {
+            for (int it = lw; it < my_tiles; it += kTMaxStages) {
                 PlanRegs<PV> now;
                 plan_fetch(now, a.plan_cnt, a.plan_src, jt, 1, 0, a.rcap, rsub);
                 const float* base = a.in + (size_t)b * a.in_rows * 32 + 4 * q;
@@ -354,7 +364,7 @@ gt_kernel(const TileArgs a) {
                 cp_async_commit();
                 w_copy.timed([&] { cp_async_wait<0>(); });
                 warp_arrive(tile_full + ts, lane);
-                for (int k = 0; k < kTLoadWarps; ++k) {                 // advance kTLoadWarps tiles of the CTA's schedule
+                for (int k = 0; k < kTMaxStages; ++k) {                 // advance kTMaxStages tiles of the CTA's schedule
                     b += db; jt += djt;
                     if (jt >= a.L) { jt -= a.L; ++b; }
                     if (++ts == NTS) { ts = 0; tph ^= 1; }
@@ -363,7 +373,7 @@ gt_kernel(const TileArgs a) {
             if (prof && lane == 0) { g_prof[8] = clock64() - t_begin; g_prof[9] = w_tempty.acc; g_prof[10] = w_copy.acc; }
         }
     } else if (warp < kTFirstSplitWarp) {
-        // ================= epilogue: hi-chain halves + lo chain -> bias / ELU / ELU'-gate -> staged rows -> global =====
+        // ================= epilogue: accumulator halves -> bias / ELU / ELU'-gate -> staged rows -> global =====
         const int q4 = warp & 3;
         const int EPI = a.epi;
         const int ldo = a.ldo;
@@ -379,22 +389,21 @@ gt_kernel(const TileArgs a) {
             tc_fence_after();
             const int r = jt * kBM + q4 * 32 + lane;
             const size_t m = (size_t)b * a.out_rows + (r < a.out_rows ? r : 0);
-            const uint32_t t_row = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * kTAccCols);
+            const uint32_t t_row = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * 2 * kTNT);
 #pragma unroll 1
             for (int c0 = 0; c0 < kTNT; c0 += 16) {
-                float v[16], d2[16], d3[16];
+                float v[16], d2[16];
                 tmem_ld16(t_row + c0, v);
                 tmem_ld16(t_row + kTNT + c0, d2);
-                tmem_ld16(t_row + 2 * kTNT + c0, d3);
                 tmem_ld_wait();
                 if (c0 + 16 >= kTNT) {
                     tc_fence_before();
                     warp_arrive(t_empty + acc, lane);
                 }
-                if (SDVAE_ABL & 8) { if (v[0] + d2[1] + d3[2] == 12345.678f) a.out[0] = 1.f; continue; }
+                if (SDVAE_ABL & 8) { if (v[0] + d2[1] == 12345.678f) a.out[0] = 1.f; continue; }
 #pragma unroll
-                for (int j = 0; j < 16; j += 2) {                // fixed order: (A_hi W_hi + A_hi W_lo) + A_lo W_hi
-                    const float2 t = add2(add2(make_float2(v[j], v[j + 1]), make_float2(d2[j], d2[j + 1])), make_float2(d3[j], d3[j + 1]));
+                for (int j = 0; j < 16; j += 2) {
+                    const float2 t = add2(make_float2(v[j], v[j + 1]), make_float2(d2[j], d2[j + 1]));
                     v[j] = t.x; v[j + 1] = t.y;
                 }
                 if (has_bias) {
@@ -457,21 +466,32 @@ gt_kernel(const TileArgs a) {
         const uint32_t T_a = smem_u32(T_s);
         const uint32_t cell_off = (uint32_t)ROWS_BYTES + (uint32_t)(q4 * 32 + l4 * 4) * 4u;
         const uint32_t ext_off = (uint32_t)(ROWS_BYTES + CELL_BYTES);
-        const uint32_t t_lane = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)kTARing;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)kTAccCols;
         const uint32_t bar_tile_full = smem_u32(tile_full), bar_tile_empty = smem_u32(tile_empty);
-        const uint32_t bar_a_full = smem_u32(a_full), bar_a_empty = smem_u32(a_empty);
+        const uint32_t bar_a_empty = smem_u32(a_empty), bar_a_full = smem_u32(a_full);
         int ts = 0; uint32_t tph = 0;
         uint32_t stage_a = T_a;
+#ifdef SDVAE_PROF
+        const bool prof = blockIdx.x == 0 && warp == kTFirstSplitWarp + SDVAE_PROF - 1;   // -DSDVAE_PROF=k: splitter warp k-1 of CTA 0, 32-bit clocks
+        unsigned seg[6] = {0, 0, 0, 0, 0, 0};
+        const unsigned t_begin = clock();
+        unsigned t_prev = t_begin;
+#define SDVAE_SEG(i) do { const unsigned t_now_ = clock(); seg[i] += t_now_ - t_prev; t_prev = t_now_; } while (0)
+#else
         const bool prof = SDVAE_DBG_ON(a, 32) && blockIdx.x == 0 && warp == kTFirstSplitWarp;
         long long seg[6] = {0, 0, 0, 0, 0, 0};
         const long long t_begin = prof ? clock64() : 0;
         long long t_prev = t_begin;
 #define SDVAE_SEG(i) do { if (prof) { const long long t_now_ = clock64(); seg[i] += t_now_ - t_prev; t_prev = t_now_; } } while (0)
+#endif
         int first = set;                                         // first slot of this set in the current tile
         int g0 = 0;                                              // chunk number of slot 0 of the current tile
-        // A warp's TMEM stores cost ~155 clk each and tcgen05.wait::st another ~300 (tools/sttm_bench.cu): the wait
-        // for the stores of unit u is therefore deferred until unit u+1 has been gathered and split.
-        uint32_t pend_bar = 0u; int pend_n = 0;                  // a_full barrier (and arrivals) owed for the previous unit
+        int st = set; uint32_t sph = 0;                          // A stage / phase of this set's current chunk (g % 6, (g / 6) & 1)
+        // The splitters are latency-bound (36 units per tile over 16 warps, ~1700 clk each), and a third of a unit is
+        // spent waiting for its two TMEM stores (~155 clk each per warp, tcgen05.wait::st another ~300,
+        // tools/sttm_bench.cu): the completion of unit u's stores is therefore awaited, and the MMA thread told, only
+        // after unit u+1 has been gathered and split.
+        uint32_t pend_bar = 0u;                                  // a_full barrier owed for the previous unit (0: none)
 #pragma unroll 1
         for (int it = 0; it < my_tiles; ++it, g0 += NCH) {
             mbar_wait_a<64>(bar_tile_full + (uint32_t)ts * 8u, tph);
@@ -480,8 +500,6 @@ gt_kernel(const TileArgs a) {
 #pragma unroll 1
             for (int ch = first; ch < NCH; ch += kTSplitSets) {
                 const int g = g0 + ch;
-                const int st = (g >> 1) & 1;
-                const uint32_t sph = (uint32_t)((g >> 2) & 1);
                 const uint4 cw = lds128u(stage_a + cell_off + (uint32_t)ch * 512u);
                 const uint32_t words[4] = {cw.x, cw.y, cw.z, cw.w};
                 float r[2][32];
@@ -529,27 +547,28 @@ gt_kernel(const TileArgs a) {
                     }
                 }
                 SDVAE_SEG(1);
-                if (pend_n) {                                    // complete the previous unit: its stores have long landed
+                if (pend_bar) {                                  // the previous unit's stores have long landed
                     tmem_st_wait();
                     tc_fence_before();
-                    if (lane == 0) { mbar_arrive_a(pend_bar); if (pend_n == 2) mbar_arrive_a(pend_bar); }
-                    pend_n = 0;
+                    if (lane == 0) mbar_arrive_a(pend_bar);
                 }
+                SDVAE_SEG(2);
                 const bool tl = SDVAE_DBG_ON(a, 64) && blockIdx.x == 0 && q4 == 0 && lane == 0 && g >= 400 && g < 416;
                 if (tl) g_tl[128 + (g - 400) * 4 + 0] = clock64();
-                mbar_wait_a<32>(bar_a_empty + (uint32_t)st * 8u, sph ^ 1);   // both MMA chains of the stage's previous round are done
+                mbar_wait_a<32>(bar_a_empty + (uint32_t)st * 8u, sph ^ 1);   // the MMAs of the stage's previous chunk are done
                 if (tl) g_tl[128 + (g - 400) * 4 + 1] = clock64();
                 __syncwarp();                                    // the cell loops and the wait diverge; tcgen05.st is warp-collective
                 tc_fence_after();
                 SDVAE_SEG(3);
-                const uint32_t t_a = t_lane + (uint32_t)(st * kTStageCols + (g & 1) * 64);
+                const uint32_t t_a = t_lane + (uint32_t)(st * 64);
                 if (!(SDVAE_ABL & 16) && !SDVAE_DBG_ON(a, 16)) {
                     tmem_st_16x256b_x8(t_a, r[0]);
                     tmem_st_16x256b_x8(t_a + (16u << 16), r[1]);
                 }
                 SDVAE_SEG(4);
                 pend_bar = bar_a_full + (uint32_t)st * 8u;
-                pend_n = (g == G - 1 && !(g & 1)) ? 2 : 1;       // odd chunk count: the last stage round holds one chunk
+                st += kTSplitSets;                               // next chunk of this set: g + 4
+                if (st >= kTAStages) { st -= kTAStages; sph ^= 1; }
                 SDVAE_SEG(5);
             }
             if (lane == 0) mbar_arrive_a(bar_tile_empty + (uint32_t)ts * 8u);     // this warp is done with the tile stage
@@ -557,20 +576,24 @@ gt_kernel(const TileArgs a) {
             if (++ts == NTS) { ts = 0; tph ^= 1; stage_a = T_a; }
             first -= NCH % kTSplitSets;
             if (first < 0) first += kTSplitSets;
-            SDVAE_SEG(2);
+            SDVAE_SEG(5);
         }
 #undef SDVAE_SEG
-        if (pend_n) {
+        if (pend_bar) {
             tmem_st_wait();
             tc_fence_before();
-            if (lane == 0) { mbar_arrive_a(pend_bar); if (pend_n == 2) mbar_arrive_a(pend_bar); }
+            if (lane == 0) mbar_arrive_a(pend_bar);
         }
+#ifdef SDVAE_PROF
+        if (prof && lane == 0) { g_prof[24] = clock() - t_begin; for (int i = 0; i < 6; ++i) g_prof[25 + i] = seg[i]; g_prof[3] = G; }
+#else
         if (prof && lane == 0) { g_prof[24] = clock64() - t_begin; for (int i = 0; i < 6; ++i) g_prof[25 + i] = seg[i]; }
+#endif
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == kTMmaWarpHi) {
+    if (warp == kTMmaWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }

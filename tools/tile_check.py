@@ -16,7 +16,7 @@ def nerr(a, b):
 
 
 def print_prof(tag):
-    if not (int(os.environ.get('SDVAE_DBG', '0')) & 32):
+    if not (int(os.environ.get('SDVAE_DBG', '0')) & 32) and not os.environ.get('SDVAE_PROF'):
         return
     import ctypes
     buf = (ctypes.c_longlong * 64)()
@@ -28,7 +28,7 @@ def print_prof(tag):
     print('    loader0  total %d  wait tile_empty %d  wait copies %d' % (p[8], p[9], p[10]))
     print('    epilogue total %d  wait t_full %d' % (p[16], p[17]))
     u = max(ch / 4, 1)
-    print('    split0   total %d [%.0f per unit]: wait tile_full %.0f  gather+split %.0f  arrive tile_empty %.0f  wait a_empty %.0f  st %.0f  arrive a_full+advance %.0f'
+    print('    split    total %d [%.0f per unit]: wait tile_full %.0f  gather+split %.0f  wait::st(prev)+arrive %.0f  wait a_empty %.0f  STTM issue %.0f  advance %.0f'
           % (p[24], p[24] / u, p[25] / u, p[26] / u, p[27] / u, p[28] / u, p[29] / u, p[30] / u), flush=True)
 
 
