@@ -157,16 +157,22 @@ static int launch_umma_staged(umma::StagedArgs& sa, cudaStream_t st) {
     return check_launch("gc_umma_staged_kernel");
 }
 
-template <bool RAGGED>
-static int launch_tile(tile::TileArgs& ta, cudaStream_t st) {
-    auto kern = tile::gt_kernel<RAGGED>;
+template <bool RAGGED, int NSETS>
+static int launch_tile_n(tile::TileArgs& ta, cudaStream_t st) {
+    auto kern = tile::gt_kernel<RAGGED, NSETS>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   // per device, cheap
     ta.nts = tile::TileCfg::stages(ta.S, ta.rcap, ta.ecap);
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SDVAE_DBG"); dbg = e ? atoi(e) : 0; } ta.dbg = dbg; }
     const long long ntiles = (long long)ta.B * ta.L;
     const int grid = ntiles < kNumSMs ? (int)ntiles : kNumSMs;
-    kern<<<grid, tile::kTThreads, tile::TileCfg::smem_bytes(ta.S, ta.rcap, ta.ecap, ta.nts), st>>>(ta);
+    kern<<<grid, tile::TileWarps<NSETS>::kThreads, tile::TileCfg::smem_bytes(ta.S, ta.rcap, ta.ecap, ta.nts), st>>>(ta);
     return check_launch("gt_kernel");
+}
+
+template <bool RAGGED>
+static int launch_tile(tile::TileArgs& ta, cudaStream_t st) {
+    // four splitter sets: five and six (fewer registers per thread) measured slower (profiles/r02_tile_kernel.md)
+    return launch_tile_n<RAGGED, 4>(ta, st);
 }
 
 // Meshes per CTA (MG) of the staged kernels: runs long enough to amortise the ring's fill, and a CTA count that
@@ -266,9 +272,6 @@ int sdvae_spiralconv_bwd_x(const float* dpre, const int32_t* cell_ptr, const int
 }
 
 /* tuning aid (not part of the product interface): cycle counters written by CTA 0 when SDVAE_DBG has bit 32 */
-int sdvae_debug_read_timeline(long long* host256) {
-    return cudaMemcpyFromSymbol(host256, tile::g_tl, 256 * sizeof(long long)) == cudaSuccess ? 0 : 2;
-}
 int sdvae_debug_read_prof(long long* host64) {
     return cudaMemcpyFromSymbol(host64, umma::g_prof, 64 * sizeof(long long)) == cudaSuccess ? 0 : 2;
 }
@@ -457,7 +460,7 @@ int sdvae_spiralconv_bwd_x_tc(const float* dpre, const int32_t* plan_cnt, const 
 
 /* ---- tcgen05 SpiralConv with tile-local staging and stage-granular hand-offs (spiral_conv_tile.cuh) -------- */
 int sdvae_tile_supported(int S, int Cin, int Cout, int rcap, int ecap) {
-    if (Cin != 32 || Cout != 32 || S < tile::kTSplitSets || S > 64) return 0;   // every splitter set needs a slot in every tile
+    if (Cin != 32 || Cout != 32 || S < 6 || S > 42 || S % tile::kTChunksPerStage != 0) return 0;   // every splitter set needs a slot in every tile
     if (rcap < 32 || rcap > tile::kTMaxRcap || rcap % 32 != 0) return 0;
     if (ecap < 0 || ecap % 64 != 0 || ecap > 1984) return 0;     // 128-byte aligned tile stages; 11-bit offsets into plan_ext
     return tile::TileCfg::stages(S, rcap, ecap) >= 2 ? 1 : 0;

@@ -1,31 +1,27 @@
-// Spiral convolution on tcgen05 with TILE-LOCAL STAGING (32 channels per slot, 32 output channels): forward
-// (model.py:27-41 + F.elu, model.py:68,84) and backward-to-input (autograd of model.py:34,40 = the same
-// contraction over the inverse table, a deterministic in-order scatter-add).
+// Spiral convolution on tcgen05 with TILE-LOCAL STAGING and stage-granular hand-offs (32 channels per slot,
+// 32 output channels): forward (model.py:27-41 + F.elu, model.py:68,84) and backward-to-input (autograd of
+// model.py:34,40 = the same contraction over the inverse table, a deterministic in-order scatter-add).
 //
 //   y[m, n] = epi( sum_{s,c} A[m, s*32 + c] * W[n, s*32 + c] ),   A[m, s*32 + c] = sum_{r in cell(m, s)} x[r, c]
 //
-// What bounded gc_umma_kernel (spiral_conv_umma.cuh) and what this kernel does about it (profiles/r02_*):
-//   * L2->SM fabric: it copies 9 x 128 gathered rows per 128-row tile.  Here a tile's DISTINCT source rows (~200
-//     once the level is numbered patch-wise) are copied ONCE into a tile stage together with the tile's cell
-//     words (host-built TILE PLAN, tables.tile_plan) and gathered from shared memory.
-//   * the TMEM A ring is the scarce resource: 384 columns = 6 K chunks of (32 hi + 32 lo) columns, and a chunk
-//     lives in it from the moment its stage is free until its MMAs have completed -- two TMEM stores (~155 clk
-//     each per warp, tools/sttm_bench.cu), tcgen05.wait::st (~300 clk), the hand-off to the MMA thread, the MMAs
-//     (192 clk of tensor pipe) and the commit back: ~1100 clk.  Six chunks in flight at that latency is just the
-//     tensor pipe's pace, so every stage is ONE chunk (the ring never waits for a neighbour), everything a
-//     splitter can do before its stage is free (gather, hi/lo split into registers) is done before, and the MMA
-//     thread polls the next chunk's barrier in the middle of the current chunk's MMAs (tools/mma_loop_bench.cu: the
-//     thread issues at the tensor pipe's pace only while nothing but MMAs sits in its instruction stream; a
-//     completed try_wait costs it 34 clk, any shared-memory load 135 clk).
-//   * shared-memory bank conflicts of a gather from arbitrary rows: the splitters write the TMEM A operand with
-//     tcgen05.st.16x256b (four threads per row); the four threads of a row read one 64-byte half of it with one
-//     LDS.128; staged rows at odd positions of the tile stage are stored high half first, and the plan builder
-//     places the rows (max-cut) so that the two rows of an 8-lane phase mostly sit at positions of different
-//     parity (~75 % of the phases conflict-free, the rest 2-way).  The price is a fixed permutation of the 32
-//     channels of a K chunk (kperm), applied to the weight image by the packer.
-//   (tools/mma_issue_bench.cu / sttm_bench.cu: one thread issues kind::tf32 MMAs at the tensor pipe's pace --
-//   32 clk for N = 64, 16 clk for N = 32 -- when nothing but the MMAs sits in its instruction stream.)
-// Precision and weight image as gc_umma_kernel (error-compensated 3xTF32, fp32 accumulation in TMEM).
+// Why this kernel exists (profiles/r01_*, r02_*): gc_umma_kernel copies 9 x 128 gathered rows per 128-row tile
+// through the L2->SM fabric (the fabric, ~7 TB/s, bounded it, not HBM) and hands every 32-wide K chunk from role
+// to role through its own mbarrier round (the MMA-issuing thread spent 350 clk per chunk on waits and commits
+// against 192 clk of tensor-pipe time).  Here
+//   * a tile's DISTINCT source rows (~200 of the 1152 gathered, once the level is numbered patch-wise) are
+//     copied ONCE into a tile stage together with the tile's cell words (host-built TILE PLAN, tables.tile_plan);
+//   * the A operand is handed to the MMA thread per STAGE of three K chunks (a third of the barrier rounds,
+//     24 MMAs per wait + commit);
+//   * the splitters gather from shared memory (almost) without bank conflicts for arbitrary rows: they write the
+//     TMEM A operand with tcgen05.st.16x256b (four threads per row), the four threads of a row read one 64-byte
+//     half of it with one LDS.128; staged rows at odd positions of the tile stage are stored high half first, and
+//     the plan builder places the rows (max-cut) so that the two rows of an 8-lane phase mostly sit at positions
+//     of different parity (~75 % of the phases conflict-free, the rest 2-way).  [Reading opposite halves by lane
+//     parity instead is always conflict-free but costs 32 selects per unit -- and the kernel is bound by the ALU
+//     pipe, profiles/r02_gt_v3_stalls.txt.]  The price is a fixed permutation of the 32 channels of a K chunk
+//     (kperm), applied to the weight image by the packer.
+// Precision, weight image, MMA form (TS: A from TMEM, B = resident weight image), epilogue: as gc_umma_kernel
+// (error-compensated 3xTF32, fp32 accumulation in TMEM).
 //
 // Tile plan (per tile t of 128 output rows; all tables static, built once on the host):
 //   plan_cnt [L]             distinct source rows of the tile (<= rcap)
@@ -36,11 +32,6 @@
 //                              (position p: p*128 + 64*(p & 1) -- rows at odd positions are stored high half first),
 //                              bits 16..20 rows in the cell, bits 21.. offset of its 2nd, 3rd, ... rows in plan_ext
 //   plan_ext [L, ecap]       16-bit byte offsets (same form) of the 2nd, 3rd ... rows of the cells (RAGGED plans only)
-//
-// Warp roles (24 warps): 0..3 epilogue | 4..19 splitters, four sets of four (warp % 4 = TMEM lane quarter), set k
-// takes the chunks g = k (mod 4) | 20..22 loaders (one tile stage each) | 23 TMEM allocation + MMA issue.
-// TMEM columns: [0, 128) two accumulators of 2*32 columns (A_hi x [W_hi; W_lo] lands in both halves, A_lo x W_hi in
-// the first; the epilogue adds the halves); [128, 512) A ring: six stages of one chunk.
 #pragma once
 #include "spiral_conv_umma.cuh"
 
@@ -50,17 +41,30 @@ namespace tile {
 using namespace umma;
 
 constexpr int kTEpilogueWarps = 4;
-constexpr int kTSplitSets = 4;
-constexpr int kTSplitWarps = 4 * kTSplitSets;
 constexpr int kTMaxStages = 3;                                  // tile-stage ring depth limit (one loader warp each)
 constexpr int kTFirstSplitWarp = kTEpilogueWarps;               // 4
-constexpr int kTFirstLoadWarp = kTFirstSplitWarp + kTSplitWarps;  // 20
-constexpr int kTMmaWarp = kTFirstLoadWarp + kTMaxStages;        // 23
-constexpr int kTThreads = (kTMmaWarp + 1) * 32;                 // 768 -> 80 registers per thread
+// Warp layout for NSETS splitter sets (4 warps each, one per TMEM lane quarter):
+//   warps 0..3 epilogue | 4 .. 4+4*NSETS-1 splitters | then kTMaxStages loader warps | then the MMA warp.
+// The splitters are LATENCY-bound (a unit is a serial chain of two barrier waits, two dependent shared-memory
+// round trips, ~70 ALU instructions, two TMEM stores and their completion wait: ~1300 clk with the SM's other
+// warps competing), so throughput = sets in flight / unit latency: more sets, fewer registers each.
+template <int NSETS>
+struct TileWarps {
+    static constexpr int kSplitWarps = 4 * NSETS;
+    static constexpr int kFirstLoadWarp = kTFirstSplitWarp + kSplitWarps;
+    static constexpr int kMmaWarp = kFirstLoadWarp + kTMaxStages;
+    static constexpr int kThreads = (kMmaWarp + 1) * 32;        // 4 sets: 768, 5: 896, 6: 1024
+    // setmaxnreg budgets per warpgroup (sum = kThreads * registers at launch)
+    static constexpr int kRegsEpilogue = NSETS == 4 ? 64 : (NSETS == 5 ? 56 : 64);
+    static constexpr int kRegsSplit = NSETS == 4 ? 88 : (NSETS == 5 ? 80 : 64);
+    static constexpr int kRegsLoad = NSETS == 4 ? 64 : (NSETS == 5 ? 48 : 64);
+    static constexpr bool kRealloc = NSETS != 6;
+};
 constexpr int kTMaxRcap = 288;                                  // distinct rows per tile (multiple of 32)
+constexpr int kTChunksPerStage = 3;                             // K chunks per TMEM A stage
 constexpr int kTNT = 32;
 constexpr int kTAccCols = 4 * kTNT;                             // two accumulators of 2*NT columns
-constexpr int kTAStages = 6;                                    // TMEM A ring: stages of ONE K chunk (32 hi + 32 lo columns)
+constexpr int kTStageCols = kTChunksPerStage * 64;              // 192: (32 hi + 32 lo) per chunk
 constexpr int kTBChunk = 2 * kTNT * 128;                        // weight image bytes per K chunk
 
 struct TileArgs {
@@ -69,7 +73,7 @@ struct TileArgs {
     const int* plan_src;          // [L, rcap/2]
     const uint32_t* plan_cell;    // [L, S*128]
     const uint16_t* plan_ext;     // [L, ecap] (RAGGED) or nullptr
-    const float* wimg;            // packed weight image with kperm applied (sdvae_tc_pack_weights, flag bit 1)
+    const float* wimg;            // packed weight image with kperm applied (sdvae_tc_pack_weights, perm = 1)
     const float* bias;            // [32] or nullptr
     const float* gate;            // EPI_GATE: out *= elu'(gate), aligned with out
     float* out;                   // [B, out_rows, ldo]
@@ -138,14 +142,6 @@ __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity), "r"(kSuspendHintNs) : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void red_add_release_a(uint32_t addr, uint32_t v) {
-    asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_a(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
 // bounded wait with a short back-off between polls (a failed try_wait returns after ~40 clk whatever the hint says;
 // 16 splitter warps polling back to back took a third of the SM's issue slots, profiles/r02_gt_v2_stalls.txt)
 template <unsigned NS>
@@ -201,14 +197,12 @@ __device__ __forceinline__ float2 elu_fast2(float2 v) {
     return make_float2(v.x > 0.f ? v.x : nx, v.y > 0.f ? v.y : ny);
 }
 
-#ifndef SDVAE_ABL
-#define SDVAE_ABL 0                // compile-time ablation mask for tuning builds: 1 no row copies, 2 no gather / split, 4 no MMAs,
-#endif                             // 8 no epilogue math / stores, 16 no TMEM stores
-__device__ long long g_tl[256];     // tuning: raw time stamps of a few stage rounds (SDVAE_DBG bit 64)
-
-template <bool RAGGED>
-__global__ void __launch_bounds__(kTThreads, 1)
+template <bool RAGGED, int NSETS>
+__global__ void __launch_bounds__(TileWarps<NSETS>::kThreads, 1)
 gt_kernel(const TileArgs a) {
+    using TW = TileWarps<NSETS>;
+    constexpr int kTSplitSets = NSETS, kTSplitWarps = TW::kSplitWarps, kTFirstLoadWarp = TW::kFirstLoadWarp;
+    constexpr int kTMmaWarp = TW::kMmaWarp, kTThreads = TW::kThreads;
     const int S = a.S;
     const int NCH = S;                                      // one 32-wide K chunk per slot
     const int NTS = a.nts;
@@ -225,9 +219,9 @@ gt_kernel(const TileArgs a) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(O_s + kOutStageBytes);
     uint64_t* tile_full = bars;                             // [NTS]  loader    -> splitters
     uint64_t* tile_empty = bars + kTMaxStages;              // [NTS]  splitters -> loader
-    uint64_t* a_empty = bars + 2 * kTMaxStages;             // [6]    MMA (commit) -> splitters, per A stage
-    uint64_t* a_full = a_empty + kTAStages;                 // [6]    splitters (one arrival per warp) -> MMA
-    uint64_t* t_full = a_full + kTAStages;                  // [2]    MMA (commit) -> epilogue
+    uint64_t* a_full = bars + 2 * kTMaxStages;              // [2]    splitters -> MMA   (per A stage of 3 chunks)
+    uint64_t* a_empty = a_full + 2;                         // [2]    MMA (commit) -> splitters
+    uint64_t* t_full = a_empty + 2;                         // [2]    MMA (commit) -> epilogue
     uint64_t* t_empty = t_full + 2;                         // [2]    epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
@@ -235,8 +229,10 @@ gt_kernel(const TileArgs a) {
 
     if (tid == 0) {
         for (int i = 0; i < kTMaxStages; ++i) { mbar_init(tile_full + i, 1); mbar_init(tile_empty + i, kTSplitWarps); }
-        for (int i = 0; i < kTAStages; ++i) { mbar_init(a_empty + i, 1); mbar_init(a_full + i, 4); }
-        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, kTEpilogueWarps); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(a_full + i, 4 * kTChunksPerStage); mbar_init(a_empty + i, 1);
+            mbar_init(t_full + i, 1); mbar_init(t_empty + i, kTEpilogueWarps);
+        }
         fence_barrier_init();
     }
     if (warp == kTMmaWarp) {
@@ -259,121 +255,112 @@ gt_kernel(const TileArgs a) {
 
     const int ntiles = a.B * a.L;
     const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int G = my_tiles * NCH;                           // chunks this CTA processes; chunk g lives in A stage g % 6
+    const int G = my_tiles * NCH;                           // chunks this CTA processes
     const int db = (int)gridDim.x / a.L, djt = (int)gridDim.x - db * a.L;
 
-    if (warp == kTMmaWarp) {
-        // ================= MMA issuer =================
-        // per chunk: 4 x (A_hi x [W_hi; W_lo], N = 64; A_lo x W_hi, N = 32), commit -> a_empty[stage]; per tile: commit ->
-        // t_full.  tools/mma_loop_bench.cu: this thread issues at the tensor pipe's pace (192 clk per chunk) as long as
-        // nothing else sits between the MMAs; a completed mbarrier.try_wait costs 34 clk there, a shared-memory load
-        // (any flavour) 135 clk -- so the hand-off is an mbarrier, and the readiness of the NEXT chunk is polled in
-        // the middle of the current chunk's MMAs, where the tensor pipe still has queued work.
-        if (elect_one()) {
-            constexpr uint32_t IDESC1 = idesc_tf32(kBM, 2 * kTNT);
-            constexpr uint32_t IDESC2 = idesc_tf32(kBM, kTNT);
-            const uint64_t desc0 = smem_desc_sw128(smem_u32(B_s));
-            const uint32_t desc_hi = (uint32_t)(desc0 >> 32), desc_lo0 = (uint32_t)desc0;
-            const uint32_t bar_full = smem_u32(a_full);
-            int st = 0; uint32_t sph = 0;                        // stage / phase of the current chunk
-            const bool prof = SDVAE_DBG_ON(a, 32) && blockIdx.x == 0;
-            WaitClock w_afull(prof), w_tempty(prof);
-            const long long t_begin = prof ? clock64() : 0;
-            bool ready = my_tiles > 0 && mbar_try_wait_a(bar_full, 0u);
+    if (warp >= kTFirstLoadWarp) {
+        if (TW::kRealloc) reg_dec<TW::kRegsLoad>();
+        if (warp == kTMmaWarp) {
+            // ================= MMA issuer: one wait + 24 MMAs + one commit per stage of three chunks =================
+            if (elect_one()) {
+                constexpr uint32_t IDESC1 = idesc_tf32(kBM, 2 * kTNT);
+                constexpr uint32_t IDESC2 = idesc_tf32(kBM, kTNT);
+                const uint64_t desc0 = smem_desc_sw128(smem_u32(B_s));
+                const uint32_t desc_hi = (uint32_t)(desc0 >> 32), desc_lo0 = (uint32_t)desc0;
+                int st = 0; uint32_t sph = 0;
+                const bool prof = SDVAE_DBG_ON(a, 32) && blockIdx.x == 0;
+                WaitClock w_afull(prof), w_tempty(prof);
+                const long long t_begin = prof ? clock64() : 0;
 #pragma unroll 1
-            for (int it = 0; it < my_tiles; ++it) {
-                const int acc = it & 1;
-                w_tempty.timed([&] { mbar_wait(t_empty + acc, ((it >> 1) & 1) ^ 1); });
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * kTNT);
+                for (int it = 0; it < my_tiles; ++it) {
+                    const int acc = it & 1;
+                    w_tempty.timed([&] { mbar_wait(t_empty + acc, ((it >> 1) & 1) ^ 1); });
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * kTNT);
 #pragma unroll 1
-                for (int ch = 0; ch < NCH; ++ch) {
-                    if (!ready) w_afull.timed([&] {
-                        int spins = 0;
-                        while (!mbar_try_wait_a(bar_full + (uint32_t)st * 8u, sph)) { if (++spins > kSpinLimit) __trap(); }
-                    });
-                    tc_fence_after();
-                    const uint32_t a_hi = tmem_base + (uint32_t)(kTAccCols + st * 64), a_lo = a_hi + 32;
-                    const uint32_t dl = desc_lo0 + (uint32_t)(ch * (kTBChunk >> 4));
-                    uint64_t* const my_empty = a_empty + st;
-                    if (++st == kTAStages) { st = 0; sph ^= 1; }
-                    const bool more = ch + 1 < NCH || it + 1 < my_tiles;
-                    if (!(SDVAE_ABL & 4) && !SDVAE_DBG_ON(a, 4)) {
+                    for (int c0 = 0; c0 < NCH; c0 += kTChunksPerStage) {
+                        w_afull.timed([&] { mbar_wait(a_full + st, sph); });
+                        tc_fence_after();
+                        if (!SDVAE_DBG_ON(a, 4))
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(dl + 2u * k);
-                            umma_tf32_ts(d_tmem, a_hi + k * 8, bd, IDESC1, (ch | k) != 0);
-                            umma_tf32_ts(d_tmem, a_lo + k * 8, bd, IDESC2, 1u);
-                            if (k == 1) ready = more && mbar_try_wait_a(bar_full + (uint32_t)st * 8u, sph);
+                        for (int c = 0; c < kTChunksPerStage; ++c) {
+                            const uint32_t a_hi = tmem_base + (uint32_t)(kTAccCols + st * kTStageCols + c * 64), a_lo = a_hi + 32;
+                            const uint32_t dl = desc_lo0 + (uint32_t)((c0 + c) * (kTBChunk >> 4));
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(dl + 2u * k);
+                                umma_tf32_ts(d_tmem, a_hi + k * 8, bd, IDESC1, (c0 | c | k) != 0);
+                                umma_tf32_ts(d_tmem, a_lo + k * 8, bd, IDESC2, 1u);
+                            }
                         }
-                    } else {
-                        ready = more && mbar_try_wait_a(bar_full + (uint32_t)st * 8u, sph);
+                        umma_commit(a_empty + st);
+                        if (c0 + kTChunksPerStage >= NCH) umma_commit(t_full + acc);
+                        if (++st == 2) { st = 0; sph ^= 1; }
                     }
-                    umma_commit(my_empty);
                 }
-                umma_commit(t_full + acc);
+                if (prof) { g_prof[0] = clock64() - t_begin; g_prof[1] = w_afull.acc; g_prof[2] = w_tempty.acc; g_prof[3] = G; }
             }
-            if (prof) { g_prof[0] = clock64() - t_begin; g_prof[1] = w_afull.acc; g_prof[2] = w_tempty.acc; g_prof[3] = G; }
-        }
-        __syncwarp();
-    } else if (warp >= kTFirstLoadWarp) {
-        // ================= loaders: warp lw owns tile stage lw, one whole tile per pass =================
-        const int lw = warp - kTFirstLoadWarp;
-        {
-            const int q = lane & 7, rsub = lane >> 3;
-            // odd positions: high half first (the parity of staged row e = 32j + 4t + rsub is that of rsub)
-            const uint32_t row_off = (uint32_t)rsub * 128u + (((uint32_t)q * 16u) ^ ((uint32_t)(rsub & 1) << 6));
-            const int n_cell16 = (CELL_BYTES + a.ecap * 2) >> 4;       // cell words and ext are contiguous in the stage
-            constexpr int PV = kTMaxRcap / 32;
-            long long t0 = (long long)blockIdx.x + (long long)lw * gridDim.x;
-            int b = (int)(t0 / a.L), jt = (int)(t0 - (long long)b * a.L);
-            int ts = lw % NTS; uint32_t tph = (uint32_t)((lw / NTS) & 1);                       // stage / phase of tile `it` (NTS may be 2: the third loader then alternates)
-            const bool prof = SDVAE_DBG_ON(a, 32) && blockIdx.x == 0 && lw == 0;
-            WaitClock w_tempty(prof), w_copy(prof);
-            const long long t_begin = prof ? clock64() : 0;
+            __syncwarp();
+        } else {
+            // ================= loaders: warp lw owns tile stage lw, one whole tile per pass =================
+            const int lw = warp - kTFirstLoadWarp;
+            if (lw < NTS) {
+                const int q = lane & 7, rsub = lane >> 3;
+                uint8_t* stage = T_s + (size_t)lw * STAGE_BYTES;
+                const uint32_t dst_rows = smem_u32(stage) + (uint32_t)rsub * 128u + (((uint32_t)q * 16u) ^ ((uint32_t)(rsub & 1) << 6));   // odd positions: high half first
+                const uint32_t dst_cell = smem_u32(stage) + (uint32_t)ROWS_BYTES;
+                const int n_cell16 = (CELL_BYTES + a.ecap * 2) >> 4;       // cell words and ext are contiguous in the stage
+                constexpr int PV = kTMaxRcap / 32;
+                long long t0 = (long long)blockIdx.x + (long long)lw * gridDim.x;
+                int b = (int)(t0 / a.L), jt = (int)(t0 - (long long)b * a.L);
+                uint32_t tph = 0;
+                const bool prof = SDVAE_DBG_ON(a, 32) && blockIdx.x == 0 && lw == 0;
+                WaitClock w_tempty(prof), w_copy(prof);
+                const long long t_begin = prof ? clock64() : 0;
 #pragma unroll 1
-            for (int it = lw; it < my_tiles; it += kTMaxStages) {
-                PlanRegs<PV> now;
-                plan_fetch(now, a.plan_cnt, a.plan_src, jt, 1, 0, a.rcap, rsub);
-                const float* base = a.in + (size_t)b * a.in_rows * 32 + 4 * q;
-                const char* cell_g = reinterpret_cast<const char*>(a.plan_cell + (size_t)jt * S * 128);
-                const char* ext_g = RAGGED ? reinterpret_cast<const char*>(a.plan_ext + (size_t)jt * a.ecap) : nullptr;
-                const uint32_t stage_a = smem_u32(T_s) + (uint32_t)ts * (uint32_t)STAGE_BYTES;
-                const uint32_t dst_rows = stage_a + row_off, dst_cell = stage_a + (uint32_t)ROWS_BYTES;
-                w_tempty.timed([&] { mbar_wait_relaxed(tile_empty + ts, tph ^ 1); });
-                if (!(SDVAE_ABL & 1) && !SDVAE_DBG_ON(a, 1)) {
-                    const char* gb = reinterpret_cast<const char*>(base);
+                for (int it = lw; it < my_tiles; it += NTS) {
+                    PlanRegs<PV> now;
+                    plan_fetch(now, a.plan_cnt, a.plan_src, jt, 1, 0, a.rcap, rsub);
+                    const float* base = a.in + (size_t)b * a.in_rows * 32 + 4 * q;
+                    const char* cell_g = reinterpret_cast<const char*>(a.plan_cell + (size_t)jt * S * 128);
+                    const char* ext_g = RAGGED ? reinterpret_cast<const char*>(a.plan_ext + (size_t)jt * a.ecap) : nullptr;
+                    w_tempty.timed([&] { mbar_wait_relaxed(tile_empty + lw, tph ^ 1); });
+                    if (!SDVAE_DBG_ON(a, 1))
+                    {   // rows: staged row e = 32*j + 4*t + rsub, piece q (no swizzle: the splitter reads are conflict-free by construction)
+                        const char* gb = reinterpret_cast<const char*>(base);
 #pragma unroll
-                    for (int j = 0; j < PV; ++j) {
-                        if (32 * j < now.n) {
-                            const uint32_t w[4] = {now.w[j].x, now.w[j].y, now.w[j].z, now.w[j].w};
+                        for (int j = 0; j < PV; ++j) {
+                            if (32 * j < now.n) {
+                                const uint32_t w[4] = {now.w[j].x, now.w[j].y, now.w[j].z, now.w[j].w};
 #pragma unroll
-                            for (int t = 0; t < 8; ++t) {
-                                const uint32_t row = (t & 1) ? (w[t >> 1] >> 16) : (w[t >> 1] & 0xffffu);
-                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n"
-                                             ::"r"(dst_rows + (uint32_t)(32 * j + 4 * t) * 128u), "l"(gb + (size_t)row * 128u));
+                                for (int t = 0; t < 8; ++t) {
+                                    const uint32_t row = (t & 1) ? (w[t >> 1] >> 16) : (w[t >> 1] & 0xffffu);
+                                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n"
+                                                 ::"r"(dst_rows + (uint32_t)(32 * j + 4 * t) * 128u), "l"(gb + (size_t)row * 128u));
+                                }
                             }
                         }
                     }
-                }
 #pragma unroll 1
-                for (int i = lane; i < n_cell16; i += 32) {
-                    const int off = i * 16;
-                    const char* src = (!RAGGED || off < CELL_BYTES) ? cell_g + off : ext_g + (off - CELL_BYTES);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst_cell + (uint32_t)off), "l"(src));
+                    for (int i = lane; i < n_cell16; i += 32) {
+                        const int off = i * 16;
+                        const char* src = (!RAGGED || off < CELL_BYTES) ? cell_g + off : ext_g + (off - CELL_BYTES);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst_cell + (uint32_t)off), "l"(src));
+                    }
+                    cp_async_commit();
+                    w_copy.timed([&] { cp_async_wait<0>(); });
+                    warp_arrive(tile_full + lw, lane);
+                    tph ^= 1;
+                    for (int k = 0; k < NTS; ++k) {
+                        b += db; jt += djt;
+                        if (jt >= a.L) { jt -= a.L; ++b; }
+                    }
                 }
-                cp_async_commit();
-                w_copy.timed([&] { cp_async_wait<0>(); });
-                warp_arrive(tile_full + ts, lane);
-                for (int k = 0; k < kTMaxStages; ++k) {                 // advance kTMaxStages tiles of the CTA's schedule
-                    b += db; jt += djt;
-                    if (jt >= a.L) { jt -= a.L; ++b; }
-                    if (++ts == NTS) { ts = 0; tph ^= 1; }
-                }
+                if (prof && lane == 0) { g_prof[8] = clock64() - t_begin; g_prof[9] = w_tempty.acc; g_prof[10] = w_copy.acc; }
             }
-            if (prof && lane == 0) { g_prof[8] = clock64() - t_begin; g_prof[9] = w_tempty.acc; g_prof[10] = w_copy.acc; }
         }
     } else if (warp < kTFirstSplitWarp) {
-        // ================= epilogue: accumulator halves -> bias / ELU / ELU'-gate -> staged rows -> global =====
+        if (TW::kRealloc) reg_dec<TW::kRegsEpilogue>();
+        // ================= epilogue (as gc_umma_kernel's forward epilogue, rows staged for coalesced stores) ======
         const int q4 = warp & 3;
         const int EPI = a.epi;
         const int ldo = a.ldo;
@@ -400,7 +387,6 @@ gt_kernel(const TileArgs a) {
                     tc_fence_before();
                     warp_arrive(t_empty + acc, lane);
                 }
-                if (SDVAE_ABL & 8) { if (v[0] + d2[1] == 12345.678f) a.out[0] = 1.f; continue; }
 #pragma unroll
                 for (int j = 0; j < 16; j += 2) {
                     const float2 t = add2(make_float2(v[j], v[j + 1]), make_float2(d2[j], d2[j + 1]));
@@ -437,7 +423,6 @@ gt_kernel(const TileArgs a) {
             }
             __syncwarp();
             const int piece = lane & 7;
-            if (!(SDVAE_ABL & 8))
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int lr2 = q4 * 32 + 4 * k + (lane >> 3);
@@ -452,13 +437,14 @@ gt_kernel(const TileArgs a) {
         }
         if (prof && lane == 0) { g_prof[16] = clock64() - t_begin; g_prof[17] = w_tfull.acc; }
     } else {
+        if (TW::kRealloc) reg_inc<TW::kRegsSplit>();
         // ================= splitters =================
         // set k takes the chunks g = k (mod 4) of the CTA's chunk sequence (tile iteration, slot); its four warps
         // own the four TMEM lane quarters.  Thread (l4 = lane >> 2, qq = lane & 3) serves the tile rows
-        // 32*q4 + 16*gg + 8*h + l4 (gg, h in {0, 1}): for each it reads the two 16-byte pieces qq and qq + 4 of the
-        // staged row(s) of the cell (the plan word holds the byte offset of the row's low half), splits hi / lo into
-        // registers -- all of that BEFORE the TMEM stage is known to be free, so that only the two TMEM stores and
-        // their completion sit between the MMAs that free a stage and the MMAs that consume it again.
+        // 32*q4 + 16*g + 8*h + l4 (g, h in {0, 1}): for each it reads the two 16-byte pieces qq and qq + 4 of the
+        // staged row(s) of the cell (the plan word holds the byte offset of the row's low half).
+        // The kernel is bound by the ALU pipe / instruction issue (profiles/r02_gt_*): everything per unit that is
+        // not a row read, a split or a TMEM store is kept out of this loop.
         const int set = (warp - kTFirstSplitWarp) >> 2;
         const int q4 = warp & 3;
         const int l4 = lane >> 2, qq = lane & 3;
@@ -468,72 +454,65 @@ gt_kernel(const TileArgs a) {
         const uint32_t ext_off = (uint32_t)(ROWS_BYTES + CELL_BYTES);
         const uint32_t t_lane = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)kTAccCols;
         const uint32_t bar_tile_full = smem_u32(tile_full), bar_tile_empty = smem_u32(tile_empty);
-        const uint32_t bar_a_empty = smem_u32(a_empty), bar_a_full = smem_u32(a_full);
+        const uint32_t bar_a_full = smem_u32(a_full), bar_a_empty = smem_u32(a_empty);
         int ts = 0; uint32_t tph = 0;
         uint32_t stage_a = T_a;
-#ifdef SDVAE_PROF
-        const bool prof = blockIdx.x == 0 && warp == kTFirstSplitWarp + SDVAE_PROF - 1;   // -DSDVAE_PROF=k: splitter warp k-1 of CTA 0, 32-bit clocks
-        unsigned seg[6] = {0, 0, 0, 0, 0, 0};
-        const unsigned t_begin = clock();
-        unsigned t_prev = t_begin;
-#define SDVAE_SEG(i) do { const unsigned t_now_ = clock(); seg[i] += t_now_ - t_prev; t_prev = t_now_; } while (0)
-#else
         const bool prof = SDVAE_DBG_ON(a, 32) && blockIdx.x == 0 && warp == kTFirstSplitWarp;
         long long seg[6] = {0, 0, 0, 0, 0, 0};
         const long long t_begin = prof ? clock64() : 0;
         long long t_prev = t_begin;
 #define SDVAE_SEG(i) do { if (prof) { const long long t_now_ = clock64(); seg[i] += t_now_ - t_prev; t_prev = t_now_; } } while (0)
-#endif
-        int first = set;                                         // first slot of this set in the current tile
-        int g0 = 0;                                              // chunk number of slot 0 of the current tile
-        int st = set; uint32_t sph = 0;                          // A stage / phase of this set's current chunk (g % 6, (g / 6) & 1)
-        // The splitters are latency-bound (36 units per tile over 16 warps, ~1700 clk each), and a third of a unit is
-        // spent waiting for its two TMEM stores (~155 clk each per warp, tcgen05.wait::st another ~300,
-        // tools/sttm_bench.cu): the completion of unit u's stores is therefore awaited, and the MMA thread told, only
-        // after unit u+1 has been gathered and split.
-        uint32_t pend_bar = 0u;                                  // a_full barrier owed for the previous unit (0: none)
+        int first = set;                                         // first slot of this set in the current tile: chunk g = it*NCH + ch belongs to set g % NSETS
 #pragma unroll 1
-        for (int it = 0; it < my_tiles; ++it, g0 += NCH) {
+        for (int it = 0; it < my_tiles; ++it) {
             mbar_wait_a<64>(bar_tile_full + (uint32_t)ts * 8u, tph);
             SDVAE_SEG(0);
             const uint32_t baseX = stage_a + offX;
 #pragma unroll 1
             for (int ch = first; ch < NCH; ch += kTSplitSets) {
-                const int g = g0 + ch;
+                const int sg = it * (NCH / kTChunksPerStage) + ((ch * 43) >> 7);     // stage round of the chunk (ch / 3)
+                const int sub = ch - 3 * ((ch * 43) >> 7);
+                const int st = sg & 1;
+                const uint32_t sph = (uint32_t)((sg >> 1) & 1);
                 const uint4 cw = lds128u(stage_a + cell_off + (uint32_t)ch * 512u);
                 const uint32_t words[4] = {cw.x, cw.y, cw.z, cw.w};
-                float r[2][32];
-                if (SDVAE_ABL & 2) {
+                const uint32_t t_a = t_lane + (uint32_t)(st * kTStageCols + sub * 64);
+                // gather (cell words -> staged rows, in-order cell sums) BEFORE the TMEM stage is known to be free; the
+                // hi/lo split and the TMEM stores follow the wait (holding the 64 split values across the wait instead
+                // costs more registers than the kernel has)
+                float4 X[4], Y[4];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { r[0][j] = __uint_as_float(words[j & 3] + j); r[1][j] = __uint_as_float(words[(j + 1) & 3] ^ j); }
-                } else
-#pragma unroll
-                for (int gg = 0; gg < 2; ++gg) {
-                    float4 X[2], Y[2];
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const uint32_t w = words[gg * 2 + h];
-                        const uint32_t ax = baseX + (w & 0xffffu);
-                        X[h] = lds128(ax);
-                        Y[h] = lds128(ax ^ 64u);
-                        if (RAGGED) {
-                            const int cnt = (int)((w >> 16) & 0x1fu);
-                            if (cnt == 0) { X[h] = make_float4(0.f, 0.f, 0.f, 0.f); Y[h] = X[h]; }
-                            uint32_t ea = stage_a + ext_off + ((w >> 21) << 1);
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t w = words[k];
+                    const uint32_t ax = baseX + (w & 0xffffu);
+                    X[k] = lds128(ax);
+                    Y[k] = lds128(ax ^ 64u);
+                    if (RAGGED) {
+                        const int cnt = (int)((w >> 16) & 0x1fu);
+                        if (cnt == 0) { X[k] = make_float4(0.f, 0.f, 0.f, 0.f); Y[k] = X[k]; }
+                        uint32_t ea = stage_a + ext_off + ((w >> 21) << 1);
 #pragma unroll 1
-                            for (int e = 1; e < cnt; ++e, ea += 2) {   // in-order sum: deterministic scatter-add
-                                const uint32_t ax2 = baseX + lds16u(ea);
-                                const float4 X2 = lds128(ax2);
-                                const float4 Y2 = lds128(ax2 ^ 64u);
-                                X[h].x += X2.x; X[h].y += X2.y; X[h].z += X2.z; X[h].w += X2.w;
-                                Y[h].x += Y2.x; Y[h].y += Y2.y; Y[h].z += Y2.z; Y[h].w += Y2.w;
-                            }
+                        for (int e = 1; e < cnt; ++e, ea += 2) {   // in-order sum: deterministic scatter-add
+                            const uint32_t ax2 = baseX + lds16u(ea);
+                            const float4 X2 = lds128(ax2);
+                            const float4 Y2 = lds128(ax2 ^ 64u);
+                            X[k].x += X2.x; X[k].y += X2.y; X[k].z += X2.z; X[k].w += X2.w;
+                            Y[k].x += Y2.x; Y[k].y += Y2.y; Y[k].z += Y2.z; Y[k].w += Y2.w;
                         }
                     }
+                }
+                SDVAE_SEG(1);
+                mbar_wait_a<32>(bar_a_empty + (uint32_t)st * 8u, sph ^ 1);   // the MMAs of the stage's previous round are done
+                __syncwarp();                                    // the wait (and the cell loops above) diverge; tcgen05.st is warp-collective
+                tc_fence_after();
+                SDVAE_SEG(3);
+#pragma unroll
+                for (int gg = 0; gg < 2; ++gg) {
+                    float r[32];
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const float4 P = X[h];                   // piece qq     : channels 4qq .. 4qq+3   -> n = 0, 1
-                        const float4 Q = Y[h];                   // piece qq + 4 : channels 16+4qq ..      -> n = 2, 3
+                        const float4 P = X[gg * 2 + h];          // piece qq     : channels 4qq .. 4qq+3   -> n = 0, 1
+                        const float4 Q = Y[gg * 2 + h];          // piece qq + 4 : channels 16+4qq ..      -> n = 2, 3
                         const float v8[8] = {P.x, P.y, P.z, P.w, Q.x, Q.y, Q.z, Q.w};
 #pragma unroll
                         for (int n = 0; n < 4; ++n) {
@@ -541,34 +520,16 @@ gt_kernel(const TileArgs a) {
                             const float2 hi = make_float2(__uint_as_float(__float_as_uint(v2.x) & 0xffffe000u),
                                                           __uint_as_float(__float_as_uint(v2.y) & 0xffffe000u));
                             const float2 lo = sub2(v2, hi);
-                            r[gg][4 * n + 2 * h] = hi.x; r[gg][4 * n + 2 * h + 1] = hi.y;
-                            r[gg][16 + 4 * n + 2 * h] = lo.x; r[gg][16 + 4 * n + 2 * h + 1] = lo.y;
+                            r[4 * n + 2 * h] = hi.x; r[4 * n + 2 * h + 1] = hi.y;
+                            r[16 + 4 * n + 2 * h] = lo.x; r[16 + 4 * n + 2 * h + 1] = lo.y;
                         }
                     }
+                    if (!SDVAE_DBG_ON(a, 16)) tmem_st_16x256b_x8(t_a + ((uint32_t)(16 * gg) << 16), r);
                 }
-                SDVAE_SEG(1);
-                if (pend_bar) {                                  // the previous unit's stores have long landed
-                    tmem_st_wait();
-                    tc_fence_before();
-                    if (lane == 0) mbar_arrive_a(pend_bar);
-                }
-                SDVAE_SEG(2);
-                const bool tl = SDVAE_DBG_ON(a, 64) && blockIdx.x == 0 && q4 == 0 && lane == 0 && g >= 400 && g < 416;
-                if (tl) g_tl[128 + (g - 400) * 4 + 0] = clock64();
-                mbar_wait_a<32>(bar_a_empty + (uint32_t)st * 8u, sph ^ 1);   // the MMAs of the stage's previous chunk are done
-                if (tl) g_tl[128 + (g - 400) * 4 + 1] = clock64();
-                __syncwarp();                                    // the cell loops and the wait diverge; tcgen05.st is warp-collective
-                tc_fence_after();
-                SDVAE_SEG(3);
-                const uint32_t t_a = t_lane + (uint32_t)(st * 64);
-                if (!(SDVAE_ABL & 16) && !SDVAE_DBG_ON(a, 16)) {
-                    tmem_st_16x256b_x8(t_a, r[0]);
-                    tmem_st_16x256b_x8(t_a + (16u << 16), r[1]);
-                }
+                tmem_st_wait();
                 SDVAE_SEG(4);
-                pend_bar = bar_a_full + (uint32_t)st * 8u;
-                st += kTSplitSets;                               // next chunk of this set: g + 4
-                if (st >= kTAStages) { st -= kTAStages; sph ^= 1; }
+                tc_fence_before();
+                if (lane == 0) mbar_arrive_a(bar_a_full + (uint32_t)st * 8u);     // (wait::st is warp-collective: every lane is done)
                 SDVAE_SEG(5);
             }
             if (lane == 0) mbar_arrive_a(bar_tile_empty + (uint32_t)ts * 8u);     // this warp is done with the tile stage
@@ -576,19 +537,10 @@ gt_kernel(const TileArgs a) {
             if (++ts == NTS) { ts = 0; tph ^= 1; stage_a = T_a; }
             first -= NCH % kTSplitSets;
             if (first < 0) first += kTSplitSets;
-            SDVAE_SEG(5);
+            SDVAE_SEG(2);
         }
 #undef SDVAE_SEG
-        if (pend_bar) {
-            tmem_st_wait();
-            tc_fence_before();
-            if (lane == 0) mbar_arrive_a(pend_bar);
-        }
-#ifdef SDVAE_PROF
-        if (prof && lane == 0) { g_prof[24] = clock() - t_begin; for (int i = 0; i < 6; ++i) g_prof[25 + i] = seg[i]; g_prof[3] = G; }
-#else
         if (prof && lane == 0) { g_prof[24] = clock64() - t_begin; for (int i = 0; i < 6; ++i) g_prof[25 + i] = seg[i]; }
-#endif
     }
 
     tc_fence_before();

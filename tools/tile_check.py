@@ -37,6 +37,8 @@ def print_timeline(tag):
         return
     import ctypes
     buf = (ctypes.c_longlong * 256)()
+    if not hasattr(cabi.load(), 'sdvae_debug_read_timeline'):
+        return
     cabi.load().sdvae_debug_read_timeline(buf)
     t = list(buf)
     t0 = min(x for x in t if x > 0)
@@ -66,7 +68,7 @@ def main():
     ap.add_argument('--iters', type=int, default=6)
     ap.add_argument('--skip-check', action='store_true')
     ap.add_argument('--skip-old', action='store_true')
-    ap.add_argument('--only', default='fwd,dx')
+    ap.add_argument('--only', default='fwd,dx,dw')
     a = ap.parse_args()
     tabs = fx.craniofacial_tables().renumbered(128)[0]
     S = 9
@@ -144,6 +146,14 @@ def main():
             if not a.skip_old:
                 po = tab.plan_bwd()
                 rep('dx  per-slot gather (gc_umma)', ev_time(lambda i: cabi.spiralconv_bwd_x_tc(xs[i], po, wimg_to, None, ys[i], B, V, V, S, 32, 32), a.iters, nbuf))
+        if 'dw' in a.only:
+            po = tab.plan_fwd()
+            sp = tb.StagedTilePlan.build(idx.numpy(), DEV)
+            ws = torch.empty(cabi.spiralconv_bwd_w_workspace(B * V, S, 32, 32) // 4 + 4, device=DEV)
+            dW = torch.empty(32, S * 32, device=DEV); db = torch.empty(32, device=DEV)
+            rep('dW  per-slot gather (bw_umma)', ev_time(lambda i: cabi.spiralconv_bwd_w_tc(xs[i], po, ys[(i + 1) % nbuf], dW, db, ws, B, V, V, S, 32, 32), a.iters, nbuf))
+            if cabi.tc_bwd_w_staged_supported(S, 32, 32, sp.rcap):
+                rep('dW  tile-staged draft (r01)', ev_time(lambda i: cabi.spiralconv_bwd_w_tc_staged(xs[i], sp, ys[(i + 1) % nbuf], dW, db, ws, B, V, V, S, 32, 32), a.iters, nbuf))
         del xs, ys
 
 
