@@ -56,10 +56,6 @@ _SIGNATURES = {
     "sdvae_tile_supported": (C.c_int, [C.c_int] * 5),
     "sdvae_spiralconv_fwd_tile": (C.c_int, [_c_fp] * 4 + [C.c_int] + [_c_fp] * 3 + [C.c_int] * 7 + [_c_fp]),
     "sdvae_spiralconv_bwd_x_tile": (C.c_int, [_c_fp] * 5 + [C.c_int] * 2 + [_c_fp] * 3 + [C.c_int] * 6 + [_c_fp]),
-    "sdvae_tc_staged_supported": (C.c_int, [C.c_int] * 4),
-    "sdvae_spiralconv_fwd_tc_staged": (C.c_int, [_c_fp] * 3 + [_c_fp, C.c_int] + [_c_fp] * 3 + [C.c_int] * 7 + [_c_fp]),
-    "sdvae_tc_bwd_w_staged_supported": (C.c_int, [C.c_int] * 4),
-    "sdvae_spiralconv_bwd_w_tc_staged": (C.c_int, [_c_fp] * 4 + [C.c_int] + [_c_fp] * 4 + [C.c_int] * 6 + [_c_fp]),
     "sdvae_narrow_in_supported": (C.c_int, [C.c_int] * 4),
     "sdvae_narrow_in_bwd_w_workspace": (C.c_size_t, [C.c_int, C.c_int]),
     "sdvae_narrow_in_fwd": (C.c_int, [_c_fp] * 5 + [C.c_int] * 7 + [_c_fp]),
@@ -117,7 +113,7 @@ _KERNELS_PER_CALL = {
     "spiralconv_fwd": 1, "weight_transpose": 1, "spiralconv_bwd_x": 1, "spiralconv_bwd_w": 2,
     "tc_pack_weights": 1, "spiralconv_fwd_tc": 1, "spiralconv_bwd_x_tc": 1,
     "spiralconv_bwd_w_tc": 2, "dense_tc": 1, "slot_pack": 1, "slot_weight": 1, "slot_grad": 1,
-    "dense_fwd": 1, "transpose2d": 1, "spiralconv_fwd_tc_staged": 1, "spiralconv_fwd_tile": 1, "spiralconv_bwd_x_tile": 1, "spiralconv_bwd_w_tc_staged": 2, "narrow_out_bwd": 2, "narrow_out_fwd": 1, "narrow_in_fwd": 1, "narrow_in_bwd_w": 2, "pool_ell_fwd": 1, "pool_ell_fwd_staged": 1, "csr_rowsum": 1, "elu_fwd": 1,
+    "dense_fwd": 1, "transpose2d": 1, "spiralconv_fwd_tile": 1, "spiralconv_bwd_x_tile": 1, "narrow_out_bwd": 2, "narrow_out_fwd": 1, "narrow_in_fwd": 1, "narrow_in_bwd_w": 2, "pool_ell_fwd": 1, "pool_ell_fwd_staged": 1, "csr_rowsum": 1, "elu_fwd": 1,
     "elu_bwd": 1, "reparam_fwd": 1, "reparam_bwd": 1, "axpy3": 1, "swap": 1, "mse_lap_fwd": 3,
     "mse_lap_bwd": 1, "kl_fwd_bwd": 2, "lc_fwd_bwd": 3, "total_loss": 1, "adam_tick": 1,
     "adam_step": 1,
@@ -403,40 +399,6 @@ def spiralconv_bwd_x_tile(dpre, plan, wimg_t, gate, dx, B, Vrows, Vdst, S, Cout,
     if rc:
         _err(rc, "spiralconv_bwd_x_tile")
     add_launches(_KERNELS_PER_CALL["spiralconv_bwd_x_tile"])
-
-
-def tc_staged_supported(S: int, Cin: int, Cout: int, rcap: int) -> bool:
-    return bool(load().sdvae_tc_staged_supported(int(S), int(Cin), int(Cout), int(rcap)))
-
-
-def spiralconv_fwd_tc_staged(x, plan, wimg, bias, y, B, Vin, Vout, S, Cin, Cout, act):
-    """EXPERIMENTAL (never run on a GPU in round 1): tcgen05 forward with tile-local staging;
-    ``plan``: tables.StagedTilePlan."""
-    rc = load().sdvae_spiralconv_fwd_tc_staged(_f(x, "x"), _i(plan.cnt, "plan_cnt"), _i(plan.src, "plan_src"),
-                                               _i(plan.loc, "plan_loc"), plan.rcap, _f(wimg, "wimg"),
-                                               _fo(bias, "bias"), _f(y, "y"), B, Vin, Vout, S, Cin, Cout, act,
-                                               _stream())
-    if rc:
-        _err(rc, "spiralconv_fwd_tc_staged")
-    add_launches(_KERNELS_PER_CALL["spiralconv_fwd_tc_staged"])
-
-
-def tc_bwd_w_staged_supported(S: int, Cin: int, Cout: int, rcap: int) -> bool:
-    return bool(load().sdvae_tc_bwd_w_staged_supported(int(S), int(Cin), int(Cout), int(rcap)))
-
-
-def spiralconv_bwd_w_tc_staged(x, plan, dpre, dW, db, ws, B, Vin, Vout, S, Cin, Cout):
-    """EXPERIMENTAL (never run on a GPU in round 1): tcgen05 weight gradient with tile-local staging;
-    ``plan``: tables.StagedTilePlan; ``ws`` as for ``spiralconv_bwd_w_tc``."""
-    need = spiralconv_bwd_w_workspace(B * max(Vin, Vout), S, Cin, Cout)
-    if ws.numel() * 4 < need:
-        raise RuntimeError("sdvae_b200: bwd_w workspace too small (%d < %d bytes)" % (ws.numel() * 4, need))
-    rc = load().sdvae_spiralconv_bwd_w_tc_staged(_f(x, "x"), _i(plan.cnt, "plan_cnt"), _i(plan.src, "plan_src"),
-                                                 _i(plan.loc, "plan_loc"), plan.rcap, _f(dpre, "dpre"), _f(dW, "dW"),
-                                                 _fo(db, "db"), _f(ws, "ws"), B, Vin, Vout, S, Cin, Cout, _stream())
-    if rc:
-        _err(rc, "spiralconv_bwd_w_tc_staged")
-    add_launches(_KERNELS_PER_CALL["spiralconv_bwd_w_tc_staged"])
 
 
 def narrow_in_supported(Vin: int, S: int, Cin: int, Cout: int) -> bool:

@@ -7,8 +7,6 @@
 #include "spiral_conv.cuh"
 #include "spiral_conv_umma.cuh"
 #include "spiral_conv_umma_bw.cuh"
-#include "spiral_conv_umma_staged.cuh"
-#include "spiral_conv_umma_bw_staged.cuh"
 #include "spiral_conv_tile.cuh"
 #include "slot_pack.cuh"
 #include "pool_misc.cuh"
@@ -138,23 +136,6 @@ static int dispatch_umma(umma::UmmaArgs& ua, int KS, cudaStream_t st) {
     if (KS == 64 && NT == 32) return launch_umma<64, 32, UNIFORM>(ua, st);
     if (KS == 64 && NT == 64) return launch_umma<64, 64, UNIFORM>(ua, st);
     return set_error(SDVAE_ERR_UNSUPPORTED, "tcgen05 path: unsupported layer shape");
-}
-
-template <int NT>
-static int launch_umma_staged(umma::StagedArgs& sa, cudaStream_t st) {
-    using Cfg = umma::StagedCfg<NT>;
-    auto kern = umma::gc_umma_staged_kernel<NT>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_done = true;
-    }
-    sa.nts = Cfg::tile_stages(sa.S, sa.rcap);
-    sa.ostage = Cfg::out_stage() ? 1 : 0;
-    const long long ntiles = (long long)sa.B * sa.L;
-    const int grid = ntiles < kNumSMs ? (int)ntiles : kNumSMs;
-    kern<<<grid, umma::kThreads, Cfg::smem_bytes(sa.S, sa.rcap, sa.nts), st>>>(sa);
-    return check_launch("gc_umma_staged_kernel");
 }
 
 template <bool RAGGED, int NSETS>
@@ -407,48 +388,6 @@ int sdvae_spiralconv_fwd_tc(const float* x, const int32_t* plan_cnt, const int32
                    Cout, ldy, epi, true, (cudaStream_t)stream, "spiralconv_fwd_tc: unsupported layer shape");
 }
 
-/* ---- EXPERIMENTAL: tcgen05 forward with tile-local staging (spiral_conv_umma_staged.cuh) ------------
- * Compiled but never run on a GPU in round 1; not dispatched by the engine / autograd functions / bench. */
-int sdvae_tc_staged_supported(int S, int Cin, int Cout, int rcap) {
-    if (Cin != 32 || S < 1 || Cout < 1 || tc_tile_n(Cout) == 0) return 0;
-    if (rcap < 32 || rcap > umma::kStagedMaxRcap || rcap % 32 != 0) return 0;
-    const int NT = tc_tile_n(Cout);
-    const int nts = NT == 16 ? umma::StagedCfg<16>::tile_stages(S, rcap)
-                  : NT == 32 ? umma::StagedCfg<32>::tile_stages(S, rcap) : umma::StagedCfg<64>::tile_stages(S, rcap);
-    return nts >= 2 ? 1 : 0;
-}
-
-int sdvae_spiralconv_fwd_tc_staged(const float* x, const int32_t* plan_cnt, const int32_t* plan_src,
-                                   const int32_t* plan_loc, int rcap, const float* wimg, const float* bias,
-                                   float* y, int B, int Vin, int Vout, int S, int Cin, int Cout, int act,
-                                   sdvae_stream_t stream) {
-    SDVAE_REQUIRE(x && plan_cnt && plan_src && plan_loc && wimg && y, "spiralconv_fwd_tc_staged: null pointer");
-    SDVAE_REQUIRE(B >= 0 && Vin > 0 && Vout > 0, "spiralconv_fwd_tc_staged: bad shape");
-    SDVAE_REQUIRE((long long)B * Vin < 2147483647LL, "spiralconv_fwd_tc_staged: B*rows exceeds int32");
-    SDVAE_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wimg) |
-                    reinterpret_cast<uintptr_t>(plan_src)) & 15) == 0,
-                  "spiralconv_fwd_tc_staged: x, wimg and plan_src must be 16-byte aligned");
-    if (!sdvae_tc_staged_supported(S, Cin, Cout, rcap))
-        return set_error(SDVAE_ERR_UNSUPPORTED, "spiralconv_fwd_tc_staged: unsupported layer shape");
-    const int NT = tc_tile_n(Cout);
-    if (NT >= 32) {
-        const uintptr_t al = reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(bias);
-        if (Cout != NT || (al & 15) != 0)
-            return set_error(SDVAE_ERR_UNSUPPORTED, "spiralconv_fwd_tc_staged: unsupported layer shape");
-    }
-    if (B == 0) return SDVAE_OK;
-    umma::StagedArgs sa{};
-    sa.in = x; sa.plan_cnt = plan_cnt; sa.plan_src = plan_src; sa.plan_loc = plan_loc;
-    sa.wimg = wimg; sa.bias = bias; sa.out = y;
-    sa.B = B; sa.in_rows = Vin; sa.out_rows = Vout; sa.L = sdvae_tc_plan_tiles(Vout);
-    sa.S = S; sa.rcap = rcap; sa.n_real = Cout; sa.ldo = Cout;
-    sa.epi = act == SDVAE_ACT_ELU ? EPI_BIAS_ELU : EPI_BIAS;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (NT == 16) return launch_umma_staged<16>(sa, st);
-    if (NT == 32) return launch_umma_staged<32>(sa, st);
-    return launch_umma_staged<64>(sa, st);
-}
-
 int sdvae_spiralconv_bwd_x_tc(const float* dpre, const int32_t* plan_cnt, const int32_t* plan_src,
                               const int32_t* plan_cell, int rcap, const float* wimg_t, const float* gate,
                               float* dx, int B, int Vrows, int Vdst, int S, int Cout, int Cin,
@@ -625,69 +564,6 @@ int sdvae_spiralconv_bwd_w_tc(const float* x, const int32_t* plan_cnt, const int
     return check_launch("split_reduce_kernel");
 }
 
-/* EXPERIMENTAL: weight gradient with tile-local staging (spiral_conv_umma_bw_staged.cuh); never run in round 1. */
-static int bw_staged_stages(int rcap) {
-    const long long budget = 226LL * 1024 - 2048 - 2 * umma::kGStage;
-    const long long st = budget / ((long long)rcap * 128);
-    return (int)(st > umma::kTileStages ? umma::kTileStages : st);
-}
-
-int sdvae_tc_bwd_w_staged_supported(int S, int Cin, int Cout, int rcap) {
-    if ((Cin != 32 && Cin != 64) || Cout < 1 || Cout > 64 || S < 1 || S > 11) return 0;
-    if (rcap < 32 || rcap > umma::kStagedMaxRcap || rcap % 32 != 0) return 0;
-    return bw_staged_stages(rcap) >= 2 ? 1 : 0;
-}
-
-int sdvae_spiralconv_bwd_w_tc_staged(const float* x, const int32_t* plan_cnt, const int32_t* plan_src,
-                                     const int32_t* plan_loc, int rcap, const float* dpre, float* dW, float* db,
-                                     void* workspace, int B, int Vin, int Vout, int S, int Cin, int Cout,
-                                     sdvae_stream_t stream) {
-    SDVAE_REQUIRE(x && plan_cnt && plan_src && plan_loc && dpre && dW && workspace, "spiralconv_bwd_w_tc_staged: null pointer");
-    SDVAE_REQUIRE(B >= 0 && Vin > 0 && Vout > 0, "spiralconv_bwd_w_tc_staged: bad shape");
-    SDVAE_REQUIRE((long long)B * Vin < 2147483647LL, "spiralconv_bwd_w_tc_staged: B*Vin exceeds int32 rows");
-    SDVAE_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(plan_src)) & 15) == 0,
-                  "spiralconv_bwd_w_tc_staged: x and plan_src must be 16-byte aligned");
-    if (!sdvae_tc_bwd_w_staged_supported(S, Cin, Cout, rcap))
-        return set_error(SDVAE_ERR_UNSUPPORTED, "spiralconv_bwd_w_tc_staged: unsupported layer shape");
-    cudaStream_t st = (cudaStream_t)stream;
-    const int K = S * Cin;
-    if (B == 0) {
-        cudaMemsetAsync(dW, 0, sizeof(float) * Cout * K, st);
-        if (db) cudaMemsetAsync(db, 0, sizeof(float) * Cout, st);
-        return check_launch("bwd_w_tc_staged memset");
-    }
-    umma::BwStagedArgs a{};
-    a.plan_cnt = plan_cnt; a.plan_src = plan_src; a.plan_loc = plan_loc;
-    a.B = B; a.in_rows = Vin; a.out_rows = Vout; a.L = sdvae_tc_plan_tiles(Vout); a.S = S; a.rcap = rcap;
-    a.nts = bw_staged_stages(rcap);
-    const long long ntiles = (long long)B * a.L;
-    const int grid = ntiles < kNumSMs ? (int)ntiles : kNumSMs;
-    float* part = static_cast<float*>(workspace);               // [grid, Cout, K]   (sdvae_spiralconv_bwd_w_workspace)
-    float* part_b = part + (size_t)grid * Cout * K;             // [grid, Cout]
-    a.flush = 2;
-    a.in_ld = Cin; a.g_ld = Cout; a.part_ld = K; a.part_cta = Cout * K; a.partb_cta = Cout;
-    cudaMemsetAsync(part, 0, sizeof(float) * (size_t)grid * (Cout * K + Cout), st);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(umma::bw_umma_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_done = true;
-    }
-    const size_t smem = 1024 + 2 * (size_t)umma::kGStage + (size_t)a.nts * rcap * 128 + 1024;
-    for (int c0 = 0; c0 < Cin; c0 += 32)
-        for (int n0 = 0; n0 < Cout; n0 += umma::kBwNT) {
-            a.in = x + c0;
-            a.g = dpre + n0;
-            a.n_real = Cout - n0 < umma::kBwNT ? Cout - n0 : umma::kBwNT;
-            a.part = part + (size_t)n0 * K + c0;
-            a.part_b = c0 == 0 ? part_b + n0 : nullptr;
-            umma::bw_umma_staged_kernel<<<grid, umma::kBwThreads, smem, st>>>(a);
-            int rc = check_launch("bw_umma_staged_kernel");
-            if (rc) return rc;
-        }
-    const long long len = (long long)Cout * K;
-    split_reduce2_kernel<<<blocks_for(len + Cout, 64), 256, 0, st>>>(part, part_b, dW, db, grid, len, Cout);
-    return check_launch("split_reduce_kernel");
-}
 
 size_t sdvae_spiralconv_bwd_w_workspace(long long M, int S, int Cin, int Cout) {
     long long rows; int nsplit;

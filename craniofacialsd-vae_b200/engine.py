@@ -73,11 +73,11 @@ class TrainEngine:
         ``region_features[k]``: vertex ids swapped for region k; ``latent_regions[k]`` = [r0, r1].
         ``use_tc``: run the wide SpiralConv contractions (C_in in {32, 64}) on the tcgen05 tensor-core
         kernels (error-compensated 3xTF32); False keeps every contraction on the fp32-FMA kernels.
-        ``renumber`` (default: env ``SDVAE_RENUMBER`` == '1', else off): EXPERIMENTAL, host side checked on CPU
-        only -- run the network on a patch-wise renumbering of the internal vertex levels
-        (``tables.renumbered_model_tables``; the batch is permuted on load, ``recon_template_order()`` undoes it):
-        what the tile-local-staging kernels need.  Losses and parameter gradients do not depend
-        on the vertex order."""
+        ``renumber`` (default: on with ``use_tc``; env ``SDVAE_RENUMBER=0`` turns it off): run the network on a
+        patch-wise renumbering of the internal vertex levels (``tables.renumbered_model_tables``; the batch is
+        permuted on load, ``recon_template_order()`` undoes it) -- what the tile-staged tcgen05 kernels
+        (csrc/spiral_conv_tile.cuh) need: a tile of 128 consecutive rows then reads ~200 distinct source rows
+        instead of ~410.  Losses and parameter gradients do not depend on the vertex order."""
         self.model = model
         self.cfg = cfg
         self.dev = next(model.parameters()).device
@@ -106,7 +106,9 @@ class TrainEngine:
         # SDVAE_DP_GRAPH=0 keeps multi-GPU steps eager.
         self.use_graph = use_graph and (self.world == 1 or os.environ.get('SDVAE_DP_GRAPH', '1') != '0')
         self.use_tc = bool(use_tc)
-        self.renumber = (os.environ.get('SDVAE_RENUMBER') == '1') if renumber is None else bool(renumber)
+        if renumber is None:
+            renumber = self.use_tc and os.environ.get('SDVAE_RENUMBER', '1') != '0'
+        self.renumber = bool(renumber)
         self._graphs: Dict[int, torch.cuda.CUDAGraph] = {}
         self.fixed_eps: Optional[torch.Tensor] = None
         self.launches_per_step = 0
@@ -266,20 +268,16 @@ class TrainEngine:
                 parts = [(0, 32), (32, 32)]
             else:
                 return
-            self.tc[(kind, name)] = dict(layer=layer, plan=plan, cin=cin, cout=cout, seq=table.seq,
-                                         parts=[(n0, nc, f(cabi.tc_wimg_floats(table.seq, ks, nc)))
-                                                for n0, nc in parts])
-            # EXPERIMENTAL switch (off unless SDVAE_STAGED_FWD=1; the kernel has never run on a GPU):
-            # forward passes with 32 input channels through the tile-local-staging kernel when a tile's distinct
-            # rows fit its stage (they do on a patch-ordered template: bench.py --renumber)
-            if kind == 'f' and ks == 32 and len(parts) == 1 and os.environ.get('SDVAE_STAGED_FWD') == '1':
-                from .tables import StagedTilePlan
-                try:
-                    sp = StagedTilePlan.build(table._np_idx, self.dev)
-                except RuntimeError:
-                    sp = None
-                if sp is not None and cabi.tc_staged_supported(table.seq, ks, n, sp.rcap):
-                    self.tc[(kind, name)]['staged'] = sp
+            e = dict(layer=layer, plan=plan, cin=cin, cout=cout, seq=table.seq, tile=None,
+                     parts=[(n0, nc, f(cabi.tc_wimg_floats(table.seq, ks, nc))) for n0, nc in parts])
+            self.tc[(kind, name)] = e
+            # 32 -> 32 layers on a patch-ordered level: tile-staged kernels (csrc/spiral_conv_tile.cuh) -- the tile's
+            # distinct rows are copied once and gathered from shared memory; their weight image carries the kernel's
+            # K permutation (flag bit 1 of the pack entry)
+            if ks == 32 and n == 32 and len(parts) == 1 and os.environ.get('SDVAE_TILE', '1') != '0':
+                tp = table.tile_fwd() if kind == 'f' else table.tile_bwd()
+                if tp is not None and cabi.tile_supported(table.seq, 32, 32, tp.rcap, tp.ecap):
+                    e['tile'] = tp
 
         for l in range(L):
             enc = m.en_layers[l].conv.layer
@@ -330,8 +328,9 @@ class TrainEngine:
             # so a device table of raw pointers stays valid for the life of the engine
             ents = []
             for (kind, _), e in self.tc.items():
+                flags = (1 if kind == 'b' else 0) | (2 if e['tile'] is not None else 0)     # sdvae_pack_entry.transposed
                 for n0, nc, wimg in e['parts']:
-                    ents.append((e['layer'].weight.data, wimg, e['seq'], e['cin'], e['cout'], kind == 'b', n0, nc))
+                    ents.append((e['layer'].weight.data, wimg, e['seq'], e['cin'], e['cout'], flags, n0, nc))
             for e in ((self.slot_en0,) if self.slot_en0 is not None else ()) + \
                      ((self.slot_out,) if self.slot_out is not None and self.narrow_out_ws is None else ()):
                 ents.append((e['Wd'], e['wimg'], 1, 32, 32, False, 0, 32))
@@ -341,9 +340,9 @@ class TrainEngine:
     # ------------------------------------------------------------------ pieces
     def _conv(self, x, table, layer, out, act, B, Vin, Cin, Cout, name=None):
         e = self.tc.get(('f', name))
-        if e is not None and e.get('staged') is not None:
-            cabi.spiralconv_fwd_tc_staged(x, e['staged'], e['parts'][0][2], layer.bias.data, out, B, Vin,
-                                          table.n_rows, table.seq, Cin, Cout, act)
+        if e is not None and e['tile'] is not None:
+            cabi.spiralconv_fwd_tile(x, e['tile'], e['parts'][0][2], layer.bias.data, out, B, Vin, table.n_rows,
+                                     table.seq, Cin, Cout, act)
             return
         if e is not None:
             for n0, nc, wimg in e['parts']:
@@ -489,7 +488,10 @@ class TrainEngine:
             cin, cout = self.cin_de[l], C[l + 1]
             self._bwd_w(self.u[l], self.full[l], self.dd[l], layer, B, V[l], cin, cout)
             e = self.tc.get(('b', 'de%d' % l))
-            if e is not None:
+            if e is not None and e['tile'] is not None:
+                cabi.spiralconv_bwd_x_tile(self.dd[l], e['tile'], e['parts'][0][2], None, self.du[l], B, V[l], V[l],
+                                           S[l], cout, cin)
+            elif e is not None:
                 for n0, nc, wimg in e['parts']:
                     full = nc == cin
                     cabi.spiralconv_bwd_x_tc(self.dd[l], e['plan'], wimg, None,
@@ -563,7 +565,10 @@ class TrainEngine:
             else:
                 self._bwd_w(x_in, self.sub[l], self.da[l], layer, B, V[l], C[l], C[l + 1])
             e = self.tc.get(('b', 'en%d' % l)) if l > 0 else None
-            if e is not None:
+            if e is not None and e['tile'] is not None:
+                cabi.spiralconv_bwd_x_tile(self.da[l], e['tile'], e['parts'][0][2], self.a[l - 1], self.da[l - 1],
+                                           B, self.sub[l].n_rows, V[l], S[l], C[l + 1], C[l])
+            elif e is not None:
                 # input gradient of the fused block straight from the kept rows (inverse table of the
                 # restricted spiral table), ELU' of the previous block fused in the epilogue
                 for n0, nc, wimg in e['parts']:

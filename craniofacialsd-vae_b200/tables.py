@@ -271,29 +271,6 @@ def pack_rows_loader_order(rows: np.ndarray) -> np.ndarray:
     return np.ascontiguousarray(w.reshape(L, rcap // 2)).view(np.int32)
 
 
-def staged_tile_plan(idx: np.ndarray, max_rcap: int = 288):
-    """Plan of the EXPERIMENTAL tcgen05 forward with tile-local staging (``sdvae_spiralconv_fwd_tc_staged``):
-    ``(cnt [L], src [L, rcap/2], loc [L, S, 128], rcap)`` for tiles of 128 output rows of the spiral table
-    ``idx [R, S]``.  Raises ``RuntimeError`` when a tile reads more than ``max_rcap`` distinct rows (the template's
-    strip order needs 547 at level 0; ``patch_order`` brings it to ~240, 262 at level 1)."""
-    idx = np.asarray(idx, np.int64)
-    R, S = idx.shape
-    tile_ptr, stage_src, loc, ucap = gather_stage_plan(idx, 128)
-    rcap = max(32, (ucap + 31) // 32 * 32)
-    if rcap > max_rcap:
-        raise RuntimeError('staged_tile_plan: a tile reads %d distinct rows (limit %d)' % (ucap, max_rcap))
-    L = tile_ptr.size - 1
-    cnt = np.diff(tile_ptr).astype(np.int32)
-    rows = np.zeros((L, rcap), np.int64)
-    for t in range(L):
-        rows[t, :cnt[t]] = stage_src[tile_ptr[t]:tile_ptr[t + 1]]
-    loc3 = np.zeros((L, S, 128), np.int32)
-    for t in range(L):
-        blk = loc[t * 128:(t + 1) * 128]                             # [<=128, S]
-        loc3[t, :, :blk.shape[0]] = blk.T
-    return cnt, pack_rows_loader_order(rows), loc3, rcap
-
-
 TILE_MAX_RCAP = 288            # distinct rows per tile the tile-staged tcgen05 kernels take (csrc/spiral_conv_tile.cuh)
 
 
@@ -643,20 +620,6 @@ class TileStagePlan:
             return TileStagePlan.build(cell_ptr, cell_src, out_rows, seq, device)
         except RuntimeError:
             return None
-
-
-@dataclass
-class StagedTilePlan:
-    """Device copy of ``staged_tile_plan`` (EXPERIMENTAL kernel, see there)."""
-    cnt: torch.Tensor            # int32 [L]
-    src: torch.Tensor            # int32 [L, rcap/2]
-    loc: torch.Tensor            # int32 [L, S, 128]
-    rcap: int
-
-    @staticmethod
-    def build(idx_np: np.ndarray, device) -> "StagedTilePlan":
-        cnt, src, loc, rcap = staged_tile_plan(idx_np)
-        return StagedTilePlan(_dev(cnt, device), _dev(src, device), _dev(loc, device), int(rcap))
 
 
 @dataclass

@@ -189,28 +189,6 @@ int sdvae_dense_fwd(const float* in, const float* W, const float* bias, float* o
 /* out[c, r] = in[r, c] */
 int sdvae_transpose2d(const float* in, float* out, int R, int C, sdvae_stream_t stream);
 
-/* EXPERIMENTAL -- compiled for sm_100a, never run on a GPU in round 1, not used by the engine, the autograd
- * functions or bench.py.  sdvae_spiralconv_fwd_tc with TILE-LOCAL STAGING: the distinct
- * source rows of every 128-row tile are copied once into shared memory and every slot's gather reads there.
- *   plan_cnt [L]: distinct rows of tile t;  plan_src [L, rcap/2]: those rows as 16-bit pairs in the loader-lane
- *   order of sdvae_tc_plan_build (S = 1);  plan_loc [L, S, 128]: position of idx[t*128+r, s] in tile t's list
- *   (tables.staged_tile_plan builds all three; rcap <= 288, a multiple of 32).  C_in = 32 only.
- * Replaces: model.py:27-41 + F.elu, as sdvae_spiralconv_fwd_tc. */
-int sdvae_tc_staged_supported(int S, int Cin, int Cout, int rcap);
-int sdvae_spiralconv_fwd_tc_staged(const float* x, const int32_t* plan_cnt, const int32_t* plan_src,
-                                   const int32_t* plan_loc, int rcap, const float* wimg, const float* bias,
-                                   float* y, int B, int Vin, int Vout, int S, int Cin, int Cout, int act,
-                                   sdvae_stream_t stream);
-
-/* EXPERIMENTAL, as above: sdvae_spiralconv_bwd_w_tc with tile-local staging (same plan as the staged forward;
- * workspace as for sdvae_spiralconv_bwd_w_tc; results are meant to be bit-identical to it).
- * Replaces: autograd of model.py:40 (grad_weight / grad_bias), as sdvae_spiralconv_bwd_w_tc. */
-int sdvae_tc_bwd_w_staged_supported(int S, int Cin, int Cout, int rcap);
-int sdvae_spiralconv_bwd_w_tc_staged(const float* x, const int32_t* plan_cnt, const int32_t* plan_src,
-                                     const int32_t* plan_loc, int rcap, const float* dpre, float* dW, float* db,
-                                     void* workspace, int B, int Vin, int Vout, int S, int Cin, int Cout,
-                                     sdvae_stream_t stream);
-
 /* ---- narrow-output layer (32 -> 3, model.py:135-136): the whole backward in one pass --------------
  * G[u, s*Cout + n] = sum_{v in cell(u,s)} dy[b, v, n]   (cell_ptr [Vin*S+1], cell_src: the inverse spiral table
  *                                                         in cell-CSR form, rows ascending inside a cell)

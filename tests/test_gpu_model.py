@@ -171,10 +171,8 @@ def test_engine_steps_vs_oracle_trainer(golden, cranio, use_graph, use_tc):
         assert float((sd[k].cpu() - params[k]).abs().max()) > 0.0, k
 
 
-@pytest.mark.skipif(__import__('os').environ.get('SDVAE_EXPERIMENTAL') != '1',
-                    reason='engine-internal renumbering: host side checked on CPU, never run on a GPU in round 1')
 @pytest.mark.parametrize('use_tc', [False, True])
-def test_experimental_engine_on_renumbered_levels_vs_oracle(golden, cranio, use_tc):
+def test_engine_on_renumbered_levels_vs_oracle(golden, cranio, use_tc):
     """TrainEngine(renumber=True): the network runs on patch-wise renumbered internal levels; losses and all 24
     parameter gradients still match the oracle on the template's own numbering, and the reconstruction comes
     back in template order."""

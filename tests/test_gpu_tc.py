@@ -413,62 +413,75 @@ def test_narrow_input_forward_and_weight_gradient_vs_fp64(cranio, orc, lvl, B, r
     assert not cabi.narrow_in_supported(V, S, 4, 32) and not cabi.narrow_in_supported(30000, S, 3, 32)
 
 
-@pytest.mark.skipif(__import__('os').environ.get('SDVAE_EXPERIMENTAL') != '1',
-                    reason='experimental kernel (compiled, never run on a GPU in round 1): set SDVAE_EXPERIMENTAL=1')
-@pytest.mark.parametrize('lvl,B,cout,act', [(3, 2, 32, 1), (0, 3, 32, 1), (1, 5, 32, 0), (3, 4, 64, 1)])
-def test_experimental_staged_tc_forward_equals_tc_forward(cranio, lvl, B, cout, act):
-    """tcgen05 forward with tile-local staging (csrc/spiral_conv_umma_staged.cuh) on the patch-ordered template
-    against the per-slot-gather tcgen05 forward: same operands, same MMA order -> identical bits."""
-    from sdvae_b200 import cabi
+def _patch_ordered(cranio, lvl):
     from sdvae_b200 import tables as tb
     idx = cranio.spiral_tensors()[lvl].numpy()
     o = tb.patch_order(idx, 128)
-    idx = tb.renumber_table(idx, o, o)
-    V, S = idx.shape
-    tab = tb.spiral_table(torch.from_numpy(idx).to(DEV))
-    plan = tab.plan_fwd()
-    sp = tb.StagedTilePlan.build(idx, DEV)
-    assert cabi.tc_staged_supported(S, 32, cout, sp.rcap)
-    x = rand((B, V, 32), 51).to(DEV)
-    w = rand((cout, S * 32), 52, 0.1).to(DEV)
-    b = rand((cout,), 53, 0.2).to(DEV)
-    wimg = torch.empty(cabi.tc_wimg_floats(S, 32, cout), device=DEV)
-    cabi.tc_pack_weights(w, wimg, S, 32, cout, False)
-    ya = torch.full((B, V, cout), float('nan'), device=DEV)
-    yb = torch.full((B, V, cout), float('nan'), device=DEV)
-    cabi.spiralconv_fwd_tc(x, plan, wimg, b, ya, B, V, V, S, 32, cout, act)
-    cabi.spiralconv_fwd_tc_staged(x, sp, wimg, b, yb, B, V, V, S, 32, cout, act)
-    torch.cuda.synchronize()
-    assert torch.equal(ya, yb)
+    return tb.renumber_table(idx, o, o)
 
 
-@pytest.mark.skipif(__import__('os').environ.get('SDVAE_EXPERIMENTAL') != '1',
-                    reason='experimental kernel (compiled, never run on a GPU in round 1): set SDVAE_EXPERIMENTAL=1')
-@pytest.mark.parametrize('lvl,B,cin,cout', [(3, 2, 32, 32), (0, 3, 32, 32), (1, 5, 32, 64), (3, 4, 64, 64)])
-def test_experimental_staged_tc_weight_gradient_equals_tc_weight_gradient(cranio, lvl, B, cin, cout):
-    """tcgen05 weight gradient with tile-local staging (csrc/spiral_conv_umma_bw_staged.cuh) on the patch-ordered
-    template against bw_umma_kernel: same operands, same MMA and drain order -> identical bits."""
+@pytest.mark.parametrize('lvl,B,act', [(3, 2, 1), (0, 3, 1), (1, 41, 0), (2, 7, 1)])
+def test_tile_staged_forward_vs_fp64(orc, cranio, lvl, B, act):
+    """sdvae_spiralconv_fwd_tile (csrc/spiral_conv_tile.cuh; model.py:27-41 + F.elu) on the patch-ordered template
+    against the fp64 oracle, and run twice bit-identical.  B = 41 at level 1 gives every CTA several tiles (all
+    barrier phases of the stage rings)."""
     from sdvae_b200 import cabi
     from sdvae_b200 import tables as tb
-    idx = cranio.spiral_tensors()[lvl].numpy()
-    o = tb.patch_order(idx, 128)
-    idx = tb.renumber_table(idx, o, o)
+    idx = _patch_ordered(cranio, lvl)
     V, S = idx.shape
     tab = tb.spiral_table(torch.from_numpy(idx).to(DEV))
-    plan = tab.plan_fwd()
-    sp = tb.StagedTilePlan.build(idx, DEV)
-    assert cabi.tc_bwd_w_supported(S, cin, cout, plan.rcap) and cabi.tc_bwd_w_staged_supported(S, cin, cout, sp.rcap)
-    x = rand((B, V, cin), 61).to(DEV)
-    g = rand((B, V, cout), 62).to(DEV)
-    ws = torch.empty(cabi.spiralconv_bwd_w_workspace(B * V, S, cin, cout) // 4 + 4, device=DEV)
+    plan = tab.tile_fwd()
+    assert plan is not None and cabi.tile_supported(S, 32, 32, plan.rcap, 0)
+    x = rand((B, V, 32), 51)
+    w = rand((32, S * 32), 52, 0.1)
+    b = rand((32,), 53, 0.2)
+    wimg = torch.empty(cabi.tc_wimg_floats(S, 32, 32), device=DEV)
+    cabi.tc_pack_weights(w.to(DEV), wimg, S, 32, 32, False, kperm=True)
+    ys = []
+    for _ in range(2):
+        y = torch.full((B, V, 32), float('nan'), device=DEV)
+        cabi.spiralconv_fwd_tile(x.to(DEV), plan, wimg, b.to(DEV), y, B, V, V, S, 32, 32, act)
+        ys.append(y)
+    want = _conv64(orc, x, torch.from_numpy(idx), w, b, act)
+    assert nerr(ys[0], want) < TC_TOL and torch.equal(ys[0], ys[1])
+
+
+@pytest.mark.parametrize('lvl,B,gate', [(3, 2, False), (0, 3, True), (1, 41, False), (2, 7, True)])
+def test_tile_staged_backward_to_input_vs_fp64(orc, cranio, lvl, B, gate):
+    """sdvae_spiralconv_bwd_x_tile (autograd of model.py:34,40 w.r.t. the input, ELU' gate fused) against the
+    fp64 oracle's autograd, deterministic (in-order cell sums, no atomics)."""
+    from sdvae_b200 import cabi
+    from sdvae_b200 import tables as tb
+    idx = _patch_ordered(cranio, lvl)
+    V, S = idx.shape
+    tab = tb.spiral_table(torch.from_numpy(idx).to(DEV))
+    plan = tab.tile_bwd()
+    assert plan is not None and cabi.tile_supported(S, 32, 32, plan.rcap, plan.ecap)
+    w = rand((32, S * 32), 62, 0.1)
+    dpre = rand((B, V, 32), 63)
+    yprev = rand((B, V, 32), 64)                                  # output of the producing ELU layer (gate)
+    wimg_t = torch.empty(cabi.tc_wimg_floats(S, 32, 32), device=DEV)
+    cabi.tc_pack_weights(w.to(DEV), wimg_t, S, 32, 32, True, kperm=True)
     outs = []
-    for fn, p in ((cabi.spiralconv_bwd_w_tc, plan), (cabi.spiralconv_bwd_w_tc_staged, sp)):
-        dW = torch.full((cout, S * cin), float('nan'), device=DEV)
-        db = torch.full((cout,), float('nan'), device=DEV)
-        fn(x, p, g, dW, db, ws, B, V, V, S, cin, cout)
-        torch.cuda.synchronize()
-        outs.append((dW, db))
-    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    for _ in range(2):
+        dx = torch.full((B, V, 32), float('nan'), device=DEV)
+        cabi.spiralconv_bwd_x_tile(dpre.to(DEV), plan, wimg_t, yprev.to(DEV) if gate else None, dx, B, V, V, S, 32, 32)
+        outs.append(dx)
+    x = torch.zeros(B, V, 32, dtype=torch.float64, requires_grad=True)
+    y = orc.spiral_conv(x, torch.from_numpy(idx), w.double(), torch.zeros(32, dtype=torch.float64))
+    y.backward(dpre.double())
+    want = x.grad
+    if gate:
+        want = want * torch.where(yprev > 0, torch.ones_like(yprev), yprev + 1).double()
+    assert nerr(outs[0], want) < TC_TOL and torch.equal(outs[0], outs[1])
+
+
+def test_tile_staged_falls_back_when_a_tile_reads_too_many_rows(cranio):
+    """The template's strip order has no tile plan at level 0 (547 distinct rows per tile): SpiralTable.tile_fwd()
+    is None and the engine / autograd functions keep the per-slot-gather kernels."""
+    from sdvae_b200 import tables as tb
+    tab = tb.spiral_table(cranio.spiral_tensors()[0].to(DEV))
+    assert tab.tile_fwd() is None and tab.plan_fwd().rcap > 0
 
 
 def test_tc_rejects_unsupported_shapes(cranio):

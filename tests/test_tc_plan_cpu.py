@@ -96,44 +96,106 @@ def test_plan_rejects_rows_that_do_not_fit_16_bits():
         cabi.tc_plan_build(ptr, src, 4, 1)
 
 
-def test_staged_tile_plan_matches_the_c_packer_and_the_table():
-    """Plan of the EXPERIMENTAL staged tcgen05 forward: the numpy packer reproduces sdvae_tc_plan_build's
-    loader-lane order bit for bit, and (cnt, src, loc) re-address every gather of the table."""
-    from sdvae_b200 import cabi, fixtures as fx, tables as tb
-    tabs = fx.craniofacial_tables()
-    idx = tabs.spiral_tensors()[3].numpy()                        # 267 rows
-    o3 = tb.patch_order(idx, 128)
-    idx = tb.renumber_table(idx, o3, o3)                          # in patch order a tile reads <= 192 distinct rows
-    R, S = idx.shape
-    cnt, src, loc, rcap = tb.staged_tile_plan(idx)
-    L = (R + 127) // 128
-    assert cnt.shape == (L,) and src.shape == (L, rcap // 2) and loc.shape == (L, S, 128) and rcap % 32 == 0
-    # unpack the loader order again
+def _unpack_loader_rows(src, rcap):
+    """Inverse of tables.pack_rows_loader_order: [L, rcap/2] packed words -> [L, rcap] staged-row list."""
+    L = src.shape[0]
     w = src.view(np.uint32).reshape(L, rcap // 32, 4, 4)          # [L, j, rsub, t>>1]
     rows = np.zeros((L, rcap // 32, 8, 4), np.int64)              # [L, j, t, rsub]
     rows[:, :, 0::2, :] = (w & 0xFFFF).transpose(0, 1, 3, 2)
     rows[:, :, 1::2, :] = (w >> 16).transpose(0, 1, 3, 2)
-    rows = rows.reshape(L, rcap)
-    for t in range(L):
-        lst = rows[t, :cnt[t]]
-        assert np.all(np.diff(lst) > 0) and not rows[t, cnt[t]:].any()
-        blk = idx[t * 128:(t + 1) * 128]
-        assert np.array_equal(lst[loc[t, :, :blk.shape[0]].T], blk)
-        assert not loc[t, :, blk.shape[0]:].any()
-    # the same lists through the C builder: one pseudo-row per tile whose only cell holds the tile's rows
-    assert rcap <= 192
-    if True:
-        ptr = np.zeros(L * 128 + 1, np.int32)
-        starts = np.concatenate([[0], np.cumsum(cnt)])
-        for t in range(L):
-            ptr[t * 128 + 1:(t + 1) * 128 + 1] = starts[t + 1]     # row 0 of tile t owns all its rows
-        flat = np.concatenate([rows[t, :cnt[t]] for t in range(L)]).astype(np.int32)
-        c_cnt, c_src, _, c_rcap = cabi.tc_plan_build(ptr, flat, L * 128, 1)
-        assert c_rcap == rcap
-        assert np.array_equal(c_cnt.ravel(), cnt) and np.array_equal(c_src.reshape(L, -1), src)
-    # the template's strip order does not fit at level 0; patch order does
+    return rows.reshape(L, rcap)
+
+
+def _decode_tile_plan(cnt, src, cell, ext, rcap, out_rows, S):
+    """Cells of a tile plan exactly as gt_kernel reads them (csrc/spiral_conv_tile.cuh): per (row, slot) the list
+    of source rows, plus the number of same-parity first-row pairs (the kernel's 2-way bank conflicts)."""
+    rows = _unpack_loader_rows(src, rcap)
+    cells, same, pairs = [], 0, 0
+    for r in range(out_rows):
+        t, lr = divmod(r, 128)
+        for s in range(S):
+            w = int(cell[t, s * 128 + (lr >> 5) * 32 + (lr & 7) * 4 + ((lr >> 3) & 3)])
+            off, c, eo = w & 0xffff, (w >> 16) & 31, w >> 21
+            got = []
+            if c:
+                p0 = off >> 7
+                assert (off & 64) == 64 * (p0 & 1) and (off & 63) == 0 and p0 < cnt[t]
+                got.append(int(rows[t, p0]))
+                for e in range(c - 1):
+                    o2 = int(ext[t, eo + e])
+                    assert (o2 & 64) == 64 * ((o2 >> 7) & 1) and (o2 >> 7) < cnt[t]
+                    got.append(int(rows[t, o2 >> 7]))
+            cells.append(got)
+    return cells
+
+
+def test_tile_plan_reproduces_the_table_forward_and_inverse():
+    """tables.tile_plan (tile-staged tcgen05 kernels): decoding the plan the way the kernel does gives back every
+    cell of the table, in order -- forward table (one row per cell) and inverse table (ragged cells)."""
+    from sdvae_b200 import fixtures as fx, tables as tb
+    tabs = fx.craniofacial_tables()
+    for lvl in (3, 2):
+        idx = tabs.spiral_tensors()[lvl].numpy()
+        o = tb.patch_order(idx, 128)
+        idx = tb.renumber_table(idx, o, o)
+        R, S = idx.shape
+        for ptr, src_rows in ((np.arange(R * S + 1), idx.ravel()), tb.inverse_cells(idx.astype(np.int32), R)):
+            cnt, src, cell, ext, rcap, ecap = tb.tile_plan(ptr, src_rows, R, S)
+            L = (R + 127) // 128
+            assert cnt.shape == (L,) and src.shape == (L, rcap // 2) and cell.shape == (L, S * 128)
+            assert rcap % 32 == 0 and rcap <= tb.TILE_MAX_RCAP and ecap % 64 == 0 and cell.dtype == np.uint32
+            cells = _decode_tile_plan(cnt, src, cell, ext, rcap, R, S)
+            for i, got in enumerate(cells):
+                assert got == [int(v) for v in src_rows[ptr[i]:ptr[i + 1]]], i
+            # rows of the last tile past the table: one valid row, never stored
+            lr0 = R - (L - 1) * 128
+            if lr0 < 128:
+                w = cell[L - 1].reshape(S, 128)
+                pos = np.array([(r >> 5) * 32 + (r & 7) * 4 + ((r >> 3) & 3) for r in range(lr0, 128)])
+                assert np.all(w[:, pos] == np.uint32(1 << 16))
+
+
+def test_tile_plan_position_parity_cuts_most_phase_pairs():
+    """The two tile rows (2i, 2i+1) of a shared-memory read phase should find their staged rows at positions of
+    different parity (conflict-free); the max-cut placement leaves well under half of the pairs conflicting."""
+    from sdvae_b200 import fixtures as fx, tables as tb
+    tabs = fx.craniofacial_tables()
+    idx = tabs.spiral_tensors()[2].numpy()
+    o = tb.patch_order(idx, 128)
+    idx = tb.renumber_table(idx, o, o)
+    R, S = idx.shape
+    cnt, src, cell, ext, rcap, ecap = tb.tile_plan(np.arange(R * S + 1), idx.ravel(), R, S)
+    same = total = 0
+    for t in range((R + 127) // 128):
+        n = min(128, R - t * 128)
+        for s in range(S):
+            pos = np.array([int(cell[t, s * 128 + (r >> 5) * 32 + (r & 7) * 4 + ((r >> 3) & 3)]) & 0xffff for r in range(n - (n & 1))]) >> 7
+            a, b = pos[0::2], pos[1::2]
+            ok = a != b
+            same += int(((a & 1) == (b & 1))[ok].sum()); total += int(ok.sum())
+    assert same / total < 0.35, same / total
+
+
+def test_tile_plan_rejects_the_template_strip_order():
+    """At level 0 the template's own numbering makes a 128-row tile read up to 547 distinct rows: no tile plan
+    (callers fall back to the per-slot-gather kernels); the patch order fits."""
+    from sdvae_b200 import fixtures as fx, tables as tb
+    tabs = fx.craniofacial_tables()
     idx0 = tabs.spiral_tensors()[0].numpy()
+    R, S = idx0.shape
     with pytest.raises(RuntimeError):
-        tb.staged_tile_plan(idx0)
+        tb.tile_plan(np.arange(R * S + 1), idx0.ravel(), R, S)
     order = tb.patch_order(idx0, 128)
-    assert tb.staged_tile_plan(tb.renumber_table(idx0, order, order))[3] <= 288
+    idx = tb.renumber_table(idx0, order, order)
+    assert tb.tile_plan(np.arange(R * S + 1), idx.ravel(), R, S)[4] <= tb.TILE_MAX_RCAP
+
+
+def test_kperm_is_a_permutation_matching_the_kernel():
+    """K position kk of a 32-wide chunk holds channel kperm(kk) (csrc/spiral_conv_umma.cuh): thread q = (kk>>1)&3
+    of a row owns the 16-byte pieces q and q+4."""
+    kperm = lambda kk: ((kk >> 4) << 4) + (((kk >> 1) & 3) << 2) + (((kk >> 3) & 1) << 1) + (kk & 1)
+    p = [kperm(k) for k in range(32)]
+    assert sorted(p) == list(range(32))
+    for kk in range(32):
+        q, n, b = (kk >> 1) & 3, kk >> 3, kk & 1
+        assert p[kk] == (16 if n >= 2 else 0) + 4 * q + 2 * (n & 1) + b

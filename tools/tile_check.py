@@ -148,12 +148,9 @@ def main():
                 rep('dx  per-slot gather (gc_umma)', ev_time(lambda i: cabi.spiralconv_bwd_x_tc(xs[i], po, wimg_to, None, ys[i], B, V, V, S, 32, 32), a.iters, nbuf))
         if 'dw' in a.only:
             po = tab.plan_fwd()
-            sp = tb.StagedTilePlan.build(idx.numpy(), DEV)
             ws = torch.empty(cabi.spiralconv_bwd_w_workspace(B * V, S, 32, 32) // 4 + 4, device=DEV)
             dW = torch.empty(32, S * 32, device=DEV); db = torch.empty(32, device=DEV)
             rep('dW  per-slot gather (bw_umma)', ev_time(lambda i: cabi.spiralconv_bwd_w_tc(xs[i], po, ys[(i + 1) % nbuf], dW, db, ws, B, V, V, S, 32, 32), a.iters, nbuf))
-            if cabi.tc_bwd_w_staged_supported(S, 32, 32, sp.rcap):
-                rep('dW  tile-staged draft (r01)', ev_time(lambda i: cabi.spiralconv_bwd_w_tc_staged(xs[i], sp, ys[(i + 1) % nbuf], dW, db, ws, B, V, V, S, 32, 32), a.iters, nbuf))
         del xs, ys
 
 
