@@ -54,6 +54,8 @@ _SIGNATURES = {
     "sdvae_narrow_out_bwd_workspace": (C.c_size_t, [C.c_int, C.c_int]),
     "sdvae_narrow_out_bwd": (C.c_int, [_c_fp] * 10 + [C.c_int] * 7 + [_c_fp]),
     "sdvae_tile_supported": (C.c_int, [C.c_int] * 5),
+    "sdvae_tile_bwd_w_supported": (C.c_int, [C.c_int] * 4),
+    "sdvae_spiralconv_bwd_w_tile": (C.c_int, [_c_fp] * 4 + [C.c_int] + [_c_fp] * 4 + [C.c_int] * 6 + [_c_fp]),
     "sdvae_spiralconv_fwd_tile": (C.c_int, [_c_fp] * 4 + [C.c_int] + [_c_fp] * 3 + [C.c_int] * 7 + [_c_fp]),
     "sdvae_spiralconv_bwd_x_tile": (C.c_int, [_c_fp] * 5 + [C.c_int] * 2 + [_c_fp] * 3 + [C.c_int] * 6 + [_c_fp]),
     "sdvae_narrow_in_supported": (C.c_int, [C.c_int] * 4),
@@ -113,7 +115,7 @@ _KERNELS_PER_CALL = {
     "spiralconv_fwd": 1, "weight_transpose": 1, "spiralconv_bwd_x": 1, "spiralconv_bwd_w": 2,
     "tc_pack_weights": 1, "spiralconv_fwd_tc": 1, "spiralconv_bwd_x_tc": 1,
     "spiralconv_bwd_w_tc": 2, "dense_tc": 1, "slot_pack": 1, "slot_weight": 1, "slot_grad": 1,
-    "dense_fwd": 1, "transpose2d": 1, "spiralconv_fwd_tile": 1, "spiralconv_bwd_x_tile": 1, "narrow_out_bwd": 2, "narrow_out_fwd": 1, "narrow_in_fwd": 1, "narrow_in_bwd_w": 2, "pool_ell_fwd": 1, "pool_ell_fwd_staged": 1, "csr_rowsum": 1, "elu_fwd": 1,
+    "dense_fwd": 1, "transpose2d": 1, "spiralconv_fwd_tile": 1, "spiralconv_bwd_x_tile": 1, "spiralconv_bwd_w_tile": 2, "narrow_out_bwd": 2, "narrow_out_fwd": 1, "narrow_in_fwd": 1, "narrow_in_bwd_w": 2, "pool_ell_fwd": 1, "pool_ell_fwd_staged": 1, "csr_rowsum": 1, "elu_fwd": 1,
     "elu_bwd": 1, "reparam_fwd": 1, "reparam_bwd": 1, "axpy3": 1, "swap": 1, "mse_lap_fwd": 3,
     "mse_lap_bwd": 1, "kl_fwd_bwd": 2, "lc_fwd_bwd": 3, "total_loss": 1, "adam_tick": 1,
     "adam_step": 1,
@@ -464,6 +466,24 @@ def narrow_out_bwd(dy, x, cell_ptr, cell_src, cell_pack, W, dx, dW, db, ws, B, R
 
 def pool_stage_supported(Cc: int, Wd: int, ucap: int) -> bool:
     return bool(load().sdvae_pool_stage_supported(int(Cc), int(Wd), int(ucap)))
+
+
+def tile_bwd_w_supported(S: int, Cin: int, Cout: int, rcap: int) -> bool:
+    return bool(load().sdvae_tile_bwd_w_supported(int(S), int(Cin), int(Cout), int(rcap)))
+
+
+def spiralconv_bwd_w_tile(x, plan, dpre, dW, db, ws, B, Vin, Vout, S, Cin, Cout):
+    """SpiralConv weight / bias gradient on tcgen05 with tile-local staging; ``plan`` = ``tables.TileStagePlan`` of
+    the FORWARD gather (``SpiralTable.tile_fwd()``)."""
+    need = spiralconv_bwd_w_workspace(B * Vout, S, Cin, Cout)
+    if ws.numel() * 4 < need:
+        raise ValueError("spiralconv_bwd_w_tile: workspace too small (%d < %d bytes)" % (ws.numel() * 4, need))
+    rc = load().sdvae_spiralconv_bwd_w_tile(_f(x, "x"), _i(plan.cnt, "plan_cnt"), _i(plan.src, "plan_src"),
+                                            _i(plan.cell, "plan_cell"), plan.rcap, _f(dpre, "dpre"), _f(dW, "dW"),
+                                            _fo(db, "db"), _f(ws, "workspace"), B, Vin, Vout, S, Cin, Cout, _stream())
+    if rc:
+        _err(rc, "spiralconv_bwd_w_tile")
+    add_launches((Cin // 32) * ((Cout + 31) // 32) + 1)      # one bt_kernel per 32 x <=32 pass + the reduction
 
 
 def pool_ell_fwd_staged(x, plan, out, B, Vin, Vout, Wd, Cc):

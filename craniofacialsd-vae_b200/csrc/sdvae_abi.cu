@@ -8,6 +8,7 @@
 #include "spiral_conv_umma.cuh"
 #include "spiral_conv_umma_bw.cuh"
 #include "spiral_conv_tile.cuh"
+#include "spiral_conv_tile_bw.cuh"
 #include "slot_pack.cuh"
 #include "pool_misc.cuh"
 #include "narrow_conv.cuh"
@@ -564,6 +565,68 @@ int sdvae_spiralconv_bwd_w_tc(const float* x, const int32_t* plan_cnt, const int
     return check_launch("split_reduce_kernel");
 }
 
+
+/* Weight gradient with tile-local staging (spiral_conv_tile_bw.cuh): sdvae_spiralconv_bwd_w_tc on the FORWARD tile
+ * plan of sdvae_spiralconv_fwd_tile (same workspace size). */
+int sdvae_tile_bwd_w_supported(int S, int Cin, int Cout, int rcap) {
+    if ((Cin != 32 && Cin != 64) || Cout < 1 || Cout > 64 || S < 1 || S * 32 + 1 > tile::kWMaxBlocks * 128) return 0;
+    if (rcap < 32 || rcap > tile::kTMaxRcap || rcap % 32 != 0) return 0;
+    return tile::TileBwCfg::stages(S, rcap) >= 2 ? 1 : 0;
+}
+
+int sdvae_spiralconv_bwd_w_tile(const float* x, const int32_t* plan_cnt, const int32_t* plan_src,
+                                const uint32_t* plan_cell, int rcap, const float* dpre, float* dW, float* db,
+                                void* workspace, int B, int Vin, int Vout, int S, int Cin, int Cout,
+                                sdvae_stream_t stream) {
+    SDVAE_REQUIRE(x && plan_cnt && plan_src && plan_cell && dpre && dW && workspace, "spiralconv_bwd_w_tile: null pointer");
+    SDVAE_REQUIRE(B >= 0 && Vin > 0 && Vout > 0, "spiralconv_bwd_w_tile: bad shape");
+    SDVAE_REQUIRE((long long)B * Vin < 2147483647LL, "spiralconv_bwd_w_tile: B*Vin exceeds int32 rows");
+    SDVAE_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(plan_src) |
+                    reinterpret_cast<uintptr_t>(plan_cell)) & 15) == 0,
+                  "spiralconv_bwd_w_tile: x and the plan tables must be 16-byte aligned");
+    if (!sdvae_tile_bwd_w_supported(S, Cin, Cout, rcap))
+        return set_error(SDVAE_ERR_UNSUPPORTED, "spiralconv_bwd_w_tile: unsupported layer shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int K = S * Cin;
+    if (B == 0) {
+        cudaMemsetAsync(dW, 0, sizeof(float) * Cout * K, st);
+        if (db) cudaMemsetAsync(db, 0, sizeof(float) * Cout, st);
+        return check_launch("bwd_w_tile memset");
+    }
+    tile::TileBwArgs a{};
+    a.plan_cnt = plan_cnt; a.plan_src = plan_src; a.plan_cell = plan_cell;
+    a.B = B; a.in_rows = Vin; a.out_rows = Vout; a.L = sdvae_tc_plan_tiles(Vout); a.S = S; a.rcap = rcap;
+    a.nts = tile::TileBwCfg::stages(S, rcap);
+    const long long ntiles = (long long)B * a.L;
+    const int grid = ntiles < kNumSMs ? (int)ntiles : kNumSMs;
+    float* part = static_cast<float*>(workspace);               // [grid, Cout, K]
+    float* part_b = part + (size_t)grid * Cout * K;             // [grid, Cout]
+    static int flush_tiles = 0;                // tiles per accumulator drain (tuning knob, default 2)
+    if (!flush_tiles) {
+        const char* e = getenv("SDVAE_BWW_FLUSH");
+        flush_tiles = e ? atoi(e) : 2;
+        if (flush_tiles < 1) flush_tiles = 1;
+    }
+    a.flush = flush_tiles;
+    a.in_ld = Cin; a.g_ld = Cout; a.part_ld = K; a.part_cta = Cout * K; a.partb_cta = Cout;
+    cudaMemsetAsync(part, 0, sizeof(float) * (size_t)grid * (Cout * K + Cout), st);
+    cudaFuncSetAttribute(tile::bt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   // per device, cheap
+    const size_t smem = tile::TileBwCfg::smem_bytes(S, rcap, a.nts);
+    for (int c0 = 0; c0 < Cin; c0 += 32)
+        for (int n0 = 0; n0 < Cout; n0 += umma::kBwNT) {
+            a.in = x + c0;
+            a.g = dpre + n0;
+            a.n_real = Cout - n0 < umma::kBwNT ? Cout - n0 : umma::kBwNT;
+            a.part = part + (size_t)n0 * K + c0;
+            a.part_b = c0 == 0 ? part_b + n0 : nullptr;
+            tile::bt_kernel<<<grid, tile::kWThreads, smem, st>>>(a);
+            int rc = check_launch("bt_kernel");
+            if (rc) return rc;
+        }
+    const long long len = (long long)Cout * K;
+    split_reduce2_kernel<<<blocks_for(len + Cout, 64), 256, 0, st>>>(part, part_b, dW, db, grid, len, Cout);
+    return check_launch("split_reduce_kernel");
+}
 
 size_t sdvae_spiralconv_bwd_w_workspace(long long M, int S, int Cin, int Cout) {
     long long rows; int nsplit;

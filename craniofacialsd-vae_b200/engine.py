@@ -409,6 +409,12 @@ class TrainEngine:
         return z
 
     def _bwd_w(self, x, table, dpre, layer, B, Vin, Cin, Cout):
+        if self.use_tc and Cin in (32, 64) and os.environ.get('SDVAE_TILE', '1') != '0':
+            tp = table.tile_fwd()
+            if tp is not None and cabi.tile_bwd_w_supported(table.seq, Cin, Cout, tp.rcap):
+                cabi.spiralconv_bwd_w_tile(x, tp, dpre, self.g(layer.weight), self.g(layer.bias), self.ws,
+                                           B, Vin, table.n_rows, table.seq, Cin, Cout)
+                return
         if self.use_tc and Cin in (32, 64):
             plan = table.plan_fwd()
             if cabi.tc_bwd_w_supported(table.seq, Cin, Cout, plan.rcap):

@@ -140,6 +140,15 @@ int sdvae_spiralconv_bwd_x_tile(const float* dpre, const int32_t* plan_cnt, cons
                                 const float* wimg_t, const float* gate, float* dx, int B, int Vrows, int Vdst, int S,
                                 int Cout, int Cin, sdvae_stream_t stream);
 
+/* Weight gradient with tile-local staging (csrc/spiral_conv_tile_bw.cuh): as sdvae_spiralconv_bwd_w_tc below (same
+ * contraction, same workspace size, same deterministic drain), on the FORWARD tile plan of sdvae_spiralconv_fwd_tile.
+ * Replaces: autograd of nn.Linear in model.py:40 over the gather of model.py:34.  C_in in {32, 64}, C_out <= 64. */
+int sdvae_tile_bwd_w_supported(int S, int Cin, int Cout, int rcap);
+int sdvae_spiralconv_bwd_w_tile(const float* x, const int32_t* plan_cnt, const int32_t* plan_src,
+                                const uint32_t* plan_cell, int rcap, const float* dpre, float* dW, float* db,
+                                void* workspace, int B, int Vin, int Vout, int S, int Cin, int Cout,
+                                sdvae_stream_t stream);
+
 /* Weight gradient on the tensor cores, as sdvae_spiralconv_bwd_w (same workspace size), for
  * C_in in {32, 64}, C_out <= 64 (passes of 32 x <= 32 channels).  (plan_cnt, plan_src, rcap) is the FORWARD tile plan of the layer's table
  * (one source row per cell).  db comes from a row of ones in the A operand; partial sums per CTA are

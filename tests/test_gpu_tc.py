@@ -476,6 +476,35 @@ def test_tile_staged_backward_to_input_vs_fp64(orc, cranio, lvl, B, gate):
     assert nerr(outs[0], want) < TC_TOL and torch.equal(outs[0], outs[1])
 
 
+@pytest.mark.parametrize('lvl,B,cin,cout', [(3, 2, 32, 32), (0, 3, 32, 32), (1, 41, 32, 32), (2, 5, 64, 32), (2, 4, 32, 64)])
+def test_tile_staged_weight_gradient_vs_fp64(cranio, lvl, B, cin, cout):
+    """sdvae_spiralconv_bwd_w_tile (csrc/spiral_conv_tile_bw.cuh; autograd of nn.Linear in model.py:40 over the gather
+    of model.py:34) on the patch-ordered template against an fp64 evaluation, run twice bit-identical (accumulators
+    drained in a fixed order, per-CTA partials summed in CTA order)."""
+    from sdvae_b200 import cabi
+    from sdvae_b200 import tables as tb
+    idx = _patch_ordered(cranio, lvl)
+    V, S = idx.shape
+    tab = tb.spiral_table(torch.from_numpy(idx).to(DEV))
+    plan = tab.tile_fwd()
+    assert plan is not None and cabi.tile_bwd_w_supported(S, cin, cout, plan.rcap)
+    x = rand((B, V, cin), 71)
+    g = rand((B, V, cout), 72)
+    ws = torch.empty(cabi.spiralconv_bwd_w_workspace(B * V, S, cin, cout) // 4 + 4, device=DEV)
+    outs = []
+    for _ in range(2):
+        dW = torch.full((cout, S * cin), float('nan'), device=DEV)
+        db = torch.full((cout,), float('nan'), device=DEV)
+        cabi.spiralconv_bwd_w_tile(x.to(DEV), plan, g.to(DEV), dW, db, ws, B, V, V, S, cin, cout)
+        torch.cuda.synchronize()
+        outs.append((dW, db))
+    A = x.double()[:, torch.from_numpy(idx).reshape(-1)].reshape(B * V, S * cin)
+    want_w = g.double().reshape(B * V, cout).t() @ A
+    want_b = g.double().sum((0, 1))
+    assert nerr(outs[0][0], want_w) < TC_TOL and nerr(outs[0][1], want_b) < TC_TOL
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 def test_tile_staged_falls_back_when_a_tile_reads_too_many_rows(cranio):
     """The template's strip order has no tile plan at level 0 (547 distinct rows per tile): SpiralTable.tile_fwd()
     is None and the engine / autograd functions keep the per-slot-gather kernels."""

@@ -125,6 +125,20 @@ def main():
                         torch.cuda.synchronize()
                         print('  dx   B=%d gate=%d: normwise err vs fp64 %.3e   deterministic %s' % (B, use_gate, nerr(dx, ref), torch.equal(dx, dx2)), flush=True)
                         del ref, dG
+                if 'dw' in a.only:
+                    gg_ = torch.randn(B, V, 32, generator=g).to(DEV)
+                    ws = torch.empty(cabi.spiralconv_bwd_w_workspace(B * V, S, 32, 32) // 4 + 4, device=DEV)
+                    res = []
+                    for _ in range(2):
+                        dW = torch.full((32, S * 32), float('nan'), device=DEV); db = torch.full((32,), float('nan'), device=DEV)
+                        cabi.spiralconv_bwd_w_tile(x, pf, gg_, dW, db, ws, B, V, V, S, 32, 32)
+                        torch.cuda.synchronize()
+                        res.append((dW, db))
+                    A = x.double()[:, idx_d.view(-1)].view(B * V, S * 32)
+                    refW = gg_.double().view(B * V, 32).t() @ A
+                    refb = gg_.double().sum((0, 1))
+                    print('  dW   B=%d: normwise err vs fp64 dW %.3e db %.3e   deterministic %s' % (B, nerr(res[0][0], refW), nerr(res[0][1], refb), torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])), flush=True)
+                    del A
         # ---- timing ----
         B = a.B
         nbuf = max(2, int(np.ceil(300e6 / (B * V * 128))) + 1)          # rotate buffers larger than L2
@@ -150,7 +164,9 @@ def main():
             po = tab.plan_fwd()
             ws = torch.empty(cabi.spiralconv_bwd_w_workspace(B * V, S, 32, 32) // 4 + 4, device=DEV)
             dW = torch.empty(32, S * 32, device=DEV); db = torch.empty(32, device=DEV)
-            rep('dW  per-slot gather (bw_umma)', ev_time(lambda i: cabi.spiralconv_bwd_w_tc(xs[i], po, ys[(i + 1) % nbuf], dW, db, ws, B, V, V, S, 32, 32), a.iters, nbuf))
+            rep('dW  tile-staged', ev_time(lambda i: cabi.spiralconv_bwd_w_tile(xs[i], pf, ys[(i + 1) % nbuf], dW, db, ws, B, V, V, S, 32, 32), a.iters, nbuf))
+            if not a.skip_old:
+                rep('dW  per-slot gather (bw_umma)', ev_time(lambda i: cabi.spiralconv_bwd_w_tc(xs[i], po, ys[(i + 1) % nbuf], dW, db, ws, B, V, V, S, 32, 32), a.iters, nbuf))
         del xs, ys
 
 
