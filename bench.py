@@ -3,7 +3,7 @@
 
     python bench.py --gpus 1 --steps K --warmup W                 # this repo's CUDA path
     torchrun ... bench.py --gpus N --steps K --warmup W           # data parallel, one rank per GPU
-    python bench.py --impl reference --gpus N --steps K --warmup W  # reference CPU path (oracle port)
+    python bench.py --impl reference --gpus N --steps K --warmup W  # the reference's own CPU path (baseline/_ref)
 
 Workload (BASELINE.json configs[1]/[2]): craniofacial.yaml training step -- device-side feature
 swap of ``bs`` synthetic N(0,1) template-shaped meshes into the ``bs x bs`` grid, forward,
@@ -13,8 +13,10 @@ bs^2 = 1024 meshes (bs = 32), sharded by grid rows over the ranks (strong scalin
 One JSON line on stdout (rank 0).  ``value`` = meshes/s with the un-swapped batch resident in
 HBM; ``e2e`` = the same step through the public API with the batch in pinned HOST memory
 (H2D copy + 28-byte loss read-back inside the timed region, one sync per step);
-``roofline`` = the dominant kernel timed alone with CUDA events; ``cpu_baseline`` = the CPU
-oracle port of the reference step on this box's host cores (bounded sample).
+``roofline`` = the LONGEST kernel of the step timed alone with CUDA events (with the other two passes of
+the same layer and the whole-step fraction beside it); ``cpu_baseline`` = the unmodified reference
+(baseline/_ref, staged by tools/stage_reference.py; the oracle port only if it is absent) on this box's
+host cores, bounded sample; ``reference_eager_cuda`` = the same reference modules run eagerly on the B200.
 """
 import argparse
 import json
@@ -123,10 +125,16 @@ def build_problem(dev, bs, seed, renumber=False):
 
 
 def cpu_step_rate(tabs, bs, steps, warmup, seed):
-    """CPU-baseline leg (the one place bench.py executes oracle/): the reference's _do_iteration on host cores
-    via the oracle port (swap included), with its own seeded xavier weights."""
-    from oracle import sdvae_oracle as orc
+    """CPU-baseline leg: the reference's own training step (model.py + the loss methods of model_manager.py +
+    SwapFeatures, baseline/refarm.py) on all host cores; only when the staged reference is absent, the oracle port
+    (the one place bench.py executes oracle/).  Returns (meshes/s, s/step, kind)."""
     torch.set_num_threads(os.cpu_count() or 1)
+    from baseline import refarm
+    ref = refarm.find_ref()
+    if ref is not None:
+        rate, sec = refarm.time_reference_steps(ref, tabs, 'cpu', bs, steps, warmup, seed)
+        return rate, sec, "reference"
+    from oracle import sdvae_oracle as orc
     sp, dn, up = tabs.spiral_tensors(), tabs.down_tensors(), tabs.up_tensors()
     net = orc.Net(3, CHANNELS, LATENT, sp, dn, up, False, True)
     params = orc.xavier_params(net.param_shapes(), seed=seed)
@@ -146,7 +154,19 @@ def cpu_step_rate(tabs, bs, steps, warmup, seed):
         if it >= warmup:
             times.append(dt)
     total = float(np.sum(times))
-    return bs * bs * len(times) / total, total / len(times)
+    return bs * bs * len(times) / total, total / len(times), "port"
+
+
+WORKLOAD = ("craniofacial.yaml train step (swap + fwd + MSE/KL/LC/Laplacian + bwd + Adam), "
+            "V=17039, global batch %d")
+
+
+def cpu_sample_text(kind, steps, bs):
+    what = ("the UNMODIFIED reference (model.py, the loss methods of model_manager.py, SwapFeatures; baseline/_ref) "
+            "on torch-CPU" if kind == "reference" else "oracle port of model.py/model_manager.py on torch-CPU "
+            "(baseline/_ref absent)")
+    return ("%d timed steps of the same training step on a BOUNDED SAMPLE of %d swapped meshes per step (bs=%d, the "
+            "reference yaml's own batch size), fp32, all host threads, %s" % (steps, bs * bs, bs, what))
 
 
 def run_reference(args):
@@ -154,45 +174,68 @@ def run_reference(args):
     if rank != 0:
         return
     tabs, _, _, _ = build_problem(None, args.ref_bs, args.seed)
-    rate, sec = cpu_step_rate(tabs, args.ref_bs, args.steps, args.warmup, args.seed)
+    rate, sec, kind = cpu_step_rate(tabs, args.ref_bs, args.steps, args.warmup, args.seed)
     cores = os.cpu_count() or 1
-    sample = ("%d steps of the craniofacial.yaml step on %d swapped meshes (bs=%d), fp32, "
-              "oracle port of model.py/model_manager.py on torch-CPU" % (args.steps, args.ref_bs ** 2, args.ref_bs))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "craniofacial.yaml train step (swap + fwd + MSE/KL/LC/Laplacian + bwd + Adam), "
-                               "V=17039, global batch %d" % (args.bs ** 2)},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD % (args.bs ** 2),
+                   "sample": "%d swapped meshes per timed step (bs=%d): a bounded sample of the workload, not the "
+                             "global batch" % (args.ref_bs ** 2, args.ref_bs)},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": cpu_sample_text(kind, args.steps, args.ref_bs)},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def time_dominant_kernel(eng, reps=10):
-    """The de4 SpiralConv+ELU forward (17039 x 288 x 32 per mesh, half of the forward FLOPs),
-    timed alone with CUDA events on the launching stream."""
-    from sdvae_b200 import cabi
-    L, V, C, B = eng.L, eng.V, eng.C, eng.B
-    layer = eng.model.de_layers[L].conv.layer
-    args = (eng.u[0], eng.full[0], layer, eng.d[0], cabi.ACT_ELU, B, V[0], eng.cin_de[0], C[1], 'de0')
-    eng._pack_tc()
+def _time(run, reps):
     for _ in range(3):
-        eng._conv(*args)
+        run()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     s.record()
     for _ in range(reps):
-        eng._conv(*args)
+        run()
     e.record()
     torch.cuda.synchronize()
-    sec = s.elapsed_time(e) / 1e3 / reps
-    cin, cout, S = eng.cin_de[0], C[1], eng.S[0]
-    alg_bytes = 4.0 * B * V[0] * (cin + cout) + 4.0 * V[0] * S + 4.0 * (S * cin * cout + cout)
-    flops = 2.0 * B * V[0] * S * cin * cout
-    return sec, alg_bytes, flops
+    return s.elapsed_time(e) / 1e3 / reps
+
+
+def time_conv_kernels(eng, reps=10):
+    """The three passes of the de4 SpiralConv (17039 x 288 x 32 per mesh: half of the model's FLOPs) -- forward+ELU,
+    weight gradient, backward-to-input -- each timed alone with CUDA events on the launching stream, on the engine's
+    own buffers (1024 x 17039 x 32 floats each: far beyond L2).  Returns {pass: (seconds, kernel name)} and the
+    algorithmic bytes / flops of one pass."""
+    from sdvae_b200 import cabi
+    L, V, C, B, S = eng.L, eng.V, eng.C, eng.B, eng.S
+    layer = eng.model.de_layers[L].conv.layer
+    cin, cout = eng.cin_de[0], C[1]
+    eng._pack_tc()
+    out = {}
+    ef, eb = eng.tc.get(('f', 'de0')), eng.tc.get(('b', 'de0'))
+    tiled = ef is not None and ef['tile'] is not None
+    out['fwd'] = (_time(lambda: eng._conv(eng.u[0], eng.full[0], layer, eng.d[0], cabi.ACT_ELU, B, V[0], cin, cout, 'de0'), reps),
+                  "gt_kernel<uniform> (tcgen05 3xTF32, tile-staged)" if tiled else
+                  ("gc_umma_kernel<32,32,uniform> (tcgen05 3xTF32)" if ef is not None else "gc_tile_kernel (fp32 FMA)"))
+    out['dW'] = (_time(lambda: eng._bwd_w(eng.u[0], eng.full[0], eng.dd[0], layer, B, V[0], cin, cout), reps),
+                 "bt_kernel (tcgen05 3xTF32, tile-staged)" if tiled and eng.full[0].tile_fwd() is not None else
+                 ("bw_umma_kernel (tcgen05 3xTF32)" if eng.use_tc else "bw_outer_kernel (fp32 FMA)"))
+    if eb is not None and eb['tile'] is not None:
+        run = lambda: cabi.spiralconv_bwd_x_tile(eng.dd[0], eb['tile'], eb['parts'][0][2], None, eng.du[0], B, V[0], V[0], S[0], cout, cin)
+        name = "gt_kernel<ragged> (tcgen05 3xTF32, tile-staged)"
+    elif eb is not None:
+        run = lambda: cabi.spiralconv_bwd_x_tc(eng.dd[0], eb['plan'], eb['parts'][0][2], None, eng.du[0], B, V[0], V[0], S[0], cout, cin, 0)
+        name = "gc_umma_kernel<32,32,ragged> (tcgen05 3xTF32)"
+    else:
+        run, name = None, None
+    if run is not None:
+        out['dx'] = (_time(run, reps), name)
+    alg_bytes = 4.0 * B * V[0] * (cin + cout) + 4.0 * V[0] * S[0] + 4.0 * (S[0] * cin * cout + cout)
+    flops = 2.0 * B * V[0] * S[0] * cin * cout
+    return out, alg_bytes, flops
 
 
 def time_pool_kernel(eng, reps=10):
@@ -299,61 +342,89 @@ def run_ours(args):
 
     if rank != 0:
         return
-    # ---- roofline of the dominant kernel (rank 0, timed alone) -------------------------
+    # ---- roofline: the LONGEST kernel of the step (rank 0, timed alone), the layer's other passes, the whole step ----
     hbm_peak, peak_src = peaks()
-    ksec, alg_bytes, flops = time_dominant_kernel(eng)
+    passes, alg_bytes, flops = time_conv_kernels(eng)
+    worst = max(passes, key=lambda k: passes[k][0])
+    ksec, kname = passes[worst]
     achieved = alg_bytes / ksec / 1e9
-    on_tc = ('f', 'de0') in eng.tc
-    kname = ("gc_umma_kernel<32,32,uniform> (tcgen05, 3xTF32)" if on_tc else "gc_tile_kernel<32,32> (fp32 FMA)")
-    # DRAM traffic of this kernel per launch from the ncu --set full capture of the same launch
-    # (profiles/r01_de4_fwd_full_metrics_final.txt: dram__bytes_read.sum + dram__bytes_write.sum =
-    # 2.234 + 2.193 GB at 1024 meshes), scaled to this run's mesh count; null off the captured path.
-    traffic = (2.233842e9 + 2.192886e9) * eng.B / 1024.0 if on_tc else None
-    roofline = {"bound": "hbm", "kernel": "%s de4 SpiralConv+ELU fwd [%d x 17039 x 288 x 32]" % (kname, eng.B),
+    # DRAM traffic per launch: dram__bytes_read.sum + dram__bytes_write.sum of an `ncu --set full` capture of the same
+    # kernel at 1024 meshes (profiles/r02_traffic.json names the capture files and the commit), scaled to this run's
+    # mesh count; null when no capture of this kernel is on file.
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(tpath):
+        t = json.load(open(tpath)).get(kname.split(" ")[0] + ":" + worst)
+        if t:
+            traffic = float(t["dram_bytes_at_1024_meshes"]) * eng.B / 1024.0
+    # whole step: forward + backward ~ 3 x the forward's fused-op bytes (19.79 MB per mesh forward)
+    step_bytes = 3.0 * 19.79e6 * eng.B
+    roofline = {"bound": "hbm",
+                "kernel": "%s de4 SpiralConv %s [%d x 17039 x 288 x 32]" % (kname, worst, eng.B),
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                 "kernel_ms": ksec * 1e3, "effective_tflops": flops / ksec / 1e12,
-                "note": ("tensor-core contraction (error-compensated 3xTF32, fp32-level parity). DRAM traffic = "
-                         "algorithmic bytes (no re-reads); the kernel is bound by the L2->SM gather of 9 neighbour "
-                         "rows per vertex (7.0 TB/s L2->SM in the ncu capture, ~8 TB/s measured ceiling for "
-                         "128-byte row gathers), by instruction issue (76 % of issue slots) and by the single "
-                         "MMA-issuing thread, not by HBM"
-                         if on_tc else "fp32-FMA contraction: compute-bound on the FMA pipe "
-                         "(peak %.1f TFLOP/s)" % (148 * 128 * 2 * 1.965e9 / 1e12))}
+                "selection": "longest launch of the step (the three passes of the de4 layer are its three longest kernels)",
+                "de4_passes": {k: {"kernel": v[1], "kernel_ms": v[0] * 1e3, "achieved": alg_bytes / v[0] / 1e9,
+                                   "frac": alg_bytes / v[0] / 1e9 / hbm_peak} for k, v in passes.items()},
+                "whole_step": {"algorithmic_bytes": step_bytes, "ms_per_step": ms / K,
+                               "achieved": step_bytes / (ms / K / 1e3) / 1e9,
+                               "frac": step_bytes / (ms / K / 1e3) / 1e9 / hbm_peak,
+                               "note": "3 x 19.79 MB per mesh (forward + two backward passes of every fused op) over this "
+                                       "rank's step time"},
+                "note": ("error-compensated 3xTF32 on tcgen05 (fp32-level parity).  Not HBM-bound: the tile's distinct "
+                         "source rows are staged once in shared memory (DRAM and L2 traffic ~ algorithmic), the kernel is "
+                         "bound by the TMEM stores of the gathered, hi/lo-split A operand (tcgen05.st ~155 clk per 4 KB "
+                         "and warp + ~300 clk tcgen05.wait::st, tools/sttm_bench.cu; profiles/r02_tile_kernel.md)")}
     psec, palg = time_pool_kernel(eng)
+    use_graph, renumbered, has_tc, meshes_per_gpu, n_params = bool(eng.use_graph), bool(eng.renumber), bool(eng.tc), eng.B, eng.n_params
+    pool_B, pool_V = eng.B, (eng.V[1], eng.V[0])
     pool_roofline = {"bound": "hbm", "kernel": "pool_ell_fwd_staged_kernel: Pool up-sampling fwd [%d x %d -> %d x 32]"
-                                               % (eng.B, eng.V[1], eng.V[0]),
+                                               % (pool_B, pool_V[0], pool_V[1]),
                      "achieved": palg / psec / 1e9, "peak": hbm_peak, "unit": "GB/s",
                      "frac": palg / psec / 1e9 / hbm_peak, "algorithmic_bytes": palg, "kernel_ms": psec * 1e3,
                      # ncu --set full of this launch at 1024 meshes (profiles/r01_pool_staged_full_metrics.txt)
-                     "traffic": (0.583874e9 + 2.175260e9) * eng.B / 1024.0, "peak_source": peak_src,
+                     "traffic": (0.583874e9 + 2.175260e9) * pool_B / 1024.0, "peak_source": peak_src,
                      "note": "distinct source rows of each 128-row tile staged in shared memory (cp.async ring); "
                              "bit-identical to the reference's storage-order arithmetic"}
     cpu = None
-    if not args.no_cpu_baseline and world == 1:      # reported baseline: rank 0 at N = 1 only
-        rate, sec = cpu_step_rate(tabs, args.ref_bs, 5, 2, args.seed)
-        cpu = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": "5 steps (2 warm-up) of the same training step on %d swapped meshes (bs=%d), "
-                         "oracle port on torch-CPU, all host threads" % (args.ref_bs ** 2, args.ref_bs),
-               "ms_per_step": sec * 1e3}
+    ref_cuda = None
+    if not args.no_cpu_baseline and world == 1:      # reported baselines: rank 0 at N = 1 only
+        rate, sec, kind = cpu_step_rate(tabs, args.ref_bs, 5, 2, args.seed)
+        cpu = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": kind,
+               "sample": cpu_sample_text(kind, 5, args.ref_bs), "ms_per_step": sec * 1e3}
+        # the kernel-for-kernel comparator: the same unmodified reference modules, eager ATen / cuBLAS
+        # kernels on this B200, fp32 (TF32 off, torch default), 256 swapped meshes per step (the reference keeps every
+        # materialised gather for backward: ~75 MB per mesh)
+        from baseline import refarm
+        ref = refarm.find_ref()
+        if ref is not None:
+            del eng
+            torch.cuda.empty_cache()
+            try:
+                r2, s2 = refarm.time_reference_steps(ref, tabs, dev, 16, 3, 2, args.seed)
+                ref_cuda = {"value": r2, "unit": UNIT, "ms_per_step": s2 * 1e3, "meshes_per_step": 256,
+                            "what": "reference model.py + lifted loss methods + SwapFeatures (CPU collate, as in the "
+                                    "reference's DataLoader), torch eager on cuda, 3 timed steps"}
+            except Exception as ex:      # never lose the bench line to the comparator
+                ref_cuda = {"unavailable": repr(ex)[:200]}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "craniofacial.yaml train step (swap + fwd + MSE/KL/LC/Laplacian + bwd + Adam), "
-                               "V=17039, global batch %d" % (bs * bs),
-                   "global_batch": bs * bs, "grid": "%dx%d" % (bs, bs), "meshes_per_gpu": eng.B,
+        "config": {"workload": WORKLOAD % (bs * bs),
+                   "global_batch": bs * bs, "grid": "%dx%d" % (bs, bs), "meshes_per_gpu": meshes_per_gpu,
                    "parallelism": "dp%d (swap-grid rows)" % world,
-                   "l2": "per-step working set (%.1f GB/GPU) exceeds the 126 MB L2" % (eng.B * 12.0e6 / 1e9),
-                   "cuda_graph": bool(eng.use_graph), "vertex_order": "patch-wise (experiment)" if args.renumber else "template",
+                   "l2": "per-step working set (%.1f GB/GPU) exceeds the 126 MB L2" % (meshes_per_gpu * 12.0e6 / 1e9),
+                   "cuda_graph": use_graph, "vertex_order": "template outside the engine; internal levels patch-wise" if renumbered else "template",
                    "contractions": ("tcgen05 3xTF32 for every 32/64-channel SpiralConv pass; the two 3-channel layers "
                                     "on the fp32 FMA units from shared-memory-resident meshes / staged rows")
-                                   if eng.tc else "fp32 FMA"},
+                                   if has_tc else "fp32 FMA"},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": int(x_pin.numel() * 4), "d2h_bytes_per_step": 32},
-        "roofline": roofline, "pool_roofline": pool_roofline, "cpu_baseline": cpu,
-        "losses_last_step": last, "params": eng.n_params,
+        "roofline": roofline, "pool_roofline": pool_roofline, "cpu_baseline": cpu, "reference_eager_cuda": ref_cuda,
+        "losses_last_step": last, "params": n_params,
     }
     print(json.dumps(line), flush=True)
 

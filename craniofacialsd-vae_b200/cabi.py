@@ -75,6 +75,8 @@ _SIGNATURES = {
     "sdvae_reparam_bwd": (C.c_int, [_c_fp] * 5 + [C.c_longlong, C.c_int, _c_fp]),
     "sdvae_axpy3": (C.c_int, [_c_fp, _c_fp, C.c_float, _c_fp, C.c_float, _c_fp, C.c_longlong, _c_fp]),
     "sdvae_swap": (C.c_int, [_c_fp] * 3 + [C.c_int] * 5 + [_c_fp]),
+    "sdvae_l1_fwd": (C.c_int, [_c_fp] * 4 + [C.c_longlong, _c_fp]),
+    "sdvae_l1_bwd": (C.c_int, [_c_fp] * 3 + [C.c_longlong, C.c_float, _c_fp]),
     "sdvae_mse_lap_partial_floats": (C.c_size_t, [C.c_int, C.c_int]),
     "sdvae_mse_lap_fwd": (C.c_int, [_c_fp] * 4 + [C.c_int] + [_c_fp] * 3 + [C.c_int, C.c_int, C.c_float, _c_fp]),
     "sdvae_mse_lap_bwd": (C.c_int, [_c_fp] * 7 + [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, _c_fp, _c_fp]),
@@ -145,6 +147,11 @@ def _stream() -> int:
 def _chk(t: torch.Tensor, dtype, name: str) -> int:
     if not t.is_cuda:
         raise RuntimeError("sdvae_b200: %s must be a CUDA tensor (no CPU fallback)" % name)
+    if t.device.index != torch.cuda.current_device():
+        # the launch goes to the current device's current stream: a tensor of another device would be read through a
+        # foreign pointer.  TrainEngine / the autograd functions set the device of their tensors before they call.
+        raise RuntimeError("sdvae_b200: %s is on %s but the current device is cuda:%d (use torch.cuda.device(...))"
+                           % (name, t.device, torch.cuda.current_device()))
     if t.dtype != dtype:
         raise TypeError("sdvae_b200: %s must be %s, got %s" % (name, dtype, t.dtype))
     if not t.is_contiguous():
@@ -563,6 +570,20 @@ def swap(x, mask_u8, out, bs, i0, i1, V, Cc):
     if rc:
         _err(rc, "swap")
     add_launches(_KERNELS_PER_CALL["swap"])
+
+
+def l1_fwd(a, b, partial, out):
+    rc = load().sdvae_l1_fwd(_f(a, "a"), _f(b, "b"), _f(partial, "partial"), _f(out, "out"), a.numel(), _stream())
+    if rc:
+        _err(rc, "l1_fwd")
+    add_launches(2)
+
+
+def l1_bwd(a, b, da, g):
+    rc = load().sdvae_l1_bwd(_f(a, "a"), _f(b, "b"), _f(da, "da"), a.numel(), float(g), _stream())
+    if rc:
+        _err(rc, "l1_bwd")
+    add_launches(1)
 
 
 def mse_lap_partial_floats(B, V) -> int:

@@ -185,6 +185,25 @@ __global__ void lc_grad_kernel(const float* __restrict__ z, const unsigned char*
 }
 
 // ---- finishing reduction ------------------------------------------------------------------
+// L1 reconstruction loss (reference model_manager.py:328-330, torch.nn.L1Loss(reduction='mean')): per-block partial
+// sums of |a - b| (warp shuffle -> block), fixed order; l1_bwd_kernel: d/da = sign(a - b) * scale.
+__global__ void __launch_bounds__(kLossThreads)
+l1_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ partial, long long n) {
+    __shared__ float sh[kLossThreads / 32];
+    const long long i = (long long)blockIdx.x * kLossThreads + threadIdx.x;
+    float v = i < n ? fabsf(a[i] - b[i]) : 0.f;
+    v = block_sum<kLossThreads>(v, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = v;
+}
+
+__global__ void l1_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ da,
+                              long long n, float scale) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float d = a[i] - b[i];
+    da[i] = d > 0.f ? scale : (d < 0.f ? -scale : 0.f);
+}
+
 // Sums `count` floats with stride `stride` starting at part[offset] in double, in one block.
 // out[slot] = scale * sum.
 __global__ void __launch_bounds__(kLossThreads)

@@ -17,6 +17,19 @@
 namespace sdvae {
 char g_last_error[512] = "";
 
+// true the first time it is asked on each device (cudaFuncSetAttribute is per device, a process may drive several)
+struct DeviceOnce {
+    unsigned long long mask = 0ull;
+    bool first() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const unsigned long long bit = 1ull << (dev & 63);
+        if (mask & bit) return false;
+        mask |= bit;
+        return true;
+    }
+};
+
 static inline unsigned blocks_for(long long n, int threads) {
     return (unsigned)((n + threads - 1) / threads);
 }
@@ -28,11 +41,8 @@ static int launch_gc(const GcArgs& a, int epi, cudaStream_t st) {
     const size_t smem = Cfg::smem_bytes(a.S, RAGGED);
     const dim3 grid((unsigned)((a.M + Cfg::BM - 1) / Cfg::BM), (unsigned)((a.n_real + NT - 1) / NT));
     auto kern = gc_tile_kernel<KS, NT, TM, TN, NWARPS, RAGGED>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_done = true;
-    }
+    static DeviceOnce attr_done;       // the attribute is per device
+    if (attr_done.first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     GcArgs b = a;
     b.epi = epi;
     kern<<<grid, Cfg::THREADS, smem, st>>>(b);
@@ -78,11 +88,8 @@ template <int KS, int S_, int NT, int TK, int TN>
 static int launch_bw(const BwArgs& a, int nsplit, cudaStream_t st) {
     using Cfg = BwCfg<KS, S_, NT, TK, TN, kBwBMW>;
     auto kern = bw_outer_kernel<KS, S_, NT, TK, TN, kBwBMW>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_done = true;
-    }
+    static DeviceOnce attr_done;       // the attribute is per device
+    if (attr_done.first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     kern<<<nsplit, Cfg::THREADS, Cfg::SMEM, st>>>(a);
     return check_launch("bw_outer_kernel");
 }
@@ -112,11 +119,8 @@ template <int KS, int NT, bool UNIFORM>
 static int launch_umma(umma::UmmaArgs& ua, cudaStream_t st) {
     using Cfg = umma::UmmaCfg<KS, NT>;
     auto kern = umma::gc_umma_kernel<KS, NT, UNIFORM>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_done = true;
-    }
+    static DeviceOnce attr_done;       // the attribute is per device
+    if (attr_done.first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     ua.nraw = Cfg::raw_stages(ua.S, ua.rcap);
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SDVAE_DBG"); dbg = e ? atoi(e) : 0; } ua.dbg = dbg; }
     const long long ntiles = (long long)ua.B * ua.L;
@@ -175,11 +179,8 @@ static int launch_pool_staged_n(const float* x, const int32_t* tile_ptr, const i
                                 const int32_t* ent, float* out, int B, int Vin, int Vout, int ucap,
                                 cudaStream_t st) {
     auto kern = pool_ell_fwd_staged_kernel<CQ, WD, NST>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_done = true;
-    }
+    static DeviceOnce attr_done;       // the attribute is per device
+    if (attr_done.first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     const size_t smem = (size_t)NST * ucap * CQ * 16;
     const int L = (Vout + kPoolTile - 1) / kPoolTile;
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (226 * 1024) / (smem + 1024)));
@@ -465,11 +466,8 @@ int sdvae_slot_pack(const float* in, const int32_t* cell_ptr, const int32_t* cel
     cudaStream_t st = (cudaStream_t)stream;
     const size_t in_bytes = (size_t)Vin * C * sizeof(float);
     if (in_bytes <= 220 * 1024) {            // the mesh's narrow input fits in shared memory
-        static bool attr_done = false;
-        if (!attr_done) {
-            cudaFuncSetAttribute(slot_pack_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-            attr_done = true;
-        }
+        static DeviceOnce attr_done;       // the attribute is per device
+        if (attr_done.first()) cudaFuncSetAttribute(slot_pack_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         int parts = 1;                         // split meshes into row ranges until the grid fills the SMs evenly
         while ((long long)B * parts < 4LL * kNumSMs && parts < 16 && R / (parts * 2) >= 256) parts *= 2;
         const long long items = (long long)B * parts;
@@ -541,11 +539,8 @@ int sdvae_spiralconv_bwd_w_tc(const float* x, const int32_t* plan_cnt, const int
     a.flush = flush_tiles;
     a.in_ld = Cin; a.g_ld = Cout; a.part_ld = K; a.part_cta = Cout * K; a.partb_cta = Cout;
     cudaMemsetAsync(part, 0, sizeof(float) * (size_t)grid * (Cout * K + Cout), st);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(umma::bw_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_done = true;
-    }
+    static DeviceOnce attr_done;       // the attribute is per device
+    if (attr_done.first()) cudaFuncSetAttribute(umma::bw_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     const size_t smem = 1024 + 2 * (size_t)umma::kGStage + (size_t)a.nraw * rcap * 128 + 1024;
     // one pass per (32 input channels, <= 32 output channels); the bias gradient comes from the first
     // input-channel pass only (its row of ones)
@@ -764,11 +759,8 @@ int sdvae_narrow_out_bwd(const float* dy, const float* x, const int32_t* cell_pt
     int grid = 0;
     if (B > 0) {
         auto kern = narrow_out_bwd_kernel<9, 3>;
-        static bool attr_done = false;
-        if (!attr_done) {
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-            attr_done = true;
-        }
+        static DeviceOnce attr_done;       // the attribute is per device
+        if (attr_done.first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         const int parts = narrow_parts(B, Vin, 6.0 * R / 17039.0, 22.0);
         const long long items = (long long)B * parts;
         grid = items < kNumSMs ? (int)items : kNumSMs;
@@ -804,11 +796,8 @@ int sdvae_narrow_in_fwd(const float* x, const int32_t* idx, const float* W, cons
     if (B == 0) return SDVAE_OK;
     using Cfg = NarrowInCfg<9, 3>;
     auto kern = narrow_in_kernel<9, 3, 0>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_done = true;
-    }
+    static DeviceOnce attr_done;       // the attribute is per device
+    if (attr_done.first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     const int parts = narrow_in_parts(B, R, Vin);
     const long long items = (long long)B * parts;
     const int grid = items < kNumSMs ? (int)items : kNumSMs;
@@ -829,11 +818,8 @@ int sdvae_narrow_in_bwd_w(const float* x, const int32_t* idx, const float* dpre,
     int grid = 0;
     if (B > 0) {
         auto kern = narrow_in_kernel<9, 3, 1>;
-        static bool attr_done = false;
-        if (!attr_done) {
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-            attr_done = true;
-        }
+        static DeviceOnce attr_done;       // the attribute is per device
+        if (attr_done.first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         const int parts = narrow_in_parts(B, R, Vin);
         const long long items = (long long)B * parts;
         grid = items < kNumSMs ? (int)items : kNumSMs;
@@ -867,11 +853,8 @@ int sdvae_narrow_out_fwd(const float* x, const int32_t* tile_ptr, const int32_t*
     { static int env = -1; if (env < 0) { const char* e = getenv("SDVAE_NARROW_STAGES"); env = e ? atoi(e) : 0; }
       if (env >= kNarrowMinStages && env <= nst) nst = env; }
     auto kern = nst == 5 ? narrow_out_fwd_kernel<9, 3, 5> : nst == 4 ? narrow_out_fwd_kernel<9, 3, 4> : narrow_out_fwd_kernel<9, 3, 3>;
-    static bool attr_done[8] = {false};
-    if (!attr_done[nst]) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_done[nst] = true;
-    }
+    static DeviceOnce attr_done[8];      // per stage count and per device
+    if (attr_done[nst].first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     const size_t smem = (size_t)nst * ucap * 128;
     const int L = (Vout + kNarrowTile - 1) / kNarrowTile;
     const int MG = pick_mesh_group(B, L, kNumSMs, nst);          // one CTA per SM (registers)
@@ -997,6 +980,21 @@ int sdvae_mse_lap_fwd(const float* recon, const float* x, const int32_t* lcol, c
     finish_sum_kernel<<<1, kLossThreads, 0, st>>>(partial, grid, 2, 0, inv_count_scale / (float)((double)BV * 3.0), losses, 0);
     if (lcol) finish_sum_kernel<<<1, kLossThreads, 0, st>>>(partial, grid, 2, 1, inv_count_scale / (float)BV, losses, 3);
     return check_launch("mse_lap_fwd");
+}
+
+int sdvae_l1_fwd(const float* a, const float* b, float* partial, float* out, long long n, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(a && b && partial && out && n > 0, "l1_fwd: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = blocks_for(n, kLossThreads);
+    l1_fwd_kernel<<<grid, kLossThreads, 0, st>>>(a, b, partial, n);
+    finish_sum_kernel<<<1, kLossThreads, 0, st>>>(partial, grid, 1, 0, 1.0f / (float)n, out, 0);
+    return check_launch("l1_fwd");
+}
+
+int sdvae_l1_bwd(const float* a, const float* b, float* da, long long n, float g, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(a && b && da && n > 0, "l1_bwd: bad argument");
+    l1_bwd_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, da, n, g / (float)n);
+    return check_launch("l1_bwd_kernel");
 }
 
 int sdvae_mse_lap_bwd(const float* recon, const float* x, const float* qn, const int32_t* tptr,

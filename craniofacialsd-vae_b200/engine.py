@@ -97,7 +97,9 @@ class TrainEngine:
         self.B = self.rows * bs                          # local meshes per step
         self.is_vae = bool(model.is_vae)
         self.L = len(model.out_channels)
-        self.lap = laplacian if cfg.laplacian_weight > 0 else None
+        # the Laplacian term is always EVALUATED (model_manager.py:283 computes it whatever its weight); with weight 0
+        # only its backward is skipped
+        self.lap = laplacian
         self.latent_regions = [tuple(int(t) for t in r) for r in latent_regions]
         self.use_lc = cfg.latent_consistency_weight > 0
         # The data-parallel step is captured too (NCCL collectives are graph-capturable; the side stream that
@@ -123,9 +125,12 @@ class TrainEngine:
             if self.lap is not None:
                 self.lap = self.lap.renumbered(self.order0)
         self.masks = torch.from_numpy(masks).to(self.dev)
-        self._build_arenas()
-        self._alloc_buffers()
-        self.side = torch.cuda.Stream(device=self.dev) if self.world > 1 else None
+        with torch.cuda.device(self.dev):
+            self._build_arenas()
+            self._alloc_buffers()
+            self.side = torch.cuda.Stream(device=self.dev) if self.world > 1 else None
+            if self.world > 1:
+                self._sync_replicas()
 
     # ------------------------------------------------------------------ tables
     def _build_tables(self):
@@ -188,6 +193,31 @@ class TrainEngine:
 
     def g(self, p):
         return self.grad[id(p)]
+
+    def _sync_replicas(self):
+        """Data-parallel start-up: every rank takes rank 0's parameters / Adam state (only GRADIENTS are all-reduced
+        afterwards, so replicas that start different stay different), and the re-parameterisation noise of each rank
+        comes from its own stream of the device generator -- with one seed everywhere every rank would draw the SAME
+        eps for its rows of the swap grid, unlike the single-GPU step."""
+        import torch.distributed as dist
+        for t in (self.flat_p, self.flat_m, self.flat_v):
+            dist.broadcast(t, src=dist.get_global_rank(self.pg, 0) if hasattr(dist, 'get_global_rank') else 0, group=self.pg)
+        step = self.step_dev.to(torch.int64)
+        dist.broadcast(step, src=dist.get_global_rank(self.pg, 0) if hasattr(dist, 'get_global_rank') else 0, group=self.pg)
+        self.step_dev.copy_(step.to(torch.int32))
+        seed = torch.tensor([torch.cuda.initial_seed()], device=self.dev, dtype=torch.int64)
+        dist.broadcast(seed, src=dist.get_global_rank(self.pg, 0) if hasattr(dist, 'get_global_rank') else 0, group=self.pg)
+        torch.cuda.manual_seed(int(seed.item()) + 7919 * (self.rank + 1))
+
+    def _check_arena(self):
+        """The kernels read the weights through pointers into the flat arena taken at construction: a later
+        ``model.to()`` / ``.half()`` / parameter re-assignment would leave them on stale memory -- fail loudly."""
+        for p in self.model.parameters():
+            v = self.grad.get(id(p))
+            if v is None or p.data.dtype != torch.float32 or not (
+                    self.flat_p.data_ptr() <= p.data.data_ptr() < self.flat_p.data_ptr() + self.flat_p.numel() * 4):
+                raise RuntimeError('TrainEngine: a model parameter no longer lives in the engine arena (the model was '
+                                   'moved / cast / re-assigned after the engine was built); rebuild the TrainEngine')
 
     # ------------------------------------------------------------------ buffers
     def _alloc_buffers(self):
@@ -462,7 +492,7 @@ class TrainEngine:
         # ---- backward: decoder ------------------------------------------------------
         if lap is not None:
             cabi.mse_lap_bwd(self.recon, self.x0, self.qn, lap.t_ptr, lap.t_row, lap.t_val,
-                             self.drecon, B, V[0], 1.0, cfg.laplacian_weight, scale, None)
+                             self.drecon, B, V[0], 1.0, cfg.laplacian_weight, scale, None)      # weight 0: no Laplacian gradient
         else:
             cabi.mse_lap_bwd(self.recon, self.x0, None, None, None, None, self.drecon, B, V[0],
                              1.0, 0.0, scale, None)
@@ -653,8 +683,7 @@ class TrainEngine:
 
     def load_local(self, x_local: torch.Tensor):
         """Copy this rank's ``B`` already-assembled meshes straight into the network input
-        (use with ``step(region=None)``: no device-side swap, no latent-consistency term
-        unless ``lc_region`` is given)."""
+        (use with ``step(region=None)``: no device-side swap, no latent-consistency term)."""
         if self.order0_dev is None:
             self.x0.copy_(x_local, non_blocking=True)
         else:
@@ -673,8 +702,13 @@ class TrainEngine:
 
     def step(self, region: Optional[int], sync_losses: bool = False):
         """One training iteration on the batch previously given to ``load_batch``.
-        ``region`` = index of the swapped region (None: ``x_in`` already holds the local
-        ``B`` meshes un-swapped in ``x0``... i.e. no swap and no latent-consistency term)."""
+        ``region`` = index of the swapped region; ``None``: the ``B`` local meshes were given ready-made through
+        ``load_local`` -- no device-side swap and no latent-consistency term."""
+        self._check_arena()
+        with torch.cuda.device(self.dev):
+            return self._step(region, sync_losses)
+
+    def _step(self, region: Optional[int], sync_losses: bool):
         if self.use_graph:
             key = -1 if region is None else int(region)
             gph = self._graphs.get(key)

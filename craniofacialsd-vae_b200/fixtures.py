@@ -440,15 +440,23 @@ def synthetic_tables(n_vertices: int, n_levels: int, seq_length: int = 9,
     return MeshTables(spirals, down, up, lap, regions, name)
 
 
-def default_golden_path() -> str:
+def default_tables_path() -> str:
+    """Package data (not a test fixture): the reference's index tables re-serialised by tools/make_golden.py."""
     here = os.path.dirname(os.path.abspath(__file__))
-    return os.path.join(os.path.dirname(here), 'tests', 'golden', 'craniofacial_tables.npz')
+    return os.path.join(here, 'data', 'craniofacial_tables.npz')
 
 
-def craniofacial_tables() -> MeshTables:
-    """The reference's craniofacial index tables, from the committed bundle
-    (generated by ``tools/make_golden.py`` out of demo_files/)."""
-    p = default_golden_path()
+def craniofacial_tables(ref_demo_dir: Optional[str] = None) -> MeshTables:
+    """The reference's craniofacial index tables.  With ``ref_demo_dir`` (a ``demo_files`` directory): straight from
+    the reference's own input files ``spirals.pkl`` / ``transforms.pkl`` / ``template.ply``
+    (``tables_from_reference_files``); otherwise from the packaged bundle ``data/craniofacial_tables.npz`` that
+    ``tools/make_golden.py`` derived from exactly those files (tests/test_tables_cpu.py checks the two agree
+    wherever the reference is staged)."""
+    if ref_demo_dir is not None:
+        return tables_from_reference_files(os.path.join(ref_demo_dir, 'spirals.pkl'),
+                                           os.path.join(ref_demo_dir, 'transforms.pkl'),
+                                           os.path.join(ref_demo_dir, 'template.ply'))
+    p = default_tables_path()
     if not os.path.exists(p):
         raise FileNotFoundError(p + ' is missing; run tools/make_golden.py where /root/reference exists')
     return MeshTables.load_npz(p)

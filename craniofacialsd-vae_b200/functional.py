@@ -220,8 +220,9 @@ def spiral_conv(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tens
     if x.shape[2] * table.seq != weight.shape[1]:
         raise RuntimeError('SpiralConv: x has %d channels, weight expects %d'
                            % (x.shape[2], weight.shape[1] // table.seq))
-    return SpiralConvFn.apply(x, _prep(weight, 'weight'),
-                              None if bias is None else _prep(bias, 'bias'), table, act)
+    with torch.cuda.device(x.device):        # launches go to the CURRENT device's stream: make it x's device
+        return SpiralConvFn.apply(x, _prep(weight, 'weight'),
+                                  None if bias is None else _prep(bias, 'bias'), table, act)
 
 
 # ---------------------------------------------------------------------------
@@ -252,13 +253,15 @@ def pool(x: torch.Tensor, trans: torch.Tensor, dim: int = 1) -> torch.Tensor:
     x = _prep(x, 'x')
     table = pool_table(trans)
     if x.dim() == 2 and dim in (0, -2):
-        return PoolFn.apply(x.unsqueeze(0), table).squeeze(0)
+        with torch.cuda.device(x.device):
+            return PoolFn.apply(x.unsqueeze(0), table).squeeze(0)
     if x.dim() != 3 or dim not in (1, -2):
         raise RuntimeError('Pool expects x [B, V, C] with dim=1, got shape %s dim=%d'
                            % (tuple(x.shape), dim))
     if x.shape[1] != table.n_cols:
         raise RuntimeError('Pool: x has %d vertices, transform expects %d' % (x.shape[1], table.n_cols))
-    return PoolFn.apply(x, table)
+    with torch.cuda.device(x.device):
+        return PoolFn.apply(x, table)
 
 
 # ---------------------------------------------------------------------------
@@ -282,4 +285,5 @@ class ReparamFn(torch.autograd.Function):
 
 
 def reparameterize(mu, logvar, eps):
-    return ReparamFn.apply(_prep(mu, 'mu'), _prep(logvar, 'logvar'), _prep(eps, 'eps'))
+    with torch.cuda.device(mu.device):
+        return ReparamFn.apply(_prep(mu, 'mu'), _prep(logvar, 'logvar'), _prep(eps, 'eps'))

@@ -5,6 +5,7 @@ Mirrors the loss methods of ``ModelManager`` (reference model_manager.py):
 =============================  ==========================================  =================
 this module                    reference                                   lines
 =============================  ==========================================  =================
+``l1_loss``                    ``_compute_l1_loss``                        :328-330
 ``mse_loss``                   ``compute_mse_loss``                        :332-334
 ``laplacian_regularizer``      ``_compute_laplacian_regularizer``          :343-349
 ``mse_and_laplacian``          both from one read of the reconstruction    --
@@ -111,6 +112,29 @@ class MseLapFn(torch.autograd.Function):
 def mse_and_laplacian(prediction, gt, lap: LaplacianTable):
     """Both reconstruction terms from a single pass over ``prediction``."""
     return MseLapFn.apply(_check(prediction, 'prediction'), _check(gt, 'gt'), lap)
+
+
+class L1Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, prediction, gt):
+        out = torch.zeros(1, device=prediction.device, dtype=torch.float32)
+        partial = torch.empty((prediction.numel() + 255) // 256, device=prediction.device, dtype=torch.float32)
+        cabi.l1_fwd(prediction, gt, partial, out)
+        ctx.save_for_backward(prediction, gt)
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        prediction, gt = ctx.saved_tensors
+        d = torch.empty_like(prediction)
+        cabi.l1_bwd(prediction, gt, d, 1.0)
+        return d * g, None
+
+
+def l1_loss(prediction, gt):
+    """``torch.nn.L1Loss(reduction='mean')`` (model_manager.py:328-330; defined by the reference, never called by
+    its training step)."""
+    return L1Fn.apply(_check(prediction, 'prediction'), _check(gt, 'gt'))
 
 
 def mse_loss(prediction, gt):

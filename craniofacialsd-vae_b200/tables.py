@@ -689,8 +689,18 @@ _pool_cache: Dict[tuple, tuple] = {}
 _restricted_cache: Dict[tuple, SpiralTable] = {}
 
 
+_CACHE_LIMIT = 64        # derived tables of at most this many caller tensors stay cached (oldest evicted first)
+
+
 def _key(t: torch.Tensor):
-    return (t.data_ptr(), tuple(t.shape), str(t.device), t.dtype)
+    # _version: an in-place edit of the caller's tensor after first use must not hit stale derived tables
+    return (t.data_ptr(), tuple(t.shape), str(t.device), t.dtype, t._version)
+
+
+def _remember(cache: dict, k, value):
+    while len(cache) >= _CACHE_LIMIT:
+        cache.pop(next(iter(cache)))
+    cache[k] = value
 
 
 def spiral_table(indices: torch.Tensor, n_src: Optional[int] = None) -> SpiralTable:
@@ -704,7 +714,7 @@ def spiral_table(indices: torch.Tensor, n_src: Optional[int] = None) -> SpiralTa
         raise ValueError('indices must be [V, S]')
     n_src_eff = int(indices.shape[0]) if n_src is None else int(n_src)
     tab = SpiralTable.build(indices.detach().cpu().numpy(), n_src_eff, indices.device)
-    _spiral_cache[k] = (indices, tab)
+    _remember(_spiral_cache, k, (indices, tab))
     return tab
 
 
@@ -712,14 +722,14 @@ def pool_table(trans: torch.Tensor) -> PoolTable:
     """``PoolTable`` for a caller-owned sparse COO matrix (model.py:50-52); only
     ``_indices()``, ``_values()`` and the shape are read, as in the reference."""
     ind, val = trans._indices(), trans._values()
-    k = (ind.data_ptr(), val.data_ptr(), tuple(trans.shape), str(ind.device))
+    k = (ind.data_ptr(), val.data_ptr(), tuple(trans.shape), str(ind.device), ind._version, val._version)
     hit = _pool_cache.get(k)
     if hit is not None:
         return hit[1]
     ind_np = ind.detach().cpu().numpy()
     tab = PoolTable.build(ind_np[0], ind_np[1], val.detach().cpu().numpy().astype(np.float32),
                           (trans.size(0), trans.size(1)), ind.device)
-    _pool_cache[k] = ((ind, val), tab)
+    _remember(_pool_cache, k, ((ind, val), tab))
     return tab
 
 
@@ -745,13 +755,14 @@ def restricted_spiral_table(indices: torch.Tensor, pool: PoolTable) -> Optional[
         return None
     k = _key(indices) + (id(pool),)
     hit = _restricted_cache.get(k)
-    if hit is None:
-        hit = spiral_table(indices).restrict(pool.kept)
-        _restricted_cache[k] = hit
-    return hit
+    if hit is None or hit[0] is not pool:          # (id() of a collected PoolTable can be reused: keep and compare the object)
+        hit = (pool, spiral_table(indices).restrict(pool.kept))
+        _remember(_restricted_cache, k, hit)
+    return hit[1]
 
 
 def clear_caches():
+    """Drop every cached derived table (they hold device memory): call after replacing a model's index tensors."""
     _spiral_cache.clear()
     _pool_cache.clear()
     _restricted_cache.clear()

@@ -295,6 +295,11 @@ int sdvae_swap(const float* x, const uint8_t* mask, float* out, int bs, int i0, 
  *      0 reconstruction, 1 kl, 2 latent_consistency, 3 laplacian, 4 classification,
  *      5 classification_acc, 6 tot) ------------------------------------------------------------ */
 
+/* Replaces: ModelManager._compute_l1_loss (model_manager.py:328-330, torch.nn.L1Loss(reduction='mean')): out[0] =
+ * mean |a - b| over n elements (partial: ceil(n / 256) floats of workspace); l1_bwd: da = g * sign(a - b) / n. */
+int sdvae_l1_fwd(const float* a, const float* b, float* partial, float* out, long long n, sdvae_stream_t stream);
+int sdvae_l1_bwd(const float* a, const float* b, float* da, long long n, float g, sdvae_stream_t stream);
+
 /* losses[0] = mean((recon-x)^2)          model_manager.py:332-334
  * losses[3] = sum_b sum_v |(L recon_b)_v| / V / B   (if lcol != NULL)   model_manager.py:343-349
  * lcol/lval [V,lw] ELL of the random-walk Laplacian; qn [B,V,3] receives q/|q| for the backward;

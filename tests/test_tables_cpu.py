@@ -205,3 +205,57 @@ def test_renumbered_model_tables_and_laplacian_are_consistent():
     want = LaplacianTable.build(*new.lap, V, 'cpu')
     for f in ('ell_col', 'ell_val', 't_ptr', 't_row', 't_val'):
         assert torch.equal(getattr(ln, f), getattr(want, f)), f
+
+
+def _staged_demo():
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    from baseline import refarm
+    ref = refarm.find_ref()
+    if ref is None or not os.path.exists(os.path.join(ref, 'demo_files', 'region_ldas.pkl')):
+        import pytest
+        pytest.skip('reference not staged (tools/stage_reference.py needs /root/reference)')
+    return os.path.join(ref, 'demo_files')
+
+
+def test_region_extraction_is_pinned_to_region_ldas_keys(cranio):
+    """fixtures.extract_regions (restating utils.py:93-135 without trimesh / networkx) must reproduce the region
+    names AND their order that the reference's own run stored in demo_files/region_ldas.pkl -- the order defines the
+    latent slices [5k, 5k+5) of model_manager.py:232-238."""
+    import pickle
+    demo = _staged_demo()
+
+    class _Any:                                   # the pickled values are sklearn LDA objects: only the keys matter
+        def __init__(self, *a, **k): pass
+        def __setstate__(self, st): pass
+
+    class U(pickle.Unpickler):
+        def find_class(self, module, name):
+            try:
+                return super().find_class(module, name)
+            except Exception:
+                return _Any
+    with open(os.path.join(demo, 'region_ldas.pkl'), 'rb') as f:
+        ldas = U(f).load()
+    assert list(ldas.keys()) == cranio.region_keys()
+    lat = cranio.latent_regions(75)
+    assert [lat[k] for k in ldas.keys()] == [[5 * i, 5 * i + 5] for i in range(15)]
+
+
+def test_packaged_tables_equal_the_reference_pkl_files(cranio):
+    """data/craniofacial_tables.npz (what the product path loads) == tables read straight from the reference's own
+    spirals.pkl / transforms.pkl / template.ply."""
+    from sdvae_b200 import fixtures as fx
+    live = fx.craniofacial_tables(_staged_demo())
+    for a, b in zip(live.spirals, cranio.spirals):
+        assert np.array_equal(a, b)
+    for la, lb in ((live.down, cranio.down), (live.up, cranio.up)):
+        for (r1, c1, v1, s1), (r2, c2, v2, s2) in zip(la, lb):
+            assert np.array_equal(r1, r2) and np.array_equal(c1, c2) and np.array_equal(v1, v2) and tuple(s1) == tuple(s2)
+    assert live.region_keys() == cranio.region_keys()
+    for (k1, i1), (k2, i2) in zip(live.regions, cranio.regions):
+        assert k1 == k2 and np.array_equal(i1, i2)
+    for a, b in zip(live.lap, cranio.lap):
+        assert np.array_equal(a, b)

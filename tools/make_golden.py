@@ -6,7 +6,7 @@ Run where ``/root/reference`` exists (it does not exist on the GPU box):
     python tools/make_golden.py [--ref /root/reference]
 
 Outputs (committed):
-  tests/golden/craniofacial_tables.npz   index tables + Laplacian + regions derived from
+  craniofacialsd-vae_b200/data/craniofacial_tables.npz   index tables + Laplacian + regions derived from
                                          demo_files/{spirals.pkl,transforms.pkl,template.ply}
   tests/golden/reference_vectors.npz     outputs / losses / gradients of the reference's own
                                          ``model.py`` and of the loss functions lifted verbatim
@@ -110,7 +110,7 @@ def main():
     tabs = fx.tables_from_reference_files(os.path.join(demo, 'spirals.pkl'),
                                           os.path.join(demo, 'transforms.pkl'),
                                           os.path.join(demo, 'template.ply'))
-    tabs.save_npz(os.path.join(gold, 'craniofacial_tables.npz'))
+    tabs.save_npz(fx.default_tables_path())
     out = {}
 
     # ---------------- case A: craniofacial, bs=2 -> 4 swapped meshes ---------
