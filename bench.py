@@ -323,16 +323,24 @@ def run_ours(args):
     value = meshes / (ms / 1e3)
 
     # ---- end to end: pinned host batch in, 7 loss scalars out, every step --------------
+    # Every step's un-swapped batch is copied from pinned host memory inside the timed region and every step's losses
+    # are read back and waited for; as in any input pipeline the copy of batch k+1 is issued while step k runs (the
+    # engine lands it in a staging buffer on its copy stream, TrainEngine.load_batch).
     seq2 = regions[W + K:2 * (W + K)]
-    for r in seq2[:W]:
+
+    def e2e_steps(rs):
         eng.load_batch(x_pin)
-        eng.step(r, sync_losses=True)
+        for i, r in enumerate(rs):
+            eng.step(r)                                   # consumes the staged batch, launches the step
+            if i + 1 < len(rs):
+                eng.load_batch(x_pin)                     # H2D of the next batch overlaps this step
+            eng.wait_losses()                             # D2H of this step's 7 loss scalars + sync
+
+    e2e_steps(seq2[:W])
     barrier()
     t0 = time.perf_counter()
     s.record()
-    for r in seq2[W:W + K]:
-        eng.load_batch(x_pin)
-        eng.step(r, sync_losses=True)
+    e2e_steps(seq2[W:W + K])
     e.record()
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3

@@ -129,6 +129,10 @@ class TrainEngine:
             self._build_arenas()
             self._alloc_buffers()
             self.side = torch.cuda.Stream(device=self.dev) if self.world > 1 else None
+            self.side_lc = torch.cuda.Stream(device=self.dev) if self.world > 1 else None
+            self.copy_stream = torch.cuda.Stream(device=self.dev)
+            self._staged = None                      # event of a batch copied to x_stage and not yet consumed
+            self._stage_free = None                  # event: the last step has read x_stage
             if self.world > 1:
                 self._sync_replicas()
 
@@ -177,7 +181,11 @@ class TrainEngine:
         n = off
         self.n_params = sum(p.numel() for p in prms)
         self.flat_p = torch.zeros(n, device=self.dev, dtype=torch.float32)
-        self.flat_g = torch.zeros(n, device=self.dev, dtype=torch.float32)
+        # 8 more floats behind the gradients: the loss scalars, so that under data parallelism they ride in the last
+        # gradient bucket's all-reduce instead of a collective of their own
+        self.n_arena = n
+        self.flat_g_all = torch.zeros(n + 8, device=self.dev, dtype=torch.float32)
+        self.flat_g = self.flat_g_all[:n]
         self.flat_m = torch.zeros(n, device=self.dev, dtype=torch.float32)
         self.flat_v = torch.zeros(n, device=self.dev, dtype=torch.float32)
         self.step_dev = torch.zeros(1, device=self.dev, dtype=torch.int32)
@@ -226,6 +234,7 @@ class TrainEngine:
         D = int(self.model.latent_size)
         self.D = D
         self.x_in = f(self.bs, V[0], C[0])                      # un-swapped batch (all ranks hold all bs)
+        self.x_stage = f(self.bs, V[0], C[0])                   # landing buffer of load_batch (template vertex order)
         self.x0 = f(B, V[0], C[0])
         self.a = [f(B, V[l + 1], C[l + 1]) for l in range(L)]   # encoder block outputs
         self.mu, self.logvar = f(B, D), f(B, D)
@@ -258,7 +267,7 @@ class TrainEngine:
         ws = max(ws, cabi.spiralconv_bwd_w_workspace(B * V[0], self.S[0], C[1], C[0]))
         self.ws = f(ws // 4 + 4)
         self._alloc_tc()
-        self.losses = torch.zeros(8, device=dev, dtype=torch.float32)
+        self.losses = self.flat_g_all[self.n_arena:self.n_arena + 8]
         self.losses_host = torch.zeros(8, dtype=torch.float32).pin_memory()
         self.part_mse = f(cabi.mse_lap_partial_floats(B, V[0]))
         self.part_kl = f((B * D + 255) // 256)
@@ -459,9 +468,11 @@ class TrainEngine:
             return
         import torch.distributed as dist
         s, e = self.buckets[k]
+        if k == len(self.buckets) - 1:
+            e = self.n_arena + 8                        # ... and the loss scalars
         self.side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.side):
-            dist.all_reduce(self.flat_g[s:e], op=dist.ReduceOp.SUM, group=self.pg)
+            dist.all_reduce(self.flat_g_all[s:e], op=dist.ReduceOp.SUM, group=self.pg)
 
     def losses_and_backward(self, z, region: Optional[int]):
         m, L, V, C, S, cfg = self.model, self.L, self.V, self.C, self.S, self.cfg
@@ -479,16 +490,23 @@ class TrainEngine:
                             self.losses, B, self.D, scale)
         use_lc = self.use_lc and region is not None
         if use_lc:
-            if self.world > 1:
-                import torch.distributed as dist
-                dist.all_gather_into_tensor(self.z_all, z.contiguous(), group=self.pg)
-                z_all = self.z_all
-            else:
-                z_all = z
             r0, r1 = self.latent_regions[region]
-            cabi.lc_fwd_bwd(z_all, self.bs, self.D, r0, r1, cfg.latent_consistency_eta1,
-                            cfg.latent_consistency_eta2, self.act_lc, self.part_lc, self.dz_lc,
-                            self.losses)
+            if self.world > 1:
+                # the loss needs the whole grid's z: all-gather + loss + its gradient on a side stream -- only the
+                # latent block of the backward pass (after the whole decoder backward) waits for it
+                import torch.distributed as dist
+                main = torch.cuda.current_stream()
+                self.side_lc.wait_stream(main)
+                with torch.cuda.stream(self.side_lc):
+                    dist.all_gather_into_tensor(self.z_all, z.contiguous(), group=self.pg)
+                    cabi.lc_fwd_bwd(self.z_all, self.bs, self.D, r0, r1, cfg.latent_consistency_eta1,
+                                    cfg.latent_consistency_eta2, self.act_lc, self.part_lc, self.dz_lc,
+                                    self.losses)
+                    self.losses[2:3].mul_(1.0 / self.world)
+            else:
+                cabi.lc_fwd_bwd(z, self.bs, self.D, r0, r1, cfg.latent_consistency_eta1,
+                                cfg.latent_consistency_eta2, self.act_lc, self.part_lc, self.dz_lc,
+                                self.losses)
         # ---- backward: decoder ------------------------------------------------------
         if lap is not None:
             cabi.mse_lap_bwd(self.recon, self.x0, self.qn, lap.t_ptr, lap.t_row, lap.t_val,
@@ -555,6 +573,8 @@ class TrainEngine:
         torch.mm(dh2, lin0.weight.data, out=self.dz)
         self._allreduce_bucket(1)
         if use_lc:
+            if self.world > 1:
+                torch.cuda.current_stream().wait_stream(self.side_lc)
             lo = self.i0 * self.bs
             cabi.axpy3(self.dz, self.dz_lc[lo:lo + B], cfg.latent_consistency_weight, None, 0.0,
                        self.dz)
@@ -624,21 +644,18 @@ class TrainEngine:
                 ptr, src = self.sub[l].inverse_flat()
                 cabi.csr_rowsum(G, ptr, src, None, self.a[l - 1], self.da[l - 1], B, R * S[l], V[l],
                                 C[l])
+        # the last bucket carries the loss scalars too: slots 0/1/3 hold this rank's share of the global means, slot 2
+        # (the full latent-consistency loss, identical on every rank) was pre-scaled by 1/world
         self._allreduce_bucket(3)
-        if self.world > 1:
-            # slots 0/1/3 hold this rank's share of the global means; slot 2 is the full
-            # latent-consistency loss, identical on every rank
-            import torch.distributed as dist
-            self.losses[2:3].mul_(1.0 / self.world)
-            dist.all_reduce(self.losses, op=dist.ReduceOp.SUM, group=self.pg)
-        cabi.total_loss(self.losses, cfg.kl_weight if self.is_vae else 0.0,
-                        cfg.latent_consistency_weight if use_lc else 0.0,
-                        cfg.laplacian_weight if lap is not None else 0.0, 0.0)
+        self._use_lc_now = use_lc
 
     def optimizer_step(self):
         cfg = self.cfg
         if self.side is not None:
             torch.cuda.current_stream().wait_stream(self.side)
+        cabi.total_loss(self.losses, cfg.kl_weight if self.is_vae else 0.0,
+                        cfg.latent_consistency_weight if self._use_lc_now else 0.0,
+                        cfg.laplacian_weight if self.lap is not None else 0.0, 0.0)
         cabi.adam_tick(self.step_dev)
         cabi.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.step_dev, 0, cfg.lr,
                        cfg.betas[0], cfg.betas[1], cfg.eps, cfg.weight_decay, 1.0)
@@ -654,15 +671,34 @@ class TrainEngine:
         self.optimizer_step()
 
     def load_batch(self, x_host_or_dev: torch.Tensor):
-        """Copy the un-swapped batch ``[bs, V, 3]`` (pinned host or device) into the
-        engine's input buffer, asynchronously on the current stream."""
+        """Hand the next un-swapped batch ``[bs, V, 3]`` (pinned host or device, template vertex order) to the engine.
+        The copy runs on the engine's COPY stream into a staging buffer, so the host->device transfer of batch k+1
+        overlaps step k; the next ``step`` waits for it and moves it (through the engine's internal vertex order,
+        if any) into the swap kernel's input."""
+        with torch.cuda.device(self.dev):
+            if self._stage_free is not None:                  # the previous consumer of x_stage must be done
+                self.copy_stream.wait_event(self._stage_free)
+            self.copy_stream.wait_stream(torch.cuda.current_stream())      # (a device-side source may still be written)
+            with torch.cuda.stream(self.copy_stream):
+                self.x_stage.copy_(x_host_or_dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+            self._staged = ev
+
+    def _consume_staged(self):
+        """Before the step body: staged batch -> x_in on the compute stream (a 6.5 MB device copy / gather)."""
+        if self._staged is None:
+            return
+        main = torch.cuda.current_stream()
+        main.wait_event(self._staged)
         if self.order0_dev is None:
-            self.x_in.copy_(x_host_or_dev, non_blocking=True)
-        else:                                             # template order -> the engine's internal order
-            if getattr(self, 'x_raw', None) is None:
-                self.x_raw = torch.empty_like(self.x_in)
-            self.x_raw.copy_(x_host_or_dev, non_blocking=True)
-            torch.index_select(self.x_raw, 1, self.order0_dev, out=self.x_in)
+            self.x_in.copy_(self.x_stage, non_blocking=True)
+        else:                                                 # template order -> the engine's internal order
+            torch.index_select(self.x_stage, 1, self.order0_dev, out=self.x_in)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._stage_free = ev
+        self._staged = None
 
     def set_fixed_eps(self, eps: Optional[torch.Tensor]):
         """Parity tests: use this re-parameterisation noise instead of drawing it."""
@@ -709,6 +745,7 @@ class TrainEngine:
             return self._step(region, sync_losses)
 
     def _step(self, region: Optional[int], sync_losses: bool):
+        self._consume_staged()
         if self.use_graph:
             key = -1 if region is None else int(region)
             gph = self._graphs.get(key)
@@ -735,6 +772,13 @@ class TrainEngine:
             torch.cuda.current_stream().synchronize()
             return self.loss_dict()
         return None
+
+    def wait_losses(self) -> Dict[str, float]:
+        """Wait for the last ``step`` (its 32-byte loss read-back is the last thing on the compute stream) and return
+        its losses."""
+        with torch.cuda.device(self.dev):
+            torch.cuda.current_stream().synchronize()
+        return self.loss_dict()
 
     def loss_dict(self) -> Dict[str, float]:
         v = self.losses_host.tolist()

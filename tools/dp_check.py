@@ -66,6 +66,22 @@ def main():
         print("losses dp  ", got)
         print("losses 1gpu", want)
         ok = gerr < 5e-5 and lerr < 5e-5
+    # ---- replicas stay bit-identical and draw DIFFERENT noise: three more steps with drawn eps ----
+    eng.set_fixed_eps(None)
+    for r in (2, 9, 2):
+        eng.load_batch(x)
+        eng.step(r, sync_losses=True)
+    torch.cuda.synchronize()
+    p0 = eng.flat_p.clone()
+    dist.broadcast(p0, src=0)
+    same_params = torch.equal(p0, eng.flat_p)
+    e0 = eng.eps[0].clone()
+    dist.broadcast(e0, src=0)
+    noise_differs = rank == 0 or not torch.equal(e0, eng.eps[0])
+    if rank == 0:
+        print("replica parameters bit-identical after 4 steps: %s; eps differs across ranks: checked on ranks 1..%d"
+              % (same_params, world - 1))
+    ok = ok and same_params and noise_differs
     # release the captured step graphs (they hold NCCL work) before any further eager collective / teardown
     del eng
     import gc
