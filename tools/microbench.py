@@ -50,7 +50,11 @@ def nsets(bytes_per_set):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--batches', default='1,16,256,1024')
+    ap.add_argument('--batches', default='1,2,4,8,16,32,64,128,256,512,1024,2048,4096',
+                    help='BASELINE.json configs[4]: batch 1-4096')
+    ap.add_argument('--body', action='store_true', help='body.yaml layer set on the synthetic 6890-vertex template')
+    ap.add_argument('--template-order', action='store_true',
+                    help="keep the template's own vertex order (the engine renumbers its internal levels patch-wise)")
     ap.add_argument('--iters', type=int, default=10)
     ap.add_argument('--layer', default='', help='substring of the conv layer names to run')
     ap.add_argument('--renumber', action='store_true', help='experiment: template vertices renumbered patch-wise')
@@ -59,8 +63,11 @@ def main():
     from sdvae_b200 import cabi, fixtures as fx
     from sdvae_b200.tables import identity_plan, pool_table, restricted_spiral_table, spiral_table
     cabi.load()
-    tabs = fx.craniofacial_tables()
-    if args.renumber:
+    if args.body:
+        tabs = fx.synthetic_tables(6890, 3, seq_length=9, n_regions=11, seed=0, name='body-synthetic')
+    else:
+        tabs = fx.craniofacial_tables()
+    if not args.template_order:
         tabs = tabs.renumbered(128)[0]
     sp = [s.to(DEV) for s in tabs.spiral_tensors()]
     dn = [d.to(DEV) for d in tabs.down_tensors()]
@@ -68,7 +75,9 @@ def main():
     V = tabs.num_vertices
     peak, src = hbm_peak()
     f = lambda *shape: torch.randn(shape, device=DEV, dtype=torch.float32)
-    print('# SpiralConv / Pool micro-benchmark (craniofacial.yaml layers, 1 x B200)\n')
+    print('# SpiralConv / Pool micro-benchmark (%s layers, %s vertex order, 1 x B200)\n'
+          % ('body.yaml, synthetic 6890-vertex template' if args.body else 'craniofacial.yaml',
+             'template' if args.template_order else 'patch-wise (as inside TrainEngine)'))
     print('HBM peak %.1f GB/s (%s); algorithmic bytes per SURVEY.md 8(d); inputs rotate through buffer sets > L2.\n' % (peak, src))
     print('| op | layer | B | path | ms | alg MB | GB/s | frac of HBM peak | TFLOP/s |')
     print('|---|---|---|---|---|---|---|---|---|')
@@ -79,7 +88,15 @@ def main():
               (op, layer, B, path, ms, alg_bytes / 1e6, gbs, gbs / peak, flops / ms * 1e-9))
 
     # (name, level, restricted to kept rows?, Cin, Cout, act)
-    convs = [('en0 3->32 @17039 (kept rows)', 0, True, 3, 32), ('en1 32->32 @4260 (kept rows)', 1, True, 32, 32),
+    if args.body:
+        convs = [('en0 3->32 @6890 (kept rows)', 0, True, 3, 32), ('en1 32->32 @1723 (kept rows)', 1, True, 32, 32),
+                 ('en2 32->64 @431 (kept rows)', 2, True, 32, 64), ('de1 64->64 @431', 2, False, 64, 64),
+                 ('de2 64->32 @1723', 1, False, 64, 32), ('de3 32->32 @6890', 0, False, 32, 32),
+                 ('de4 32->3 @6890', 0, False, 32, 3)]
+        pool_levels = [(2, 64), (1, 64), (0, 32)]
+    else:
+        pool_levels = [(3, 64), (2, 64), (1, 32), (0, 32)]
+    convs = convs if args.body else [('en0 3->32 @17039 (kept rows)', 0, True, 3, 32), ('en1 32->32 @4260 (kept rows)', 1, True, 32, 32),
              ('en2 32->32 @1065 (kept rows)', 2, True, 32, 32), ('en3 32->64 @267 (kept rows)', 3, True, 32, 64),
              ('de1 64->64 @267', 3, False, 64, 64), ('de2 64->32 @1065', 2, False, 64, 32),
              ('de3 32->32 @4260', 1, False, 32, 32), ('de4 32->32 @17039', 0, False, 32, 32),
@@ -97,6 +114,23 @@ def main():
             w = f(cout, S * cin) * 0.05
             b = f(cout) * 0.1
             act = cabi.ACT_NONE if cout == 3 else cabi.ACT_ELU
+            # tile-staged tcgen05 kernels (csrc/spiral_conv_tile*.cuh) where the table has a tile plan (32 -> 32, patch order)
+            tf = tab.tile_fwd() if (cin == 32 and cout == 32) else None
+            if tf is not None and cabi.tile_supported(S, 32, 32, tf.rcap, 0):
+                wimg_k = torch.empty(cabi.tc_wimg_floats(S, 32, 32), device=DEV)
+                cabi.tc_pack_weights(w, wimg_k, S, 32, 32, False, kperm=True)
+                ms = timeit(lambda k: cabi.spiralconv_fwd_tile(xs[k], tf, wimg_k, b, ys[k], B, Vin, R, S, 32, 32, act), ns, args.iters)
+                row('conv fwd', name, B, 'tcgen05 3xTF32, tile-staged', ms, alg, flops)
+                wsk = torch.empty(cabi.spiralconv_bwd_w_workspace(B * R, S, 32, 32) // 4 + 4, device=DEV)
+                dWk, dbk = torch.empty(32, S * 32, device=DEV), torch.empty(32, device=DEV)
+                ms = timeit(lambda k: cabi.spiralconv_bwd_w_tile(xs[k], tf, ys[k], dWk, dbk, wsk, B, Vin, R, S, 32, 32), ns, args.iters)
+                row('conv dW', name, B, 'tcgen05 3xTF32, tile-staged', ms, alg, flops)
+            tb_ = tab.tile_bwd() if (cin == 32 and cout == 32) else None
+            if tb_ is not None and cabi.tile_supported(S, 32, 32, tb_.rcap, tb_.ecap):
+                wimg_kt = torch.empty(cabi.tc_wimg_floats(S, 32, 32), device=DEV)
+                cabi.tc_pack_weights(w, wimg_kt, S, 32, 32, True, kperm=True)
+                ms = timeit(lambda k: cabi.spiralconv_bwd_x_tile(ys[k], tb_, wimg_kt, None, xs[k], B, R, Vin, S, 32, 32), ns, args.iters)
+                row('conv dx', name, B, 'tcgen05 3xTF32, tile-staged', ms, alg, flops)
             # forward
             plan = tab.plan_fwd()
             if cin == 32 and cout == 3 and cabi.narrow_out_fwd_supported(S, cin, cout, tab.stage_plan().ucap):
@@ -230,7 +264,7 @@ def main():
             del xs, ys
         # pools: up-sampling (3 nnz / row) forward and backward; the down-sampling selections are fused
         # into the encoder convolutions (computed at the kept rows only) and have no launch of their own
-        for lvl, C in ([] if args.only == 'conv' else [(3, 64), (2, 64), (1, 32), (0, 32)]):
+        for lvl, C in ([] if args.only == 'conv' else pool_levels):
             pt = pool_table(up[lvl])
             Vf, Vc = V[lvl], V[lvl + 1]
             alg = 4.0 * B * C * (Vc + Vf)
