@@ -324,17 +324,20 @@ def run_ours(args):
 
     # ---- end to end: pinned host batch in, 7 loss scalars out, every step --------------
     # Every step's un-swapped batch is copied from pinned host memory inside the timed region and every step's losses
-    # are read back and waited for; as in any input pipeline the copy of batch k+1 is issued while step k runs (the
-    # engine lands it in a staging buffer on its copy stream, TrainEngine.load_batch).
+    # are read back to the host and waited for.  As in any training loop with an input pipeline, the copy of batch k+1
+    # is issued while step k runs (the engine lands it in a staging buffer on its copy stream, TrainEngine.load_batch)
+    # and the losses of step k are consumed after step k+1 has been launched (logging one step late).
     seq2 = regions[W + K:2 * (W + K)]
 
     def e2e_steps(rs):
         eng.load_batch(x_pin)
         for i, r in enumerate(rs):
-            eng.step(r)                                   # consumes the staged batch, launches the step
+            eng.step(r)                                   # consumes the staged batch, launches step i + its loss read-back
             if i + 1 < len(rs):
                 eng.load_batch(x_pin)                     # H2D of the next batch overlaps this step
-            eng.wait_losses()                             # D2H of this step's 7 loss scalars + sync
+            if i > 0:
+                eng.wait_losses(lag=1)                    # losses of step i-1 (D2H done long ago)
+        eng.wait_losses()                                 # ... and of the last step
 
     e2e_steps(seq2[:W])
     barrier()

@@ -268,7 +268,10 @@ class TrainEngine:
         self.ws = f(ws // 4 + 4)
         self._alloc_tc()
         self.losses = self.flat_g_all[self.n_arena:self.n_arena + 8]
-        self.losses_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        # two pinned read-back slots: the losses of step k can be waited for after step k+1 has been launched
+        self._loss_slots = [(torch.zeros(8, dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(2)]
+        self._loss_k = 0
+        self.losses_host = self._loss_slots[0][0]
         self.part_mse = f(cabi.mse_lap_partial_floats(B, V[0]))
         self.part_kl = f((B * D + 255) // 256)
         nh = self.bs * (self.bs - 1) // 2 * self.bs
@@ -767,18 +770,22 @@ class TrainEngine:
             cabi.add_launches(self.launches_per_step)
         else:
             self._body(region)
+        self._loss_k ^= 1
+        self.losses_host, ev = self._loss_slots[self._loss_k]
         self.losses_host.copy_(self.losses, non_blocking=True)
+        ev.record(torch.cuda.current_stream())
         if sync_losses:
-            torch.cuda.current_stream().synchronize()
+            ev.synchronize()
             return self.loss_dict()
         return None
 
-    def wait_losses(self) -> Dict[str, float]:
-        """Wait for the last ``step`` (its 32-byte loss read-back is the last thing on the compute stream) and return
-        its losses."""
-        with torch.cuda.device(self.dev):
-            torch.cuda.current_stream().synchronize()
-        return self.loss_dict()
+    def wait_losses(self, lag: int = 0) -> Dict[str, float]:
+        """Wait for the 32-byte loss read-back of the last ``step`` (``lag=0``) or of the step before it (``lag=1``:
+        a training loop that logs one step late never idles the GPU between steps) and return those losses."""
+        buf, ev = self._loss_slots[self._loss_k ^ (lag & 1)]
+        ev.synchronize()
+        v = buf.tolist()
+        return {k: v[i] for i, k in enumerate(LOSS_KEYS)}
 
     def loss_dict(self) -> Dict[str, float]:
         v = self.losses_host.tolist()
