@@ -51,8 +51,6 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tc", action="store_true", help="keep every contraction on the fp32-FMA kernels")
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--renumber", action="store_true",
-                    help="experiment: template vertices renumbered patch-wise (same meshes, isomorphic tables)")
     return ap.parse_args()
 
 
@@ -109,14 +107,12 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_problem(dev, bs, seed, renumber=False):
-    """Tables, the drop-in model on ``dev`` (seeded xavier init), the synthetic un-swapped batch and the
-    sequence of swapped regions.  No oracle on this path.  ``renumber``: the same template with its vertices
-    listed patch-wise (experiment switch for tile-local staging; off in every reported number)."""
+def build_problem(dev, bs, seed):
+    """Tables (template vertex order; the engine renumbers its internal levels itself), the drop-in model on ``dev``
+    (seeded xavier init), the synthetic un-swapped batch and the sequence of swapped regions.  No oracle on this
+    path."""
     from sdvae_b200 import fixtures as fx
     tabs = fx.craniofacial_tables()
-    if renumber:
-        tabs = tabs.renumbered(128)[0]
     model = fx.build_model(tabs, 3, CHANNELS, LATENT, False, True, seed, dev) if dev is not None else None
     rng = np.random.RandomState(seed)
     x = torch.from_numpy(rng.randn(bs, tabs.num_vertices[0], 3).astype(np.float32))
@@ -277,7 +273,7 @@ def run_ours(args):
     from sdvae_b200.engine import StepConfig, TrainEngine
 
     bs = args.bs
-    tabs, model, x_host, regions = build_problem(dev, bs, args.seed, renumber=args.renumber)
+    tabs, model, x_host, regions = build_problem(dev, bs, args.seed)
     cfg = StepConfig(batch_size=bs)
     lt = losses.LaplacianTable.build(*tabs.lap, tabs.num_vertices[0], dev)
     lat = tabs.latent_regions(LATENT)

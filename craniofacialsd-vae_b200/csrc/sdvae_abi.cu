@@ -30,6 +30,19 @@ struct DeviceOnce {
     }
 };
 
+// Tuning knobs are read from the environment ONLY in tuning builds (-DSDVAE_TUNING, build.py SDVAE_TUNING=1): the
+// shipped library's dispatch does not depend on environment variables.
+static int tuning_env(const char* name, int dflt) {
+#ifdef SDVAE_TUNING
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+#else
+    (void)name;
+    return dflt;
+#endif
+}
+
+
 static inline unsigned blocks_for(long long n, int threads) {
     return (unsigned)((n + threads - 1) / threads);
 }
@@ -122,7 +135,7 @@ static int launch_umma(umma::UmmaArgs& ua, cudaStream_t st) {
     static DeviceOnce attr_done;       // the attribute is per device
     if (attr_done.first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     ua.nraw = Cfg::raw_stages(ua.S, ua.rcap);
-    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SDVAE_DBG"); dbg = e ? atoi(e) : 0; } ua.dbg = dbg; }
+    { static int dbg = -1; if (dbg < 0) dbg = tuning_env("SDVAE_DBG", 0); ua.dbg = dbg; }
     const long long ntiles = (long long)ua.B * ua.L;
     const int grid = ntiles < kNumSMs ? (int)ntiles : kNumSMs;
     ua.ostage = (UNIFORM && Cfg::out_stage(ua.S, ua.rcap)) ? 1 : 0;
@@ -148,7 +161,7 @@ static int launch_tile_n(tile::TileArgs& ta, cudaStream_t st) {
     auto kern = tile::gt_kernel<RAGGED, NSETS>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   // per device, cheap
     ta.nts = tile::TileCfg::stages(ta.S, ta.rcap, ta.ecap);
-    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SDVAE_DBG"); dbg = e ? atoi(e) : 0; } ta.dbg = dbg; }
+    { static int dbg = -1; if (dbg < 0) dbg = tuning_env("SDVAE_DBG", 0); ta.dbg = dbg; }
     const long long ntiles = (long long)ta.B * ta.L;
     const int grid = ntiles < kNumSMs ? (int)ntiles : kNumSMs;
     kern<<<grid, tile::TileWarps<NSETS>::kThreads, tile::TileCfg::smem_bytes(ta.S, ta.rcap, ta.ecap, ta.nts), st>>>(ta);
@@ -532,8 +545,7 @@ int sdvae_spiralconv_bwd_w_tc(const float* x, const int32_t* plan_cnt, const int
     float* part_b = part + (size_t)grid * Cout * K;             // [grid, Cout]
     static int flush_tiles = 0;                // tiles per accumulator drain (tuning knob, default 2)
     if (!flush_tiles) {
-        const char* e = getenv("SDVAE_BWW_FLUSH");
-        flush_tiles = e ? atoi(e) : 2;
+        flush_tiles = tuning_env("SDVAE_BWW_FLUSH", 2);
         if (flush_tiles < 1) flush_tiles = 1;
     }
     a.flush = flush_tiles;
@@ -556,7 +568,7 @@ int sdvae_spiralconv_bwd_w_tc(const float* x, const int32_t* plan_cnt, const int
             if (rc) return rc;
         }
     const long long len = (long long)Cout * K;
-    split_reduce2_kernel<<<blocks_for(len + Cout, 64), 256, 0, st>>>(part, part_b, dW, db, grid, len, Cout);
+    split_reduce2_kernel<<<blocks_for(len + Cout, 64), 64 * kSplitGroups, 0, st>>>(part, part_b, dW, db, grid, len, Cout);
     return check_launch("split_reduce_kernel");
 }
 
@@ -598,8 +610,7 @@ int sdvae_spiralconv_bwd_w_tile(const float* x, const int32_t* plan_cnt, const i
     float* part_b = part + (size_t)grid * Cout * K;             // [grid, Cout]
     static int flush_tiles = 0;                // tiles per accumulator drain (tuning knob, default 2)
     if (!flush_tiles) {
-        const char* e = getenv("SDVAE_BWW_FLUSH");
-        flush_tiles = e ? atoi(e) : 2;
+        flush_tiles = tuning_env("SDVAE_BWW_FLUSH", 2);
         if (flush_tiles < 1) flush_tiles = 1;
     }
     a.flush = flush_tiles;
@@ -619,7 +630,7 @@ int sdvae_spiralconv_bwd_w_tile(const float* x, const int32_t* plan_cnt, const i
             if (rc) return rc;
         }
     const long long len = (long long)Cout * K;
-    split_reduce2_kernel<<<blocks_for(len + Cout, 64), 256, 0, st>>>(part, part_b, dW, db, grid, len, Cout);
+    split_reduce2_kernel<<<blocks_for(len + Cout, 64), 64 * kSplitGroups, 0, st>>>(part, part_b, dW, db, grid, len, Cout);
     return check_launch("split_reduce_kernel");
 }
 
@@ -664,7 +675,7 @@ int sdvae_spiralconv_bwd_w(const float* x, const int32_t* idx, const float* dpre
     }
     if (rc) return rc;
     const long long len = (long long)Cout * K;
-    split_reduce2_kernel<<<blocks_for(len + Cout, 64), 256, 0, st>>>(a.part, a.part_b, dW, db, nsplit, len, Cout);
+    split_reduce2_kernel<<<blocks_for(len + Cout, 64), 64 * kSplitGroups, 0, st>>>(a.part, a.part_b, dW, db, nsplit, len, Cout);
     return check_launch("split_reduce_kernel");
 }
 
@@ -725,7 +736,7 @@ int sdvae_pool_ell_fwd(const float* x, const int32_t* col, const float* val, flo
 // SM) take ceil(B*parts/SMs) items each.  Measured on B200: staging 204 KB ~6 us; 13 ns per row for the 3 -> 32
 // kernels, 22 ns per row for the fused 32 -> 3 backward (model error < 10 % over B = 64..1024, parts = 1..8).
 static int narrow_parts(int B, int rows, double stage_us, double row_ns) {
-    { static int env = -1; if (env < 0) { const char* e = getenv("SDVAE_NARROW_PARTS"); env = e ? atoi(e) : 0; }
+    { static int env = -1; if (env < 0) env = tuning_env("SDVAE_NARROW_PARTS", 0);
       if (env > 0) return env; }
     int best = 1;
     double best_cost = 0.0;
@@ -850,7 +861,7 @@ int sdvae_narrow_out_fwd(const float* x, const int32_t* tile_ptr, const int32_t*
     if (B == 0) return SDVAE_OK;
     int nst = (int)((220LL * 1024) / ((long long)ucap * 128));
     nst = std::max(kNarrowMinStages, std::min(kNarrowMaxStages, nst));
-    { static int env = -1; if (env < 0) { const char* e = getenv("SDVAE_NARROW_STAGES"); env = e ? atoi(e) : 0; }
+    { static int env = -1; if (env < 0) env = tuning_env("SDVAE_NARROW_STAGES", 0);
       if (env >= kNarrowMinStages && env <= nst) nst = env; }
     auto kern = nst == 5 ? narrow_out_fwd_kernel<9, 3, 5> : nst == 4 ? narrow_out_fwd_kernel<9, 3, 4> : narrow_out_fwd_kernel<9, 3, 3>;
     static DeviceOnce attr_done[8];      // per stage count and per device

@@ -558,15 +558,18 @@ __global__ void split_reduce_kernel(const float* __restrict__ part, float* __res
     out[i] = acc;
 }
 
-// The same for a weight-gradient / bias-gradient pair in ONE launch, four partial groups per element:
+// The same for a weight-gradient / bias-gradient pair in ONE launch, kSplitGroups partial groups per element:
 //   dW[i] = sum_c part[c*len + i] (i < len),   db[j] = sum_c part_b[c*nb + j] (j < nb)
-// A block holds 64 elements x 4 groups; group g adds the partials c = g, g+4, g+8, ... in order, the four
-// group sums are combined as (s0 + s1) + (s2 + s3): a fixed order, so the result is deterministic.  (One
-// thread per element left 36 blocks on 148 SMs for a 32 x 288 weight: 10 us per layer, 18 layers a step.)
-__global__ void split_reduce2_kernel(const float* __restrict__ part, const float* __restrict__ part_b,
-                                     float* __restrict__ dW, float* __restrict__ db, int nsplit,
-                                     long long len, int nb) {
-    __shared__ float sm[4][64];
+// A block holds 64 elements x 16 groups; group g adds the partials c = g, g+16, g+32, ... in order, the group sums
+// are combined by a fixed pairwise tree: the result is deterministic.  (One thread per element left 36 blocks on
+// 148 SMs for a 32 x 288 weight: 10 us per layer; four groups still ran 37 dependent-latency loads per thread,
+// 12.6 us per launch and seven launches a step -- 2 % of the 8-GPU step, profiles/r02_dp_floor.md.)
+constexpr int kSplitGroups = 16;
+__global__ void __launch_bounds__(64 * kSplitGroups)
+split_reduce2_kernel(const float* __restrict__ part, const float* __restrict__ part_b,
+                     float* __restrict__ dW, float* __restrict__ db, int nsplit,
+                     long long len, int nb) {
+    __shared__ float sm[kSplitGroups][64];
     const int e = threadIdx.x & 63, g = threadIdx.x >> 6;
     const long long i = (long long)blockIdx.x * 64 + e;
     const long long total = len + (db ? nb : 0);
@@ -574,13 +577,19 @@ __global__ void split_reduce2_kernel(const float* __restrict__ part, const float
     if (i < total) {
         const float* src = i < len ? part + i : part_b + (i - len);
         const long long stride = i < len ? len : nb;
-        for (int c = g; c < nsplit; c += 4) acc += src[(size_t)c * stride];
+        for (int c = g; c < nsplit; c += kSplitGroups) acc += src[(size_t)c * stride];
     }
     sm[g][e] = acc;
     __syncthreads();
     if (g == 0 && i < total) {
-        const float r = (sm[0][e] + sm[1][e]) + (sm[2][e] + sm[3][e]);
-        if (i < len) dW[i] = r; else db[i - len] = r;
+        float t[kSplitGroups];
+#pragma unroll
+        for (int k = 0; k < kSplitGroups; ++k) t[k] = sm[k][e];
+#pragma unroll
+        for (int w = 1; w < kSplitGroups; w *= 2)
+#pragma unroll
+            for (int k = 0; k < kSplitGroups; k += 2 * w) t[k] = t[k] + t[k + w];
+        if (i < len) dW[i] = t[0]; else db[i - len] = t[0];
     }
 }
 

@@ -17,8 +17,8 @@
 //     half of it with one LDS.128; staged rows at odd positions of the tile stage are stored high half first, and
 //     the plan builder places the rows (max-cut) so that the two rows of an 8-lane phase mostly sit at positions
 //     of different parity (~75 % of the phases conflict-free, the rest 2-way).  [Reading opposite halves by lane
-//     parity instead is always conflict-free but costs 32 selects per unit -- and the kernel is bound by the ALU
-//     pipe, profiles/r02_gt_v3_stalls.txt.]  The price is a fixed permutation of the 32 channels of a K chunk
+//     parity instead is always conflict-free but costs 32 selects per unit and measured 0.2 ms slower,
+//     profiles/r02_tile_kernel.md.]  The price is a fixed permutation of the 32 channels of a K chunk
 //     (kperm), applied to the weight image by the packer.
 // Precision, weight image, MMA form (TS: A from TMEM, B = resident weight image), epilogue: as gc_umma_kernel
 // (error-compensated 3xTF32, fp32 accumulation in TMEM).
@@ -47,7 +47,8 @@ constexpr int kTFirstSplitWarp = kTEpilogueWarps;               // 4
 //   warps 0..3 epilogue | 4 .. 4+4*NSETS-1 splitters | then kTMaxStages loader warps | then the MMA warp.
 // The splitters are LATENCY-bound (a unit is a serial chain of two barrier waits, two dependent shared-memory
 // round trips, ~70 ALU instructions, two TMEM stores and their completion wait: ~1300 clk with the SM's other
-// warps competing), so throughput = sets in flight / unit latency: more sets, fewer registers each.
+// warps competing), so throughput = sets in flight / unit latency.  Measured (profiles/r02_tile_kernel.md): 4 sets at
+// 88 registers beat 5 at 80 and 6 at 64 (2.04 / 2.13 / 2.24 ms); launch_tile uses 4.
 template <int NSETS>
 struct TileWarps {
     static constexpr int kSplitWarps = 4 * NSETS;
@@ -143,7 +144,7 @@ __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 // bounded wait with a short back-off between polls (a failed try_wait returns after ~40 clk whatever the hint says;
-// 16 splitter warps polling back to back took a third of the SM's issue slots, profiles/r02_gt_v2_stalls.txt)
+// 16 splitter warps polling back to back took a third of the SM's issue slots)
 template <unsigned NS>
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait_a(bar, parity)) return;
@@ -443,8 +444,9 @@ gt_kernel(const TileArgs a) {
         // own the four TMEM lane quarters.  Thread (l4 = lane >> 2, qq = lane & 3) serves the tile rows
         // 32*q4 + 16*g + 8*h + l4 (g, h in {0, 1}): for each it reads the two 16-byte pieces qq and qq + 4 of the
         // staged row(s) of the cell (the plan word holds the byte offset of the row's low half).
-        // The kernel is bound by the ALU pipe / instruction issue (profiles/r02_gt_*): everything per unit that is
-        // not a row read, a split or a TMEM store is kept out of this loop.
+        // The kernel is bound by this loop -- above all by its TMEM stores and their completion waits
+        // (profiles/r02_tile_kernel.md): everything per unit that is not a row read, a split or a TMEM store is
+        // kept out of it.
         const int set = (warp - kTFirstSplitWarp) >> 2;
         const int q4 = warp & 3;
         const int l4 = lane >> 2, qq = lane & 3;

@@ -72,6 +72,31 @@ __device__ __forceinline__ float lds32(uint32_t addr) {
     return v;
 }
 
+
+// Two k-steps (K = 8 each) of one A chunk against the hi / lo images of g: six tcgen05.mma in one block, the B
+// descriptors derived from the chunk's first one by immediate adds (1 KB = 64 descriptor units to the lo image,
+// 2 KB = 128 to the next k-step).  The issuing thread is the kernel's critical path and competes for issue slots with
+// five other warps of its SM sub-partition (profiles/r02_tile_kernel.md): every instruction saved here counts.
+__device__ __forceinline__ void umma_bw_2k(uint32_t d_tmem, uint32_t a_hi, uint64_t bd_hi, uint32_t idesc, uint32_t acc_first) {
+    asm volatile(
+        "{\n.reg .pred p, q;\n.reg .b64 dl, dh1, dl1;\n.reg .b32 al, ah1, al1;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "setp.eq.b32 q, %4, %4;\n"
+        "add.s64 dl, %2, 64;\n"
+        "add.s64 dh1, %2, 128;\n"
+        "add.s64 dl1, %2, 192;\n"
+        "add.u32 al, %1, 32;\n"
+        "add.u32 ah1, %1, 8;\n"
+        "add.u32 al1, %1, 40;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], dl, %3, q;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [al], %2, %3, q;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah1], dh1, %3, q;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah1], dl1, %3, q;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [al1], dh1, %3, q;\n}\n"
+        ::"r"(d_tmem), "r"(a_hi), "l"(bd_hi), "r"(idesc), "r"(acc_first) : "memory");
+}
+
 __global__ void __launch_bounds__(kWThreads, 1)
 bt_kernel(const TileBwArgs a) {
     const int S = a.S;
@@ -130,7 +155,7 @@ bt_kernel(const TileBwArgs a) {
         // ================= MMA issuer =================
         if (elect_one()) {
             constexpr uint32_t IDESC = umma::idesc_tf32_bmn(kBM, umma::kBwNT);
-            const uint32_t g_base = smem_u32(G_s);
+            const uint64_t g_desc = umma::smem_desc_mn_sw128(smem_u32(G_s));   // + (byte offset >> 4): the address field has room
             const uint32_t bar_full = smem_u32(a_full);
             int as = 0; uint32_t aph = 0;
             int tf = 0, nfl = 0;                           // tile index inside the flush group, flushes done
@@ -154,21 +179,16 @@ bt_kernel(const TileBwArgs a) {
                     }
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)((ab * NBLK + blk) * umma::kBwNT);
-                    const uint32_t a_hi = tmem_base + (uint32_t)(kWAColBase + as * 64), a_lo = a_hi + 32;
-                    const uint32_t g_t = g_base + gb * umma::kGStage + r4 * 4 * 2048;
+                    const uint32_t a_hi = tmem_base + (uint32_t)(kWAColBase + as * 64);   // lo columns: + 32
+                    const uint64_t bd0 = g_desc + (uint64_t)((gb * umma::kGStage + r4 * 4 * 2048) >> 4);
                     uint64_t* const my_empty = a_empty + as;
                     if (++as == kWAStages) { as = 0; aph ^= 1; }
                     const bool more = c + 1 < CPT || it + 1 < my_tiles;
                     if (SDVAE_ABL & 4) ready = more && mbar_try_wait_a(bar_full + (uint32_t)as * 8u, aph);
-                    else
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t bd_hi = umma::smem_desc_mn_sw128(g_t + k * 2048);
-                        const uint64_t bd_lo = umma::smem_desc_mn_sw128(g_t + k * 2048 + 1024);
-                        umma_tf32_ts(d_tmem, a_hi + k * 8, bd_hi, IDESC, (tf | r4 | k) != 0);
-                        umma_tf32_ts(d_tmem, a_hi + k * 8, bd_lo, IDESC, 1u);
-                        umma_tf32_ts(d_tmem, a_lo + k * 8, bd_hi, IDESC, 1u);
-                        if (k == 1) ready = more && mbar_try_wait_a(bar_full + (uint32_t)as * 8u, aph);
+                    else {
+                        umma_bw_2k(d_tmem, a_hi, bd0, IDESC, (uint32_t)(tf | r4));
+                        ready = more && mbar_try_wait_a(bar_full + (uint32_t)as * 8u, aph);
+                        umma_bw_2k(d_tmem, a_hi + 16, bd0 + 256, IDESC, 1u);
                     }
                     umma_commit(my_empty);
                 }
@@ -354,16 +374,18 @@ bt_kernel(const TileBwArgs a) {
                 } else if (s < S) {
                     // the 32 cell words of (slot s, tile rows 32*r4 ..): word of row 32*r4 + j at (j & 7)*4 + (j >> 3)
                     const uint32_t wbase = stage_a + (uint32_t)ROWS_BYTES + (uint32_t)(s * 128 + r4 * 32) * 4u;
+                    const uint32_t rbase = stage_a + cy;
+                    const bool whole = 32 * r4 + 32 <= nvalid;    // warp-uniform: all 32 rows of the group exist
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const uint4 w4 = lds128u(wbase + (uint32_t)i * 16u);          // warp-uniform address: broadcast
                         const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            const int j = i + 8 * h;
-                            const float t = lds32(stage_a + (((w[h] & 0xffffu) ^ cx) + cy));
-                            v[j] = 32 * r4 + j < nvalid ? t : 0.f;      // rows past the mesh: plan word = staged row 0 (valid), value dropped
-                        }
+                        for (int h = 0; h < 4; ++h) v[i + 8 * h] = lds32(rbase + ((w[h] & 0xffffu) ^ cx));
+                    }
+                    if (!whole) {                                  // rows past the mesh: plan word = staged row 0 (valid), value dropped
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 32 * r4 + j < nvalid ? v[j] : 0.f;
                     }
                     have = true;
                 } else if (row0 <= ONES_ROW && ONES_ROW < row0 + 32) {
@@ -372,7 +394,7 @@ bt_kernel(const TileBwArgs a) {
                     for (int j = 0; j < 32; ++j) v[j] = (row0 + lane == ONES_ROW && 32 * r4 + j < nvalid) ? 1.f : 0.f;
                     have = true;
                 }
-                mbar_wait_a<32>(bar_a_empty + (uint32_t)as * 8u, aph ^ 1);
+                mbar_wait_a<128>(bar_a_empty + (uint32_t)as * 8u, aph ^ 1);
                 __syncwarp();
                 if (have) {                                        // (warps past the ones row leave their TMEM lanes alone)
                     float lo[32];

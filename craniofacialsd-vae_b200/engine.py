@@ -12,9 +12,10 @@ preallocated buffers, without autograd:
   gradient (backward-to-input conv or pool-transpose), so every gradient tensor is
   written once, already w.r.t. the pre-activation;
 * all parameters / gradients / Adam moments live in flat arenas ordered in
-  backward-ready order, so the data-parallel all-reduce is four contiguous buckets
-  launched on a side stream as soon as their layers are done (NCCL over NVLink),
-  overlapping the rest of backward; Adam is one launch over the arena;
+  backward-ready order, so the data-parallel exchange is ONE NCCL all-reduce of a
+  contiguous arena (gradients + loss scalars) after the backward pass -- or, opt-in,
+  four contiguous buckets on a side stream overlapping the backward pass, which
+  measured slower next to the persistent kernels; Adam is one launch over the arena;
 * the seven loss scalars come back in ONE 28-byte D2H copy (the reference issues
   seven ``.item()`` syncs, model_manager.py:320-326);
 * the whole step -- data-parallel collectives included -- is replayed from a CUDA graph
@@ -108,6 +109,13 @@ class TrainEngine:
         # SDVAE_DP_GRAPH=0 keeps multi-GPU steps eager.
         self.use_graph = use_graph and (self.world == 1 or os.environ.get('SDVAE_DP_GRAPH', '1') != '0')
         self.use_tc = bool(use_tc)
+        # data-parallel gradient exchange: ONE all-reduce of the gradient arena after the backward pass on the compute
+        # stream (default), or bucketed all-reduces on a side stream overlapped with the backward pass
+        # (SDVAE_DP_OVERLAP=1).  The overlapped form measured SLOWER (12.48 vs 12.23 ms at 2 GPUs): the persistent
+        # one-CTA-per-SM kernels leave no SM for a concurrent NCCL kernel, which then delays the CTAs of the next
+        # kernel by its own duration, while the 4.3 MB all-reduce alone costs ~50 us over NVSwitch
+        # (profiles/r02_dp_floor.md)
+        self.dp_overlap = os.environ.get('SDVAE_DP_OVERLAP', '0') == '1'
         if renumber is None:
             renumber = self.use_tc and os.environ.get('SDVAE_RENUMBER', '1') != '0'
         self.renumber = bool(renumber)
@@ -473,6 +481,12 @@ class TrainEngine:
         s, e = self.buckets[k]
         if k == len(self.buckets) - 1:
             e = self.n_arena + 8                        # ... and the loss scalars
+        if not self.dp_overlap:
+            # one all-reduce of the whole arena (+ losses) on the compute stream after the backward pass: nothing
+            # competes with the persistent one-CTA-per-SM kernels for SMs, the collective's latency is exposed
+            if k == len(self.buckets) - 1:
+                dist.all_reduce(self.flat_g_all[0:e], op=dist.ReduceOp.SUM, group=self.pg)
+            return
         self.side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.side):
             dist.all_reduce(self.flat_g_all[s:e], op=dist.ReduceOp.SUM, group=self.pg)
@@ -499,8 +513,9 @@ class TrainEngine:
                 # latent block of the backward pass (after the whole decoder backward) waits for it
                 import torch.distributed as dist
                 main = torch.cuda.current_stream()
-                self.side_lc.wait_stream(main)
-                with torch.cuda.stream(self.side_lc):
+                lc_stream = self.side_lc if self.dp_overlap else main
+                lc_stream.wait_stream(main)
+                with torch.cuda.stream(lc_stream):
                     dist.all_gather_into_tensor(self.z_all, z.contiguous(), group=self.pg)
                     cabi.lc_fwd_bwd(self.z_all, self.bs, self.D, r0, r1, cfg.latent_consistency_eta1,
                                     cfg.latent_consistency_eta2, self.act_lc, self.part_lc, self.dz_lc,
@@ -577,7 +592,8 @@ class TrainEngine:
         self._allreduce_bucket(1)
         if use_lc:
             if self.world > 1:
-                torch.cuda.current_stream().wait_stream(self.side_lc)
+                if self.dp_overlap:
+                    torch.cuda.current_stream().wait_stream(self.side_lc)
             lo = self.i0 * self.bs
             cabi.axpy3(self.dz, self.dz_lc[lo:lo + B], cfg.latent_consistency_weight, None, 0.0,
                        self.dz)
@@ -654,7 +670,7 @@ class TrainEngine:
 
     def optimizer_step(self):
         cfg = self.cfg
-        if self.side is not None:
+        if self.side is not None and self.dp_overlap:
             torch.cuda.current_stream().wait_stream(self.side)
         cabi.total_loss(self.losses, cfg.kl_weight if self.is_vae else 0.0,
                         cfg.latent_consistency_weight if self._use_lc_now else 0.0,

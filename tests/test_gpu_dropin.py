@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 W = dict(kl=1e-4, lc=0.5, lap=0.1, eta1=0.5, eta2=0.5)      # craniofacial.yaml:22-27
 
 # Whole-network bars against the oracle evaluated in FLOAT64 (normwise max|a-b| / max|b|), set at <= 2x the values
-# measured on B200 (printed by the tests; profiles/r02_parity.md): the fp32-FMA engine meets north_star's 1e-5 on every
+# measured on B200 (printed by the tests; profiles/r02_parity_tests.log): the fp32-FMA engine meets north_star's 1e-5 on every
 # tensor; the tcgen05 engine (error-compensated 3xTF32, accumulators drained every two tiles) is stated separately.
 # Measured (B200, this test, craniofacial case A): fp32-FMA engine recon 1.3e-6, z 8.6e-7, losses <= 5.9e-7, gradients max
 # 3.6e-6 / median 8.5e-7; tcgen05 engine recon 1.4e-5, z 8.2e-6, losses <= 1.2e-5, gradients max 2.3e-5 / median 1.2e-5

@@ -57,7 +57,6 @@ def main():
                     help="keep the template's own vertex order (the engine renumbers its internal levels patch-wise)")
     ap.add_argument('--iters', type=int, default=10)
     ap.add_argument('--layer', default='', help='substring of the conv layer names to run')
-    ap.add_argument('--renumber', action='store_true', help='experiment: template vertices renumbered patch-wise')
     ap.add_argument('--only', default='', help="'pool' or 'conv': run only that half of the sweep")
     args = ap.parse_args()
     from sdvae_b200 import cabi, fixtures as fx
