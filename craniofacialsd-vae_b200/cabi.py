@@ -58,6 +58,8 @@ _SIGNATURES = {
     "sdvae_spiralconv_bwd_w_tile": (C.c_int, [_c_fp] * 4 + [C.c_int] + [_c_fp] * 4 + [C.c_int] * 6 + [_c_fp]),
     "sdvae_spiralconv_fwd_tile": (C.c_int, [_c_fp] * 4 + [C.c_int] + [_c_fp] * 3 + [C.c_int] * 7 + [_c_fp]),
     "sdvae_spiralconv_bwd_x_tile": (C.c_int, [_c_fp] * 5 + [C.c_int] * 2 + [_c_fp] * 3 + [C.c_int] * 6 + [_c_fp]),
+    "sdvae_narrow_out_fwd_tc_supported": (C.c_int, [C.c_int] * 4),
+    "sdvae_narrow_out_fwd_tc": (C.c_int, [_c_fp] * 4 + [C.c_int] + [_c_fp] * 3 + [C.c_int] * 6 + [_c_fp]),
     "sdvae_narrow_in_supported": (C.c_int, [C.c_int] * 4),
     "sdvae_narrow_in_bwd_w_workspace": (C.c_size_t, [C.c_int, C.c_int]),
     "sdvae_narrow_in_fwd": (C.c_int, [_c_fp] * 5 + [C.c_int] * 7 + [_c_fp]),
@@ -396,6 +398,21 @@ def spiralconv_fwd_tile(x, plan, wimg, bias, y, B, Vin, Vout, S, Cin, Cout, act)
     if rc:
         _err(rc, "spiralconv_fwd_tile")
     add_launches(_KERNELS_PER_CALL["spiralconv_fwd_tile"])
+
+
+def narrow_out_fwd_tc_supported(S, Cin, Cout, rcap):
+    return bool(load().sdvae_narrow_out_fwd_tc_supported(S, Cin, Cout, rcap))
+
+
+def narrow_out_fwd_tc(x, plan, w, bias, y, B, Vin, Vout, S, Cin, Cout):
+    """Narrow-output SpiralConv forward (32 -> 3) on tcgen05, project-then-gather; ``plan`` = the forward
+    ``tables.TileStagePlan`` of the layer's table, ``w`` the layer's own [Cout, S*32] weight."""
+    rc = load().sdvae_narrow_out_fwd_tc(_f(x, "x"), _i(plan.cnt, "plan_cnt"), _i(plan.src, "plan_src"),
+                                        _i(plan.cell, "plan_cell"), plan.rcap, _f(w, "w"), _fo(bias, "bias"),
+                                        _f(y, "y"), B, Vin, Vout, S, Cin, Cout, _stream())
+    if rc:
+        _err(rc, "narrow_out_fwd_tc")
+    add_launches(1)
 
 
 def spiralconv_bwd_x_tile(dpre, plan, wimg_t, gate, dx, B, Vrows, Vdst, S, Cout, Cin):

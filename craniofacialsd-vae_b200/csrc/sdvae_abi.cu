@@ -9,6 +9,7 @@
 #include "spiral_conv_umma_bw.cuh"
 #include "spiral_conv_tile.cuh"
 #include "spiral_conv_tile_bw.cuh"
+#include "spiral_conv_tile_out.cuh"
 #include "slot_pack.cuh"
 #include "pool_misc.cuh"
 #include "narrow_conv.cuh"
@@ -461,6 +462,40 @@ int sdvae_spiralconv_bwd_x_tile(const float* dpre, const int32_t* plan_cnt, cons
     return tile_conv(dpre, plan_cnt, plan_src, plan_cell, plan_ext, rcap, ecap, wimg_t, nullptr, gate, dx, B, Vrows, Vdst,
                      S, gate ? EPI_GATE : EPI_NONE, true, (cudaStream_t)stream,
                      "spiralconv_bwd_x_tile: unsupported layer shape");
+}
+
+/* ---- narrow-output layer forward on tcgen05, project-then-gather (spiral_conv_tile_out.cuh) ------------------- */
+int sdvae_narrow_out_fwd_tc_supported(int S, int Cin, int Cout, int rcap) {
+    if (Cin != 32 || Cout < 1 || Cout > 4 || S < 1 || S > 9 || S * Cout > 27) return 0;   // 29 floats per projected row, 27 used + 2 zero
+    if (rcap < 32 || rcap > tile::kOMaxRcap || rcap % 32 != 0) return 0;
+    return tile::OutCfg::stages(S, rcap) >= 2 ? 1 : 0;
+}
+
+int sdvae_narrow_out_fwd_tc(const float* x, const int32_t* plan_cnt, const int32_t* plan_src,
+                            const uint32_t* plan_cell, int rcap, const float* W, const float* bias, float* y,
+                            int B, int Vin, int Vout, int S, int Cin, int Cout, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(x && plan_cnt && plan_src && plan_cell && W && y, "narrow_out_fwd_tc: null pointer");
+    SDVAE_REQUIRE(B >= 0 && Vin > 0 && Vout > 0, "narrow_out_fwd_tc: bad shape");
+    SDVAE_REQUIRE((long long)B * Vin < 2147483647LL && (long long)B * Vout < 2147483647LL,
+                  "narrow_out_fwd_tc: B*rows exceeds int32");
+    SDVAE_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(plan_src) |
+                    reinterpret_cast<uintptr_t>(plan_cell)) & 15) == 0,
+                  "narrow_out_fwd_tc: x and the plan tables must be 16-byte aligned");
+    if (!sdvae_narrow_out_fwd_tc_supported(S, Cin, Cout, rcap))
+        return set_error(SDVAE_ERR_UNSUPPORTED, "narrow_out_fwd_tc: unsupported layer shape");
+    if (B == 0) return SDVAE_OK;
+    tile::OutArgs a{};
+    a.in = x; a.plan_cnt = plan_cnt; a.plan_src = plan_src; a.plan_cell = plan_cell; a.W = W; a.bias = bias; a.out = y;
+    a.B = B; a.in_rows = Vin; a.out_rows = Vout; a.L = sdvae_tc_plan_tiles(Vout); a.S = S; a.NO = Cout; a.rcap = rcap;
+    a.nts = tile::OutCfg::stages(S, rcap);
+    const bool fixed = S == 9 && Cout == 3;
+    auto kern = fixed ? tile::pt_kernel<9, 3> : tile::pt_kernel<0, 0>;
+    static DeviceOnce attr_done[2];
+    if (attr_done[fixed].first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    const long long ntiles = (long long)B * a.L;
+    const int grid = ntiles < kNumSMs ? (int)ntiles : kNumSMs;
+    kern<<<grid, tile::kOThreads, tile::OutCfg::smem_bytes(S, rcap, a.nts), (cudaStream_t)stream>>>(a);
+    return check_launch("narrow_out_fwd_tc");
 }
 
 int sdvae_dense_tc(const float* x, const int32_t* plan_cnt, const int32_t* plan_src, int rcap,

@@ -297,6 +297,7 @@ class TrainEngine:
         self.slot_en0 = self.slot_out = None
         self.narrow_out_ws = None
         self.narrow_out_plan = None
+        self.narrow_out_tile = None
         self.narrow_in_ws = None
         if not self.use_tc:
             return
@@ -365,6 +366,11 @@ class TrainEngine:
         sp = self.full[0].stage_plan()
         if self.full[0].n_rows == V[0] and cabi.narrow_out_fwd_supported(S[0], C[1], C[0], sp.ucap):
             self.narrow_out_plan = sp
+        # ... or, on the tensor cores, by project-then-gather over the level's forward tile plan (spiral_conv_tile_out.cuh)
+        if self.use_tc and self.full[0].n_rows == V[0] and C[1] == 32 and os.environ.get('SDVAE_TILE', '1') != '0':
+            tp = self.full[0].tile_fwd()
+            if tp is not None and cabi.narrow_out_fwd_tc_supported(S[0], C[1], C[0], tp.rcap):
+                self.narrow_out_tile = tp
 
     def _pack_tc(self):
         """Re-pack every tensor-core weight image from the current weights (they change each step)."""
@@ -450,7 +456,11 @@ class TrainEngine:
                        cabi.ACT_ELU, B, V[l], self.cin_de[l], C[l + 1], name='de%d' % l)
             x = self.d[l]
         out_layer = m.de_layers[L + 1].layer
-        if self.narrow_out_plan is not None:
+        if self.narrow_out_tile is not None:
+            # 32 -> 3 on tcgen05: the tile's staged rows projected once, nine 3-vectors summed per output row
+            cabi.narrow_out_fwd_tc(x, self.narrow_out_tile, out_layer.weight.data, out_layer.bias.data, self.recon,
+                                   B, V[0], V[0], S[0], C[1], C[0])
+        elif self.narrow_out_plan is not None:
             # 32 -> 3 on the FMA units over shared-memory-staged source rows (csrc/narrow_conv.cuh)
             cabi.narrow_out_fwd(x, self.narrow_out_plan, out_layer.weight.data, out_layer.bias.data, self.recon,
                                 B, V[0], V[0], S[0], C[1], C[0])

@@ -77,7 +77,14 @@ class SpiralConvFn(torch.autograd.Function):
         y = torch.empty((B, R, Cout), device=x.device, dtype=torch.float32)
         packed = None                       # slot-packed input of a 3-channel first layer, kept for dW
         done = False
-        if _USE_TC and B > 0 and _aligned(x, weight, bias) and act == cabi.ACT_NONE and Cout == 3 and Cin == 32 \
+        tp = table.tile_fwd() if (_USE_TC and B > 0 and act == cabi.ACT_NONE and Cout == 3 and Cin == 32
+                                  and _aligned(x, weight, bias)) else None
+        if tp is not None and cabi.narrow_out_fwd_tc_supported(S, Cin, Cout, tp.rcap):
+            # 3-channel OUTPUT layer on tcgen05 by project-then-gather (csrc/spiral_conv_tile_out.cuh); needs a tile plan
+            # with <= 256 distinct source rows per tile (patch-ordered levels)
+            cabi.narrow_out_fwd_tc(x, tp, weight, bias, y, B, Vin, R, S, Cin, Cout)
+            done = True
+        elif _USE_TC and B > 0 and _aligned(x, weight, bias) and act == cabi.ACT_NONE and Cout == 3 and Cin == 32 \
                 and S == 9 and cabi.narrow_out_fwd_supported(S, Cin, Cout, table.stage_plan().ucap):
             # 3-channel OUTPUT layer: fp32 FMA over shared-memory-staged source rows (csrc/narrow_conv.cuh)
             cabi.narrow_out_fwd(x, table.stage_plan(), weight, bias, y, B, Vin, R, S, Cin, Cout)

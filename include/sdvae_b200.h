@@ -158,6 +158,16 @@ int sdvae_spiralconv_bwd_w_tc(const float* x, const int32_t* plan_cnt, const int
                               const float* dpre, float* dW, float* db, void* workspace, int B, int Vin,
                               int Vout, int S, int Cin, int Cout, sdvae_stream_t stream);
 
+/* Narrow-output SpiralConv forward (Cin = 32, S*Cout <= 27: the 32 -> 3 output layer, model.py:135-136, 172 through
+ * model.py:27-41) on tcgen05 by project-then-gather: the tile's distinct staged source rows (FORWARD tile plan of the
+ * layer's table, tables.tile_plan, rcap <= 256) are multiplied by the 32 x (S*Cout) weight block once, every output
+ * row sums its S Cout-vectors from shared memory.  W is the layer's own [Cout, S*32] weight (no packed image), no
+ * activation (the output layer has none).  y [B, Vout, Cout]. */
+int sdvae_narrow_out_fwd_tc_supported(int S, int Cin, int Cout, int rcap);
+int sdvae_narrow_out_fwd_tc(const float* x, const int32_t* plan_cnt, const int32_t* plan_src,
+                            const uint32_t* plan_cell, int rcap, const float* W, const float* bias, float* y,
+                            int B, int Vin, int Vout, int S, int Cin, int Cout, sdvae_stream_t stream);
+
 /* ---- narrow-channel layers (C = 3: model.py:104-106 first encoder block, model.py:135-136 output
  * layer) through slot packing: the S*C <= 32 gathered columns of a vertex are materialised once as a
  * 128-byte row, after which every pass of the layer is a dense 32 x 32 contraction on the tcgen05

@@ -107,8 +107,13 @@ def test_benchmarked_configuration_three_steps_vs_oracle(cranio):
         eng.set_fixed_eps(eps.to(DEV))
         eng.load_batch((x * (1.0 + 0.1 * it)).to(DEV))
         got = eng.step(ridx, sync_losses=True)
+        # step 0 is a parity statement (same weights, same inputs).  Steps 1 and 2 run on weights that went through Adam:
+        # its first update is lr * sign(g) whatever |g| is, so a gradient element whose sign is decided by rounding moves
+        # a weight by +lr in one implementation and -lr in the other; the trajectories stay close, not rounding-close
+        # (measured here: <= 3.1e-5 on every loss through two updates at lr = 1e-3).
+        tol = 3e-5 if it == 0 else 1e-4
         for k in ('reconstruction', 'kl', 'latent_consistency', 'laplacian', 'tot'):
-            assert got[k] == pytest.approx(want[k], rel=3e-5), (it, k, got[k], want[k])
+            assert got[k] == pytest.approx(want[k], rel=tol), (it, k, got[k], want[k])
         if it == 0:
             errs = {k: nerr(eng.g(named[k]), v.grad) for k, v in trainer.params.items()}
             assert max(errs.values()) < 5e-5, {k: v for k, v in errs.items() if v >= 5e-5}

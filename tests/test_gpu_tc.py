@@ -342,6 +342,38 @@ def test_fused_narrow_output_backward_vs_fp64_autograd(cranio, orc, lvl, B, gate
     assert not cabi.narrow_out_bwd_supported(30000, S, 32, 3)          # dy of one mesh must fit shared memory
 
 
+@pytest.mark.parametrize('lvl,B', [(0, 1), (0, 5), (0, 37), (2, 3), (3, 2)])
+@pytest.mark.parametrize('with_bias', [True, False])
+def test_project_then_gather_output_forward_vs_fp64_oracle(cranio, orc, lvl, B, with_bias):
+    """32 -> 3 output layer forward on tcgen05 by project-then-gather (csrc/spiral_conv_tile_out.cuh) on the
+    patch-ordered template: against the oracle in fp64; deterministic; ragged last tile; plans with more than 256
+    distinct rows per tile are rejected."""
+    from sdvae_b200 import cabi
+    from sdvae_b200.tables import spiral_table
+    tabs = cranio.renumbered(128)[0]
+    idx = tabs.spiral_tensors()[lvl]
+    V, S = idx.shape
+    tab = spiral_table(idx.to(DEV))
+    plan = tab.tile_fwd()
+    assert plan is not None
+    if not cabi.narrow_out_fwd_tc_supported(S, 32, 3, plan.rcap):
+        assert plan.rcap > 256
+        pytest.skip('level %d: %d distinct rows per tile' % (lvl, plan.rcap))
+    x = rand((B, V, 32), 41)
+    w = rand((3, S * 32), 42, 0.1)
+    b = rand((3,), 43, 0.5) if with_bias else None
+    y64 = orc.spiral_conv(x.double(), idx, w.double(), None if b is None else b.double())
+    outs = []
+    for _ in range(2):
+        y = torch.full((B, V, 3), float('nan'), device=DEV)
+        cabi.narrow_out_fwd_tc(x.to(DEV), plan, w.to(DEV), None if b is None else b.to(DEV), y, B, V, V, S, 32, 3)
+        outs.append(y)
+    assert nerr(outs[0], y64) < TC_TOL
+    assert torch.equal(outs[0], outs[1])
+    assert not cabi.narrow_out_fwd_tc_supported(S, 64, 3, plan.rcap) and not cabi.narrow_out_fwd_tc_supported(S, 32, 4, plan.rcap)
+    assert not cabi.narrow_out_fwd_tc_supported(S, 32, 3, 288)
+
+
 @pytest.mark.parametrize('lvl,B', [(2, 3), (0, 2), (0, 21), (1, 37), (3, 1)])
 @pytest.mark.parametrize('with_bias', [True, False])
 def test_staged_narrow_output_forward_vs_fp64_oracle(cranio, orc, lvl, B, with_bias):

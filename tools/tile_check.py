@@ -69,7 +69,10 @@ def main():
     ap.add_argument('--skip-check', action='store_true')
     ap.add_argument('--skip-old', action='store_true')
     ap.add_argument('--only', default='fwd,dx,dw')
+    ap.add_argument('--lib', default='', help='path of a variant build of libsdvae_b200.so (tuning runs)')
     a = ap.parse_args()
+    if a.lib:
+        cabi.LIB_PATH = os.path.abspath(a.lib)
     tabs = fx.craniofacial_tables().renumbered(128)[0]
     S = 9
     for lvl in [int(t) for t in a.levels.split(',')]:
@@ -139,6 +142,35 @@ def main():
                     refb = gg_.double().sum((0, 1))
                     print('  dW   B=%d: normwise err vs fp64 dW %.3e db %.3e   deterministic %s' % (B, nerr(res[0][0], refW), nerr(res[0][1], refb), torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])), flush=True)
                     del A
+        if 'out' in a.only:
+            # narrow-output layer (32 -> 3) by project-then-gather (csrc/spiral_conv_tile_out.cuh)
+            assert cabi.narrow_out_fwd_tc_supported(S, 32, 3, pf.rcap), 'pt_kernel: unsupported plan'
+            W3 = (torch.randn(3, S * 32, generator=g) * 0.1).to(DEV)
+            b3 = (torch.randn(3, generator=g) * 0.2).to(DEV)
+            if not a.skip_check:
+                for B in (1, 3, 41):
+                    x = torch.randn(B, V, 32, generator=g).to(DEV)
+                    ys = []
+                    for _ in range(2):
+                        y = torch.full((B, V, 3), float('nan'), device=DEV)
+                        cabi.narrow_out_fwd_tc(x, pf, W3, b3, y, B, V, V, S, 32, 3)
+                        torch.cuda.synchronize()
+                        ys.append(y)
+                    ref = (x.double()[:, idx_d.view(-1)].view(B, V, S * 32) @ W3.double().t()) + b3.double()
+                    print('  out  B=%d: normwise err vs fp64 %.3e   deterministic %s' % (B, nerr(ys[0], ref), torch.equal(ys[0], ys[1])), flush=True)
+                    del ref
+            Bt = a.B
+            nb3 = max(2, int(np.ceil(300e6 / (Bt * V * 140))) + 1)
+            xs3 = [torch.randn(Bt, V, 32, device=DEV) for _ in range(nb3)]
+            ys3 = [torch.empty(Bt, V, 3, device=DEV) for _ in range(nb3)]
+            alg3 = Bt * V * 140
+            ms = ev_time(lambda i: cabi.narrow_out_fwd_tc(xs3[i], pf, W3, b3, ys3[i], Bt, V, V, S, 32, 3), a.iters, nb3)
+            print('  %-34s B=%d  %.4f ms  %.0f GB/s alg (%.3f of 6556)' % ('out project-then-gather (tcgen05)', Bt, ms, alg3 / ms / 1e6, alg3 / ms / 1e6 / 6556.2), flush=True)
+            sp_ = tab.stage_plan()
+            if cabi.narrow_out_fwd_supported(S, 32, 3, sp_.ucap):
+                ms = ev_time(lambda i: cabi.narrow_out_fwd(xs3[i], sp_, W3, b3, ys3[i], Bt, V, V, S, 32, 3), a.iters, nb3)
+                print('  %-34s B=%d  %.4f ms  %.0f GB/s alg (%.3f of 6556)' % ('out fp32 FMA, staged rows', Bt, ms, alg3 / ms / 1e6, alg3 / ms / 1e6 / 6556.2), flush=True)
+            del xs3, ys3
         # ---- timing ----
         B = a.B
         nbuf = max(2, int(np.ceil(300e6 / (B * V * 128))) + 1)          # rotate buffers larger than L2
