@@ -8,7 +8,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libsdvae_b200.so")
 SOURCES = ["sdvae_abi.cu"]
-HEADERS = ["common.cuh", "spiral_conv.cuh", "spiral_conv_umma.cuh", "spiral_conv_umma_bw.cuh", "spiral_conv_tile.cuh", "spiral_conv_tile_bw.cuh", "slot_pack.cuh", "pool_misc.cuh", "narrow_conv.cuh", "loss.cuh"]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh"))       # every header: a stale check that misses one runs old code
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 

@@ -60,6 +60,9 @@ _SIGNATURES = {
     "sdvae_spiralconv_bwd_x_tile": (C.c_int, [_c_fp] * 5 + [C.c_int] * 2 + [_c_fp] * 3 + [C.c_int] * 6 + [_c_fp]),
     "sdvae_narrow_out_fwd_tc_supported": (C.c_int, [C.c_int] * 4),
     "sdvae_narrow_out_fwd_tc": (C.c_int, [_c_fp] * 4 + [C.c_int] + [_c_fp] * 3 + [C.c_int] * 6 + [_c_fp]),
+    "sdvae_narrow_out_bwd_tc_supported": (C.c_int, [C.c_int] * 5),
+    "sdvae_narrow_out_bwd_tc_workspace": (C.c_size_t, [C.c_int, C.c_int]),
+    "sdvae_narrow_out_bwd_tc": (C.c_int, [_c_fp] * 6 + [C.c_int] * 2 + [_c_fp] * 5 + [C.c_int] * 7 + [_c_fp]),
     "sdvae_narrow_in_supported": (C.c_int, [C.c_int] * 4),
     "sdvae_narrow_in_bwd_w_workspace": (C.c_size_t, [C.c_int, C.c_int]),
     "sdvae_narrow_in_fwd": (C.c_int, [_c_fp] * 5 + [C.c_int] * 7 + [_c_fp]),
@@ -413,6 +416,26 @@ def narrow_out_fwd_tc(x, plan, w, bias, y, B, Vin, Vout, S, Cin, Cout):
     if rc:
         _err(rc, "narrow_out_fwd_tc")
     add_launches(1)
+
+
+def narrow_out_bwd_tc_supported(S, Cin, Cout, rcap, ecap):
+    return bool(load().sdvae_narrow_out_bwd_tc_supported(S, Cin, Cout, rcap, ecap))
+
+
+def narrow_out_bwd_tc_workspace(S, Cout):
+    return int(load().sdvae_narrow_out_bwd_tc_workspace(S, Cout))
+
+
+def narrow_out_bwd_tc(dy, x, plan, w, dx, dW, db, ws, B, Vrows, Vdst, S, Cin, Cout, gate):
+    """Narrow-output SpiralConv backward (32 -> 3) on tcgen05 in one pass (dx with the previous ELU', dW, db);
+    ``plan`` = the INVERSE ``tables.TileStagePlan`` (``SpiralTable.tile_bwd()``)."""
+    rc = load().sdvae_narrow_out_bwd_tc(_f(dy, "dy"), _f(x, "x"), _i(plan.cnt, "plan_cnt"), _i(plan.src, "plan_src"),
+                                        _i(plan.cell, "plan_cell"), _i16(plan.ext, "plan_ext"), plan.rcap, plan.ecap,
+                                        _f(w, "w"), _f(dx, "dx"), _f(dW, "dW"), _f(db, "db"), _f(ws, "workspace"),
+                                        B, Vrows, Vdst, S, Cin, Cout, 1 if gate else 0, _stream())
+    if rc:
+        _err(rc, "narrow_out_bwd_tc")
+    add_launches(2)
 
 
 def spiralconv_bwd_x_tile(dpre, plan, wimg_t, gate, dx, B, Vrows, Vdst, S, Cout, Cin):

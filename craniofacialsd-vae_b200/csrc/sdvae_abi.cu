@@ -10,6 +10,7 @@
 #include "spiral_conv_tile.cuh"
 #include "spiral_conv_tile_bw.cuh"
 #include "spiral_conv_tile_out.cuh"
+#include "spiral_conv_tile_out_bw.cuh"
 #include "slot_pack.cuh"
 #include "pool_misc.cuh"
 #include "narrow_conv.cuh"
@@ -496,6 +497,57 @@ int sdvae_narrow_out_fwd_tc(const float* x, const int32_t* plan_cnt, const int32
     const int grid = ntiles < kNumSMs ? (int)ntiles : kNumSMs;
     kern<<<grid, tile::kOThreads, tile::OutCfg::smem_bytes(S, rcap, a.nts), (cudaStream_t)stream>>>(a);
     return check_launch("narrow_out_fwd_tc");
+}
+
+/* ---- narrow-output layer backward on tcgen05, gather-then-project (spiral_conv_tile_out_bw.cuh) --------------- */
+int sdvae_narrow_out_bwd_tc_supported(int S, int Cin, int Cout, int rcap, int ecap) {
+    if (Cin != 32 || Cout < 1 || Cout > 3 || S < 1 || S > 9 || S * Cout > 32) return 0;
+    if (rcap < 32 || rcap > tile::kTMaxRcap || rcap % 32 != 0) return 0;
+    if (ecap < 0 || ecap % 64 != 0 || ecap > 1984) return 0;
+    return tile::OutBwCfg::stages(S, rcap, ecap) >= 2 ? 1 : 0;
+}
+
+size_t sdvae_narrow_out_bwd_tc_workspace(int S, int Cout) {
+    return sizeof(float) * (size_t)kNumSMs * ((size_t)Cout * S * 32 + Cout);
+}
+
+int sdvae_narrow_out_bwd_tc(const float* dy, const float* x, const int32_t* plan_cnt, const int32_t* plan_src,
+                            const uint32_t* plan_cell, const uint16_t* plan_ext, int rcap, int ecap, const float* W,
+                            float* dx, float* dW, float* db, void* workspace, int B, int Vrows, int Vdst, int S,
+                            int Cin, int Cout, int gate, sdvae_stream_t stream) {
+    SDVAE_REQUIRE(dy && x && plan_cnt && plan_src && plan_cell && (plan_ext || ecap == 0) && W && dx && dW && db && workspace,
+                  "narrow_out_bwd_tc: null pointer");
+    SDVAE_REQUIRE(B >= 0 && Vrows > 0 && Vdst > 0, "narrow_out_bwd_tc: bad shape");
+    SDVAE_REQUIRE((long long)B * Vrows < 2147483647LL && (long long)B * Vdst < 2147483647LL,
+                  "narrow_out_bwd_tc: B*rows exceeds int32");
+    SDVAE_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(plan_src) |
+                    reinterpret_cast<uintptr_t>(plan_cell) | reinterpret_cast<uintptr_t>(plan_ext)) & 15) == 0,
+                  "narrow_out_bwd_tc: x, dx and the plan tables must be 16-byte aligned");
+    if (!sdvae_narrow_out_bwd_tc_supported(S, Cin, Cout, rcap, ecap))
+        return set_error(SDVAE_ERR_UNSUPPORTED, "narrow_out_bwd_tc: unsupported layer shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long len = (long long)Cout * S * 32;
+    if (B == 0) {
+        cudaMemsetAsync(dW, 0, sizeof(float) * len, st);
+        cudaMemsetAsync(db, 0, sizeof(float) * Cout, st);
+        return check_launch("narrow_out_bwd_tc memset");
+    }
+    tile::OutBwArgs a{};
+    a.dy = dy; a.x = x; a.plan_cnt = plan_cnt; a.plan_src = plan_src; a.plan_cell = plan_cell; a.plan_ext = plan_ext;
+    a.W = W; a.dx = dx;
+    a.B = B; a.rows_v = Vrows; a.rows_u = Vdst; a.L = sdvae_tc_plan_tiles(Vdst); a.S = S; a.NO = Cout;
+    a.rcap = rcap; a.ecap = ecap; a.nts = tile::OutBwCfg::stages(S, rcap, ecap); a.flush = 2; a.gate = gate;
+    const long long ntiles = (long long)B * a.L;
+    const int grid = ntiles < kNumSMs ? (int)ntiles : kNumSMs;
+    a.part = static_cast<float*>(workspace);
+    a.part_b = a.part + (size_t)grid * len;
+    const bool fixed = S == 9 && Cout == 3;
+    auto kern = fixed ? tile::qt_kernel<9, 3> : tile::qt_kernel<0, 0>;
+    static DeviceOnce attr_done[2];
+    if (attr_done[fixed].first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    kern<<<grid, tile::kQThreads, tile::OutBwCfg::smem_bytes(S, rcap, ecap, a.nts), st>>>(a);
+    split_reduce2_kernel<<<blocks_for(len + Cout, 64), 64 * kSplitGroups, 0, st>>>(a.part, a.part_b, dW, db, grid, len, Cout);
+    return check_launch("narrow_out_bwd_tc");
 }
 
 int sdvae_dense_tc(const float* x, const int32_t* plan_cnt, const int32_t* plan_src, int rcap,

@@ -298,6 +298,8 @@ class TrainEngine:
         self.narrow_out_ws = None
         self.narrow_out_plan = None
         self.narrow_out_tile = None
+        self.narrow_out_tile_bwd = None
+        self.narrow_out_tc_ws = None
         self.narrow_in_ws = None
         if not self.use_tc:
             return
@@ -371,6 +373,11 @@ class TrainEngine:
             tp = self.full[0].tile_fwd()
             if tp is not None and cabi.narrow_out_fwd_tc_supported(S[0], C[1], C[0], tp.rcap):
                 self.narrow_out_tile = tp
+            # ... and its backward by gather-then-project over the inverse tile plan (spiral_conv_tile_out_bw.cuh)
+            tb_ = self.full[0].tile_bwd()
+            if tb_ is not None and cabi.narrow_out_bwd_tc_supported(S[0], C[1], C[0], tb_.rcap, tb_.ecap):
+                self.narrow_out_tile_bwd = tb_
+                self.narrow_out_tc_ws = f(cabi.narrow_out_bwd_tc_workspace(S[0], C[0]) // 4)
 
     def _pack_tc(self):
         """Re-pack every tensor-core weight image from the current weights (they change each step)."""
@@ -544,7 +551,12 @@ class TrainEngine:
                              1.0, 0.0, scale, None)
         out_layer = m.de_layers[L + 1].layer
         cp, cs = self.full[0].inverse()
-        if self.narrow_out_ws is not None:
+        if self.narrow_out_tile_bwd is not None:
+            # one fused tcgen05 pass: G = in-order cell sums of drecon, dd0 = (G W') * elu'(d0), dW = G^T d0, db
+            cabi.narrow_out_bwd_tc(self.drecon, self.d[0], self.narrow_out_tile_bwd, out_layer.weight.data, self.dd[0],
+                                   self.g(out_layer.weight), self.g(out_layer.bias), self.narrow_out_tc_ws,
+                                   B, V[0], V[0], S[0], C[1], C[0], True)
+        elif self.narrow_out_ws is not None:
             # dd0 = (G Wd^T) * elu'(d0), dW and db from one pass over drecon and d0 (G in registers)
             cabi.narrow_out_bwd(self.drecon, self.d[0], cp, cs, self.full[0].inverse_packed(), out_layer.weight.data, self.dd[0],
                                 self.g(out_layer.weight), self.g(out_layer.bias), self.narrow_out_ws,

@@ -141,7 +141,15 @@ class SpiralConvFn(torch.autograd.Function):
             db = torch.empty(Cout, device=x.device, dtype=torch.float32) if ctx.has_bias else None
             ws = torch.empty(cabi.spiralconv_bwd_w_workspace(B * max(R, Vin), S, max(Cin, 32), max(Cout, 32)) // 4 + 4,
                              device=x.device, dtype=torch.float32)
-        if tc and (want_w or want_x) and cabi.narrow_out_bwd_supported(R, S, Cin, Cout):
+        tpb = table.tile_bwd() if (tc and want_w and want_x and ctx.has_bias and Cin == 32 and Cout <= 3) else None
+        if tpb is not None and cabi.narrow_out_bwd_tc_supported(S, Cin, Cout, tpb.rcap, tpb.ecap):
+            # 3-channel OUTPUT layer, whole backward in one tcgen05 pass (csrc/spiral_conv_tile_out_bw.cuh); needs the
+            # inverse tile plan (patch-ordered levels) and computes all three gradients
+            dx = torch.empty_like(x)
+            nws = _f32(cabi.narrow_out_bwd_tc_workspace(S, Cout) // 4, like=x)
+            cabi.narrow_out_bwd_tc(dpre, x, tpb, weight, dx, dw, db, nws, B, R, Vin, S, Cin, Cout, False)
+            want_w = want_x = False
+        elif tc and (want_w or want_x) and cabi.narrow_out_bwd_supported(R, S, Cin, Cout):
             # 3-channel OUTPUT layer, fused (csrc/narrow_conv.cuh): dx, dW, db from one pass over dpre and x
             cell_ptr, cell_src = table.inverse()
             nws = _f32(cabi.narrow_out_bwd_workspace(S, Cout) // 4, like=x)

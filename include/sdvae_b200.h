@@ -168,6 +168,18 @@ int sdvae_narrow_out_fwd_tc(const float* x, const int32_t* plan_cnt, const int32
                             const uint32_t* plan_cell, int rcap, const float* W, const float* bias, float* y,
                             int B, int Vin, int Vout, int S, int Cin, int Cout, sdvae_stream_t stream);
 
+/* Narrow-output SpiralConv backward (Cin = 32, Cout <= 3, S <= 9: autograd of model.py:34,40 for the 32 -> 3 output
+ * layer) on tcgen05 in one fused pass: G[u, s*Cout+n] = in-order sum of dy over the inverse cells (INVERSE tile plan
+ * of the layer's table: tables.tile_plan of inverse_cells, rcap <= 288), dx = (G W') * elu'(x) when `gate` (x is the ELU
+ * output that fed the layer), dW = sum_u G x, db = sum dy.  dy [B, Vrows, Cout], x and dx [B, Vdst, 32], dW [Cout, S*32],
+ * db [Cout]; workspace: sdvae_narrow_out_bwd_tc_workspace bytes.  Deterministic. */
+int sdvae_narrow_out_bwd_tc_supported(int S, int Cin, int Cout, int rcap, int ecap);
+size_t sdvae_narrow_out_bwd_tc_workspace(int S, int Cout);
+int sdvae_narrow_out_bwd_tc(const float* dy, const float* x, const int32_t* plan_cnt, const int32_t* plan_src,
+                            const uint32_t* plan_cell, const uint16_t* plan_ext, int rcap, int ecap, const float* W,
+                            float* dx, float* dW, float* db, void* workspace, int B, int Vrows, int Vdst, int S,
+                            int Cin, int Cout, int gate, sdvae_stream_t stream);
+
 /* ---- narrow-channel layers (C = 3: model.py:104-106 first encoder block, model.py:135-136 output
  * layer) through slot packing: the S*C <= 32 gathered columns of a vertex are materialised once as a
  * 128-byte row, after which every pass of the layer is a dense 32 x 32 contraction on the tcgen05

@@ -342,6 +342,46 @@ def test_fused_narrow_output_backward_vs_fp64_autograd(cranio, orc, lvl, B, gate
     assert not cabi.narrow_out_bwd_supported(30000, S, 32, 3)          # dy of one mesh must fit shared memory
 
 
+@pytest.mark.parametrize('lvl,B', [(0, 1), (0, 4), (0, 37), (1, 5), (2, 3), (3, 2)])
+@pytest.mark.parametrize('gated', [False, True])
+def test_gather_then_project_output_backward_vs_fp64_autograd(cranio, orc, lvl, B, gated):
+    """32 -> 3 output layer, whole backward in one tcgen05 pass (csrc/spiral_conv_tile_out_bw.cuh) on the
+    patch-ordered template: input gradient (with and without the ELU' gate), weight and bias gradients against fp64
+    autograd of the oracle; deterministic; ragged last tile; several tiles per CTA and more than one accumulator
+    flush (B = 37)."""
+    from sdvae_b200 import cabi
+    from sdvae_b200.tables import spiral_table
+    tabs = cranio.renumbered(128)[0]
+    idx = tabs.spiral_tensors()[lvl]
+    V, S = idx.shape
+    tab = spiral_table(idx.to(DEV))
+    plan = tab.tile_bwd()
+    assert plan is not None and cabi.narrow_out_bwd_tc_supported(S, 32, 3, plan.rcap, plan.ecap)
+    u = rand((B, V, 32), 51).double().requires_grad_(True)
+    w2 = rand((3, S * 32), 52, 0.1).double().requires_grad_(True)
+    b2 = torch.zeros(3, dtype=torch.float64, requires_grad=True)
+    gr = rand((B, V, 3), 53)
+    d0 = orc.elu(u) if gated else u
+    orc.spiral_conv(d0, idx, w2, b2).backward(gr.double())
+    d0f = d0.detach().float().to(DEV).contiguous()
+    wf = w2.detach().float().to(DEV)
+    ws = torch.empty(cabi.narrow_out_bwd_tc_workspace(S, 3) // 4, device=DEV)
+    outs = []
+    for _ in range(2):
+        du = torch.full((B, V, 32), float('nan'), device=DEV)
+        dW = torch.full((3, S * 32), float('nan'), device=DEV)
+        db = torch.full((3,), float('nan'), device=DEV)
+        cabi.narrow_out_bwd_tc(gr.to(DEV), d0f, plan, wf, du, dW, db, ws, B, V, V, S, 32, 3, gated)
+        outs.append((du, dW, db))
+    du, dW, db = outs[0]
+    assert nerr(du, u.grad) < TC_TOL
+    assert nerr(dW, w2.grad) < TC_TOL and nerr(db, b2.grad) < TC_TOL
+    assert all(torch.equal(outs[0][i], outs[1][i]) for i in range(3))
+    assert not cabi.narrow_out_bwd_tc_supported(S, 64, 3, plan.rcap, plan.ecap)
+    assert not cabi.narrow_out_bwd_tc_supported(S, 32, 4, plan.rcap, plan.ecap)
+    assert not cabi.narrow_out_bwd_tc_supported(S, 32, 3, 320, plan.ecap)
+
+
 @pytest.mark.parametrize('lvl,B', [(0, 1), (0, 5), (0, 37), (2, 3), (3, 2)])
 @pytest.mark.parametrize('with_bias', [True, False])
 def test_project_then_gather_output_forward_vs_fp64_oracle(cranio, orc, lvl, B, with_bias):

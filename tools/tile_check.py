@@ -171,6 +171,49 @@ def main():
                 ms = ev_time(lambda i: cabi.narrow_out_fwd(xs3[i], sp_, W3, b3, ys3[i], Bt, V, V, S, 32, 3), a.iters, nb3)
                 print('  %-34s B=%d  %.4f ms  %.0f GB/s alg (%.3f of 6556)' % ('out fp32 FMA, staged rows', Bt, ms, alg3 / ms / 1e6, alg3 / ms / 1e6 / 6556.2), flush=True)
             del xs3, ys3
+        if 'bwo' in a.only:
+            # narrow-output layer backward (32 -> 3), gather-then-project (csrc/spiral_conv_tile_out_bw.cuh)
+            assert cabi.narrow_out_bwd_tc_supported(S, 32, 3, pb.rcap, pb.ecap), 'qt_kernel: unsupported plan'
+            W3 = (torch.randn(3, S * 32, generator=g) * 0.1).to(DEV)
+            ws3 = torch.empty(cabi.narrow_out_bwd_tc_workspace(S, 3) // 4, device=DEV)
+            if not a.skip_check:
+                for B in (1, 3, 41):
+                    x = torch.randn(B, V, 32, generator=g).to(DEV)
+                    dy = torch.randn(B, V, 3, generator=g).to(DEV)
+                    res = []
+                    for _ in range(2):
+                        dx = torch.full((B, V, 32), float('nan'), device=DEV)
+                        dW = torch.full((3, S * 32), float('nan'), device=DEV); db_ = torch.full((3,), float('nan'), device=DEV)
+                        cabi.narrow_out_bwd_tc(dy, x, pb, W3, dx, dW, db_, ws3, B, V, V, S, 32, 3, True)
+                        torch.cuda.synchronize()
+                        res.append((dx, dW, db_))
+                    dG = (dy.double() @ W3.double()).view(B, V * S, 32)
+                    rdx = torch.zeros(B, V, 32, dtype=torch.float64, device=DEV)
+                    rdx.index_add_(1, idx_d.view(-1), dG)
+                    rdx = rdx * torch.where(x > 0, torch.ones_like(x), x + 1).double()
+                    A = x.double()[:, idx_d.view(-1)].view(B * V, S * 32)
+                    rdW = dy.double().view(B * V, 3).t() @ A
+                    rdb = dy.double().sum((0, 1))
+                    det = all(torch.equal(res[0][i], res[1][i]) for i in range(3))
+                    print('  bwo  B=%d: normwise err vs fp64 dx %.3e dW %.3e db %.3e   deterministic %s'
+                          % (B, nerr(res[0][0], rdx), nerr(res[0][1], rdW), nerr(res[0][2], rdb), det), flush=True)
+                    del A, dG, rdx
+            Bt = a.B
+            nb3 = max(2, int(np.ceil(300e6 / (Bt * V * 268))) + 1)
+            xs3 = [torch.randn(Bt, V, 32, device=DEV) for _ in range(nb3)]
+            dys3 = [torch.randn(Bt, V, 3, device=DEV) for _ in range(nb3)]
+            dxs3 = [torch.empty(Bt, V, 32, device=DEV) for _ in range(nb3)]
+            dW = torch.empty(3, S * 32, device=DEV); db_ = torch.empty(3, device=DEV)
+            alg3 = Bt * V * 268
+            ms = ev_time(lambda i: cabi.narrow_out_bwd_tc(dys3[i], xs3[i], pb, W3, dxs3[i], dW, db_, ws3, Bt, V, V, S, 32, 3, True), a.iters, nb3)
+            print('  %-34s B=%d  %.4f ms  %.0f GB/s alg (%.3f of 6556)' % ('out bwd gather-then-project (tc)', Bt, ms, alg3 / ms / 1e6, alg3 / ms / 1e6 / 6556.2), flush=True)
+            if cabi.narrow_out_bwd_supported(V, S, 32, 3):
+                nws = torch.empty(cabi.narrow_out_bwd_workspace(S, 3) // 4, device=DEV)
+                cp, cs = tab.inverse()
+                cpk = tab.inverse_packed()
+                ms = ev_time(lambda i: cabi.narrow_out_bwd(dys3[i], xs3[i], cp, cs, cpk, W3, dxs3[i], dW, db_, nws, Bt, V, V, S, 32, 3, True), a.iters, nb3)
+                print('  %-34s B=%d  %.4f ms  %.0f GB/s alg (%.3f of 6556)' % ('out bwd fused fp32 FMA', Bt, ms, alg3 / ms / 1e6, alg3 / ms / 1e6 / 6556.2), flush=True)
+            del xs3, dys3, dxs3
         # ---- timing ----
         B = a.B
         nbuf = max(2, int(np.ceil(300e6 / (B * V * 128))) + 1)          # rotate buffers larger than L2
