@@ -16,8 +16,8 @@
 //
 // Tile plan: the INVERSE tile plan of the layer's table (tables.tile_plan of inverse_cells: plan_cnt / plan_src = the
 // distinct dy rows of a tile, plan_cell / plan_ext = the cells), rcap <= 288.
-// Warp roles (24 warps): 0..3 / 4..7 / 20..23 G builders, three sets that take the tiles round-robin (thread = vertex;
-// the builders are the busiest role) | 8..11 dx epilogue | 12, 17, 18, 19 x^T transposers, one per TMEM lane quarter, which
+// Warp roles (24 warps): 0..3 / 4..7 G builders of even / odd tiles (thread = vertex; each set owns one G slot) | 8..11
+// and 20..23 dx epilogue of even / odd tiles | 12, 17, 18, 19 x^T transposers, one per TMEM lane quarter, which
 // also drain their quarter of the weight-gradient accumulators | 13..15 loaders | 16 TMEM allocation + MMA issue.
 // The weight gradient's A operand x^T has only 32 rows (channels) but an MMA spans 128 TMEM lanes: chunk r4 (tile rows
 // 32 r4 ..) lives in lane quarter r4 of ITS OWN column range, whose other three quarters are zeroed once -- so four
@@ -56,7 +56,7 @@ struct OutBwArgs {
 
 struct OutBwCfg {
     static size_t stage_bytes(int S, int rcap, int ecap) { return (size_t)rcap * 16 + kQXBytes + (size_t)S * 512 + (size_t)ecap * 2; }
-    static size_t fixed_bytes() { return 1024 + kTBChunk + 2 * (size_t)umma::kGStage + umma::kOutStageBytes + 512 + 4608; }
+    static size_t fixed_bytes() { return 1024 + kTBChunk + 2 * (size_t)umma::kGStage + 2 * (size_t)umma::kOutStageBytes + 512 + 4608; }
     static int stages(int S, int rcap, int ecap) {
         const long long budget = 227LL * 1024 - (long long)fixed_bytes();
         long long st = budget / (long long)stage_bytes(S, rcap, ecap);
@@ -84,8 +84,8 @@ qt_kernel(const OutBwArgs a) {
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
     uint8_t* B_s = smem;                                    // [64][128 B] dx weight image: row c (hi) / 32 + c (lo), K = j
     uint8_t* G_s = B_s + kTBChunk;                          // [2] G tiles as MN-major B operand (hi image | lo image per K atom)
-    uint8_t* O_s = G_s + 2 * umma::kGStage;                 // [128][144 B] dx staging
-    uint8_t* T_s = O_s + umma::kOutStageBytes;              // [NTS] tile stages: dy rows (16 B) | x tile | cell words | ext
+    uint8_t* O_s0 = G_s + 2 * umma::kGStage;                // [2][128][144 B] dx staging, one per epilogue group
+    uint8_t* T_s = O_s0 + 2 * umma::kOutStageBytes;             // [NTS] tile stages: dy rows (16 B) | x tile | cell words | ext
     uint64_t* bars = reinterpret_cast<uint64_t*>(T_s + (size_t)NTS * STAGE_BYTES);
     uint64_t* tile_full = bars;                             // [4] loader lanes (async) -> builders, transposers, epilogue
     uint64_t* tile_empty = tile_full + kQMaxStages;         // [4] 4 builder + 4 transposer + 4 epilogue warps -> loader
@@ -248,10 +248,11 @@ qt_kernel(const OutBwArgs a) {
                 if (jt >= a.L) { jt -= a.L; ++b; }
             }
         }
-    } else if (warp < 8 || warp >= 20) {
-        // ================= G builders: thread = vertex u of the tile; three sets take the tiles round-robin, the G
-        // slot (TMEM stage + G_s buffer) of tile it is it & 1: a set gathers while the slots are busy =================
-        const int set = warp < 8 ? warp >> 2 : 2;              // tiles it = set (mod 3)
+    } else if (warp < 8) {
+        // ================= G builders: thread = vertex u of the tile.  Two sets, each the ONLY producer of its G slot
+        // (TMEM stage + G_s buffer): a third set sharing the slots would be two barrier phases away from the slot's
+        // previous producer, which a parity wait cannot tell apart =================
+        const int set = warp >> 2;                             // tiles it = set (mod 2), slot = set
         const int q4 = warp & 3;
         const int r = q4 * 32 + lane;
         const uint32_t cell_idx = (uint32_t)((r >> 5) * 32 + (r & 7) * 4 + ((r >> 3) & 3)) * 4u;
@@ -259,10 +260,10 @@ qt_kernel(const OutBwArgs a) {
         float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
         long long t0 = (long long)blockIdx.x + (long long)set * gridDim.x;
         int jt = (int)(t0 % a.L);
-        const int djt2 = (3 * djt) % a.L;
+        const int djt2 = (2 * djt) % a.L;
 #pragma unroll 1
-        for (int it = set; it < my_tiles; it += 3) {
-            const int sl = it & 1;
+        for (int it = set; it < my_tiles; it += 2) {
+            const int sl = set;
             const uint32_t ph = (uint32_t)((it >> 1) & 1);
             const uint32_t t_g = t_g0 + (uint32_t)(sl * 64);
             uint8_t* gs = G_s + (size_t)sl * umma::kGStage;
@@ -344,13 +345,17 @@ qt_kernel(const OutBwArgs a) {
             if (lane == 0) mbar_arrive_a(smem_u32(adx_full + sl));
         }
         for (int n = 0; n < 3; ++n) db_s[((set * 4 + q4) * 32 + lane) * 3 + n] = n < NO ? dbacc[n] : 0.f;
-    } else if (warp >= kQEpiWarp0 && warp < kQEpiWarp0 + 4) {
-        // ================= dx epilogue: TMEM -> staging -> elu' gate -> coalesced store =================
+    } else if ((warp >= kQEpiWarp0 && warp < kQEpiWarp0 + 4) || warp >= 20) {
+        // ================= dx epilogue: TMEM -> staging -> elu' gate -> coalesced store; two groups of four warps, group g
+        // owns the accumulator slot g and takes the tiles it = g (mod 2) =================
+        const int grp = warp >= 20 ? 1 : 0;
         const int q4 = warp & 3;
-        int b = (int)blockIdx.x / a.L, jt = (int)blockIdx.x - b * a.L;
+        uint8_t* O_s = O_s0 + (size_t)grp * umma::kOutStageBytes;
+        long long t0 = (long long)blockIdx.x + (long long)grp * gridDim.x;
+        int b = (int)(t0 / a.L), jt = (int)(t0 - (long long)b * a.L);
 #pragma unroll 1
-        for (int it = 0; it < my_tiles; ++it) {
-            const int sl = it & 1;
+        for (int it = grp; it < my_tiles; it += 2) {
+            const int sl = grp;
             const int ts = it % NTS;
             mbar_wait_relaxed(tdx_full + sl, (uint32_t)((it >> 1) & 1));
             tc_fence_after();
@@ -387,8 +392,10 @@ qt_kernel(const OutBwArgs a) {
                     *reinterpret_cast<float4*>(a.dx + ((size_t)b * a.rows_u + r2) * 32 + piece * 4) = t;
             }
             warp_arrive(tile_empty + ts, lane);
-            b += db; jt += djt;
-            if (jt >= a.L) { jt -= a.L; ++b; }
+            for (int k = 0; k < 2; ++k) {
+                b += db; jt += djt;
+                if (jt >= a.L) { jt -= a.L; ++b; }
+            }
         }
     } else if (warp == 12 || (warp >= 17 && warp <= 19)) {
         // ================= x^T transposers: warp of lane quarter q4 serves chunk r4 = q4 of every tile =================
@@ -485,7 +492,7 @@ qt_kernel(const OutBwArgs a) {
     }
     if (tid < NO) {                                            // db partial of this CTA: the 256 builder threads in order
         float t = 0.f;
-        for (int i = 0; i < 384; ++i) t += db_s[i * 3 + tid];
+        for (int i = 0; i < 256; ++i) t += db_s[i * 3 + tid];
         a.part_b[(size_t)blockIdx.x * NO + tid] = t;
     }
     if (warp == kQMmaWarp) {

@@ -1,0 +1,6 @@
+set -x; mkdir -p gpurun_out
+timeout 200 python tools/tile_check.py --levels 0 --B 1024 --only bwo --iters 5 > gpurun_out/g29_bwo.log 2>&1; echo "rc=$?" >> gpurun_out/g29_bwo.log; cat gpurun_out/g29_bwo.log
+CMD="python tools/tile_check.py --levels 0 --B 1024 --skip-check --skip-old --iters 1 --only fwd,dx,dw,out,bwo"
+timeout 300 $CMD > gpurun_out/r02_tile_plain.log 2>&1 &&
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gt_kernel|bt_kernel|pt_kernel|qt_kernel' -c 10 -o gpurun_out/r02_tile_full -f $CMD > gpurun_out/r02_tile_ncu.log 2>&1
+tail -4 gpurun_out/r02_tile_ncu.log

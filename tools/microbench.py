@@ -130,6 +130,19 @@ def main():
                 cabi.tc_pack_weights(w, wimg_kt, S, 32, 32, True, kperm=True)
                 ms = timeit(lambda k: cabi.spiralconv_bwd_x_tile(ys[k], tb_, wimg_kt, None, xs[k], B, R, Vin, S, 32, 32), ns, args.iters)
                 row('conv dx', name, B, 'tcgen05 3xTF32, tile-staged', ms, alg, flops)
+            # output layer (32 -> 3) on tcgen05: project-then-gather forward, gather-then-project fused backward
+            if cin == 32 and cout == 3 and not restricted:
+                tpf, tpb = tab.tile_fwd(), tab.tile_bwd()
+                if tpf is not None and cabi.narrow_out_fwd_tc_supported(S, cin, cout, tpf.rcap):
+                    ms = timeit(lambda k: cabi.narrow_out_fwd_tc(xs[k], tpf, w, b, ys[k], B, Vin, R, S, cin, cout), ns, args.iters)
+                    row('conv fwd', name, B, 'tcgen05 3xTF32, project-then-gather', ms, alg, flops)
+                if tpb is not None and cabi.narrow_out_bwd_tc_supported(S, cin, cout, tpb.rcap, tpb.ecap):
+                    wsq = torch.empty(cabi.narrow_out_bwd_tc_workspace(S, cout) // 4, device=DEV)
+                    dWq, dbq = torch.empty(cout, S * cin, device=DEV), torch.empty(cout, device=DEV)
+                    dxq = torch.empty(B, Vin, cin, device=DEV)
+                    ms = timeit(lambda k: cabi.narrow_out_bwd_tc(ys[k], xs[k], tpb, w, dxq, dWq, dbq, wsq, B, R, Vin, S, cin, cout, True), ns, args.iters)
+                    row('conv dx+dW+db', name, B, 'tcgen05 3xTF32, fused gather-then-project', ms, alg + 4.0 * B * Vin * cin, 2 * flops)
+                    del dxq
             # forward
             plan = tab.plan_fwd()
             if cin == 32 and cout == 3 and cabi.narrow_out_fwd_supported(S, cin, cout, tab.stage_plan().ucap):
@@ -176,7 +189,9 @@ def main():
                 ms = timeit(lambda k: cabi.spiralconv_fwd(xs[k], tab.idx, w, b, ys[k], B, Vin, R, S, cin, cout, act), ns, args.iters)
                 row('conv fwd', name, B, 'fp32 FMA', ms, alg, flops)
             # weight gradient (reads x and dy, writes dW)
-            ws = torch.empty(cabi.spiralconv_bwd_w_workspace(B * R, S, cin, cout) // 4 + 4, device=DEV)
+            # (the slot-packed paths of the 3-channel layers run a dense 32 x 32 contraction over R or Vin rows: size for both)
+            ws = torch.empty(max(cabi.spiralconv_bwd_w_workspace(B * R, S, cin, cout),
+                                 cabi.spiralconv_bwd_w_workspace(B * max(R, Vin), 1, 32, 32)) // 4 + 4, device=DEV)
             dW, db = torch.empty(cout, S * cin, device=DEV), torch.empty(cout, device=DEV)
             dWd, dbd = torch.empty(32, 32, device=DEV), torch.empty(32, device=DEV)
             if cabi.narrow_in_supported(Vin, S, cin, cout):
