@@ -234,6 +234,26 @@ def time_conv_kernels(eng, reps=10):
     return out, alg_bytes, flops
 
 
+def time_out_layer(eng, reps=10):
+    """The two passes of the 32 -> 3 output layer (forward; fused backward = dx with the previous ELU', dW, db), each
+    timed alone with CUDA events.  Returns {pass: (seconds, kernel name, algorithmic bytes)} (the forward
+    moves 4*(32 + 3) floats per vertex, the backward reads dy and x and writes dx: 4*(3 + 32 + 32))."""
+    from sdvae_b200 import cabi
+    L, V, C, B, S = eng.L, eng.V, eng.C, eng.B, eng.S
+    lay = eng.model.de_layers[L + 1].layer
+    out = {}
+    if eng.narrow_out_tile is not None:
+        out['fwd'] = (_time(lambda: cabi.narrow_out_fwd_tc(eng.d[0], eng.narrow_out_tile, lay.weight.data, lay.bias.data,
+                                                           eng.recon, B, V[0], V[0], S[0], C[1], C[0]), reps),
+                      "pt_kernel (tcgen05 3xTF32, project-then-gather)", 4.0 * B * V[0] * (C[1] + C[0]))
+    if eng.narrow_out_tile_bwd is not None:
+        out['bwd'] = (_time(lambda: cabi.narrow_out_bwd_tc(eng.drecon, eng.d[0], eng.narrow_out_tile_bwd, lay.weight.data,
+                                                           eng.dd[0], eng.g(lay.weight), eng.g(lay.bias), eng.narrow_out_tc_ws,
+                                                           B, V[0], V[0], S[0], C[1], C[0], True), reps),
+                      "qt_kernel (tcgen05 3xTF32, fused gather-then-project: dx, dW, db)", 4.0 * B * V[0] * (C[0] + 2 * C[1]))
+    return out
+
+
 def time_pool_kernel(eng, reps=10):
     """The finest up-sampling Pool forward ([B, 4260, 32] -> [B, 17039, 32], the largest memory-bound Pool of
     the step), timed alone with CUDA events on the launching stream; inputs / outputs exceed L2 at the bench batch."""
@@ -380,9 +400,15 @@ def run_ours(args):
                                "note": "3 x 19.79 MB per mesh (forward + two backward passes of every fused op) over this "
                                        "rank's step time"},
                 "note": ("error-compensated 3xTF32 on tcgen05 (fp32-level parity).  Not HBM-bound: the tile's distinct "
-                         "source rows are staged once in shared memory (DRAM and L2 traffic ~ algorithmic), the kernel is "
-                         "bound by the TMEM stores of the gathered, hi/lo-split A operand (tcgen05.st ~155 clk per 4 KB "
-                         "and warp + ~300 clk tcgen05.wait::st, tools/sttm_bench.cu; profiles/r02_tile_kernel.md)")}
+                         "source rows are staged once in shared memory (DRAM traffic = algorithmic bytes, `traffic`); the "
+                         "weight gradient is bound by instruction issue (64-72 % of the issue slots: one LDS.32 per element "
+                         "in the transposing splitter) and, like the forward / input-gradient kernels, by the TMEM stores "
+                         "of the gathered, hi/lo-split A operand (tcgen05.st ~155 clk per 4 KB and warp + ~300 clk "
+                         "tcgen05.wait::st, tools/sttm_bench.cu; profiles/r02_tile_kernel.md)")}
+    out_passes = time_out_layer(eng)
+    roofline["out_layer_passes"] = {k: {"kernel": v[1], "kernel_ms": v[0] * 1e3, "algorithmic_bytes": v[2],
+                                        "achieved": v[2] / v[0] / 1e9, "frac": v[2] / v[0] / 1e9 / hbm_peak}
+                                    for k, v in out_passes.items()}
     psec, palg = time_pool_kernel(eng)
     use_graph, renumbered, has_tc, meshes_per_gpu, n_params = bool(eng.use_graph), bool(eng.renumber), bool(eng.tc), eng.B, eng.n_params
     pool_B, pool_V = eng.B, (eng.V[1], eng.V[0])

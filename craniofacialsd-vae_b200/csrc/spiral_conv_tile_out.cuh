@@ -17,8 +17,10 @@
 // memory -> gather-sum -> coalesced store; with one group the epilogue bounded the kernel: 1.00 ms at 1024 meshes) |
 // 8..19 splitters: chunk g = 2*tile + block goes to set g % 3, warp % 4 = TMEM lane quarter, staged rows -> hi/lo ->
 // tcgen05.st.16x256b |
-// 20..22 loaders (tile it by warp it % 3 into stage it % NTS; the stage's barrier is armed by the copies themselves --
-// cp.async.mbarrier.arrive -- so a loader never waits for data and NTS tiles are in flight) | 23 TMEM allocation + MMA issue.
+// 20, 21 loaders (warp w takes the tiles it = w (mod 2) into stage it % NTS, NTS even: ONE producer per stage barrier,
+// so its parity waits are never two phases away; the stage's barrier is armed by the copies themselves --
+// cp.async.mbarrier.arrive -- so a loader never waits for data and has two tiles in flight) | 22 idle | 23 TMEM
+// allocation + MMA issue.
 // TMEM columns: [0, 128) two accumulator sets of two blocks x 32 columns (the three 3xTF32 terms are three N = 32 MMAs
 // into the same columns); [128, 512) three A stages of two blocks x (32 hi + 32 lo) columns.
 #pragma once
@@ -34,7 +36,7 @@ constexpr int kOFirstLoadWarp = kOFirstSplitWarp + 4 * kOSplitSets;   // 20
 constexpr int kOLoadWarps = 3;
 constexpr int kOMmaWarp = kOFirstLoadWarp + kOLoadWarps;              // 23
 constexpr int kOThreads = (kOMmaWarp + 1) * 32;                       // 768 -> 80 registers per thread
-constexpr int kOMaxStages = 4;                                        // tile-stage ring depth limit
+constexpr int kOMaxStages = 4;                                        // tile-stage ring depth: 4 or 2 (two loader warps, warp w owns the stages = w mod 2)
 constexpr int kOBlocks = 2;                                           // M = 128 blocks of staged rows per tile
 constexpr int kOAStages = 3;                                          // TMEM A ring (128 columns each)
 constexpr int kOAColBase = 128;
@@ -58,7 +60,7 @@ struct OutCfg {
     static int stages(int S, int rcap) {
         const long long budget = 227LL * 1024 - 1024 - 512 - kTBChunk - 2 * kOPBytes;
         long long st = budget / (long long)stage_bytes(S, rcap);
-        return (int)(st > kOMaxStages ? kOMaxStages : st);
+        return st >= 4 ? 4 : (st >= 2 ? 2 : 0);
     }
     static size_t smem_bytes(int S, int rcap, int nts) { return 1024 + kTBChunk + (size_t)nts * stage_bytes(S, rcap) + 2 * kOPBytes + 512; }
 };
@@ -168,7 +170,7 @@ pt_kernel(const OutArgs a) {
         }
         __syncwarp();
     } else if (warp >= kOFirstLoadWarp) {
-        // ================= loaders: tile it by warp it % 3 into stage it % NTS =================
+        // ================= loaders: warp lw < 2 takes the tiles it = lw (mod 2); stage it % NTS (NTS even) =================
         const int lw = warp - kOFirstLoadWarp;
         const int q = lane & 7, rsub = lane >> 3;
         const int n_cell16 = (S * 512) >> 4;
@@ -176,7 +178,7 @@ pt_kernel(const OutArgs a) {
         long long t0 = (long long)blockIdx.x + (long long)lw * gridDim.x;
         int b = (int)(t0 / a.L), jt = (int)(t0 - (long long)b * a.L);
 #pragma unroll 1
-        for (int it = lw; it < my_tiles; it += kOLoadWarps) {
+        for (int it = lw; lw < 2 && it < my_tiles; it += 2) {
             const int ts = it % NTS;
             const uint32_t tph = (uint32_t)((it / NTS) & 1);
             const uint32_t stage_a = smem_u32(T_s) + (uint32_t)ts * (uint32_t)STAGE_BYTES;
@@ -204,7 +206,7 @@ pt_kernel(const OutArgs a) {
             for (int i = lane; i < n_cell16; i += 32)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst_cell + (uint32_t)i * 16u), "l"(cell_g + i * 16));
             cp_async_arrive_noinc(smem_u32(tile_full + ts));   // fires when this lane's copies have landed
-            for (int k = 0; k < kOLoadWarps; ++k) {
+            for (int k = 0; k < 2; ++k) {
                 b += db; jt += djt;
                 if (jt >= a.L) { jt -= a.L; ++b; }
             }

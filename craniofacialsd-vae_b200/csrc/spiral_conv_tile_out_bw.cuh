@@ -37,7 +37,7 @@ constexpr int kQEpiWarp0 = 8;
 constexpr int kQLoadWarp0 = 13;
 constexpr int kQLoadWarps = 3;
 constexpr int kQMmaWarp = 16;
-constexpr int kQMaxStages = 4;
+constexpr int kQMaxStages = 4;                                        // 4 or 2: two loader warps, warp w owns the stages = w (mod 2)
 constexpr int kQXBytes = 128 * 128;                                   // the tile's own x rows
 
 struct OutBwArgs {
@@ -60,7 +60,7 @@ struct OutBwCfg {
     static int stages(int S, int rcap, int ecap) {
         const long long budget = 227LL * 1024 - (long long)fixed_bytes();
         long long st = budget / (long long)stage_bytes(S, rcap, ecap);
-        return (int)(st > kQMaxStages ? kQMaxStages : st);
+        return st >= 4 ? 4 : (st >= 2 ? 2 : 0);
     }
     static size_t smem_bytes(int S, int rcap, int ecap, int nts) { return fixed_bytes() + (size_t)nts * stage_bytes(S, rcap, ecap); }
 };
@@ -193,13 +193,14 @@ qt_kernel(const OutBwArgs a) {
         }
         __syncwarp();
     } else if (warp >= kQLoadWarp0 && warp < kQLoadWarp0 + kQLoadWarps) {
-        // ================= loaders: tile it by warp it % 3 into stage it % NTS (asynchronous arrival) =================
+        // ================= loaders: warp lw < 2 takes the tiles it = lw (mod 2) into stage it % NTS (NTS even): one producer
+        // per stage barrier (a parity wait cannot tell phases two apart); asynchronous arrival, two tiles in flight per warp ====
         const int lw = warp - kQLoadWarp0;
         long long t0 = (long long)blockIdx.x + (long long)lw * gridDim.x;
         int b = (int)(t0 / a.L), jt = (int)(t0 - (long long)b * a.L);
         const int n_tail16 = (S * 512 + a.ecap * 2) >> 4;
 #pragma unroll 1
-        for (int it = lw; it < my_tiles; it += kQLoadWarps) {
+        for (int it = lw; lw < 2 && it < my_tiles; it += 2) {
             const int ts = it % NTS;
             const uint32_t stage_a = smem_u32(T_s) + (uint32_t)ts * (uint32_t)STAGE_BYTES;
             // the tile's source list first (independent 16-byte loads; a dependent index load per row made the loader
@@ -243,7 +244,7 @@ qt_kernel(const OutBwArgs a) {
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(stage_a + (uint32_t)CELL_OFF + (uint32_t)off), "l"(src));
             }
             cp_async_arrive_noinc(smem_u32(tile_full + ts));
-            for (int k = 0; k < kQLoadWarps; ++k) {
+            for (int k = 0; k < 2; ++k) {
                 b += db; jt += djt;
                 if (jt >= a.L) { jt -= a.L; ++b; }
             }
