@@ -88,87 +88,6 @@ __global__ void mse_lap_bwd_kernel(const float* __restrict__ recon, const float*
     o[0] = g0; o[1] = g1; o[2] = g2;
 }
 
-// ---- MSE + Laplacian with the mesh RESIDENT in shared memory -------------------------------------------------
-// The two kernels above gather the 9 neighbour rows of every vertex (12 bytes each) through L1/L2: ~80 instructions
-// and 27 scattered loads per vertex, 0.30-0.35 of the HBM roofline (profiles/r02_microbench.md).  A mesh's
-// reconstruction (forward) or its normalised Laplacian qn (backward) is only 12 V bytes (204 KB for V = 17 039): it is
-// staged once per mesh (narrow_stage_mesh, narrow_conv.cuh) and the neighbour reads hit shared memory; the other
-// operands stream through coalesced.  One persistent CTA per SM walks the meshes b = blockIdx.x, + gridDim.x, ...
-// Same arithmetic per vertex as the kernels above; the partial sums are per CTA (thread-private accumulation in vertex
-// order, then the block tree): deterministic.
-constexpr int kResThreads = 1024;
-inline size_t mse_lap_res_smem(int V) { return sizeof(float) * (8 + (size_t)V * 3 + 4 + kResThreads / 32); }
-inline bool mse_lap_res_ok(int B, int V) { return B >= 16 && mse_lap_res_smem(V) <= 227 * 1024; }
-
-__global__ void __launch_bounds__(kResThreads, 1)
-mse_lap_fwd_res_kernel(const float* __restrict__ recon, const float* __restrict__ x,
-                       const int* __restrict__ lcol, const float* __restrict__ lval, int lw,
-                       float* __restrict__ qn, float* __restrict__ partial /* [grid][2] */, int B, int V) {
-    extern __shared__ float res_smem[];
-    float* scratch = res_smem + 8 + (((size_t)V * 3 + 3) & ~(size_t)3);
-    float se = 0.f, nq = 0.f;
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
-        const float* rs = narrow_stage_mesh(res_smem, recon + (size_t)b * V * 3, V * 3);
-        const float* xb = x + (size_t)b * V * 3;
-        float* qb = qn ? qn + (size_t)b * V * 3 : nullptr;
-        for (int v = threadIdx.x; v < V; v += kResThreads) {
-            const float r0 = rs[v * 3], r1 = rs[v * 3 + 1], r2 = rs[v * 3 + 2];
-            const float d0 = r0 - xb[v * 3], d1 = r1 - xb[v * 3 + 1], d2 = r2 - xb[v * 3 + 2];
-            se += d0 * d0 + d1 * d1 + d2 * d2;
-            if (lcol) {
-                float q0 = 0.f, q1 = 0.f, q2 = 0.f;
-                for (int j = 0; j < lw; ++j) {
-                    const int c = __ldg(lcol + v * lw + j);
-                    if (c < 0) continue;
-                    const float w = __ldg(lval + v * lw + j);
-                    q0 = fmaf(w, rs[c * 3], q0);
-                    q1 = fmaf(w, rs[c * 3 + 1], q1);
-                    q2 = fmaf(w, rs[c * 3 + 2], q2);
-                }
-                const float n = sqrtf(q0 * q0 + q1 * q1 + q2 * q2);
-                nq += n;
-                const float inv = n > 0.f ? 1.f / n : 0.f;
-                qb[v * 3] = q0 * inv; qb[v * 3 + 1] = q1 * inv; qb[v * 3 + 2] = q2 * inv;
-            }
-        }
-    }
-    __syncthreads();
-    const float s0 = block_sum<kResThreads>(se, scratch);
-    const float s1 = block_sum<kResThreads>(nq, scratch);
-    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = s0; partial[2 * blockIdx.x + 1] = s1; }
-}
-
-__global__ void __launch_bounds__(kResThreads, 1)
-mse_lap_bwd_res_kernel(const float* __restrict__ recon, const float* __restrict__ x,
-                       const float* __restrict__ qn, const int* __restrict__ tptr,
-                       const int* __restrict__ trow, const float* __restrict__ tval,
-                       float* __restrict__ drecon, int B, int V, float c_mse, float c_lap,
-                       const float* __restrict__ dscale) {
-    extern __shared__ float res_smem[];
-    if (dscale) { c_mse *= dscale[0]; c_lap *= dscale[1]; }
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
-        const float* qs = narrow_stage_mesh(res_smem, qn + (size_t)b * V * 3, V * 3);
-        const float* rb = recon + (size_t)b * V * 3;
-        const float* xb = x + (size_t)b * V * 3;
-        float* ob = drecon + (size_t)b * V * 3;
-        for (int u = threadIdx.x; u < V; u += kResThreads) {
-            float g0 = 2.f * c_mse * (rb[u * 3] - xb[u * 3]);
-            float g1 = 2.f * c_mse * (rb[u * 3 + 1] - xb[u * 3 + 1]);
-            float g2 = 2.f * c_mse * (rb[u * 3 + 2] - xb[u * 3 + 2]);
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-            const int e0 = __ldg(tptr + u), e1 = __ldg(tptr + u + 1);
-            for (int e = e0; e < e1; ++e) {
-                const int r = __ldg(trow + e);
-                const float w = __ldg(tval + e);
-                a0 = fmaf(w, qs[r * 3], a0);
-                a1 = fmaf(w, qs[r * 3 + 1], a1);
-                a2 = fmaf(w, qs[r * 3 + 2], a2);
-            }
-            ob[u * 3] = fmaf(c_lap, a0, g0); ob[u * 3 + 1] = fmaf(c_lap, a1, g1); ob[u * 3 + 2] = fmaf(c_lap, a2, g2);
-        }
-    }
-}
-
 // ---- KL ---------------------------------------------------------------------------
 //   L = (1/B) sum_b -1/2 sum_d (1 + lv - mu^2 - e^lv);  dmu = mu/B;  dlv = (e^lv - 1)/(2B)
 __global__ void __launch_bounds__(kLossThreads)

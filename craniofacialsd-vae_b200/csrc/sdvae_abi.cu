@@ -1073,14 +1073,7 @@ int sdvae_mse_lap_fwd(const float* recon, const float* x, const int32_t* lcol, c
     SDVAE_REQUIRE(!lcol || (lval && qn && lw > 0), "mse_lap_fwd: Laplacian tables incomplete");
     cudaStream_t st = (cudaStream_t)stream;
     const long long BV = (long long)B * V;
-    unsigned grid = blocks_for(BV, kLossThreads);
-    if (lcol && mse_lap_res_ok(B, V)) {
-        // the mesh's reconstruction resident in shared memory (loss.cuh); `partial` holds at least blocks_for(BV, 256) pairs
-        static DeviceOnce attr_done;
-        if (attr_done.first()) cudaFuncSetAttribute(mse_lap_fwd_res_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        grid = (unsigned)std::min(B, kNumSMs);
-        mse_lap_fwd_res_kernel<<<grid, kResThreads, mse_lap_res_smem(V), st>>>(recon, x, lcol, lval, lw, qn, partial, B, V);
-    } else
+    const unsigned grid = blocks_for(BV, kLossThreads);
     mse_lap_fwd_kernel<<<grid, kLossThreads, 0, st>>>(recon, x, lcol, lval, lw, qn, partial, BV, V);
     finish_sum_kernel<<<1, kLossThreads, 0, st>>>(partial, grid, 2, 0, inv_count_scale / (float)((double)BV * 3.0), losses, 0);
     if (lcol) finish_sum_kernel<<<1, kLossThreads, 0, st>>>(partial, grid, 2, 1, inv_count_scale / (float)BV, losses, 3);
@@ -1111,14 +1104,6 @@ int sdvae_mse_lap_bwd(const float* recon, const float* x, const float* qn, const
     const long long BV = (long long)B * V;
     const float c_mse = g_mse * inv_count_scale / (float)((double)BV * 3.0);
     const float c_lap = g_lap * inv_count_scale / (float)BV;
-    if (tptr && g_lap != 0.f && mse_lap_res_ok(B, V)) {
-        // the mesh's normalised Laplacian qn resident in shared memory (loss.cuh)
-        static DeviceOnce attr_done;
-        if (attr_done.first()) cudaFuncSetAttribute(mse_lap_bwd_res_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        mse_lap_bwd_res_kernel<<<std::min(B, kNumSMs), kResThreads, mse_lap_res_smem(V), (cudaStream_t)stream>>>(
-            recon, x, qn, tptr, trow, tval, drecon, B, V, c_mse, c_lap, dscale);
-        return check_launch("mse_lap_bwd_res_kernel");
-    }
     mse_lap_bwd_kernel<<<blocks_for(BV, 256), 256, 0, (cudaStream_t)stream>>>(
         recon, x, qn, tptr, trow, tval, drecon, BV, V, c_mse, c_lap, dscale);
     return check_launch("mse_lap_bwd_kernel");

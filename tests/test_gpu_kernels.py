@@ -237,30 +237,6 @@ def test_mse_kl_laplacian(cranio, orc):
     assert nerr(mg.grad, mr.grad) < TOL and nerr(lg.grad, lr_.grad) < TOL
 
 
-@pytest.mark.parametrize('B', [16, 37, 160])
-def test_mse_laplacian_mesh_resident_kernels(cranio, orc, B):
-    """B >= 16: the MSE + Laplacian kernels with the mesh's reconstruction / normalised Laplacian resident in shared
-    memory (csrc/loss.cuh; 160 > one mesh per CTA): losses and gradient against the oracle in fp64, deterministic."""
-    from sdvae_b200 import losses
-    V = cranio.num_vertices[0]
-    lap = tuple(torch.from_numpy(a) for a in cranio.lap)
-    lt = losses.LaplacianTable.build(*cranio.lap, V, DEV)
-    p, t = rand((B, V, 3), 112), rand((B, V, 3), 113)
-    pr = p.double().requires_grad_(True)
-    ref = orc.mse_loss(pr, t.double()) * 0.7 + orc.laplacian_loss(pr, *lap) * 0.3
-    ref.backward()
-    outs = []
-    for _ in range(2):
-        pg = p.to(DEV).requires_grad_(True)
-        mse, lp = losses.mse_and_laplacian(pg, t.to(DEV), lt)
-        (mse * 0.7 + lp * 0.3).backward()
-        outs.append((float(mse), float(lp), pg.grad.clone()))
-    assert outs[0][0] == pytest.approx(float(orc.mse_loss(p.double(), t.double())), rel=2e-6)
-    assert outs[0][1] == pytest.approx(float(orc.laplacian_loss(p.double(), *lap)), rel=2e-6)
-    assert nerr(outs[0][2], pr.grad) < TOL
-    assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1] and torch.equal(outs[0][2], outs[1][2])
-
-
 def test_adam_matches_torch():
     from sdvae_b200 import cabi
     n = 10007
