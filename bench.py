@@ -450,8 +450,9 @@ def run_ours(args):
                    "parallelism": "dp%d (swap-grid rows)" % world,
                    "l2": "per-step working set (%.1f GB/GPU) exceeds the 126 MB L2" % (meshes_per_gpu * 12.0e6 / 1e9),
                    "cuda_graph": use_graph, "vertex_order": "template outside the engine; internal levels patch-wise" if renumbered else "template",
-                   "contractions": ("tcgen05 3xTF32 for every 32/64-channel SpiralConv pass; the two 3-channel layers "
-                                    "on the fp32 FMA units from shared-memory-resident meshes / staged rows")
+                   "contractions": ("tcgen05 3xTF32 for every 32/64-channel SpiralConv pass and for the 32->3 output layer "
+                                    "(project-then-gather forward, fused gather-then-project backward); the 3->32 first "
+                                    "block on the fp32 FMA units from shared-memory-resident meshes")
                                    if has_tc else "fp32 FMA"},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,

@@ -1,3 +1,2 @@
-set -x; mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "mse or lap" > gpurun_out/try_tests.log 2>&1; echo "rc=$?" >> gpurun_out/try_tests.log; tail -5 gpurun_out/try_tests.log
-timeout 300 python tools/microbench.py --batches 1024 --only none --iters 3 > /dev/null 2>&1
+mkdir -p gpurun_out
+timeout 300 python tools/infer_bench.py > gpurun_out/r02_infer_bench.md 2> gpurun_out/r02_infer_bench.err; echo "rc=$?"; cat gpurun_out/r02_infer_bench.md; tail -3 gpurun_out/r02_infer_bench.err

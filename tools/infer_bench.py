@@ -102,6 +102,23 @@ def main():
             ms = gpu_time(lambda: model.decode(z), 10)
             print('| decode (generate) | %d | z ~ N(0,1) | 1xB200, drop-in model.py (tcgen05) | %.3f | %.0f |'
                   % (B, ms, B / ms * 1e3))
+    # generate_for_opt (model_manager.py:253-255, Tester.fit_mesh test.py:395-421): decoder in train mode, loss on the
+    # output, gradient w.r.t. z -- with the weights frozen the backward launches no weight-gradient kernel
+    model.train()
+    for freeze in (False, True):
+        model.requires_grad_(not freeze)
+        for B in (16, 256):
+            z = torch.randn(B, 75, device=DEV, requires_grad=True)
+            tgt = torch.randn(B, V, 3, device=DEV)
+
+            def fit_step():
+                z.grad = None
+                ((model.decode(z) - tgt) ** 2).mean().backward()
+            ms = gpu_time(fit_step, 10)
+            print('| generate_for_opt: decode + backward to z%s | %d | z ~ N(0,1) | 1xB200, drop-in model.py (tcgen05) | %.3f | %.0f |'
+                  % (' (weights frozen: no dW)' if freeze else '', B, ms, B / ms * 1e3))
+    model.requires_grad_(True)
+    model.eval()
     if '--no-cpu' in sys.argv:
         return
     ref = refarm.find_ref()
