@@ -8,6 +8,11 @@ namespace sdvae { char g_last_error[512] = ""; }
 using namespace sdvae::umma;
 using namespace sdvae::tile;
 
+__device__ __forceinline__ uint32_t ld_acquire_a(uint32_t addr) {   // (lived in spiral_conv_tile.cuh while the counter hand-off variant did)
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint32_t ld_relaxed_a(uint32_t addr) {
     uint32_t v; asm volatile("ld.relaxed.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v;
 }
