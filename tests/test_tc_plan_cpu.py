@@ -77,6 +77,20 @@ def test_shape_support_matrix():
     assert cabi.tc_wimg_floats(9, 32, 32) == 9 * 2 * 32 * 32
 
 
+def test_output_layer_tc_support_matrix():
+    """Host-side shape predicates of the tcgen05 output-layer kernels (csrc/spiral_conv_tile_out*.cuh): 32 input
+    channels, S*Cout <= 27, forward plans with at most 256 distinct rows per tile (two M = 128 blocks), inverse plans
+    with at most 288 and a 128-byte aligned extension list; the workspace holds one partial per SM."""
+    assert cabi.narrow_out_fwd_tc_supported(9, 32, 3, 256) and cabi.narrow_out_fwd_tc_supported(9, 32, 3, 224)
+    assert not cabi.narrow_out_fwd_tc_supported(9, 32, 3, 288)          # a third block of staged rows
+    assert not cabi.narrow_out_fwd_tc_supported(9, 64, 3, 256) and not cabi.narrow_out_fwd_tc_supported(9, 32, 4, 256)
+    assert not cabi.narrow_out_fwd_tc_supported(10, 32, 3, 256) and not cabi.narrow_out_fwd_tc_supported(9, 32, 3, 250)
+    assert cabi.narrow_out_bwd_tc_supported(9, 32, 3, 288, 384) and cabi.narrow_out_bwd_tc_supported(9, 32, 3, 256, 0)
+    assert not cabi.narrow_out_bwd_tc_supported(9, 32, 3, 320, 384) and not cabi.narrow_out_bwd_tc_supported(9, 32, 3, 256, 100)
+    assert not cabi.narrow_out_bwd_tc_supported(9, 32, 4, 256, 384) and not cabi.narrow_out_bwd_tc_supported(9, 64, 3, 256, 384)
+    assert cabi.narrow_out_bwd_tc_workspace(9, 3) == 4 * 148 * (3 * 9 * 32 + 3)
+
+
 def test_identity_plan_for_slot_packed_layers():
     """S = 1 identity table (row r gathers row r): the plan the dense 32 x 32 contractions of the slot-packed
     3-channel layers run with."""
